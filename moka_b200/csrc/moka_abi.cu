@@ -1,0 +1,206 @@
+// extern "C" entry points of libmoka.so (see include/moka.h for the contract).
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "moka_common.cuh"
+#include "moka_kernels.h"
+
+namespace moka {
+
+static std::atomic<int64_t> g_launches{0};
+static thread_local char g_errbuf[256] = "";
+
+void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void set_cuda_error(cudaError_t e) {
+  snprintf(g_errbuf, sizeof(g_errbuf), "CUDA error %d: %s", (int)e, cudaGetErrorString(e));
+}
+
+static int num_sms() {
+  static int cached = 0;
+  if (!cached) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+static int validate(const MokaDesc* m) {
+  if (!m) return MOKA_EINVAL;
+  if (m->B <= 0 || m->S <= 0 || m->d_in <= 0 || m->d_out <= 0) return MOKA_EINVAL;
+  if ((m->d_in & 7) || (m->d_out & 7)) return MOKA_EINVAL;
+  if (m->r < 1 || m->r > 256) return MOKA_EINVAL;
+  if (m->M < 1 || m->M > 3) return MOKA_EINVAL;
+  if (m->dtype != MOKA_BF16 && m->dtype != MOKA_F32) return MOKA_EINVAL;
+  if (m->Lk < 0) return MOKA_EINVAL;
+  if (!(m->dropout_p >= 0.f && m->dropout_p < 1.f)) return MOKA_EINVAL;
+  if ((long long)m->B * m->S > 0x7fffffffLL / 256) return MOKA_EINVAL;
+  return MOKA_OK;
+}
+
+static DevDesc make_dev(const MokaDesc* m, uint64_t seed, uint64_t offset) {
+  DevDesc d;
+  memset(&d, 0, sizeof(d));
+  d.B = m->B; d.S = m->S; d.T = m->B * m->S;
+  d.d_in = m->d_in; d.d_out = m->d_out; d.r = m->r; d.M = m->M; d.Lk = m->Lk;
+  d.pre = m->pre;
+  d.post[0] = 0.f; d.post[1] = m->post[0]; d.post[2] = m->post[1]; d.post[3] = m->post[2];
+  d.attn_w = m->attn_w;
+  d.sm_scale = 1.0f / sqrtf((float)m->r);
+  if (m->dropout_p > 0.f) {
+    d.drop_scale = 1.0f / (1.0f - m->dropout_p);
+    long t = lrintf(m->dropout_p * 65536.0f);
+    if (t < 1) t = 1;
+    if (t > 65535) t = 65535;
+    d.drop_thresh = (uint32_t)t;
+  } else {
+    d.drop_scale = 1.0f; d.drop_thresh = 0;
+  }
+  d.seed = seed; d.offset = offset;
+  return d;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static size_t ws_dh_bytes(const MokaDesc* m) { return align_up((size_t)m->B * m->S * m->r * 4, 256); }
+static size_t ws_dk_bytes(const MokaDesc* m) { return align_up((size_t)m->B * (m->Lk > 0 ? m->Lk : 1) * m->r * 4, 256); }
+
+// stages the tcgen05 path takes for this call (flags bits 8..11 veto individual stages)
+static int tc_stages(const MokaDesc* m, const DevDesc& d) {
+  if (m->flags & MOKA_FLAG_FORCE_SIMT) return 0;
+  return tc_stage_mask(d, m->dtype) & ~((m->flags >> 8) & kStageAll);
+}
+
+}  // namespace moka
+
+using namespace moka;
+
+extern "C" {
+
+size_t moka_workspace_bytes(const MokaDesc* desc) {
+  if (validate(desc) != MOKA_OK) return 0;
+  return ws_dh_bytes(desc) + ws_dk_bytes(desc) + 256;
+}
+
+int moka_uses_tensor_cores(const MokaDesc* desc) {
+  if (validate(desc) != MOKA_OK) return 0;
+  DevDesc d = make_dev(desc, 0, 0);
+  return tc_stages(desc, d) ? 1 : 0;
+}
+
+int moka_forward(const MokaDesc* desc, const void* x, const void* y0, void* y,
+                 const void* const* A, const void* Bw,
+                 const uint8_t* tokmeta, const int32_t* kidx, const int32_t* klen,
+                 float* h_stash, uint64_t seed, uint64_t offset,
+                 void* workspace, size_t workspace_bytes, moka_stream_t stream) {
+  if (int e = validate(desc)) return e;
+  if (!x || !y0 || !y || !A || !Bw || !tokmeta || !klen || !h_stash) return MOKA_EINVAL;
+  if (desc->Lk > 0 && !kidx) return MOKA_EINVAL;
+  for (int m = 0; m < desc->M; ++m) if (!A[m]) return MOKA_EINVAL;
+  if (!aligned16(x) || !aligned16(y0) || !aligned16(y) || !aligned16(Bw) || !aligned16(h_stash)) return MOKA_EALIGN;
+  for (int m = 0; m < desc->M; ++m) if (!aligned16(A[m])) return MOKA_EALIGN;
+  (void)workspace; (void)workspace_bytes;
+  DevDesc d = make_dev(desc, seed, offset);
+  SimtArgs a;
+  memset(&a, 0, sizeof(a));
+  a.x = x; a.y0 = y0; a.y = y; a.Bw = Bw;
+  for (int m = 0; m < desc->M; ++m) a.A[m] = A[m];
+  a.tokmeta = tokmeta; a.kidx = kidx; a.klen = klen; a.h_stash = h_stash; a.klen_hint = desc->Lk;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int tcs = tc_stages(desc, d) & (kStageDown | kStageUp);
+  if ((desc->flags & MOKA_FLAG_FORCE_TC) && tcs != (kStageDown | kStageUp)) return MOKA_EUNSUPPORTED;
+  // stage order matters: down (h) before up (y)
+  if (tcs & kStageDown) { if (int e = tc_forward(d, a, num_sms(), st, kStageDown)) return e; }
+  else if (int e = simt_forward(d, desc->dtype, a, num_sms(), st, kStageDown)) return e;
+  if (tcs & kStageUp) return tc_forward(d, a, num_sms(), st, kStageUp);
+  return simt_forward(d, desc->dtype, a, num_sms(), st, kStageUp);
+}
+
+int moka_backward(const MokaDesc* desc, const void* dy, const void* x, const float* h_stash,
+                  const void* const* A, const void* Bw,
+                  const uint8_t* tokmeta, const int32_t* kidx, const int32_t* klen,
+                  void* dx, float* const* dA, float* dB,
+                  uint64_t seed, uint64_t offset,
+                  void* workspace, size_t workspace_bytes, moka_stream_t stream) {
+  if (int e = validate(desc)) return e;
+  if (!dy || !x || !h_stash || !A || !Bw || !tokmeta || !klen || !dA || !dB || !workspace) return MOKA_EINVAL;
+  if (desc->Lk > 0 && !kidx) return MOKA_EINVAL;
+  for (int m = 0; m < desc->M; ++m) if (!A[m] || !dA[m]) return MOKA_EINVAL;
+  if (!aligned16(dy) || !aligned16(x) || !aligned16(Bw) || !aligned16(h_stash) || !aligned16(dB) ||
+      !aligned16(workspace) || (dx && !aligned16(dx))) return MOKA_EALIGN;
+  for (int m = 0; m < desc->M; ++m) if (!aligned16(A[m]) || !aligned16(dA[m])) return MOKA_EALIGN;
+  if (workspace_bytes < moka_workspace_bytes(desc)) return MOKA_EWORKSPACE;
+  DevDesc d = make_dev(desc, seed, offset);
+  SimtArgs a;
+  memset(&a, 0, sizeof(a));
+  a.dy = dy; a.x = x; a.dx = dx; a.Bw = Bw; a.dB = dB;
+  for (int m = 0; m < desc->M; ++m) { a.A[m] = A[m]; a.dA[m] = dA[m]; }
+  a.tokmeta = tokmeta; a.kidx = kidx; a.klen = klen; a.h_stash = const_cast<float*>(h_stash);
+  a.klen_hint = desc->Lk;
+  char* ws = static_cast<char*>(workspace);
+  a.dh = reinterpret_cast<float*>(ws);
+  a.dK = reinterpret_cast<float*>(ws + ws_dh_bytes(desc));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaError_t ce = cudaMemsetAsync(a.dK, 0, ws_dk_bytes(desc), st);
+  if (ce != cudaSuccess) { set_cuda_error(ce); return MOKA_ECUDA; }
+  const int tcs = tc_stages(desc, d) & (kStageDgrad | kStageWgrad);
+  if ((desc->flags & MOKA_FLAG_FORCE_TC) && tcs != (kStageDgrad | kStageWgrad)) return MOKA_EUNSUPPORTED;
+  if (tcs & kStageDgrad) { if (int e = tc_backward(d, a, num_sms(), st, kStageDgrad)) return e; }
+  else if (int e = simt_backward(d, desc->dtype, a, num_sms(), st, kStageDgrad)) return e;
+  if (tcs & kStageWgrad) return tc_backward(d, a, num_sms(), st, kStageWgrad);
+  return simt_backward(d, desc->dtype, a, num_sms(), st, kStageWgrad);
+}
+
+int moka_build_token_meta(int32_t variant, int32_t B, int32_t S, int32_t Lk,
+                          const void* const* masks, int32_t mask_elem_bytes,
+                          uint8_t* tokmeta, int32_t* kidx, int32_t* klen, int32_t* status,
+                          moka_stream_t stream) {
+  if (variant != MOKA_VARIANT_AVT && variant != MOKA_VARIANT_VT) return MOKA_EINVAL;
+  if (B <= 0 || S <= 0 || Lk <= 0 || !masks || !tokmeta || !kidx || !klen || !status) return MOKA_EINVAL;
+  if (mask_elem_bytes != 1 && mask_elem_bytes != 4 && mask_elem_bytes != 8) return MOKA_EINVAL;
+  if (!masks[0] || !masks[1] || !masks[3]) return MOKA_EINVAL;
+  return launch_build_meta(variant, B, S, Lk, masks, mask_elem_bytes, tokmeta, kidx, klen, status,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int moka_dropout_keep_mask(const MokaDesc* desc, uint64_t seed, uint64_t offset, uint8_t* keep,
+                           moka_stream_t stream) {
+  if (int e = validate(desc)) return e;
+  if (!keep) return MOKA_EINVAL;
+  DevDesc d = make_dev(desc, seed, offset);
+  return launch_keep_mask(d, keep, static_cast<cudaStream_t>(stream));
+}
+
+int moka_adamw_step(int64_t n, float* master, float* exp_avg, float* exp_avg_sq, const float* grad,
+                    void* param_out, int32_t dtype, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int32_t step, float grad_scale, moka_stream_t stream) {
+  if (n < 0 || !master || !exp_avg || !exp_avg_sq || !grad || step < 1) return MOKA_EINVAL;
+  if (dtype != MOKA_BF16 && dtype != MOKA_F32) return MOKA_EINVAL;
+  return launch_adamw(n, master, exp_avg, exp_avg_sq, grad, param_out, dtype, lr, beta1, beta2, eps,
+                      weight_decay, step, grad_scale, static_cast<cudaStream_t>(stream));
+}
+
+int64_t moka_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+const char* moka_strerror(int code) {
+  switch (code) {
+    case MOKA_OK: return "ok";
+    case MOKA_EINVAL: return "invalid descriptor or null pointer";
+    case MOKA_EWORKSPACE: return "workspace too small (see moka_workspace_bytes)";
+    case MOKA_ECUDA: return g_errbuf[0] ? g_errbuf : "CUDA launch failed";
+    case MOKA_EUNSUPPORTED: return "requested kernel path not available for this shape";
+    case MOKA_EALIGN: return "pointer not 16-byte aligned";
+    default: return "unknown error";
+  }
+}
+
+int moka_version(void) { return 100; }
+
+}  // extern "C"

@@ -1,0 +1,268 @@
+// Rank-r cross-modal attention of the MokA layer, forward and backward, on smem-resident
+// token rows.  One warp per query token; keys of the sample staged in shared memory
+// (lane <-> key for the scores, lane <-> rank index for the weighted sums); softmax
+// reductions by warp shuffles.  A generic slow path (keys read from the global stash)
+// covers key lists that do not fit in shared memory.
+//
+// Semantics: AudioVisualText/peft_hyper/tuners/lora.py:480-521 and
+// VisualText/modified_peft/tuners/lora/layer.py:627-653 (see oracle/moka_oracle.py,
+// fused_forward / fused_backward, for the restatement this follows).
+#pragma once
+#include "moka_common.cuh"
+
+namespace moka {
+
+constexpr int kKeyBlocksMax = 8;   // fast path handles up to 256 keys per sample
+
+struct AttnCtx {
+  const uint8_t* tokmeta;   // global [T]
+  const int32_t* kidx;      // global [B, Lk]
+  const int32_t* klen;      // global [B]
+  const float* h_stash;     // global [T, r] pre-attention projections
+  float* dK_glob;           // global [B, Lk, r] (backward only)
+  float* Ks;                // smem  [kcap, ks]
+  float* dKs;               // smem  [kcap, ks] (backward only)
+  int ks;                   // row stride of Ks (r + 1: conflict-free lane<->key reads)
+  int kcap;                 // keys that fit in Ks
+};
+
+// ------------------------------------------------------------------ fast path (smem keys)
+template <bool BWD>
+__device__ __forceinline__ void attn_token_fast(const DevDesc& d, const AttnCtx& c, int L,
+                                                const float* hq, float* gq, float* dgq, int lane) {
+  const int r = d.r;
+  const int nb = (L + 31) >> 5;
+  float p[kKeyBlocksMax];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int kb = 0; kb < kKeyBlocksMax; ++kb) {
+    p[kb] = -INFINITY;
+    if (kb < nb) {
+      const int k = kb * 32 + lane;
+      if (k < L) {
+        const float* Kr = c.Ks + k * c.ks;
+        float s = 0.f;
+        for (int j = 0; j < r; ++j) s = fmaf(hq[j], Kr[j], s);
+        p[kb] = s * d.sm_scale * kLog2e;
+      }
+      mx = fmaxf(mx, p[kb]);
+    }
+  }
+  mx = warp_max(mx);
+  float l = 0.f;
+#pragma unroll
+  for (int kb = 0; kb < kKeyBlocksMax; ++kb) {
+    if (kb < nb) {
+      const int k = kb * 32 + lane;
+      p[kb] = (k < L) ? exp2f(p[kb] - mx) : 0.f;
+      l += p[kb];
+    } else {
+      p[kb] = 0.f;
+    }
+  }
+  l = warp_sum(l);
+  const float inv = 1.f / l;
+#pragma unroll
+  for (int kb = 0; kb < kKeyBlocksMax; ++kb) p[kb] *= inv;
+
+  if (!BWD) {
+    __syncwarp();                      // gq may alias hq: every lane has finished reading the row
+    for (int jb = 0; jb < r; jb += 32) {
+      const int jj = jb + lane;
+      const bool act = jj < r;
+      float a = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < kKeyBlocksMax; ++kb) {
+        if (kb < nb) {
+          const int kend = min(32, L - kb * 32);
+          for (int kk = 0; kk < kend; ++kk) {
+            const float pk = __shfl_sync(0xffffffffu, p[kb], kk);
+            if (act) a = fmaf(pk, c.Ks[(kb * 32 + kk) * c.ks + jj], a);
+          }
+        }
+      }
+      if (act) gq[jj] = hq[jj] + d.attn_w * a;
+    }
+    return;
+  }
+
+  // ---- backward: da = w * dg ; dp_k = da . K_k ; ds = p (dp - <p,dp>)
+  float ds[kKeyBlocksMax];
+  float Dsum = 0.f;
+#pragma unroll
+  for (int kb = 0; kb < kKeyBlocksMax; ++kb) {
+    ds[kb] = 0.f;
+    if (kb < nb) {
+      const int k = kb * 32 + lane;
+      if (k < L) {
+        const float* Kr = c.Ks + k * c.ks;
+        float s = 0.f;
+        for (int j = 0; j < r; ++j) s = fmaf(dgq[j], Kr[j], s);
+        ds[kb] = s * d.attn_w;          // dp_k
+        Dsum = fmaf(p[kb], ds[kb], Dsum);
+      }
+    }
+  }
+  Dsum = warp_sum(Dsum);
+#pragma unroll
+  for (int kb = 0; kb < kKeyBlocksMax; ++kb) ds[kb] = p[kb] * (ds[kb] - Dsum);
+  __syncwarp();
+  for (int jb = 0; jb < r; jb += 32) {
+    const int jj = jb + lane;
+    const bool act = jj < r;
+    const float dgv = act ? dgq[jj] : 0.f;
+    const float hv = act ? hq[jj] : 0.f;
+    const float dav = d.attn_w * dgv;
+    float acc = 0.f;
+#pragma unroll
+    for (int kb = 0; kb < kKeyBlocksMax; ++kb) {
+      if (kb < nb) {
+        const int kend = min(32, L - kb * 32);
+        for (int kk = 0; kk < kend; ++kk) {
+          const float pk = __shfl_sync(0xffffffffu, p[kb], kk);
+          const float dsk = __shfl_sync(0xffffffffu, ds[kb], kk);
+          if (act) {
+            const int off = (kb * 32 + kk) * c.ks + jj;
+            acc = fmaf(dsk, c.Ks[off], acc);
+            atomicAdd(&c.dKs[off], fmaf(pk, dav, d.sm_scale * dsk * hv));
+          }
+        }
+      }
+    }
+    if (act) dgq[jj] = dgv + d.sm_scale * acc;      // dh of the query token, in place
+  }
+}
+
+// ------------------------------------------------------------------ slow path (global keys)
+// lanes <-> rank index (up to 8 per lane, r <= 256); one key at a time.
+template <bool BWD>
+__device__ __forceinline__ void attn_token_slow(const DevDesc& d, const AttnCtx& c, int b, int L,
+                                                const float* hq, float* gq, float* dgq, int lane) {
+  const int r = d.r;
+  float hv[8], dav[8], acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int jj = lane + 32 * i;
+    hv[i] = jj < r ? hq[jj] : 0.f;
+    dav[i] = (BWD && jj < r) ? d.attn_w * dgq[jj] : 0.f;
+    acc[i] = 0.f;
+  }
+  const float sl = d.sm_scale * kLog2e;
+  auto load_key = [&](int k, float (&kv)[8]) -> bool {
+    const int pos = c.kidx[(size_t)b * d.Lk + k];
+    const size_t t = (size_t)b * d.S + pos;
+    const bool valid = (c.tokmeta[t] & MOKA_KEY_VALID) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int jj = lane + 32 * i;
+      kv[i] = (valid && jj < r) ? c.h_stash[t * r + jj] : 0.f;
+    }
+    return valid;
+  };
+  auto dot8 = [&](const float (&a)[8], const float (&kv)[8]) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(a[i], kv[i], s);
+    return warp_sum(s);
+  };
+  float kv[8];
+  float mx = -INFINITY;
+  for (int k = 0; k < L; ++k) { load_key(k, kv); mx = fmaxf(mx, dot8(hv, kv) * sl); }
+  float l = 0.f, E = 0.f;
+  for (int k = 0; k < L; ++k) {
+    load_key(k, kv);
+    const float e = exp2f(dot8(hv, kv) * sl - mx);
+    l += e;
+    if (!BWD) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(e, kv[i], acc[i]);
+    } else {
+      E = fmaf(e, dot8(dav, kv), E);
+    }
+  }
+  const float inv = 1.f / l;
+  if (!BWD) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int jj = lane + 32 * i;
+      if (jj < r) gq[jj] = hv[i] + d.attn_w * acc[i] * inv;
+    }
+    return;
+  }
+  const float Dsum = E * inv;
+  for (int k = 0; k < L; ++k) {
+    const bool valid = load_key(k, kv);
+    const float pk = exp2f(dot8(hv, kv) * sl - mx) * inv;
+    const float dsk = pk * (dot8(dav, kv) - Dsum);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int jj = lane + 32 * i;
+      acc[i] = fmaf(dsk, kv[i], acc[i]);
+      if (valid && jj < r)
+        red_add_f32(&c.dK_glob[((size_t)b * d.Lk + k) * r + jj], fmaf(pk, dav[i], d.sm_scale * dsk * hv[i]));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int jj = lane + 32 * i;
+    if (jj < r) dgq[jj] = dgq[jj] + d.sm_scale * acc[i];
+  }
+}
+
+// ------------------------------------------------------------------ per-tile driver
+// hs : [nt, r] pre-attention rows (read-only here)
+// gs : forward  -> receives g rows of query tokens (may alias hs: a row is only touched by its own warp)
+// dgs: backward -> holds dg rows, overwritten with dh rows of query tokens
+// meta_s: tile-local tokmeta bytes.  Must be called by every thread of the CTA.
+template <bool BWD>
+__device__ __forceinline__ void attention_tile(const DevDesc& d, const AttnCtx& c, int t0, int nt,
+                                               const uint8_t* meta_s, const float* hs, float* gs, float* dgs) {
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  const int r = d.r;
+  const int b_first = t0 / d.S, b_last = (t0 + nt - 1) / d.S;
+  for (int b = b_first; b <= b_last; ++b) {
+    const int lo = max(t0, b * d.S) - t0;
+    const int hi = min(t0 + nt, (b + 1) * d.S) - t0;
+    int q = 0;
+    for (int i = lo + tid; i < hi; i += nthr) q |= ((meta_s[i] & MOKA_MOD_MASK) >= MOKA_MOD_VIS);
+    if (!__syncthreads_or(q)) continue;
+    const int L = c.klen[b];
+    if (L <= 0) continue;
+    const bool fast = (L <= c.kcap) && (L <= 32 * kKeyBlocksMax);
+    if (fast) {
+      for (int idx = tid; idx < L * r; idx += nthr) {
+        const int k = idx / r, j = idx - k * r;
+        const int pos = c.kidx[(size_t)b * d.Lk + k];
+        const size_t t = (size_t)b * d.S + pos;
+        const bool valid = (c.tokmeta[t] & MOKA_KEY_VALID) != 0;
+        c.Ks[k * c.ks + j] = valid ? c.h_stash[t * r + j] : 0.f;
+        if (BWD) c.dKs[k * c.ks + j] = 0.f;
+      }
+      __syncthreads();
+    }
+    for (int tt = lo + warp; tt < hi; tt += nwarps) {
+      if ((meta_s[tt] & MOKA_MOD_MASK) < MOKA_MOD_VIS) continue;
+      const float* hq = hs + (size_t)tt * r;
+      float* gq = BWD ? nullptr : gs + (size_t)tt * r;
+      float* dgq = BWD ? dgs + (size_t)tt * r : nullptr;
+      if (fast) attn_token_fast<BWD>(d, c, L, hq, gq, dgq, lane);
+      else attn_token_slow<BWD>(d, c, b, L, hq, gq, dgq, lane);
+    }
+    if (fast) {
+      __syncthreads();
+      if (BWD) {
+        for (int idx = tid; idx < L * r; idx += nthr) {
+          const int k = idx / r, j = idx - k * r;
+          const int pos = c.kidx[(size_t)b * d.Lk + k];
+          const size_t t = (size_t)b * d.S + pos;
+          if (c.tokmeta[t] & MOKA_KEY_VALID)
+            red_add_f32(&c.dK_glob[((size_t)b * d.Lk + k) * r + j], c.dKs[k * c.ks + j]);
+        }
+        __syncthreads();
+      }
+    }
+  }
+}
+
+}  // namespace moka

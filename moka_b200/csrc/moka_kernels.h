@@ -1,0 +1,40 @@
+// Internal launch interfaces between the ABI layer and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "moka_common.cuh"
+
+namespace moka {
+
+struct SimtArgs {
+  const void* x; const void* y0; void* y; const void* dy; void* dx;
+  const void* A[3]; const void* Bw;
+  float* dA[3]; float* dB;
+  const uint8_t* tokmeta; const int32_t* kidx; const int32_t* klen;
+  float* h_stash;
+  float* dh;        // workspace [T, r]
+  float* dK;        // workspace [B, Lk, r]
+  int klen_hint;    // upper bound on klen (kidx row stride)
+};
+
+enum { kStageDown = 1, kStageUp = 2, kStageDgrad = 4, kStageWgrad = 8, kStageAll = 15 };
+
+// `stages` selects which of the four streaming kernels run (the rest are done by the tcgen05 path)
+int simt_forward(const DevDesc& d, int dtype, const SimtArgs& a, int num_sms, cudaStream_t st, int stages = kStageAll);
+int simt_backward(const DevDesc& d, int dtype, const SimtArgs& a, int num_sms, cudaStream_t st, int stages = kStageAll);
+int launch_keep_mask(const DevDesc& d, uint8_t* keep, cudaStream_t st);
+
+int launch_build_meta(int variant, int B, int S, int Lk, const void* const* masks, int elem_bytes,
+                      uint8_t* tokmeta, int32_t* kidx, int32_t* klen, int32_t* status, cudaStream_t st);
+
+int launch_adamw(int64_t n, float* master, float* m, float* v, const float* grad, void* param_out, int dtype,
+                 float lr, float b1, float b2, float eps, float wd, int step, float grad_scale, cudaStream_t st);
+
+// tensor-core (tcgen05 + TMA) path; returns MOKA_EUNSUPPORTED when the shape does not qualify
+// Returns the mask of stages the tcgen05 path implements for this shape (0 = none).
+int tc_stage_mask(const DevDesc& d, int dtype);
+int tc_forward(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, int stages);
+int tc_backward(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, int stages);
+
+}  // namespace moka

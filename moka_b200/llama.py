@@ -1,0 +1,224 @@
+"""Frozen Llama-2 host wrapper that threads the MokA masks to the 7 projections of every layer.
+
+This is the CALLER of the hot path, not part of it: the frozen math is
+stock PyTorch (cuBLAS GEMMs, F.scaled_dot_product_attention -> flash kernels, RMSNorm, RoPE,
+SiLU).  What it mirrors from the reference is the mask plumbing:
+
+* AVT ``AudioVisualText/models/modeling_llama.py``: ``LlamaModel.forward`` unpacks
+  ``inputs_embeds = [emb, text, video, audio, question]`` (:647-654) and every decoder layer
+  passes the same list to ``q/k/v/o_proj`` (:326-328, :384) and ``gate/up/down_proj`` (:222-224);
+  per-layer gradient checkpointing (:719-733).
+* VT ``VisualText/modified_models/modeling_llama.py``: ``my_text_mask / my_image_mask /
+  question_mask`` ride in kwargs (:495) to the same 7 projections (:152-159, :251-253, :279).
+
+Module names match HF Llama (``model.layers.N.self_attn.q_proj`` ...) so that
+``get_peft_model`` target matching and checkpoint keys are the reference's.
+Weights are random-initialised from the config (no checkpoints on the box).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Any, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.utils.checkpoint import checkpoint
+
+from .layer import MokaLinearAVT, MokaLinearVT
+from .metadata import TokenMeta, build_token_meta_avt, build_token_meta_vt
+
+
+@dataclass
+class LlamaConfig:
+    hidden_size: int = 4096
+    intermediate_size: int = 11008
+    num_hidden_layers: int = 32
+    num_attention_heads: int = 32
+    vocab_size: int = 32000
+    rms_norm_eps: float = 1e-5
+    rope_theta: float = 10000.0
+    initializer_range: float = 0.02
+    max_position_embeddings: int = 4096
+
+    @staticmethod
+    def llama2_7b() -> 'LlamaConfig':
+        return LlamaConfig()
+
+    @staticmethod
+    def llama2_13b() -> 'LlamaConfig':
+        return LlamaConfig(hidden_size=5120, intermediate_size=13824, num_hidden_layers=40,
+                           num_attention_heads=40)
+
+    @staticmethod
+    def tiny(layers: int = 2, hidden: int = 256, inter: int = 512, heads: int = 4, vocab: int = 512) -> 'LlamaConfig':
+        return LlamaConfig(hidden_size=hidden, intermediate_size=inter, num_hidden_layers=layers,
+                           num_attention_heads=heads, vocab_size=vocab)
+
+
+def _proj(mod: nn.Module, x: torch.Tensor, mask_args: Optional[tuple]) -> torch.Tensor:
+    """Call a projection the way the reference decoder layers do: MokA layers get the masks."""
+    if mask_args is not None and isinstance(mod, (MokaLinearAVT, MokaLinearVT)):
+        return mod(x, *mask_args)
+    if isinstance(mod, MokaLinearVT):
+        return mod(x, None, None, None)
+    return mod(x)
+
+
+class RMSNorm(nn.Module):
+    def __init__(self, dim: int, eps: float):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.variance_epsilon = eps
+
+    def forward(self, x):
+        return F.rms_norm(x, (x.shape[-1],), self.weight, self.variance_epsilon)
+
+
+def _rope_tables(S: int, head_dim: int, theta: float, device, dtype):
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, device=device, dtype=torch.float32) / head_dim))
+    t = torch.arange(S, device=device, dtype=torch.float32)
+    fr = torch.outer(t, inv)
+    emb = torch.cat((fr, fr), dim=-1)
+    return emb.cos().to(dtype)[None, None], emb.sin().to(dtype)[None, None]
+
+
+def _rotate_half(x):
+    x1, x2 = x[..., : x.shape[-1] // 2], x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+class LlamaAttention(nn.Module):
+    def __init__(self, cfg: LlamaConfig):
+        super().__init__()
+        self.num_heads = cfg.num_attention_heads
+        self.head_dim = cfg.hidden_size // cfg.num_attention_heads
+        d = cfg.hidden_size
+        self.q_proj = nn.Linear(d, d, bias=False)
+        self.k_proj = nn.Linear(d, d, bias=False)
+        self.v_proj = nn.Linear(d, d, bias=False)
+        self.o_proj = nn.Linear(d, d, bias=False)
+
+    def forward(self, h, rope, mask_args):
+        B, S, _ = h.shape
+        q = _proj(self.q_proj, h, mask_args).view(B, S, self.num_heads, self.head_dim).transpose(1, 2)
+        k = _proj(self.k_proj, h, mask_args).view(B, S, self.num_heads, self.head_dim).transpose(1, 2)
+        v = _proj(self.v_proj, h, mask_args).view(B, S, self.num_heads, self.head_dim).transpose(1, 2)
+        cos, sin = rope
+        q = q * cos + _rotate_half(q) * sin
+        k = k * cos + _rotate_half(k) * sin
+        o = F.scaled_dot_product_attention(q, k, v, is_causal=True)
+        o = o.transpose(1, 2).reshape(B, S, -1)
+        return _proj(self.o_proj, o, mask_args)
+
+
+class LlamaMLP(nn.Module):
+    def __init__(self, cfg: LlamaConfig):
+        super().__init__()
+        self.gate_proj = nn.Linear(cfg.hidden_size, cfg.intermediate_size, bias=False)
+        self.up_proj = nn.Linear(cfg.hidden_size, cfg.intermediate_size, bias=False)
+        self.down_proj = nn.Linear(cfg.intermediate_size, cfg.hidden_size, bias=False)
+
+    def forward(self, x, mask_args):
+        return _proj(self.down_proj, F.silu(_proj(self.gate_proj, x, mask_args)) * _proj(self.up_proj, x, mask_args),
+                     mask_args)
+
+
+class LlamaDecoderLayer(nn.Module):
+    def __init__(self, cfg: LlamaConfig):
+        super().__init__()
+        self.self_attn = LlamaAttention(cfg)
+        self.mlp = LlamaMLP(cfg)
+        self.input_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
+        self.post_attention_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
+
+    def forward(self, h, cos, sin, *mask_args):
+        ma = mask_args if mask_args else None
+        h = h + self.self_attn(self.input_layernorm(h), (cos, sin), ma)
+        return h + self.mlp(self.post_attention_layernorm(h), ma)
+
+
+class LlamaModel(nn.Module):
+    def __init__(self, cfg: LlamaConfig):
+        super().__init__()
+        self.config = cfg
+        self.embed_tokens = nn.Embedding(cfg.vocab_size, cfg.hidden_size)
+        self.layers = nn.ModuleList([LlamaDecoderLayer(cfg) for _ in range(cfg.num_hidden_layers)])
+        self.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
+        self.gradient_checkpointing = False
+
+    def forward(self, input_ids=None, inputs_embeds=None, mask_args: Optional[tuple] = None):
+        if isinstance(inputs_embeds, (list, tuple)):
+            # AVT packing: [embeddings, text, video, audio, question] (modeling_llama.py:647-654)
+            packed = list(inputs_embeds)
+            inputs_embeds, mask_args = packed[0], (packed[1:5],)
+        h = self.embed_tokens(input_ids) if inputs_embeds is None else inputs_embeds
+        B, S, _ = h.shape
+        hd = self.config.hidden_size // self.config.num_attention_heads
+        cos, sin = _rope_tables(S, hd, self.config.rope_theta, h.device, h.dtype)
+        ma = tuple(mask_args) if mask_args is not None else ()
+        for layer in self.layers:
+            if self.gradient_checkpointing and self.training:
+                h = checkpoint(layer, h, cos, sin, *ma, use_reentrant=False)
+            else:
+                h = layer(h, cos, sin, *ma)
+        return self.norm(h)
+
+
+class LlamaForCausalLM(nn.Module):
+    """``forward(input_ids | inputs_embeds, labels, modality_masks=[t,v,a,q] | my_text_mask=...,
+    my_image_mask=..., question_mask=... | token_meta=TokenMeta)`` -> (loss, logits)."""
+
+    def __init__(self, cfg: LlamaConfig):
+        super().__init__()
+        self.config = cfg
+        self.model = LlamaModel(cfg)
+        self.lm_head = nn.Linear(cfg.hidden_size, cfg.vocab_size, bias=False)
+        self.apply(self._init_weights)
+
+    def _init_weights(self, m):
+        std = self.config.initializer_range
+        if isinstance(m, nn.Linear):
+            m.weight.data.normal_(mean=0.0, std=std)
+        elif isinstance(m, nn.Embedding):
+            m.weight.data.normal_(mean=0.0, std=std)
+
+    def gradient_checkpointing_enable(self, enabled: bool = True):
+        self.model.gradient_checkpointing = enabled
+
+    def forward(self, input_ids=None, inputs_embeds=None, labels=None, modality_masks: Optional[Sequence] = None,
+                my_text_mask=None, my_image_mask=None, question_mask=None,
+                token_meta: Optional[TokenMeta] = None, return_logits: bool = False):
+        if token_meta is not None:
+            mask_args: Optional[tuple] = (token_meta,)
+        elif modality_masks is not None:
+            # build the token metadata ONCE per step and hand it to all 7 x L projections
+            mask_args = (build_token_meta_avt(list(modality_masks)),)
+        elif my_text_mask is not None:
+            mask_args = (build_token_meta_vt(my_text_mask, my_image_mask, question_mask),)
+        else:
+            mask_args = None
+        h = self.model(input_ids=input_ids, inputs_embeds=inputs_embeds, mask_args=mask_args)
+        loss = None
+        logits = None
+        if labels is not None:
+            loss = chunked_causal_lm_loss(h, self.lm_head.weight, labels)
+        if return_logits or labels is None:
+            logits = self.lm_head(h)
+        return loss, logits
+
+
+def chunked_causal_lm_loss(h: torch.Tensor, lm_weight: torch.Tensor, labels: torch.Tensor,
+                           chunk: int = 2048) -> torch.Tensor:
+    """Shifted next-token cross entropy, computed in token chunks so the fp32 logits never exist
+    for the whole batch at once (HF computes the same loss un-chunked)."""
+    B, S, d = h.shape
+    hs = h[:, :-1, :].reshape(-1, d)
+    tg = labels[:, 1:].reshape(-1)
+    total = hs.new_zeros((), dtype=torch.float32)
+    count = (tg != -100).sum().clamp_min(1)
+    for i in range(0, hs.shape[0], chunk):
+        logits = F.linear(hs[i:i + chunk], lm_weight).float()
+        total = total + F.cross_entropy(logits, tg[i:i + chunk], ignore_index=-100, reduction='sum')
+    return total / count

@@ -1,0 +1,369 @@
+"""GPU parity tests (run with -m gpu on the B200 box): libmoka.so, called through its C ABI,
+against the CPU oracle and the committed reference-generated golden vectors.
+
+Bars: fp32 kernels rel <= 1e-5 vs the fp64 truth; bf16 kernels
+rel(out, bf16(truth)) <= 1e-3 where truth adds the exact adapter term to the SAME bf16 base
+output the kernel was given (the frozen GEMM's rounding is not the adapter's); weight gradients
+are fp32 outputs and must meet 1e-4 even for bf16 inputs; span indexing is bit-exact."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import moka_oracle as mo
+
+pytestmark = pytest.mark.gpu
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', '*vt_*.pt')))
+IDS = [os.path.basename(p)[:-3] for p in GOLD]
+
+
+def _load(path):
+    g = torch.load(path, weights_only=False)
+    f = lambda t: t.to(torch.float64)
+    return g, f(g['x']), f(g['W0']), [f(a) for a in g['A']], f(g['Bw']), f(g['dy'])
+
+
+def _run_case(g, x, W0, A, Bw, dy, dtype, flags=0):
+    from tests import gpu_util as gu
+    meta = gu.gpu_meta(g['variant'], g['masks'])
+    sc, osc = gu.scalars_for(g['variant'], g['alpha'], g['r'], g['w'])
+    to = lambda t: t.to(dtype).to(gu.DEV)
+    y0 = x @ W0.t()
+    dx0 = dy @ W0
+    y0d, dx0d = to(y0), to(dx0)
+    y, h = gu.abi_forward(meta, to(x), y0d, [to(a) for a in A], to(Bw), sc, flags)
+    dx, dA, dB = gu.abi_backward(meta, to(x), to(dy), h, [to(a) for a in A], to(Bw), sc, dx0=dx0d, flags=flags)
+    return dict(y=y.cpu(), dx=dx.cpu(), dA=[a.cpu() for a in dA], dB=dB.cpu(), h=h.cpu(),
+                y0=y0d.cpu().double(), dx0=dx0d.cpu().double(), y0_exact=y0, dx0_exact=dx0)
+
+
+@pytest.mark.parametrize('path', GOLD, ids=IDS)
+def test_meta_builder_bit_exact(path):
+    from tests import gpu_util as gu
+    g = torch.load(path, weights_only=False)
+    om = gu.oracle_meta(g['variant'], g['masks'])
+    gm = gu.gpu_meta(g['variant'], g['masks'])
+    assert torch.equal(gm.tokmeta.cpu(), om.tokmeta)
+    assert torch.equal(gm.klen.cpu(), om.klen)
+    L = int(om.klen.max())
+    assert gm.Lk == max(L, 1)
+    assert torch.equal(gm.kidx.cpu()[:, :L], om.kidx[:, :L])
+
+
+@pytest.mark.parametrize('path', GOLD, ids=IDS)
+def test_golden_fp32(path):
+    g, x, W0, A, Bw, dy = _load(path)
+    o = _run_case(g, x, W0, A, Bw, dy, torch.float32)
+    assert mo.rel_l2(o['y'], g['y_f64']) <= 1e-5
+    assert mo.rel_l2(o['dx'], g['dx_f64']) <= 1e-5
+    # adapter-only deltas, a much sharper check than the totals
+    assert mo.rel_l2(o['y'].double() - o['y0'], g['y_f64'] - o['y0_exact']) <= 2e-5
+    assert mo.rel_l2(o['dx'].double() - o['dx0'], g['dx_f64'] - o['dx0_exact']) <= 2e-5
+    for m in range(g['M']):
+        ref = g['dA_f64'][m]
+        if float(ref.norm()) == 0:
+            assert float(o['dA'][m].norm()) == 0
+        else:
+            assert mo.rel_l2(o['dA'][m], ref) <= 1e-5
+    assert mo.rel_l2(o['dB'], g['dB_f64']) <= 1e-5
+
+
+@pytest.mark.parametrize('flags', [0, 1], ids=['auto', 'force_fma'])
+@pytest.mark.parametrize('path', GOLD, ids=IDS)
+def test_golden_bf16(path, flags):
+    g, x, W0, A, Bw, dy = _load(path)
+    o = _run_case(g, x, W0, A, Bw, dy, torch.bfloat16, flags)
+    bf = lambda t: t.to(torch.bfloat16).double()
+    y_truth = o['y0'] + (g['y_f64'] - o['y0_exact'])          # same bf16 base + exact adapter term
+    dx_truth = o['dx0'] + (g['dx_f64'] - o['dx0_exact'])
+    assert mo.rel_l2(o['y'], bf(y_truth)) <= 1e-3
+    assert mo.rel_l2(o['dx'], bf(dx_truth)) <= 1e-3
+    # never less accurate than the reference's own bf16 run
+    assert mo.rel_l2(o['y'], g['y_f64']) <= mo.rel_l2(g['y_bf16'], g['y_f64']) * 1.05 + 1e-6
+    assert mo.rel_l2(o['dx'], g['dx_f64']) <= mo.rel_l2(g['dx_bf16'], g['dx_f64']) * 1.05 + 1e-6
+    # fp32 outputs of the bf16-input kernels
+    for m in range(g['M']):
+        ref = g['dA_f64'][m]
+        if float(ref.norm()) == 0:
+            assert float(o['dA'][m].norm()) == 0
+        else:
+            assert mo.rel_l2(o['dA'][m], ref) <= 1e-4
+    assert mo.rel_l2(o['dB'], g['dB_f64']) <= 1e-4
+
+
+def _oracle_case(variant, B, S, d_in, d_out, r, M, layout, alpha, w, dtype, seed=7, flags=0, masks=None,
+                 p=0.0, rng=(0, 0)):
+    """Seeded synthetic case: random y0 / dx0 stand in for the frozen GEMM outputs."""
+    from tests import gpu_util as gu
+    x, _, A, Bw, dy, lm = mo.synth_layer_inputs(variant, B, S, d_in, d_out, r, M, layout, seed=seed)
+    masks = lm if masks is None else masks
+    gen = torch.Generator().manual_seed(seed + 1)
+    y0 = torch.randn(B, S, d_out, generator=gen, dtype=torch.float64).to(dtype).double()
+    dx0 = torch.randn(B, S, d_in, generator=gen, dtype=torch.float64).to(dtype).double()
+    meta = gu.gpu_meta(variant, masks)
+    ometa = gu.oracle_meta(variant, masks)
+    sc, osc = gu.scalars_for(variant, alpha, r, w, p)
+    to = lambda t: t.to(dtype).to(gu.DEV)
+    keep = None
+    if p > 0:
+        keep = gu.keep_mask(B, S, d_in, d_out, r, M, dtype, p, rng[0], rng[1]).cpu()
+    y, h = gu.abi_forward(meta, to(x), to(y0), [to(a) for a in A], to(Bw), sc, flags, rng[0], rng[1])
+    dx, dA, dB = gu.abi_backward(meta, to(x), to(dy), h, [to(a) for a in A], to(Bw), sc, dx0=to(dx0),
+                                 flags=flags, seed=rng[0], offset=rng[1])
+    ty, th = mo.fused_forward(ometa, x, y0, A, Bw, osc, keep, p)
+    tdxa, tdA, tdB, _ = mo.fused_backward(ometa, x, dy, th, A, Bw, osc, keep, p)
+    return dict(y=y.cpu(), dx=dx.cpu(), dA=[a.cpu() for a in dA], dB=dB.cpu(), h=h.cpu(),
+                ty=ty, tdx=dx0 + tdxa, tdA=tdA, tdB=tdB, th=th, y0=y0, dx0=dx0, keep=keep, ometa=ometa)
+
+
+def _assert_case(o, dtype, M):
+    if dtype == torch.float32:
+        assert mo.rel_l2(o['h'], o['th']) <= 1e-5
+        assert mo.rel_l2(o['y'].double() - o['y0'], o['ty'] - o['y0']) <= 2e-5
+        assert mo.rel_l2(o['dx'].double() - o['dx0'], o['tdx'] - o['dx0']) <= 2e-5
+        tol = 1e-5
+    else:
+        bf = lambda t: t.to(torch.bfloat16).double()
+        assert mo.rel_l2(o['h'], o['th']) <= 1e-5
+        assert mo.rel_l2(o['y'], bf(o['ty'])) <= 1e-3
+        assert mo.rel_l2(o['dx'], bf(o['tdx'])) <= 1e-3
+        tol = 1e-4
+    for m in range(M):
+        if float(o['tdA'][m].norm()) == 0:
+            assert float(o['dA'][m].norm()) == 0
+        else:
+            assert mo.rel_l2(o['dA'][m], o['tdA'][m]) <= tol
+    assert mo.rel_l2(o['dB'], o['tdB']) <= tol
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+def test_c1_full_size(dtype):
+    """BASELINE config 1: single MokaLinear d=4096 r=8, 2 modalities, batch 2 seq 128."""
+    o = _oracle_case(mo.VARIANT_VT, 2, 128, 4096, 4096, 8, 2, 'c1', 16, 0.05, dtype)
+    _assert_case(o, dtype, 2)
+
+
+@pytest.mark.parametrize('variant,M,layout,r,dtype', [
+    (mo.VARIANT_VT, 2, 'c2', 8, torch.bfloat16),
+    (mo.VARIANT_AVT, 3, 'c3', 4, torch.bfloat16),
+    (mo.VARIANT_AVT, 3, 'c3', 16, torch.bfloat16),
+    (mo.VARIANT_VT, 2, 'c2', 16, torch.float32),
+    (mo.VARIANT_VT, 2, 'c2', 64, torch.bfloat16),
+    (mo.VARIANT_AVT, 3, 'c3', 32, torch.float32),
+    (mo.VARIANT_AVT, 3, 'c3', 128, torch.bfloat16),
+], ids=['vt_r8_bf16', 'avt_r4_bf16', 'avt_r16_bf16', 'vt_r16_fp32', 'vt_r64_bf16', 'avt_r32_fp32', 'avt_r128_bf16'])
+@pytest.mark.parametrize('flags', [0, 1], ids=['auto', 'force_fma'])
+def test_seq2048_layouts(variant, M, layout, r, dtype, flags):
+    """The S=2048 span layouts of SURVEY.md 8(d) at a reduced width (oracle runs in seconds)."""
+    w = 1.0 if variant == mo.VARIANT_AVT else 0.05
+    o = _oracle_case(variant, 2, 2048, 512, 768, r, M, layout, 16, w, dtype, flags=flags)
+    _assert_case(o, dtype, M)
+
+
+@pytest.mark.parametrize('d_in,d_out', [(4096, 11008), (11008, 4096), (5120, 5120)])
+def test_llama_projection_shapes(d_in, d_out):
+    o = _oracle_case(mo.VARIANT_VT, 1, 256, d_in, d_out, 8, 2, 'c2', 16, 0.05, torch.bfloat16)
+    _assert_case(o, torch.bfloat16, 2)
+
+
+def test_long_key_list_slow_path():
+    """AVT question span of 400 tokens (> 256 keys): exercises the global-memory attention path."""
+    B, S = 2, 1024
+    masks = mo.layout_masks(mo.VARIANT_AVT, B, S, 'c3')
+    masks[3][:, 300:700] = 0
+    masks[3][:, 300:305] = 1
+    masks[3][:, 690:700] = 1
+    o = _oracle_case(mo.VARIANT_AVT, B, S, 256, 256, 8, 3, 'c3', 16, 1.0, torch.float32, masks=masks)
+    assert int(o['ometa'].klen.max()) > 256
+    _assert_case(o, torch.float32, 3)
+
+
+def test_forward_out_of_place_and_untouched_tokens_bitwise():
+    from tests import gpu_util as gu
+    variant = mo.VARIANT_VT
+    B, S, d_in, d_out, r = 2, 128, 256, 320, 8
+    x, _, A, Bw, dy, masks = mo.synth_layer_inputs(variant, B, S, d_in, d_out, r, 2, 'c1')
+    t, i, q = masks
+    t[:, -7:] = False
+    i[:, 12] = False
+    meta = gu.gpu_meta(variant, (t, i, q))
+    sc, _ = gu.scalars_for(variant, 16, r, 0.05)
+    to = lambda v: v.to(torch.bfloat16).to(gu.DEV)
+    y0 = to(torch.randn(B, S, d_out, dtype=torch.float64))
+    y_in, _ = gu.abi_forward(meta, to(x), y0, [to(a) for a in A], to(Bw), sc, inplace=True)
+    y_out, _ = gu.abi_forward(meta, to(x), y0, [to(a) for a in A], to(Bw), sc, inplace=False)
+    assert torch.equal(y_in, y_out)
+    none = ((meta.tokmeta.cpu() & 7) == 0)
+    assert int(none.sum()) == B * 8
+    assert torch.equal(y_in.cpu()[none], y0.cpu()[none])
+    assert not torch.equal(y_in.cpu()[~none], y0.cpu()[~none])
+
+
+def test_span_indexing_perturbations():
+    """Perturbing a non-question text token leaves every image token's output unchanged;
+    perturbing one question token changes all and only that sample's image tokens (+ itself)."""
+    from tests import gpu_util as gu
+    variant = mo.VARIANT_VT
+    B, S, d_in, d_out, r = 2, 128, 128, 128, 8
+    x, _, A, Bw, dy, masks = mo.synth_layer_inputs(variant, B, S, d_in, d_out, r, 2, 'c1')
+    meta = gu.gpu_meta(variant, masks)
+    sc, _ = gu.scalars_for(variant, 16, r, 0.5)
+    to = lambda v: v.to(torch.float32).to(gu.DEV)
+    y0 = torch.zeros(B, S, d_out, dtype=torch.float32, device=gu.DEV)
+    Ad, Bd = [to(a) for a in A], to(Bw)
+    base, _ = gu.abi_forward(meta, to(x), y0, Ad, Bd, sc)
+    text, image, question = masks
+    # (1) non-question text token of sample 0
+    tpos = int(torch.where(text[0] & ~question[0])[0][3])
+    x1 = x.clone(); x1[0, tpos] += 1.0
+    y1, _ = gu.abi_forward(meta, to(x1), y0, Ad, Bd, sc)
+    changed = (y1 != base).any(-1).cpu()
+    assert changed[0, tpos] and int(changed.sum()) == 1
+    # (2) one question token of sample 1
+    qpos = int(torch.where(question[1])[0][2])
+    x2 = x.clone(); x2[1, qpos] += 1.0
+    y2, _ = gu.abi_forward(meta, to(x2), y0, Ad, Bd, sc)
+    changed = (y2 != base).any(-1).cpu()
+    expect = torch.zeros(B, S, dtype=torch.bool)
+    expect[1] = image[1]
+    expect[1, qpos] = True
+    assert torch.equal(changed, expect)
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+def test_dropout_matches_oracle_on_same_mask(dtype):
+    p = 0.25
+    o = _oracle_case(mo.VARIANT_AVT, 2, 256, 512, 256, 8, 3, 'c3', 16, 1.0, dtype, p=p, rng=(1234, 77))
+    rate = 1.0 - float(o['keep'].double().mean())
+    assert abs(rate - p) < 0.01
+    _assert_case(o, dtype, 3)
+    o2 = _oracle_case(mo.VARIANT_AVT, 2, 256, 512, 256, 8, 3, 'c3', 16, 1.0, dtype, p=p, rng=(1234, 78))
+    assert not torch.equal(o['keep'], o2['keep'])           # offset changes the mask
+    o3 = _oracle_case(mo.VARIANT_AVT, 2, 256, 512, 256, 8, 3, 'c3', 16, 1.0, dtype, p=p, rng=(1234, 77))
+    assert torch.equal(o['y'], o3['y'])                     # same (seed, offset) -> same result
+
+
+def test_abi_error_codes():
+    from moka_b200 import _cabi
+    from moka_b200.layer import FusedScalars, _make_desc
+    lib = _cabi.load()
+    sc = FusedScalars(1.0, (1.0, 1.0, 1.0), 0.0, 0.0)
+    d = _make_desc((4, 60), 1, 4, 64, 4, 2, torch.float32, 1, sc, 0)      # d_in % 8 != 0
+    assert lib.moka_workspace_bytes(d) == 0
+    t = torch.zeros(1024, device='cuda')
+    code = lib.moka_forward(d, t.data_ptr(), t.data_ptr(), t.data_ptr(), _cabi.ptr_array([t.data_ptr()] * 2),
+                            t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), 0, 0, None, 0, None)
+    assert code == -1
+    d = _make_desc((4, 64), 1, 4, 64, 4, 2, torch.float32, 1, sc, 0)
+    code = lib.moka_forward(d, None, t.data_ptr(), t.data_ptr(), _cabi.ptr_array([t.data_ptr()] * 2),
+                            t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), 0, 0, None, 0, None)
+    assert code == -1
+    code = lib.moka_forward(d, t.data_ptr() + 4, t.data_ptr(), t.data_ptr(), _cabi.ptr_array([t.data_ptr()] * 2),
+                            t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), 0, 0, None, 0, None)
+    assert code == -5
+    code = lib.moka_backward(d, t.data_ptr(), t.data_ptr(), t.data_ptr(), _cabi.ptr_array([t.data_ptr()] * 2),
+                             t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(), t.data_ptr(),
+                             _cabi.ptr_array([t.data_ptr()] * 2), t.data_ptr(), 0, 0, t.data_ptr(), 16, None)
+    assert code == -2
+    assert b'workspace' in lib.moka_strerror(-2)
+
+
+def test_avt_empty_question_raises_like_reference():
+    from tests import gpu_util as gu
+    masks = mo.layout_masks(mo.VARIANT_AVT, 2, 128, 'c3')
+    masks[3][0] = 0
+    with pytest.raises(IndexError):
+        gu.gpu_meta(mo.VARIANT_AVT, masks)
+
+
+def test_overlapping_masks_rejected():
+    from tests import gpu_util as gu
+    t, i, q = mo.layout_masks(mo.VARIANT_VT, 2, 128, 'c1')
+    t[0, 11] = True
+    with pytest.raises(ValueError):
+        gu.gpu_meta(mo.VARIANT_VT, (t, i, q))
+
+
+def test_full_size_properties_c2():
+    """BASELINE full size (d=4096, S=2048, T=8192, bf16): size-independent properties --
+    untouched tokens bitwise, linearity of the adapter term in B, launch accounting."""
+    from moka_b200 import _cabi
+    from tests import gpu_util as gu
+    variant, B, S, d, r = mo.VARIANT_VT, 4, 2048, 4096, 8
+    masks = mo.layout_masks(variant, B, S, 'c2')
+    t, i, q = masks
+    t[:, -100:] = False
+    meta = gu.gpu_meta(variant, (t, i, q))
+    sc, _ = gu.scalars_for(variant, 16, r, 0.05)
+    gen = torch.Generator(device=gu.DEV).manual_seed(5)
+    bf = torch.bfloat16
+    x = torch.randn(B, S, d, generator=gen, device=gu.DEV, dtype=torch.float32).to(bf)
+    A = [(torch.rand(r, d, generator=gen, device=gu.DEV) * 2 - 1).mul_(d ** -0.5).to(bf) for _ in range(2)]
+    Bw = (torch.randn(d, r, generator=gen, device=gu.DEV) * 0.02).to(bf)
+    y0 = torch.zeros(B, S, d, device=gu.DEV, dtype=bf)
+    n0 = _cabi.launch_count()
+    y1, h1 = gu.abi_forward(meta, x, y0, A, Bw, sc)
+    assert _cabi.launch_count() - n0 == 2
+    y2, _ = gu.abi_forward(meta, x, y0, A, (Bw.float() * 2).to(bf), sc)
+    none = ((meta.tokmeta & 7) == 0)
+    assert int(none.sum()) == B * 100
+    assert float(y1[none].abs().max()) == 0.0
+    assert float(y1[~none].abs().max()) > 0.0
+    # y0 == 0 so y is the bf16-rounded adapter term; doubling B doubles it exactly (power of two)
+    assert torch.equal(y2, (y1.float() * 2).to(bf))
+    # backward: dB is linear in dy
+    dy = torch.randn(B, S, d, generator=gen, device=gu.DEV, dtype=torch.float32).to(bf)
+    _, dA1, dB1 = gu.abi_backward(meta, x, dy, h1, A, Bw, sc)
+    _, dA2, dB2 = gu.abi_backward(meta, x, (dy.float() * 2).to(bf), h1, A, Bw, sc)
+    assert mo.rel_l2(dB2.cpu(), 2 * dB1.cpu()) <= 1e-5
+    assert mo.rel_l2(dA2[0].cpu(), 2 * dA1[0].cpu()) <= 1e-5
+    assert mo.rel_l2(dA2[1].cpu(), 2 * dA1[1].cpu()) <= 1e-5
+
+
+# ----------------------------------------------------------------------------- tcgen05 path
+FORCE_SIMT = 1
+
+
+@pytest.mark.parametrize('variant,M,layout,r,d_in,d_out,S', [
+    (mo.VARIANT_VT, 2, 'c2', 8, 512, 768, 2048),
+    (mo.VARIANT_VT, 2, 'c2', 16, 4096, 4096, 2048),
+    (mo.VARIANT_AVT, 3, 'c3', 16, 1024, 512, 2048),
+    (mo.VARIANT_AVT, 3, 'c3', 64, 512, 512, 2048),
+    (mo.VARIANT_AVT, 3, 'c3', 128, 512, 256, 1024),
+    (mo.VARIANT_VT, 2, 'c1', 32, 256, 256, 200),        # ragged last token tile (T % 128 != 0)
+], ids=['vt_r8', 'vt_r16_d4096', 'avt_r16', 'avt_r64', 'avt_r128_n384', 'vt_r32_ragged'])
+def test_tensor_core_path_matches_warp_fma_path(variant, M, layout, r, d_in, d_out, S):
+    """Same inputs through the tcgen05 kernels and through the warp-FMA kernels: the fp32
+    intermediates (h stash, dA, dB) agree to fp32 round-off, the bf16 outputs to <= 1 ulp-level
+    differences, and both meet the oracle bars."""
+    from moka_b200 import _cabi
+    from moka_b200.layer import _make_desc
+    from tests import gpu_util as gu
+    B = 2
+    w = 1.0 if variant == mo.VARIANT_AVT else 0.05
+    o_tc = _oracle_case(variant, B, S, d_in, d_out, r, M, layout, 16, w, torch.bfloat16, flags=0)
+    o_fma = _oracle_case(variant, B, S, d_in, d_out, r, M, layout, 16, w, torch.bfloat16, flags=FORCE_SIMT)
+    sc, _ = gu.scalars_for(variant, 16, r, w)
+    desc = _make_desc((B * S, d_in), B, S, d_out, r, M, torch.bfloat16, 8, sc, 0)
+    assert _cabi.load().moka_uses_tensor_cores(desc) == 1
+    _assert_case(o_tc, torch.bfloat16, M)
+    _assert_case(o_fma, torch.bfloat16, M)
+    assert mo.rel_l2(o_tc['h'], o_fma['h']) <= 2e-6
+    assert mo.rel_l2(o_tc['y'], o_fma['y']) <= 1e-3
+    assert mo.rel_l2(o_tc['dx'], o_fma['dx']) <= 1e-3
+    assert mo.rel_l2(o_tc['dB'], o_fma['dB']) <= 1e-4
+    for m in range(M):
+        if float(o_fma['dA'][m].norm()) > 0:
+            assert mo.rel_l2(o_tc['dA'][m], o_fma['dA'][m]) <= 1e-4
+
+
+def test_forward_is_bit_reproducible():
+    """Two runs of the forward on the same inputs give identical bits (checkpoint recomputation
+    relies on it), on both kernel paths."""
+    for flags in (0, FORCE_SIMT):
+        a = _oracle_case(mo.VARIANT_AVT, 2, 2048, 1024, 512, 16, 3, 'c3', 16, 1.0, torch.bfloat16, flags=flags)
+        b = _oracle_case(mo.VARIANT_AVT, 2, 2048, 1024, 512, 16, 3, 'c3', 16, 1.0, torch.bfloat16, flags=flags)
+        assert torch.equal(a['h'], b['h'])
+        assert torch.equal(a['y'], b['y'])

@@ -1,0 +1,120 @@
+"""MokaLinear microbench (BASELINE config 5): adapter fwd+bwd through the C ABI, CUDA-event timed,
+inputs larger than L2 rotated between iterations.  Prints one JSON line per point."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from moka_b200 import _cabi  # noqa: E402
+from moka_b200.layer import FusedScalars, _make_desc  # noqa: E402
+from moka_b200.metadata import build_token_meta_avt, build_token_meta_vt  # noqa: E402
+from oracle.moka_oracle import VARIANT_AVT, VARIANT_VT, layout_masks  # noqa: E402  (mask layouts only)
+
+PEAK = 6550.4
+try:
+    PEAK = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']
+except Exception:
+    pass
+
+
+def run_point(variant, B, S, d_in, d_out, r, dtype, flags, iters, warmup, p=0.0, nbuf=3):
+    lib = _cabi.load()
+    dev = 'cuda:0'
+    M = 3 if variant == VARIANT_AVT else 2
+    layout = 'c3' if variant == VARIANT_AVT else 'c2'
+    masks = [m.to(dev) for m in layout_masks(variant, B, S, layout)]
+    meta = build_token_meta_avt(masks) if variant == VARIANT_AVT else build_token_meta_vt(*masks)
+    s = 16.0 / r
+    sc = FusedScalars(s, (1, 1, 1), 1.0, p) if variant == VARIANT_AVT else FusedScalars(1.0, (s, s, s), 0.05, p)
+    T = B * S
+    e = 2 if dtype == torch.bfloat16 else 4
+    bufs = []
+    for i in range(nbuf):      # rotate buffers so that nothing stays in the 126 MB L2
+        g = torch.Generator(device=dev).manual_seed(i)
+        x = torch.randn(T, d_in, device=dev, generator=g).to(dtype)
+        y = torch.randn(T, d_out, device=dev, generator=g).to(dtype)
+        dy = torch.randn(T, d_out, device=dev, generator=g).to(dtype)
+        dx = torch.randn(T, d_in, device=dev, generator=g).to(dtype)
+        bufs.append((x, y, dy, dx))
+    A = [(torch.rand(r, d_in, device=dev) * 2 - 1).mul_(d_in ** -0.5).to(dtype) for _ in range(M)]
+    Bw = (torch.randn(d_out, r, device=dev) * 0.02).to(dtype)
+    dA = [torch.zeros(r, d_in, device=dev) for _ in range(M)]
+    dB = torch.zeros(d_out, r, device=dev)
+    h = torch.empty(T, r, device=dev)
+    desc = _make_desc((T, d_in), B, S, d_out, r, M, dtype, meta.Lk, sc, flags)
+    ws = torch.empty(int(lib.moka_workspace_bytes(desc)), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    Ap = _cabi.ptr_array([a.data_ptr() for a in A])
+    dAp = _cabi.ptr_array([a.data_ptr() for a in dA])
+
+    def fwd(i):
+        x, y, dy, dx = bufs[i % nbuf]
+        _cabi.check(lib.moka_forward(desc, x.data_ptr(), y.data_ptr(), y.data_ptr(), Ap, Bw.data_ptr(),
+                                     meta.tokmeta.data_ptr(), meta.kidx.data_ptr(), meta.klen.data_ptr(),
+                                     h.data_ptr(), 1, i, None, 0, st), 'fwd')
+
+    def bwd(i):
+        x, y, dy, dx = bufs[i % nbuf]
+        _cabi.check(lib.moka_backward(desc, dy.data_ptr(), x.data_ptr(), h.data_ptr(), Ap, Bw.data_ptr(),
+                                      meta.tokmeta.data_ptr(), meta.kidx.data_ptr(), meta.klen.data_ptr(),
+                                      dx.data_ptr(), dAp, dB.data_ptr(), 1, i, ws.data_ptr(), ws.numel(), st), 'bwd')
+
+    for i in range(warmup):
+        fwd(i); bwd(i)
+    torch.cuda.synchronize()
+    res = {}
+    for name, fn in (('fwd', fwd), ('bwd', bwd), ('fwd+bwd', lambda i: (fwd(i), bwd(i)))):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(iters):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = e0.elapsed_time(e1) / iters * 1e3       # us
+    bytes_f = e * (d_in + 2 * d_out) * T
+    bytes_b = e * (3 * d_in + d_out) * T
+    out = dict(variant='avt' if variant == VARIANT_AVT else 'vt', T=T, d_in=d_in, d_out=d_out, r=r,
+               dtype=str(dtype).split('.')[-1], tc=bool(lib.moka_uses_tensor_cores(desc)), dropout=p,
+               fwd_us=round(res['fwd'], 2), bwd_us=round(res['bwd'], 2), both_us=round(res['fwd+bwd'], 2),
+               fwd_gbs=round(bytes_f / res['fwd'] / 1e3, 1), bwd_gbs=round(bytes_b / res['bwd'] / 1e3, 1),
+               both_gbs=round((bytes_f + bytes_b) / res['fwd+bwd'] / 1e3, 1))
+    out['frac'] = round(out['both_gbs'] / PEAK, 4)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--ranks', default='4,8,16')
+    ap.add_argument('--dims', default='4096')
+    ap.add_argument('--variants', default='vt,avt')
+    ap.add_argument('--dtype', default='bf16')
+    ap.add_argument('--B', type=int, default=4)
+    ap.add_argument('--S', type=int, default=2048)
+    ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--flags', type=int, default=0)
+    ap.add_argument('--dropout', type=float, default=0.0)
+    ap.add_argument('--out', default='')
+    a = ap.parse_args()
+    dtype = torch.bfloat16 if a.dtype == 'bf16' else torch.float32
+    rows = []
+    for v in a.variants.split(','):
+        for d in [int(t) for t in a.dims.split(',')]:
+            for r in [int(t) for t in a.ranks.split(',')]:
+                row = run_point(VARIANT_AVT if v == 'avt' else VARIANT_VT, a.B, a.S, d, d, r, dtype, a.flags,
+                                a.iters, a.warmup, a.dropout)
+                print(json.dumps(row), flush=True)
+                rows.append(row)
+    if a.out:
+        with open(a.out, 'w') as f:
+            for row in rows:
+                f.write(json.dumps(row) + '\n')
+
+
+if __name__ == '__main__':
+    main()
