@@ -89,8 +89,9 @@ size_t moka_workspace_bytes(const MokaDesc* desc);
  * every token MOKA_MOD_TEXT and klen == 0 it is the plain-LoRA decode branch
  * (lora.py:373-381, layer.py:672-678).  ``y0`` is the frozen base output W0 x (+bias) and may
  * alias ``y`` (in-place residual add, like layer.py:663).  ``A`` is a HOST array of M device
- * pointers to [r, d_in] matrices, ``Bw`` is [d_out, r].  ``h_stash`` receives the fp32
- * pre-attention projections [B*S, r] that moka_backward re-uses.
+ * pointers to [r, d_in] matrices, ``Bw`` is [d_out, r].  ``h_stash`` is fp32 [2, B*S, r]: it
+ * receives the pre-attention projections h and the post-attention rows g that moka_backward
+ * re-uses.
  */
 int moka_forward(const MokaDesc* desc, const void* x, const void* y0, void* y,
                  const void* const* A, const void* Bw,

@@ -117,10 +117,15 @@ int moka_forward(const MokaDesc* desc, const void* x, const void* y0, void* y,
   const int tcs = tc_stages(desc, d) & (kStageDown | kStageUp);
   if ((desc->flags & MOKA_FLAG_FORCE_TC) && tcs != (kStageDown | kStageUp)) return MOKA_EUNSUPPORTED;
   // stage order matters: down (h) before up (y)
-  if (tcs & kStageDown) { if (int e = tc_forward(d, a, num_sms(), st, kStageDown)) return e; }
-  else if (int e = simt_forward(d, desc->dtype, a, num_sms(), st, kStageDown)) return e;
-  if (tcs & kStageUp) return tc_forward(d, a, num_sms(), st, kStageUp);
-  return simt_forward(d, desc->dtype, a, num_sms(), st, kStageUp);
+  const bool force = (desc->flags & MOKA_FLAG_FORCE_TC) != 0;
+  for (int stage : {kStageDown, kStageUp}) {
+    int e = MOKA_EUNSUPPORTED;
+    if (tcs & stage) e = tc_forward(d, a, num_sms(), st, stage);
+    // a shape the tensor-core kernel cannot tile (shared-memory budget) takes the warp-FMA kernel
+    if (e == MOKA_EUNSUPPORTED && !force) e = simt_forward(d, desc->dtype, a, num_sms(), st, stage);
+    if (e) return e;
+  }
+  return MOKA_OK;
 }
 
 int moka_backward(const MokaDesc* desc, const void* dy, const void* x, const float* h_stash,
@@ -152,10 +157,14 @@ int moka_backward(const MokaDesc* desc, const void* dy, const void* x, const flo
   if (ce != cudaSuccess) { set_cuda_error(ce); return MOKA_ECUDA; }
   const int tcs = tc_stages(desc, d) & (kStageDgrad | kStageWgrad);
   if ((desc->flags & MOKA_FLAG_FORCE_TC) && tcs != (kStageDgrad | kStageWgrad)) return MOKA_EUNSUPPORTED;
-  if (tcs & kStageDgrad) { if (int e = tc_backward(d, a, num_sms(), st, kStageDgrad)) return e; }
-  else if (int e = simt_backward(d, desc->dtype, a, num_sms(), st, kStageDgrad)) return e;
-  if (tcs & kStageWgrad) return tc_backward(d, a, num_sms(), st, kStageWgrad);
-  return simt_backward(d, desc->dtype, a, num_sms(), st, kStageWgrad);
+  const bool force = (desc->flags & MOKA_FLAG_FORCE_TC) != 0;
+  for (int stage : {kStageDgrad, kStageWgrad}) {
+    int e = MOKA_EUNSUPPORTED;
+    if (tcs & stage) e = tc_backward(d, a, num_sms(), st, stage);
+    if (e == MOKA_EUNSUPPORTED && !force) e = simt_backward(d, desc->dtype, a, num_sms(), st, stage);
+    if (e) return e;
+  }
+  return MOKA_OK;
 }
 
 int moka_build_token_meta(int32_t variant, int32_t B, int32_t S, int32_t Lk,

@@ -133,6 +133,51 @@ __device__ __forceinline__ void attn_token_fast(const DevDesc& d, const AttnCtx&
   }
 }
 
+// ------------------------------------------------------------------ thread-per-token forward
+// One thread owns one query token: h and the running weighted sum live in registers, the key
+// rows are broadcast reads from shared memory (row stride = r), softmax is the online form with
+// the rescale skipped unless the running max moves.  Used when r <= 32 and the keys fit in smem.
+template <int R>
+__device__ __forceinline__ void attn_thread_fwd(const DevDesc& d, const float* __restrict__ Ks, int L,
+                                                float* row) {
+  const int r = d.r;
+  float h[R], acc[R];
+#pragma unroll
+  for (int j = 0; j < R; ++j) { h[j] = (j < r) ? row[j] : 0.f; acc[j] = 0.f; }
+  const float sl = d.sm_scale * kLog2e;
+  float m = -INFINITY, l = 0.f;
+  for (int k = 0; k < L; ++k) {
+    const float* Kr = Ks + k * r;
+    float kv[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) kv[j] = (j < r) ? Kr[j] : 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < R; j += 4) {
+      s0 = fmaf(h[j], kv[j], s0);
+      s1 = fmaf(h[j + 1], kv[j + 1], s1);
+      s2 = fmaf(h[j + 2], kv[j + 2], s2);
+      s3 = fmaf(h[j + 3], kv[j + 3], s3);
+    }
+    const float s = ((s0 + s1) + (s2 + s3)) * sl;
+    if (s > m) {
+      const float corr = exp2f(m - s);
+      l *= corr;
+#pragma unroll
+      for (int j = 0; j < R; ++j) acc[j] *= corr;
+      m = s;
+    }
+    const float e = exp2f(s - m);
+    l += e;
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[j] = fmaf(e, kv[j], acc[j]);
+  }
+  const float sc = d.attn_w / l;
+#pragma unroll
+  for (int j = 0; j < R; ++j)
+    if (j < r) row[j] = fmaf(sc, acc[j], h[j]);
+}
+
 // ------------------------------------------------------------------ slow path (global keys)
 // lanes <-> rank index (up to 8 per lane, r <= 256); one key at a time.
 template <bool BWD>
@@ -210,14 +255,33 @@ __device__ __forceinline__ void attn_token_slow(const DevDesc& d, const AttnCtx&
 }
 
 // ------------------------------------------------------------------ per-tile driver
+// A group of threads (the whole CTA, or the worker warps of a warp-specialised kernel) that
+// synchronises on its own named barrier.
+struct SyncGroup {
+  int tid, nthr, bar_id;
+  int* or_slot;                 // one int of shared memory for sync_or
+  __device__ __forceinline__ void sync() const {
+    asm volatile("bar.sync %0, %1;" :: "r"(bar_id), "r"(nthr) : "memory");
+  }
+  __device__ __forceinline__ int sync_or(int pred) const {
+    if (tid == 0) *or_slot = 0;
+    sync();
+    if (pred) atomicOr(or_slot, 1);
+    sync();
+    const int v = *or_slot;
+    sync();
+    return v;
+  }
+};
+
 // hs : [nt, r] pre-attention rows (read-only here)
 // gs : forward  -> receives g rows of query tokens (may alias hs: a row is only touched by its own warp)
 // dgs: backward -> holds dg rows, overwritten with dh rows of query tokens
-// meta_s: tile-local tokmeta bytes.  Must be called by every thread of the CTA.
-template <bool BWD>
-__device__ __forceinline__ void attention_tile(const DevDesc& d, const AttnCtx& c, int t0, int nt,
+// meta_s: tile-local tokmeta bytes.  Must be called by every thread of the group.
+template <bool BWD, int MAXR = 16>
+__device__ __forceinline__ void attention_tile(const DevDesc& d, const AttnCtx& c, const SyncGroup& g, int t0, int nt,
                                                const uint8_t* meta_s, const float* hs, float* gs, float* dgs) {
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int tid = g.tid, nthr = g.nthr;
   const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
   const int r = d.r;
   const int b_first = t0 / d.S, b_last = (t0 + nt - 1) / d.S;
@@ -226,20 +290,34 @@ __device__ __forceinline__ void attention_tile(const DevDesc& d, const AttnCtx& 
     const int hi = min(t0 + nt, (b + 1) * d.S) - t0;
     int q = 0;
     for (int i = lo + tid; i < hi; i += nthr) q |= ((meta_s[i] & MOKA_MOD_MASK) >= MOKA_MOD_VIS);
-    if (!__syncthreads_or(q)) continue;
+    if (!g.sync_or(q)) continue;
     const int L = c.klen[b];
     if (L <= 0) continue;
     const bool fast = (L <= c.kcap) && (L <= 32 * kKeyBlocksMax);
+    // forward with a small rank: one thread per query token, keys packed with row stride r
+    const bool per_thread = !BWD && fast && r <= MAXR;
+    const int ks = per_thread ? r : c.ks;
     if (fast) {
       for (int idx = tid; idx < L * r; idx += nthr) {
         const int k = idx / r, j = idx - k * r;
         const int pos = c.kidx[(size_t)b * d.Lk + k];
         const size_t t = (size_t)b * d.S + pos;
         const bool valid = (c.tokmeta[t] & MOKA_KEY_VALID) != 0;
-        c.Ks[k * c.ks + j] = valid ? c.h_stash[t * r + j] : 0.f;
-        if (BWD) c.dKs[k * c.ks + j] = 0.f;
+        c.Ks[k * ks + j] = valid ? c.h_stash[t * r + j] : 0.f;
+        if (BWD) c.dKs[k * ks + j] = 0.f;
       }
-      __syncthreads();
+      g.sync();
+    }
+    if (per_thread) {
+      for (int tt = lo + tid; tt < hi; tt += nthr) {
+        if ((meta_s[tt] & MOKA_MOD_MASK) < MOKA_MOD_VIS) continue;
+        float* rowp = gs + (size_t)tt * r;
+        if (r <= 8) attn_thread_fwd<8>(d, c.Ks, L, rowp);
+        else if (r <= 16) attn_thread_fwd<16>(d, c.Ks, L, rowp);
+        else if constexpr (MAXR >= 32) attn_thread_fwd<32>(d, c.Ks, L, rowp);
+      }
+      g.sync();
+      continue;
     }
     for (int tt = lo + warp; tt < hi; tt += nwarps) {
       if ((meta_s[tt] & MOKA_MOD_MASK) < MOKA_MOD_VIS) continue;
@@ -250,7 +328,7 @@ __device__ __forceinline__ void attention_tile(const DevDesc& d, const AttnCtx& 
       else attn_token_slow<BWD>(d, c, b, L, hq, gq, dgq, lane);
     }
     if (fast) {
-      __syncthreads();
+      g.sync();
       if (BWD) {
         for (int idx = tid; idx < L * r; idx += nthr) {
           const int k = idx / r, j = idx - k * r;
@@ -259,7 +337,7 @@ __device__ __forceinline__ void attention_tile(const DevDesc& d, const AttnCtx& 
           if (c.tokmeta[t] & MOKA_KEY_VALID)
             red_add_f32(&c.dK_glob[((size_t)b * d.Lk + k) * r + j], c.dKs[k * c.ks + j]);
         }
-        __syncthreads();
+        g.sync();
       }
     }
   }

@@ -29,7 +29,9 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // the GPU box); callers trap so the failure is loud.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  for (uint32_t it = 0; it < (1u << 22); ++it) {
+  // ~2 s worst case: 2^21 probes, each allowed to sleep up to ~1 us in hardware
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 21); ++it) {
     uint32_t done;
     asm volatile(
         "{\n\t"
@@ -37,7 +39,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
-        : "=r"(done) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
+        : "=r"(done) : "r"(addr), "r"(parity), "r"(1000u) : "memory");
     if (done) return true;
   }
   return false;

@@ -151,7 +151,8 @@ template <typename T, int RB, bool MULTI>
 __global__ void __launch_bounds__(kThreads, 2)
 k_up(DevDesc d, const T* y0, T* y, const T* __restrict__ Bw,
      const uint8_t* __restrict__ tokmeta, const int32_t* __restrict__ kidx,
-     const int32_t* __restrict__ klen, const float* __restrict__ h_stash, int kcap) {
+     const int32_t* __restrict__ klen, const float* __restrict__ h_stash, float* __restrict__ g_out,
+     int kcap) {
   constexpr int U = 4;
   extern __shared__ __align__(16) float smem[];
   const int r = d.r;
@@ -163,6 +164,8 @@ k_up(DevDesc d, const T* y0, T* y, const T* __restrict__ Bw,
   const int nrb = (r + RB - 1) / RB;
   const bool inplace = (y0 == y);
   AttnCtx c{tokmeta, kidx, klen, h_stash, nullptr, Ks, nullptr, r + 1, kcap};
+  __shared__ int s_or;
+  const SyncGroup grp{(int)threadIdx.x, kThreads, 0, &s_or};
 
   for (int tile = blockIdx.x; tile < d.num_tiles; tile += gridDim.x) {
     const int t0 = tile * d.tile_tokens;
@@ -170,8 +173,9 @@ k_up(DevDesc d, const T* y0, T* y, const T* __restrict__ Bw,
     for (int i = tid; i < nt; i += kThreads) meta_s[i] = tokmeta[t0 + i];
     for (int i = tid; i < nt * r; i += kThreads) gs[i] = h_stash[(size_t)t0 * r + i];
     __syncthreads();
-    attention_tile<false>(d, c, t0, nt, meta_s, gs, gs, nullptr);
+    attention_tile<false>(d, c, grp, t0, nt, meta_s, gs, gs, nullptr);
     __syncthreads();
+    for (int i = tid; i < nt * r; i += kThreads) g_out[(size_t)t0 * r + i] = gs[i];   // post-attention stash
 
     for (int chunk = warp; chunk < nchunks; chunk += kWarps) {
       const int col = (chunk << 8) + lane * 8;
@@ -244,6 +248,8 @@ k_dgrad(DevDesc d, const T* __restrict__ dy, const T* __restrict__ Bw,
   const int nchunks = (d.d_out + 255) >> 8;
   const int nrb = (r + RB - 1) / RB;
   AttnCtx c{tokmeta, kidx, klen, h_stash, dK_glob, Ks, dKs, r + 1, kcap};
+  __shared__ int s_or;
+  const SyncGroup grp{(int)threadIdx.x, kThreads, 0, &s_or};
 
   for (int tile = blockIdx.x; tile < d.num_tiles; tile += gridDim.x) {
     const int t0 = tile * d.tile_tokens;
@@ -254,7 +260,7 @@ k_dgrad(DevDesc d, const T* __restrict__ dy, const T* __restrict__ Bw,
       hs[i] = v; gs[i] = v; dgs[i] = 0.f;
     }
     __syncthreads();
-    attention_tile<false>(d, c, t0, nt, meta_s, hs, gs, nullptr);     // recompute g
+    attention_tile<false>(d, c, grp, t0, nt, meta_s, hs, gs, nullptr);     // recompute g
     __syncthreads();
 
     for (int chunk = warp; chunk < nchunks; chunk += kWarps) {
@@ -321,7 +327,7 @@ k_dgrad(DevDesc d, const T* __restrict__ dy, const T* __restrict__ Bw,
       }
     }
     __syncthreads();
-    attention_tile<true>(d, c, t0, nt, meta_s, hs, nullptr, dgs);      // dg -> dh, dK
+    attention_tile<true>(d, c, grp, t0, nt, meta_s, hs, nullptr, dgs);      // dg -> dh, dK
     __syncthreads();
     for (int i = tid; i < nt * r; i += kThreads) dh_out[(size_t)t0 * r + i] = dgs[i];
     __syncthreads();
@@ -570,12 +576,12 @@ static int launch_forward_t(DevDesc d, const SimtArgs& a, int num_sms, cudaStrea
       if (int e = set_smem(k_up<T, RB, false>, smem)) return e;
       k_up<T, RB, false><<<grid, kThreads, smem, st>>>(dd, static_cast<const T*>(a.y0), static_cast<T*>(a.y),
                                                        static_cast<const T*>(a.Bw), a.tokmeta, a.kidx, a.klen,
-                                                       a.h_stash, kcap);
+                                                       a.h_stash, a.h_stash + (size_t)d.T * d.r, kcap);
     } else {
       if (int e = set_smem(k_up<T, RB, true>, smem)) return e;
       k_up<T, RB, true><<<grid, kThreads, smem, st>>>(dd, static_cast<const T*>(a.y0), static_cast<T*>(a.y),
                                                       static_cast<const T*>(a.Bw), a.tokmeta, a.kidx, a.klen,
-                                                      a.h_stash, kcap);
+                                                      a.h_stash, a.h_stash + (size_t)d.T * d.r, kcap);
     }
     if (int e = check_launch()) return e;
   }

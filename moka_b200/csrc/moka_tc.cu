@@ -222,6 +222,546 @@ static int launch_down_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cuda
   return check_launch_tc();
 }
 
+// ---------------------------------------------------------------------------- k_up_tc
+//   Y[128 tok, 128 cols] = Y0 + (post_m g)[128 tok, r] . B[128 cols, r]^T   per column chunk
+// Warp 0 streams the y0 tiles in with TMA, the 128 worker threads (warps 2..5) run the rank-r
+// cross-modal attention for the token tile while those loads are in flight, stage the bf16
+// operand tiles (manual 128-byte swizzle), and per chunk add the TMEM accumulator onto the
+// y0 tile in shared memory, which one thread TMA-stores back.  Warp 1 issues the MMAs.
+struct UpTcParams {
+  int T, d_out, r, rk;             // rk = r rounded up to 16 (UMMA K step)
+  int nsplit, chunks;              // chunks = d_out / 128, split across nsplit CTAs per token tile
+  int ystages, kcap;
+  int write_g;
+};
+
+constexpr int kWorkers = 128;
+
+__device__ __forceinline__ void named_sync(int id, int n) {
+  asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory");
+}
+
+__global__ void __launch_bounds__(kTcThreads)
+k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUtensorMap tm_y, DevDesc d,
+        UpTcParams p, const __nv_bfloat16* __restrict__ Bw, const uint8_t* __restrict__ tokmeta,
+        const int32_t* __restrict__ kidx, const int32_t* __restrict__ klen, const float* __restrict__ h_stash,
+        float* __restrict__ g_out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int kblocks = (p.rk + 63) / 64;                       // 64-wide K blocks of the operand tiles
+  uint8_t* ytiles = base;                                     // [ystages][2 boxes][128 x 128 B]
+  uint8_t* gtile = ytiles + (size_t)p.ystages * 32768;        // [kblocks][128 x 128 B]  A operand
+  uint8_t* btiles = gtile + (size_t)kblocks * 16384;          // [2][kblocks][128 x 128 B] B operand
+  float* gs = reinterpret_cast<float*>(btiles + (size_t)2 * kblocks * 16384);   // [128, r]
+  float* Ks = gs + 128 * d.r;                                 // [kcap, r+1]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Ks + (size_t)p.kcap * (d.r + 1) + ((p.kcap * (d.r + 1)) & 1));
+  uint64_t* y_full = bars;                                    // [ystages]
+  uint64_t* y_empty = y_full + p.ystages;                     // [ystages]
+  uint64_t* b_full = y_empty + p.ystages;                     // [2]
+  uint64_t* t_full = b_full + 2;                              // [2]
+  uint64_t* t_empty = t_full + 2;                             // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  int* or_slot = reinterpret_cast<int*>(tmem_slot + 1);
+  uint8_t* meta_s = reinterpret_cast<uint8_t*>(or_slot + 1);  // [128]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / p.nsplit, split = blockIdx.x % p.nsplit;
+  const int t0 = tile * 128;
+  const int nt = min(128, p.T - t0);
+  const int c_beg = (int)((long long)split * p.chunks / p.nsplit);
+  const int c_end = (int)((long long)(split + 1) * p.chunks / p.nsplit);
+  const int nch = c_end - c_beg;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.ystages; ++s) { ptx::mbar_init(&y_full[s], 1); ptx::mbar_init(&y_empty[s], 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&b_full[i], kWorkers); ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], kWorkers);
+    }
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tm_y0); ptx::prefetch_tmap(&tm_y);
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 256);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: y0 tiles, as far ahead as the ring allows
+    if (lane == 0) {
+      for (int j = 0; j < nch; ++j) {
+        const int s = j % p.ystages;
+        const uint32_t ph = (uint32_t)(j / p.ystages) & 1u;
+        ptx::mbar_wait_or_trap(&y_empty[s], ph ^ 1u);
+        uint8_t* yt = ytiles + (size_t)s * 32768;
+        ptx::mbar_arrive_expect_tx(&y_full[s], 32768u);
+        const int col = (c_beg + j) * 128;
+        ptx::tma_load_2d(yt, &tm_y0, &y_full[s], col, t0, ptx::kEvictFirst);
+        ptx::tma_load_2d(yt + 16384, &tm_y0, &y_full[s], col + 64, t0, ptx::kEvictFirst);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = ptx::idesc_bf16(128, 128, 0, 0);
+      const uint32_t ga = ptx::smem_u32(gtile);
+      for (int j = 0; j < nch; ++j) {
+        const int i = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        ptx::mbar_wait_or_trap(&b_full[i], ph);
+        ptx::mbar_wait_or_trap(&t_empty[i], ph ^ 1u);
+        ptx::tc_fence_after_sync();
+        const uint32_t ba = ptx::smem_u32(btiles + (size_t)i * kblocks * 16384);
+        int kdone = 0;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int ksteps = min(4, (p.rk - kb * 64) / 16);
+          for (int k = 0; k < ksteps; ++k, ++kdone) {
+            const uint64_t adesc = ptx::smem_desc_sw128(ga + kb * 16384 + k * 32, 1024, 0);
+            const uint64_t bdesc = ptx::smem_desc_sw128(ba + kb * 16384 + k * 32, 1024, 0);
+            ptx::umma_bf16(tmem_base + (uint32_t)i * 128u, adesc, bdesc, idesc, kdone > 0 ? 1u : 0u);
+          }
+        }
+        ptx::umma_commit(&t_full[i]);
+      }
+    }
+  } else {
+    // ================= workers: attention, operand staging, epilogue
+    const int wt = threadIdx.x - 64;                 // 0..127
+    const int q = warp & 3;                          // TMEM lane quadrant of this warp
+    const int row = q * 32 + lane;                   // token row handled in the epilogue
+    const int r = d.r;
+    const SyncGroup grp{wt, kWorkers, 1, or_slot};
+    AttnCtx c{tokmeta, kidx, klen, h_stash, nullptr, Ks, nullptr, r + 1, p.kcap};
+
+    // B operand tile of a chunk: rows = 128 output columns, K = rank (bf16, 128B swizzle)
+    auto fill_b = [&](int j, int i) {
+      const int n0 = (c_beg + j) * 128;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        uint8_t* bt = btiles + ((size_t)i * kblocks + kb) * 16384;
+        const int kw = min(64, p.rk - kb * 64);               // K extent of this block
+        const int cpr = kw / 8;                               // 16-byte chunks per row
+        for (int idx = wt; idx < 128 * cpr; idx += kWorkers) {
+          const int n = idx / cpr, ch = idx - n * cpr;
+          const int k = kb * 64 + ch * 8;
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (k < r) v = __ldg(reinterpret_cast<const uint4*>(Bw + (size_t)(n0 + n) * r + k));
+          *reinterpret_cast<uint4*>(bt + ptx::sw128_offset((uint32_t)n, (uint32_t)ch)) = v;
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&b_full[i]);
+    };
+
+    if (wt < nt) meta_s[wt] = tokmeta[t0 + wt]; else meta_s[wt] = 0;
+    for (int i2 = wt; i2 < 128 * r; i2 += kWorkers)
+      gs[i2] = (i2 < nt * r) ? h_stash[(size_t)t0 * r + i2] : 0.f;
+    grp.sync();
+    attention_tile<false, 32>(d, c, grp, t0, nt, meta_s, gs, gs, nullptr);
+    grp.sync();
+    if (p.write_g && split == 0)
+      for (int i2 = wt; i2 < nt * r; i2 += kWorkers) g_out[(size_t)t0 * r + i2] = gs[i2];
+    // A operand tile: post_m * g, bf16, rows = tokens
+    for (int kb = 0; kb < kblocks; ++kb) {
+      const int kw = min(64, p.rk - kb * 64);
+      const int cpr = kw / 8;
+      for (int idx = wt; idx < 128 * cpr; idx += kWorkers) {
+        const int n = idx / cpr, ch = idx - n * cpr;
+        const int k = kb * 64 + ch * 8;
+        const int code = meta_s[n] & MOKA_MOD_MASK;
+        const float ps = code ? d.post[code] : 0.f;
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = (k + e < r) ? gs[n * r + k + e] * ps : 0.f;
+        uint4 v;
+        v.x = pack_bf16(f[0], f[1]); v.y = pack_bf16(f[2], f[3]);
+        v.z = pack_bf16(f[4], f[5]); v.w = pack_bf16(f[6], f[7]);
+        *reinterpret_cast<uint4*>(gtile + (size_t)kb * 16384 + ptx::sw128_offset((uint32_t)n, (uint32_t)ch)) = v;
+      }
+    }
+    ptx::fence_proxy_async_smem();
+    if (nch > 0) fill_b(0, 0);
+    if (nch > 1) fill_b(1, 1);
+
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int j = 0; j < nch; ++j) {
+      const int i = j & 1;
+      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+      const int s = j % p.ystages;
+      const uint32_t yph = (uint32_t)(j / p.ystages) & 1u;
+      ptx::mbar_wait_or_trap(&t_full[i], ph);
+      ptx::mbar_wait_or_trap(&y_full[s], yph);
+      ptx::tc_fence_after_sync();
+      uint8_t* yt = ytiles + (size_t)s * 32768;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+          float acc[16];
+          ptx::tmem_ld16(lane_base + (uint32_t)(i * 128 + half * 64 + c16 * 16), acc);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint4* pv = reinterpret_cast<uint4*>(yt + half * 16384 + ptx::sw128_offset((uint32_t)row, (uint32_t)(c16 * 2 + hh)));
+            uint4 v = *pv;
+            const float* a = acc + hh * 8;
+            v.x = pack_bf16(bf16lo(v.x) + a[0], bf16hi(v.x) + a[1]);
+            v.y = pack_bf16(bf16lo(v.y) + a[2], bf16hi(v.y) + a[3]);
+            v.z = pack_bf16(bf16lo(v.z) + a[4], bf16hi(v.z) + a[5]);
+            v.w = pack_bf16(bf16lo(v.w) + a[6], bf16hi(v.w) + a[7]);
+            *pv = v;
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&t_empty[i]);
+      ptx::fence_proxy_async_smem();
+      named_sync(2, kWorkers);
+      if (wt == 0) {
+        const int col = (c_beg + j) * 128;
+        ptx::tma_store_2d(&tm_y, yt, col, t0);
+        ptx::tma_store_2d(&tm_y, yt + 16384, col + 64, t0);
+        ptx::tma_store_commit();
+        if (j > 0) {
+          ptx::tma_store_wait_read<1>();                       // store j-1 has finished reading smem
+          ptx::mbar_arrive(&y_empty[(j - 1) % p.ystages]);
+        }
+      }
+      if (j + 2 < nch) fill_b(j + 2, i);
+    }
+    if (wt == 0) ptx::tma_store_wait_all<0>();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
+}
+
+static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st) {
+  UpTcParams p;
+  p.T = d.T; p.d_out = d.d_out; p.r = d.r; p.rk = round_up(d.r, 16);
+  p.chunks = d.d_out / 128;
+  const int ntiles = (d.T + 127) / 128;
+  p.nsplit = 1;
+  while (ntiles * p.nsplit * 2 <= num_sms + num_sms / 4 && p.chunks / (p.nsplit * 2) >= 4) p.nsplit *= 2;
+  const int kblocks = (p.rk + 63) / 64;
+  p.kcap = min(max(a.klen_hint, 1), 32 * kKeyBlocksMax);
+  const size_t fixed = (size_t)3 * kblocks * 16384 + (size_t)128 * d.r * 4 + 1024 + 512;
+  const size_t limit = 220 * 1024;
+  while (p.kcap > 1 && fixed + (size_t)p.kcap * (d.r + 1) * 4 + 2 * 32768 > limit) p.kcap /= 2;
+  const size_t key_bytes = ((size_t)p.kcap * (d.r + 1) + 1) * 4;
+  p.ystages = (int)((limit - fixed - key_bytes) / 32768);
+  if (p.ystages > 4) p.ystages = 4;
+  if (p.ystages < 2) return MOKA_EUNSUPPORTED;
+  p.write_g = 1;
+  CUtensorMap ty0, ty;
+  if (!make_tmap(&ty0, a.y0, (uint64_t)d.T, (uint64_t)d.d_out, 128)) return MOKA_EUNSUPPORTED;
+  if (!make_tmap(&ty, a.y, (uint64_t)d.T, (uint64_t)d.d_out, 128)) return MOKA_EUNSUPPORTED;
+  const size_t smem = (size_t)p.ystages * 32768 + fixed + key_bytes;
+  cudaError_t e = cudaFuncSetAttribute(k_up_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+  k_up_tc<<<ntiles * p.nsplit, kTcThreads, smem, st>>>(ty0, ty, d, p, static_cast<const __nv_bfloat16*>(a.Bw),
+                                                        a.tokmeta, a.kidx, a.klen, a.h_stash,
+                                                        a.h_stash + (size_t)d.T * d.r);
+  return check_launch_tc();
+}
+
+// ---------------------------------------------------------------------------- k_dgrad_tc
+// Streams dY once.  Per 128-token tile and per pair of 64-column TMA boxes (128 columns):
+//   MMA1  dG[128 tok, rk]   += dY[128 tok, 128 cols] . B[128 cols, rk]          (dY K-major)
+//   MMA2  dB[128 cols, rk]   = dY^T[128 cols, 128 tok] . (post g)[128 tok, rk]  (dY MN-major, the
+//         same shared-memory tile read through a transposing descriptor; g split hi+lo bf16)
+// dB leaves through fp32 vector reductions, dG through a (2-way, hence order-independent)
+// reduction into the zeroed dG buffer; the attention backward runs afterwards in k_attn_bwd.
+struct DgradTcParams {
+  int T, d_out, r, rk;
+  int csplit, pairs;               // pairs = d_out / 128 column pairs, split across csplit CTAs
+  int stages;
+  uint32_t stage_bytes, bt_bytes;  // stage = [box0 16K][box1 16K][Bt kb0][Bt kb1]
+  uint32_t tmem_cols, d2_col;      // D2 buffers start at column d2_col
+};
+
+__global__ void __launch_bounds__(kTcThreads)
+k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, DevDesc d, DgradTcParams p,
+           const __nv_bfloat16* __restrict__ Bw, const uint8_t* __restrict__ tokmeta,
+           const float* __restrict__ g_stash, float* __restrict__ dG, float* __restrict__ dB) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t gt_block = (uint32_t)p.rk * 128u;            // one 64-token K block of G^T
+  uint8_t* gt = ring + (size_t)p.stages * p.stage_bytes;      // [hi/lo][2 kblocks][rk x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gt + 4 * gt_block);
+  uint64_t* full = bars;                       // TMA landed            [stages]
+  uint64_t* wfull = full + p.stages;           // B^T block staged      [stages]
+  uint64_t* empty = wfull + p.stages;          // MMAs done with stage  [stages]
+  uint64_t* d2_full = empty + p.stages;        // [2]
+  uint64_t* d2_empty = d2_full + 2;            // [2]
+  uint64_t* dg_full = d2_empty + 2;            // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dg_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / p.csplit, split = blockIdx.x % p.csplit;
+  const int t0 = tile * 128;
+  const int nt = min(128, p.T - t0);
+  const int p_beg = (int)((long long)split * p.pairs / p.csplit);
+  const int p_end = (int)((long long)(split + 1) * p.pairs / p.csplit);
+  const int np = p_end - p_beg;
+  const int r = p.r;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full[s], 1); ptx::mbar_init(&wfull[s], kWorkers); ptx::mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&d2_full[i], 1); ptx::mbar_init(&d2_empty[i], kWorkers); }
+    ptx::mbar_init(dg_full, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tm_dy);
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int j = 0; j < np; ++j) {
+        const int s = j % p.stages;
+        const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
+        ptx::mbar_wait_or_trap(&empty[s], ph ^ 1u);
+        uint8_t* st = ring + (size_t)s * p.stage_bytes;
+        ptx::mbar_arrive_expect_tx(&full[s], 32768u);
+        const int col = (p_beg + j) * 128;
+        ptx::tma_load_2d(st, &tm_dy, &full[s], col, t0, ptx::kEvictFirst);
+        ptx::tma_load_2d(st + 16384, &tm_dy, &full[s], col + 64, t0, ptx::kEvictFirst);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc1 = ptx::idesc_bf16(128, (uint32_t)p.rk, 0, 0);     // dG: A K-major, B K-major
+      const uint32_t idesc2 = ptx::idesc_bf16(128, (uint32_t)p.rk, 1, 0);     // dB: A MN-major (transposed view)
+      const uint32_t gta = ptx::smem_u32(gt);
+      for (int j = 0; j < np; ++j) {
+        const int s = j % p.stages;
+        const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
+        const int i = j & 1;
+        const uint32_t ph2 = (uint32_t)(j >> 1) & 1u;
+        ptx::mbar_wait_or_trap(&full[s], ph);
+        ptx::mbar_wait_or_trap(&wfull[s], ph);
+        ptx::mbar_wait_or_trap(&d2_empty[i], ph2 ^ 1u);
+        ptx::tc_fence_after_sync();
+        const uint32_t sa = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
+        const uint32_t bta = sa + 32768u;
+        // MMA1: K = 128 columns of this pair (two boxes, four 16-wide steps each)
+#pragma unroll
+        for (int box = 0; box < 2; ++box)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = ptx::smem_desc_sw128(sa + box * 16384 + k * 32, 1024, 0);
+            const uint64_t bdesc = ptx::smem_desc_sw128(bta + box * gt_block + k * 32, 1024, 0);
+            ptx::umma_bf16(tmem_base, adesc, bdesc, idesc1, (j > 0 || box > 0 || k > 0) ? 1u : 0u);
+          }
+        // MMA2: M = 128 columns (two 64-wide atoms 16 KB apart), K = 128 tokens in 8 steps of 16
+#pragma unroll
+        for (int part = 0; part < 2; ++part)           // g = hi + lo
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t adesc = ptx::smem_desc_sw128(sa + k * 2048, 1024, 16384);
+            const uint64_t bdesc = ptx::smem_desc_sw128(gta + (uint32_t)part * 2u * gt_block +
+                                                        (uint32_t)(k >> 2) * gt_block + (k & 3) * 32, 1024, 0);
+            ptx::umma_bf16(tmem_base + p.d2_col + (uint32_t)i * p.rk, adesc, bdesc, idesc2,
+                           (part > 0 || k > 0) ? 1u : 0u);
+          }
+        ptx::umma_commit(&empty[s]);
+        ptx::umma_commit(&d2_full[i]);
+      }
+      ptx::umma_commit(dg_full);
+    }
+  } else {
+    const int wt = threadIdx.x - 64;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    // B^T block of a column pair: rows = rank index, K = 64 columns per block (two blocks)
+    auto fill_bt = [&](int j) {
+      const int s = j % p.stages;
+      uint8_t* bt = ring + (size_t)s * p.stage_bytes + 32768;
+      const int n0 = (p_beg + j) * 128;
+      const int cpr = p.rk / 8;                              // 16-byte chunks of one B row
+      for (int idx = wt; idx < 128 * cpr; idx += kWorkers) {
+        const int n = idx / cpr, ch = idx - n * cpr;         // n = column within the pair
+        const int k0 = ch * 8;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (k0 < r) v = __ldg(reinterpret_cast<const uint4*>(Bw + (size_t)(n0 + n) * r + k0));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint8_t* blk = bt + (size_t)(n >> 6) * gt_block;     // K block (64 columns each)
+        const int kk = n & 63;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const uint16_t val = (uint16_t)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
+          *reinterpret_cast<uint16_t*>(blk + ptx::sw128_offset((uint32_t)(k0 + e), (uint32_t)(kk >> 3)) + (kk & 7) * 2) = val;
+        }
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&wfull[s]);
+    };
+    // G^T operand (post_m * g as hi + lo bf16): rows = rank index, K = tokens
+    {
+      const int t = t0 + row;
+      const int code = (row < nt) ? (tokmeta[t] & MOKA_MOD_MASK) : 0;
+      const float ps = code ? d.post[code] : 0.f;
+      for (int jj = 0; jj < p.rk; ++jj) {
+        const float gv = (code && jj < r) ? g_stash[(size_t)t * r + jj] * ps : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(gv);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(gv - __bfloat162float(hi));
+        const uint32_t off = (uint32_t)(row >> 6) * gt_block + ptx::sw128_offset((uint32_t)jj, (uint32_t)((row & 63) >> 3)) + (row & 7) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(gt + off) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(gt + 2 * gt_block + off) = lo;
+      }
+    }
+    ptx::fence_proxy_async_smem();
+    const int pre_n = min(np, p.stages);
+    for (int j = 0; j < pre_n; ++j) fill_bt(j);
+
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    for (int j = 0; j < np; ++j) {
+      const int i = j & 1;
+      const uint32_t ph2 = (uint32_t)(j >> 1) & 1u;
+      ptx::mbar_wait_or_trap(&d2_full[i], ph2);
+      ptx::tc_fence_after_sync();
+      const int col = (p_beg + j) * 128 + row;               // TMEM lane <-> output column
+      float* dst = dB + (size_t)col * r;
+      for (int c8 = 0; c8 < p.rk; c8 += 8) {
+        float v[8];
+        ptx::tmem_ld8(lane_base + p.d2_col + (uint32_t)(i * p.rk + c8), v);
+        ptx::tmem_ld_wait();
+        if (c8 < r) {                                        // r % 8 == 0 on this path
+          red_add_v4_f32(dst + c8, v[0], v[1], v[2], v[3]);
+          red_add_v4_f32(dst + c8 + 4, v[4], v[5], v[6], v[7]);
+        }
+      }
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(&d2_empty[i]);
+      // the stage that pair j occupied is recycled for pair j + stages
+      if (j + p.stages < np) {
+        const int s = j % p.stages;
+        const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
+        ptx::mbar_wait_or_trap(&empty[s], ph);               // MMAs of pair j have drained the stage
+        fill_bt(j + p.stages);
+      }
+    }
+    // dG partial of this CTA
+    ptx::mbar_wait_or_trap(dg_full, 0);
+    ptx::tc_fence_after_sync();
+    {
+      // tcgen05.ld is warp-collective: every lane issues it, only live token rows store
+      const int t = t0 + row;
+      const int code = (row < nt) ? (tokmeta[t] & MOKA_MOD_MASK) : 0;
+      const float ps = code ? d.post[code] : 0.f;
+      for (int c8 = 0; c8 < p.rk; c8 += 8) {
+        float v[8];
+        ptx::tmem_ld8(lane_base + (uint32_t)c8, v);
+        ptx::tmem_ld_wait();
+        if (c8 < r && code) {
+          float* dst = dG + (size_t)t * r + c8;
+          if (p.csplit == 1) {
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0] * ps, v[1] * ps, v[2] * ps, v[3] * ps);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4] * ps, v[5] * ps, v[6] * ps, v[7] * ps);
+          } else {
+            red_add_v4_f32(dst, v[0] * ps, v[1] * ps, v[2] * ps, v[3] * ps);
+            red_add_v4_f32(dst + 4, v[4] * ps, v[5] * ps, v[6] * ps, v[7] * ps);
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------- k_attn_bwd
+// dG [T, r] -> dh [T, r] (+ dK into the per-sample scratch): the attention backward of
+// SURVEY.md A.3 on 32-token tiles, all data O(T r).  Runs between k_dgrad_tc and k_wgrad_tc.
+__global__ void __launch_bounds__(256)
+k_attn_bwd(DevDesc d, const uint8_t* __restrict__ tokmeta, const int32_t* __restrict__ kidx,
+           const int32_t* __restrict__ klen, const float* __restrict__ h_stash, float* __restrict__ dh,
+           float* __restrict__ dK_glob, int kcap) {
+  extern __shared__ __align__(16) float smem_f[];
+  const int r = d.r;
+  const int TT = d.tile_tokens;
+  float* hs = smem_f;
+  float* dgs = hs + (size_t)TT * r;
+  float* Ks = dgs + (size_t)TT * r;
+  float* dKs = Ks + (size_t)kcap * (r + 1);
+  uint8_t* meta_s = reinterpret_cast<uint8_t*>(dKs + (size_t)kcap * (r + 1));
+  __shared__ int s_or;
+  const SyncGroup grp{(int)threadIdx.x, 256, 0, &s_or};
+  AttnCtx c{tokmeta, kidx, klen, h_stash, dK_glob, Ks, dKs, r + 1, kcap};
+  const int tid = threadIdx.x;
+  for (int tile = blockIdx.x; tile < d.num_tiles; tile += gridDim.x) {
+    const int t0 = tile * TT;
+    const int nt = min(TT, d.T - t0);
+    int anyq = 0;
+    for (int i = tid; i < nt; i += 256) {
+      const uint8_t mb = tokmeta[t0 + i];
+      meta_s[i] = mb;
+      anyq |= (mb & MOKA_MOD_MASK) >= MOKA_MOD_VIS;
+    }
+    if (!grp.sync_or(anyq)) continue;                        // dh == dG for tiles without query tokens
+    for (int i = tid; i < nt * r; i += 256) { hs[i] = h_stash[(size_t)t0 * r + i]; dgs[i] = dh[(size_t)t0 * r + i]; }
+    __syncthreads();
+    attention_tile<true>(d, c, grp, t0, nt, meta_s, hs, nullptr, dgs);
+    __syncthreads();
+    for (int i = tid; i < nt * r; i += 256)
+      if ((meta_s[i / r] & MOKA_MOD_MASK) >= MOKA_MOD_VIS) dh[(size_t)t0 * r + i] = dgs[i];
+    __syncthreads();
+  }
+}
+
+static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st) {
+  DgradTcParams p;
+  p.T = d.T; p.d_out = d.d_out; p.r = d.r; p.rk = round_up(d.r, 16);
+  p.pairs = d.d_out / 128;
+  const int ntiles = (d.T + 127) / 128;
+  p.csplit = (ntiles < num_sms && ntiles * 2 <= num_sms + num_sms / 4 && p.pairs >= 8) ? 2 : 1;
+  p.bt_bytes = 2u * (uint32_t)p.rk * 128u;
+  p.stage_bytes = 32768u + p.bt_bytes;
+  const size_t fixed = (size_t)4 * p.rk * 128 + 1024 + 512;
+  const size_t limit = 200 * 1024;
+  p.stages = (int)((limit - fixed) / p.stage_bytes);
+  if (p.stages > 5) p.stages = 5;
+  if (p.stages < 2) return MOKA_EUNSUPPORTED;
+  const uint32_t dgc = tmem_cols_for(p.rk);
+  p.d2_col = dgc;
+  p.tmem_cols = tmem_cols_for((int)dgc + 2 * p.rk);
+  CUtensorMap tdy;
+  if (!make_tmap(&tdy, a.dy, (uint64_t)d.T, (uint64_t)d.d_out, 128)) return MOKA_EUNSUPPORTED;
+  // dG lives in the dh workspace; zero it when two CTAs reduce into it
+  cudaError_t e = cudaMemsetAsync(a.dh, 0, (size_t)d.T * d.r * sizeof(float), st);
+  if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + fixed;
+  e = cudaFuncSetAttribute(k_dgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+  k_dgrad_tc<<<ntiles * p.csplit, kTcThreads, smem, st>>>(tdy, d, p, static_cast<const __nv_bfloat16*>(a.Bw),
+                                                           a.tokmeta, a.h_stash + (size_t)d.T * d.r, a.dh, a.dB);
+  if (int rc = check_launch_tc()) return rc;
+  // attention backward on the small [T, r] tensors
+  DevDesc dd = d;
+  dd.tile_tokens = 32;
+  dd.num_tiles = (d.T + 31) / 32;
+  int kcap = min(max(a.klen_hint, 1), 32 * kKeyBlocksMax);
+  const size_t per_key = (size_t)2 * (d.r + 1) * 4;
+  const size_t row_bytes = (size_t)2 * 32 * d.r * 4;
+  while (kcap > 1 && row_bytes + kcap * per_key > 96 * 1024) kcap /= 2;
+  const size_t smem2 = row_bytes + kcap * per_key + 64;
+  if (smem2 > 48 * 1024) {
+    e = cudaFuncSetAttribute(k_attn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+  }
+  k_attn_bwd<<<min(dd.num_tiles, num_sms * 2), 256, smem2, st>>>(dd, a.tokmeta, a.kidx, a.klen, a.h_stash, a.dh,
+                                                                  a.dK, kcap);
+  return check_launch_tc();
+}
+
 // ---------------------------------------------------------------------------- dispatch
 int tc_stage_mask(const DevDesc& d, int dtype) {
   if (dtype != MOKA_BF16) return 0;                 // fp32 storage keeps exact fp32 FMA (1e-5 bar)
@@ -229,17 +769,27 @@ int tc_stage_mask(const DevDesc& d, int dtype) {
   if (d.d_in % 64 || d.d_out % 64) return 0;
   if (d.r % 8 || d.r > 128) return 0;
   if (!get_encode_fn()) return 0;
-  return kStageDown;
+  int mask = kStageDown;
+  if (d.d_out % 128 == 0) mask |= kStageUp | kStageDgrad;
+  return mask;
 }
 
 int tc_forward(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, int stages) {
   if (stages & kStageDown) {
     if (int e = launch_down_tc(d, a, num_sms, st)) return e;
   }
-  if (stages & kStageUp) return MOKA_EUNSUPPORTED;
+  if (stages & kStageUp) {
+    if (int e = launch_up_tc(d, a, num_sms, st)) return e;
+  }
   return MOKA_OK;
 }
 
-int tc_backward(const DevDesc&, const SimtArgs&, int, cudaStream_t, int) { return MOKA_EUNSUPPORTED; }
+int tc_backward(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, int stages) {
+  if (stages & kStageDgrad) {
+    if (int e = launch_dgrad_tc(d, a, num_sms, st)) return e;
+  }
+  if (stages & kStageWgrad) return MOKA_EUNSUPPORTED;
+  return MOKA_OK;
+}
 
 }  // namespace moka

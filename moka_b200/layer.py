@@ -87,7 +87,7 @@ class _MokaFn(torch.autograd.Function):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         y = F.linear(x2, weight, bias)                      # frozen base, cuBLAS; adapter added in place
-        h = torch.empty(B * S, r, dtype=torch.float32, device=x.device)
+        h = torch.empty(2, B * S, r, dtype=torch.float32, device=x.device)
         seed = offset = 0
         if sc.p > 0.0:
             # CPU generator draws are restored by torch.utils.checkpoint, so a recomputed forward

@@ -32,7 +32,7 @@ def abi_forward(meta: TokenMeta, x, y0, A, Bw, sc: FusedScalars, flags=0, seed=0
     y0c = y0.reshape(B * S, d_out).contiguous()
     y = y0c.clone() if inplace else torch.empty_like(y0c)
     src = y if inplace else y0c
-    h = torch.full((B * S, r), float('nan'), dtype=torch.float32, device=x.device)
+    h = torch.full((2, B * S, r), float('nan'), dtype=torch.float32, device=x.device)
     desc = _make_desc(x2.shape, B, S, d_out, r, len(A), x.dtype, meta.Lk, sc, flags)
     code = lib.moka_forward(desc, x2.data_ptr(), src.data_ptr(), y.data_ptr(),
                             _cabi.ptr_array([a.data_ptr() for a in A]), Bw.data_ptr(),
@@ -40,7 +40,7 @@ def abi_forward(meta: TokenMeta, x, y0, A, Bw, sc: FusedScalars, flags=0, seed=0
                             h.data_ptr(), seed, offset, None, 0, torch.cuda.current_stream().cuda_stream)
     _cabi.check(code, 'moka_forward')
     torch.cuda.synchronize()
-    return y.view(B, S, d_out), h.view(B, S, r)
+    return y.view(B, S, d_out), h
 
 
 def abi_backward(meta: TokenMeta, x, dy, h, A, Bw, sc: FusedScalars, dx0=None, flags=0, seed=0, offset=0):
@@ -56,7 +56,7 @@ def abi_backward(meta: TokenMeta, x, dy, h, A, Bw, sc: FusedScalars, dx0=None, f
     desc = _make_desc(x2.shape, B, S, d_out, r, len(A), x.dtype, meta.Lk, sc, flags)
     nbytes = int(lib.moka_workspace_bytes(desc))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-    code = lib.moka_backward(desc, dy2.data_ptr(), x2.data_ptr(), h.reshape(B * S, r).contiguous().data_ptr(),
+    code = lib.moka_backward(desc, dy2.data_ptr(), x2.data_ptr(), h.contiguous().data_ptr(),
                              _cabi.ptr_array([a.data_ptr() for a in A]), Bw.data_ptr(),
                              meta.tokmeta.data_ptr(), meta.kidx.data_ptr(), meta.klen.data_ptr(),
                              0 if dx is None else dx.data_ptr(),
