@@ -86,7 +86,7 @@ extern "C" {
 
 size_t moka_workspace_bytes(const MokaDesc* desc) {
   if (validate(desc) != MOKA_OK) return 0;
-  return ws_dh_bytes(desc) + ws_dk_bytes(desc) + 256;
+  return ws_dh_bytes(desc) + ws_dk_bytes(desc) + align_up(tc_pack_bytes(desc->B * desc->S, desc->r, desc->M), 256) + 256;
 }
 
 int moka_uses_tensor_cores(const MokaDesc* desc) {
@@ -152,6 +152,7 @@ int moka_backward(const MokaDesc* desc, const void* dy, const void* x, const flo
   char* ws = static_cast<char*>(workspace);
   a.dh = reinterpret_cast<float*>(ws);
   a.dK = reinterpret_cast<float*>(ws + ws_dh_bytes(desc));
+  a.pack = ws + ws_dh_bytes(desc) + ws_dk_bytes(desc);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   cudaError_t ce = cudaMemsetAsync(a.dK, 0, ws_dk_bytes(desc), st);
   if (ce != cudaSuccess) { set_cuda_error(ce); return MOKA_ECUDA; }

@@ -15,8 +15,12 @@ struct SimtArgs {
   float* h_stash;
   float* dh;        // workspace [T, r]
   float* dK;        // workspace [B, Lk, r]
+  void* pack;       // workspace for the packed bf16 dh operands of k_wgrad_tc (tc_pack_bytes)
   int klen_hint;    // upper bound on klen (kidx row stride)
 };
+
+// bytes of the packed-operand workspace the tensor-core wgrad kernel needs
+size_t tc_pack_bytes(int T, int r, int M);
 
 enum { kStageDown = 1, kStageUp = 2, kStageDgrad = 4, kStageWgrad = 8, kStageAll = 15 };
 

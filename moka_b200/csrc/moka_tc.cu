@@ -762,6 +762,352 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   return check_launch_tc();
 }
 
+// ---------------------------------------------------------------------------- k_pack_dh
+// dh (+ the per-sample dK rows folded back onto their key tokens) -> the bf16 operand tensors
+// k_wgrad_tc loads with TMA:
+//   dHc  [T, KP]   row t is zero except the rank block of the token's modality (K-major operand
+//                  of  dx = dHc . [A_0;A_1;A_2]),
+//   dHcT [2, NPW, T]  its transpose, split into hi + lo bf16 so that the weight gradient
+//                  dA = dHcT . X keeps fp32-level accuracy.
+struct PackLayout { int rp, NPW, KP; size_t hc_bytes, hct_bytes; };
+
+static PackLayout pack_layout(int T, int r, int M) {
+  PackLayout L;
+  L.rp = round_up(r, 8);
+  L.NPW = round_up(M * L.rp, 16);
+  L.KP = round_up(L.NPW, 64);
+  L.hc_bytes = ((size_t)T * L.KP * 2 + 255) & ~size_t(255);
+  L.hct_bytes = ((size_t)L.NPW * T * 2 + 255) & ~size_t(255);
+  return L;
+}
+size_t tc_pack_bytes(int T, int r, int M) {
+  PackLayout L = pack_layout(T, r, M);
+  return L.hc_bytes + 2 * L.hct_bytes;
+}
+
+__device__ __forceinline__ int find_key_slot(const int32_t* __restrict__ row, int L, int pos) {
+  int lo = 0, hi = L - 1;                                     // key positions are strictly increasing
+  while (lo <= hi) {
+    const int mid = (lo + hi) >> 1;
+    const int v = row[mid];
+    if (v == pos) return mid;
+    if (v < pos) lo = mid + 1; else hi = mid - 1;
+  }
+  return -1;
+}
+
+__global__ void __launch_bounds__(256)
+k_pack_dh(DevDesc d, int rp, int NPW, int KP, const uint8_t* __restrict__ tokmeta,
+          const int32_t* __restrict__ kidx, const int32_t* __restrict__ klen, const float* __restrict__ dh,
+          const float* __restrict__ dK, __nv_bfloat16* __restrict__ hc, __nv_bfloat16* __restrict__ hct_hi,
+          __nv_bfloat16* __restrict__ hct_lo, float scale) {
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= d.T) return;
+  const int r = d.r;
+  const uint8_t mb = tokmeta[t];
+  const int code = mb & MOKA_MOD_MASK;
+  const int b = t / d.S, pos = t - b * d.S;
+  int slot = -1;
+  if (code && (mb & MOKA_KEY_VALID)) slot = find_key_slot(kidx + (size_t)b * d.Lk, klen[b], pos);
+  const int n_lo = (code - 1) * rp;                           // first row of the token's rank block
+  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+  for (int n = 0; n < KP; ++n) {
+    float v = 0.f;
+    const int j = n - n_lo;
+    if (code && j >= 0 && j < r) {
+      v = dh[(size_t)t * r + j];
+      if (slot >= 0) v += dK[((size_t)b * d.Lk + slot) * r + j];
+      v *= scale;
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    hc[(size_t)t * KP + n] = hi;
+    if (n < NPW) {
+      hct_hi[(size_t)n * d.T + t] = hi;
+      hct_lo[(size_t)n * d.T + t] = (v != 0.f) ? __float2bfloat16_rn(v - __bfloat162float(hi)) : zero;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------- k_wgrad_tc
+// A CTA owns 128 columns of d_in and walks token tiles:
+//   MMA-A  dAcat[128 cols, NPW] += X^T[128 cols, 128 tok] . dHc[128 tok, NPW]   (X tile MN-major,
+//          accumulator resident in TMEM for the CTA's whole token range: one flush, no per-tile atomics)
+//   MMA-X  dXadd[128 tok, 128 cols] = dHc[128 tok, KP] . Acat[KP, 128 cols]      (weights MN-major, loaded once)
+// and adds dXadd onto the dx tile in shared memory before the TMA store (read-modify-write of dx).
+struct WgradTcParams {
+  int T, d_in, r, rp, M, NPW, KP;
+  int tsplit, ntiles;
+  int xs, ds;                      // ring depths: X pairs / dX pairs (32 KB slots)
+  int has_dx;
+  uint32_t w_box_bytes;            // one 64-column box of the weight slice: NPW x 128 B
+  uint32_t op_bytes;               // operand buffer: dHc tile + dHcT hi/lo tiles
+  uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(kTcThreads)
+k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dx,
+           const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
+           const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_hc,
+           const __grid_constant__ CUtensorMap tm_hct_hi, const __grid_constant__ CUtensorMap tm_hct_lo,
+           WgradTcParams p, float* __restrict__ dA0, float* __restrict__ dA1, float* __restrict__ dA2) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t hct_blk = (uint32_t)p.NPW * 128u;            // [NPW rows x 64 tokens] block
+  const int kbx = p.KP / 64;                                  // K blocks of the dHc tile
+  uint8_t* xring = base;                                      // [xs][2 boxes][128 x 128 B]
+  uint8_t* dring = xring + (size_t)p.xs * 32768;              // [ds][2 boxes][128 x 128 B]
+  uint8_t* wtile = dring + (size_t)p.ds * 32768;              // [2 boxes][NPW x 128 B]  weights (MN-major B operand)
+  uint8_t* op = wtile + 2 * p.w_box_bytes;                    // dHc [kbx][128x128B], dHcT hi [2][blk], lo [2][blk]
+  uint8_t* hc_t = op;
+  uint8_t* hct_t = op + (size_t)kbx * 16384;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(op + p.op_bytes);
+  uint64_t* x_full = bars;                     // [xs]
+  uint64_t* x_empty = x_full + p.xs;           // [xs]
+  uint64_t* d_full = x_empty + p.xs;           // [ds]
+  uint64_t* d_empty = d_full + p.ds;           // [ds]
+  uint64_t* op_full = d_empty + p.ds;          // [1]
+  uint64_t* op_empty = op_full + 1;            // [1]
+  uint64_t* w_full = op_empty + 1;             // [1]
+  uint64_t* t_full = w_full + 1;               // [2] dx accumulator ready
+  uint64_t* t_empty = t_full + 2;              // [2]
+  uint64_t* a_full = t_empty + 2;              // [1] dA accumulator final
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int slice = blockIdx.x / p.tsplit, split = blockIdx.x % p.tsplit;
+  const int col0 = slice * 128;
+  const int tt_beg = (int)((long long)split * p.ntiles / p.tsplit);
+  const int tt_end = (int)((long long)(split + 1) * p.ntiles / p.tsplit);
+  const int ntt = tt_end - tt_beg;
+
+  // weight rows that TMA never writes (padding of the rank blocks) must read as zero
+  for (uint32_t i = threadIdx.x; i < 2 * p.w_box_bytes / 16; i += kTcThreads)
+    reinterpret_cast<uint4*>(wtile)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.xs; ++s) { ptx::mbar_init(&x_full[s], 1); ptx::mbar_init(&x_empty[s], 1); }
+    for (int s = 0; s < p.ds; ++s) { ptx::mbar_init(&d_full[s], 1); ptx::mbar_init(&d_empty[s], 1); }
+    ptx::mbar_init(op_full, 1); ptx::mbar_init(op_empty, 1); ptx::mbar_init(w_full, 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], kWorkers); }
+    ptx::mbar_init(a_full, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tm_x); ptx::prefetch_tmap(&tm_dx); ptx::prefetch_tmap(&tm_hc);
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t d1_col = 256;                                // dx accumulators at [0,256), dA at [256, 256+NPW)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // weights of this column slice, once
+      ptx::mbar_arrive_expect_tx(w_full, 2u * (uint32_t)p.M * (uint32_t)p.r * 128u);
+      for (int box = 0; box < 2; ++box) {
+        uint8_t* wb = wtile + (size_t)box * p.w_box_bytes;
+        ptx::tma_load_2d(wb, &tm_a0, w_full, col0 + box * 64, 0, ptx::kEvictLast);
+        if (p.M > 1) ptx::tma_load_2d(wb + (size_t)p.rp * 128, &tm_a1, w_full, col0 + box * 64, 0, ptx::kEvictLast);
+        if (p.M > 2) ptx::tma_load_2d(wb + (size_t)2 * p.rp * 128, &tm_a2, w_full, col0 + box * 64, 0, ptx::kEvictLast);
+      }
+      const uint32_t op_tx = (uint32_t)kbx * 16384u + 4u * hct_blk;
+      for (int j = 0; j < ntt; ++j) {
+        const int t0 = (tt_beg + j) * 128;
+        // operands of tile j (single buffer: wait until the MMAs of tile j-1 are done with it)
+        ptx::mbar_wait_or_trap(op_empty, ((uint32_t)j & 1u) ^ 1u);
+        ptx::mbar_arrive_expect_tx(op_full, op_tx);
+        for (int kb = 0; kb < kbx; ++kb) ptx::tma_load_2d(hc_t + (size_t)kb * 16384, &tm_hc, op_full, kb * 64, t0, ptx::kEvictLast);
+        for (int kb = 0; kb < 2; ++kb) {
+          ptx::tma_load_2d(hct_t + (size_t)kb * hct_blk, &tm_hct_hi, op_full, t0 + kb * 64, 0, ptx::kEvictLast);
+          ptx::tma_load_2d(hct_t + (size_t)(2 + kb) * hct_blk, &tm_hct_lo, op_full, t0 + kb * 64, 0, ptx::kEvictLast);
+        }
+        {
+          const int s = j % p.xs;
+          const uint32_t ph = (uint32_t)(j / p.xs) & 1u;
+          ptx::mbar_wait_or_trap(&x_empty[s], ph ^ 1u);
+          uint8_t* xt = xring + (size_t)s * 32768;
+          ptx::mbar_arrive_expect_tx(&x_full[s], 32768u);
+          ptx::tma_load_2d(xt, &tm_x, &x_full[s], col0, t0, ptx::kEvictFirst);
+          ptx::tma_load_2d(xt + 16384, &tm_x, &x_full[s], col0 + 64, t0, ptx::kEvictFirst);
+        }
+        if (p.has_dx) {
+          const int s = j % p.ds;
+          const uint32_t ph = (uint32_t)(j / p.ds) & 1u;
+          ptx::mbar_wait_or_trap(&d_empty[s], ph ^ 1u);
+          uint8_t* dt = dring + (size_t)s * 32768;
+          ptx::mbar_arrive_expect_tx(&d_full[s], 32768u);
+          ptx::tma_load_2d(dt, &tm_dx, &d_full[s], col0, t0, ptx::kEvictFirst);
+          ptx::tma_load_2d(dt + 16384, &tm_dx, &d_full[s], col0 + 64, t0, ptx::kEvictFirst);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_a = ptx::idesc_bf16(128, (uint32_t)p.NPW, 1, 0);   // X^T (MN-major) . dHcT (K-major)
+      const uint32_t idesc_x = ptx::idesc_bf16(128, 128, 0, 1);               // dHc (K-major) . Acat (MN-major)
+      const uint32_t wa = ptx::smem_u32(wtile);
+      const uint32_t hca = ptx::smem_u32(hc_t);
+      const uint32_t hcta = ptx::smem_u32(hct_t);
+      ptx::mbar_wait_or_trap(w_full, 0);
+      for (int j = 0; j < ntt; ++j) {
+        const int s = j % p.xs;
+        const uint32_t ph = (uint32_t)(j / p.xs) & 1u;
+        const int i = j & 1;
+        const uint32_t ph2 = (uint32_t)(j >> 1) & 1u;
+        ptx::mbar_wait_or_trap(op_full, (uint32_t)j & 1u);
+        ptx::mbar_wait_or_trap(&x_full[s], ph);
+        if (p.has_dx) ptx::mbar_wait_or_trap(&t_empty[i], ph2 ^ 1u);
+        ptx::tc_fence_after_sync();
+        const uint32_t xa = ptx::smem_u32(xring + (size_t)s * 32768);
+        // MMA-A: K = 128 tokens (8 steps), hi then lo
+#pragma unroll
+        for (int part = 0; part < 2; ++part)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t adesc = ptx::smem_desc_sw128(xa + k * 2048, 1024, 16384);
+            const uint64_t bdesc = ptx::smem_desc_sw128(hcta + (uint32_t)(2 * part + (k >> 2)) * hct_blk + (k & 3) * 32, 1024, 0);
+            ptx::umma_bf16(tmem_base + d1_col, adesc, bdesc, idesc_a, (j > 0 || part > 0 || k > 0) ? 1u : 0u);
+          }
+        ptx::umma_commit(&x_empty[s]);
+        if (p.has_dx) {
+          // MMA-X: K = NPW rank rows in steps of 16 (K block kb of the dHc tile, 16 weight rows = 2048 B)
+          const int ksteps = p.NPW / 16;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adesc = ptx::smem_desc_sw128(hca + (uint32_t)(k >> 2) * 16384u + (k & 3) * 32, 1024, 0);
+            const uint64_t bdesc = ptx::smem_desc_sw128(wa + (uint32_t)k * 2048u, 1024, p.w_box_bytes);
+            ptx::umma_bf16(tmem_base + (uint32_t)i * 128u, adesc, bdesc, idesc_x, k > 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&t_full[i]);
+        }
+        ptx::umma_commit(op_empty);
+      }
+      ptx::umma_commit(a_full);
+    }
+  } else {
+    const int wt = threadIdx.x - 64;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    if (p.has_dx) {
+      for (int j = 0; j < ntt; ++j) {
+        const int i = j & 1;
+        const uint32_t ph2 = (uint32_t)(j >> 1) & 1u;
+        const int s = j % p.ds;
+        const uint32_t dph = (uint32_t)(j / p.ds) & 1u;
+        const int t0 = (tt_beg + j) * 128;
+        ptx::mbar_wait_or_trap(&t_full[i], ph2);
+        ptx::mbar_wait_or_trap(&d_full[s], dph);
+        ptx::tc_fence_after_sync();
+        uint8_t* dt = dring + (size_t)s * 32768;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+#pragma unroll
+          for (int c16 = 0; c16 < 4; ++c16) {
+            float acc[16];
+            ptx::tmem_ld16(lane_base + (uint32_t)(i * 128 + half * 64 + c16 * 16), acc);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              uint4* pv = reinterpret_cast<uint4*>(dt + half * 16384 + ptx::sw128_offset((uint32_t)row, (uint32_t)(c16 * 2 + hh)));
+              uint4 v = *pv;
+              const float* a = acc + hh * 8;
+              v.x = pack_bf16(bf16lo(v.x) + a[0], bf16hi(v.x) + a[1]);
+              v.y = pack_bf16(bf16lo(v.y) + a[2], bf16hi(v.y) + a[3]);
+              v.z = pack_bf16(bf16lo(v.z) + a[4], bf16hi(v.z) + a[5]);
+              v.w = pack_bf16(bf16lo(v.w) + a[6], bf16hi(v.w) + a[7]);
+              *pv = v;
+            }
+          }
+        }
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(&t_empty[i]);
+        ptx::fence_proxy_async_smem();
+        named_sync(2, kWorkers);
+        if (wt == 0) {
+          ptx::tma_store_2d(&tm_dx, dt, col0, t0);
+          ptx::tma_store_2d(&tm_dx, dt + 16384, col0 + 64, t0);
+          ptx::tma_store_commit();
+          if (j > 0) {
+            ptx::tma_store_wait_read<1>();
+            ptx::mbar_arrive(&d_empty[(j - 1) % p.ds]);
+          }
+        }
+      }
+      if (wt == 0) ptx::tma_store_wait_all<0>();
+    }
+    // ---- dA of this column slice: TMEM lane <-> column, TMEM column <-> (modality, rank index)
+    ptx::mbar_wait_or_trap(a_full, 0);
+    ptx::tc_fence_after_sync();
+    const int col = col0 + row;
+    for (int n8 = 0; n8 < p.NPW; n8 += 8) {
+      float v[8];
+      ptx::tmem_ld8(lane_base + d1_col + (uint32_t)n8, v);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int n = n8 + e;
+        const int m = n / p.rp, jj = n - m * p.rp;
+        if (m < p.M && jj < p.r) {
+          float* dAm = m == 0 ? dA0 : (m == 1 ? dA1 : dA2);
+          red_add_f32(dAm + (size_t)jj * p.d_in + col, v[e]);
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// Tensor map over a row-major bf16 matrix with an explicit box (cols multiple of 8 elements).
+static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st) {
+  if (d.T % 8) return MOKA_EUNSUPPORTED;                      // transposed operand rows must be 16-byte multiples
+  PackLayout L = pack_layout(d.T, d.r, d.M);
+  if (L.NPW > 256) return MOKA_EUNSUPPORTED;
+  WgradTcParams p;
+  p.T = d.T; p.d_in = d.d_in; p.r = d.r; p.rp = L.rp; p.M = d.M; p.NPW = L.NPW; p.KP = L.KP;
+  p.ntiles = (d.T + 127) / 128;
+  const int slices = d.d_in / 128;
+  p.tsplit = max(1, min(p.ntiles, num_sms / slices));
+  p.has_dx = a.dx != nullptr;
+  p.w_box_bytes = (uint32_t)p.NPW * 128u;
+  p.op_bytes = (uint32_t)(p.KP / 64) * 16384u + 4u * p.w_box_bytes;
+  p.tmem_cols = 512;
+  const size_t fixed = (size_t)2 * p.w_box_bytes + p.op_bytes + 1024 + 512;
+  const size_t limit = 224 * 1024;
+  if (fixed + 3 * 32768 > limit) return MOKA_EUNSUPPORTED;
+  int slots = (int)((limit - fixed) / 32768);
+  if (p.has_dx) {
+    p.ds = min(3, max(2, slots / 2 + (slots & 1)));
+    p.xs = min(2, slots - p.ds);
+    if (p.xs < 1) { p.xs = 1; p.ds = slots - 1; }
+    if (p.ds < 2) return MOKA_EUNSUPPORTED;
+  } else {
+    p.xs = min(4, slots); p.ds = 0;
+  }
+  char* pk = static_cast<char*>(a.pack);
+  __nv_bfloat16* hc = reinterpret_cast<__nv_bfloat16*>(pk);
+  __nv_bfloat16* hct_hi = reinterpret_cast<__nv_bfloat16*>(pk + L.hc_bytes);
+  __nv_bfloat16* hct_lo = reinterpret_cast<__nv_bfloat16*>(pk + L.hc_bytes + L.hct_bytes);
+  k_pack_dh<<<(d.T + 255) / 256, 256, 0, st>>>(d, L.rp, L.NPW, L.KP, a.tokmeta, a.kidx, a.klen, a.dh, a.dK, hc,
+                                               hct_hi, hct_lo, d.pre * d.drop_scale);
+  if (int rc = check_launch_tc()) return rc;
+  CUtensorMap tx, tdx, ta[3], thc, thh, thl;
+  if (!make_tmap(&tx, a.x, (uint64_t)d.T, (uint64_t)d.d_in, 128)) return MOKA_EUNSUPPORTED;
+  if (!make_tmap(&tdx, p.has_dx ? a.dx : a.x, (uint64_t)d.T, (uint64_t)d.d_in, 128)) return MOKA_EUNSUPPORTED;
+  for (int m = 0; m < 3; ++m)
+    if (!make_tmap(&ta[m], a.A[m < d.M ? m : 0], (uint64_t)d.r, (uint64_t)d.d_in, (uint32_t)d.r)) return MOKA_EUNSUPPORTED;
+  if (!make_tmap(&thc, hc, (uint64_t)d.T, (uint64_t)L.KP, 128)) return MOKA_EUNSUPPORTED;
+  if (!make_tmap(&thh, hct_hi, (uint64_t)L.NPW, (uint64_t)d.T, (uint32_t)L.NPW)) return MOKA_EUNSUPPORTED;
+  if (!make_tmap(&thl, hct_lo, (uint64_t)L.NPW, (uint64_t)d.T, (uint32_t)L.NPW)) return MOKA_EUNSUPPORTED;
+  const size_t smem = (size_t)(p.xs + p.ds) * 32768 + fixed;
+  cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+  k_wgrad_tc<<<slices * p.tsplit, kTcThreads, smem, st>>>(tx, tdx, ta[0], ta[1], ta[2], thc, thh, thl, p,
+                                                           a.dA[0], a.dA[d.M > 1 ? 1 : 0], a.dA[d.M > 2 ? 2 : 0]);
+  return check_launch_tc();
+}
+
 // ---------------------------------------------------------------------------- dispatch
 int tc_stage_mask(const DevDesc& d, int dtype) {
   if (dtype != MOKA_BF16) return 0;                 // fp32 storage keeps exact fp32 FMA (1e-5 bar)
@@ -771,6 +1117,7 @@ int tc_stage_mask(const DevDesc& d, int dtype) {
   if (!get_encode_fn()) return 0;
   int mask = kStageDown;
   if (d.d_out % 128 == 0) mask |= kStageUp | kStageDgrad;
+  if (d.d_in % 128 == 0) mask |= kStageWgrad;
   return mask;
 }
 
@@ -788,7 +1135,9 @@ int tc_backward(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t s
   if (stages & kStageDgrad) {
     if (int e = launch_dgrad_tc(d, a, num_sms, st)) return e;
   }
-  if (stages & kStageWgrad) return MOKA_EUNSUPPORTED;
+  if (stages & kStageWgrad) {
+    if (int e = launch_wgrad_tc(d, a, num_sms, st)) return e;
+  }
   return MOKA_OK;
 }
 
