@@ -159,6 +159,11 @@ class _MokaFn(torch.autograd.Function):
         if ev is not None:
             ev[1].record()
             TIMING['events'].append(('bwd', B * S, d_in, d_out, x2.element_size(), ev))
+        # tell the data-parallel engine that these parameters' gradients are complete
+        for prm in (Bw_param, *A_params):
+            cb = getattr(prm, '_moka_dp_ready', None)
+            if cb is not None:
+                cb()
         gB = None if dB_main else dB.to(Bw_param.dtype)
         gA = [None if main else g.to(p.dtype) for (g, main), p in zip(dAs, A_params)]
         gx = None if dx is None else dx.view(ctx.x_shape)

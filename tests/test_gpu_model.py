@@ -1,0 +1,190 @@
+"""GPU tests of the layers above the C ABI: the two MokaLinear facades under autograd against the
+reference-generated golden vectors, the fused AdamW kernel, the data-parallel engine at world size
+1, and a tiny frozen-Llama fine-tune step end to end."""
+import glob
+import os
+
+import pytest
+import torch
+
+from oracle import moka_oracle as mo
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), 'golden', '*vt_*.pt')))
+IDS = [os.path.basename(p)[:-3] for p in GOLD]
+
+
+def _facade(g, dtype):
+    from moka_b200.layer import MokaLinearAVT, MokaLinearVT
+    f = lambda t: t.to(torch.float64)
+    W0, A, Bw = f(g['W0']), [f(a) for a in g['A']], f(g['Bw'])
+    if g['variant'] == mo.VARIANT_VT:
+        base = torch.nn.Linear(g['d_in'], g['d_out'], bias=False)
+        layer = MokaLinearVT(base, 'image', r=g['r'], lora_alpha=g['alpha'], lora_dropout=0.0, attn_weight=g['w'])
+        layer.update_layer('text', g['r'], lora_alpha=g['alpha'], lora_dropout=0.0)
+        layer.set_adapter(['image', 'text'])
+        layer = layer.to(DEV, dtype)
+        with torch.no_grad():
+            layer.base_layer.weight.copy_(W0)
+            layer.lora_A['text'].weight.copy_(A[0]); layer.lora_A['image'].weight.copy_(A[1])
+            layer.lora_B['text'].weight.copy_(Bw)
+        args = [m.to(DEV) for m in g['masks']]
+        params = [layer.lora_A['text'].weight, layer.lora_A['image'].weight, layer.lora_B['text'].weight]
+        unused = layer.lora_B['image'].weight
+    else:
+        layer = MokaLinearAVT(g['d_in'], g['d_out'], rank=g['r'], lora_alpha=g['alpha'], lora_nums=g['M'],
+                              blc_weight=g['w'], loramethod='train', bias=False).to(DEV, dtype)
+        with torch.no_grad():
+            layer.weight.copy_(W0)
+            for i in range(g['M']):
+                getattr(layer, f'lora_A{i}').weight.copy_(A[i])
+            layer.lora_B0.weight.copy_(Bw)
+        args = [[m.to(DEV) for m in g['masks']]]
+        params = [getattr(layer, f'lora_A{i}').weight for i in range(g['M'])] + [layer.lora_B0.weight]
+        unused = None
+    return layer, args, params, unused
+
+
+@pytest.mark.parametrize('path', GOLD, ids=IDS)
+def test_facades_match_reference_autograd_fp32(path):
+    """MokaLinearAVT / MokaLinearVT (frozen GEMM by cuBLAS + libmoka.so) vs the reference layer's
+    own forward and autograd gradients, fp32, rel <= 1e-5."""
+    g = torch.load(path, weights_only=False)
+    layer, args, params, unused = _facade(g, torch.float32)
+    x = g['x'].to(torch.float32).to(DEV).requires_grad_(True)
+    y = layer(x, *args)
+    y.backward(g['dy'].to(torch.float32).to(DEV))
+    assert mo.rel_l2(y.detach().cpu(), g['y_f64']) <= 1e-5
+    assert mo.rel_l2(x.grad.cpu(), g['dx_f64']) <= 1e-5
+    for m in range(g['M']):
+        ref = g['dA_f64'][m]
+        got = params[m].grad
+        if float(ref.norm()) == 0:
+            assert got is None or float(got.norm()) == 0
+        else:
+            assert mo.rel_l2(got.cpu(), ref) <= 1e-5
+    assert mo.rel_l2(params[-1].grad.cpu(), g['dB_f64']) <= 1e-5
+    if unused is not None:
+        assert unused.grad is None                       # lora_B.image never receives a gradient
+
+
+def test_decode_branches_match_reference(golden_dir):
+    from moka_b200.layer import MokaLinearAVT, MokaLinearVT
+    g = torch.load(os.path.join(golden_dir, 'decode_plain_lora.pt'), weights_only=False)
+    f = lambda t: t.to(torch.float32).to(DEV)
+    x = f(g['x'])
+    base = torch.nn.Linear(64, 96, bias=False)
+    vt = MokaLinearVT(base, 'image', r=8, lora_alpha=g['alpha'], attn_weight=0.05)
+    vt.update_layer('text', 8, lora_alpha=g['alpha'], lora_dropout=0.0)
+    vt = vt.to(DEV)
+    with torch.no_grad():
+        vt.base_layer.weight.copy_(f(g['W0'])); vt.lora_A['text'].weight.copy_(f(g['A_text']))
+        vt.lora_B['text'].weight.copy_(f(g['Bw']))
+    assert mo.rel_l2(vt(x, None, None, None).cpu(), g['y_vt']) <= 1e-5
+    avt = MokaLinearAVT(64, 96, rank=8, lora_alpha=g['alpha'], lora_nums=3, blc_weight=1.0, loramethod='test',
+                        bias=False).to(DEV)
+    with torch.no_grad():
+        avt.weight.copy_(f(g['W0'])); avt.lora_A0.weight.copy_(f(g['A_text'])); avt.lora_B0.weight.copy_(f(g['Bw']))
+    assert mo.rel_l2(avt(x, None).cpu(), g['y_avt']) <= 1e-5
+
+
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16], ids=['fp32', 'bf16'])
+def test_fused_adamw_matches_torch(dtype):
+    from moka_b200.dp import _cuda_adamw
+    n = 100003
+    gen = torch.Generator(device=DEV).manual_seed(1)
+    w0 = torch.randn(n, device=DEV, generator=gen)
+    ref_p = torch.nn.Parameter(w0.clone())
+    opt = torch.optim.AdamW([ref_p], lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.05)
+    master, m, v = w0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    out = torch.empty(n, device=DEV, dtype=dtype)
+    for step in range(1, 6):
+        g = torch.randn(n, device=DEV, generator=gen)
+        ref_p.grad = g.clone()
+        opt.step()
+        _cuda_adamw(n, master, m, v, g, out, 3e-3, 0.9, 0.999, 1e-8, 0.05, step, 1.0)
+    torch.cuda.synchronize()
+    assert mo.rel_l2(master.cpu(), ref_p.detach().cpu()) <= 2e-6
+    assert torch.equal(out, master.to(dtype))
+
+
+def _tiny_model(variant, dtype=torch.bfloat16, r=8, dropout=0.0, ckpt=False):
+    from moka_b200.config import MokaConfig
+    from moka_b200.inject import PeftMixedModel, get_peft_model
+    from moka_b200.llama import LlamaConfig, LlamaForCausalLM
+    torch.manual_seed(0)
+    model = LlamaForCausalLM(LlamaConfig.tiny(layers=2, hidden=256, inter=512, heads=4, vocab=512)).to(DEV, dtype)
+    if variant == 'avt':
+        pm = get_peft_model(model, MokaConfig(variant='avt', r=r, lora_alpha=16, blc_weight=1.0, lora_dropout=dropout))
+    else:
+        cfg = MokaConfig(variant='vt', r=r, lora_alpha=16, attn_weight=0.05, lora_dropout=dropout)
+        pm = PeftMixedModel(model, cfg, 'image')
+        pm.add_adapter('text', cfg)
+        pm.set_adapter(['image', 'text'])
+    model.gradient_checkpointing_enable(ckpt)
+    pm.train()
+    return pm
+
+
+def _batch(variant, B=2, S=256):
+    gen = torch.Generator().manual_seed(5)
+    ids = torch.randint(3, 500, (B, S), generator=gen)
+    if variant == 'avt':
+        masks = [m.to(DEV) for m in mo.layout_masks(mo.VARIANT_AVT, B, S, 'c3')]
+        kw = dict(modality_masks=masks)
+    else:
+        t, i, q = [m.to(DEV) for m in mo.layout_masks(mo.VARIANT_VT, B, S, 'c2')]
+        kw = dict(my_text_mask=t, my_image_mask=i, question_mask=q)
+    labels = ids.clone()
+    labels[:, : S // 2] = -100
+    return ids.to(DEV), labels.to(DEV), kw
+
+
+@pytest.mark.parametrize('variant', ['avt', 'vt'])
+def test_tiny_llama_finetune_step_trains(variant):
+    """Frozen tiny Llama + injected MokaLinear + flat-bucket AdamW (world size 1): the loss goes
+    down, only lora_ parameters change, gradients land in the flat fp32 bucket."""
+    from moka_b200 import _cabi
+    from moka_b200.dp import AdamWConfig, AdapterDataParallel
+    pm = _tiny_model(variant)
+    with torch.no_grad():       # B starts at zero (reference init): give it signal so every path is live
+        for n, p in pm.named_parameters():
+            if 'lora_B' in n:
+                p.normal_(std=0.02)
+    frozen_before = {n: p.detach().clone() for n, p in pm.named_parameters() if not p.requires_grad}
+    eng = AdapterDataParallel(pm, AdamWConfig(lr=2e-3), zero_stage=2, num_buckets=2)
+    ids, labels, kw = _batch(variant)
+    n0 = _cabi.launch_count()
+    losses = []
+    for _ in range(6):
+        loss, _ = pm(input_ids=ids, labels=labels, **kw)
+        loss.backward()
+        assert float(eng.flat_grad.abs().max()) > 0
+        eng.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0] - 1e-3, losses
+    assert _cabi.launch_count() - n0 >= 6 * (14 * 4 + 1)
+    for n, p in pm.named_parameters():
+        if not p.requires_grad:
+            assert torch.equal(p, frozen_before[n]), n
+
+
+def test_checkpointed_forward_with_dropout_is_consistent():
+    """Per-layer gradient checkpointing (AVT recipe) re-runs the forward in backward; the
+    dropout mask must be the one of the first run, so gradients equal the non-checkpointed ones."""
+    grads = []
+    for ckpt in (False, True):
+        pm = _tiny_model('avt', dropout=0.1, ckpt=ckpt)
+        with torch.no_grad():
+            for n, p in pm.named_parameters():
+                if 'lora_B' in n:
+                    p.normal_(std=0.02, generator=torch.Generator(device=DEV).manual_seed(len(n)))
+        ids, labels, kw = _batch('avt')
+        torch.manual_seed(123)
+        loss, _ = pm(input_ids=ids, labels=labels, **kw)
+        loss.backward()
+        grads.append({n: p.grad.detach().float().clone() for n, p in pm.named_parameters() if p.grad is not None})
+    assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 0
+    for n in grads[0]:
+        assert mo.rel_l2(grads[1][n].cpu(), grads[0][n].cpu()) <= 2e-2, n
