@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- Llama-2-7B MokA fine-tune step throughput on B200 (tokens/s, whole job).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's arm (N=1 plain, N>1 under torchrun)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what every key means.
+A "step" = forward + backward + adapter-gradient sync + sharded AdamW of one micro-batch of
+synthetic image/audio/text token sequences through a frozen, randomly initialised Llama-2-7B whose
+224 projections are MokaLinear layers.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[2] shape (per GPU): the metric's "Llama-2-7B MokA r=16", 3 modalities
+    'llama2-7b-avt-m3-r16-s2048': dict(variant='avt', model='7b', r=16, M=3, S=2048, B=4, layout='c3', w=1.0),
+    # BASELINE.json configs[1]
+    'llama2-7b-vt-m2-r8-s2048': dict(variant='vt', model='7b', r=8, M=2, S=2048, B=4, layout='c2', w=0.05),
+    # BASELINE.json configs[3] (13B, r=64, seq 4096)
+    'llama2-13b-vt-m2-r64-s4096': dict(variant='vt', model='13b', r=64, M=2, S=4096, B=1, layout='c4', w=0.05),
+    # smoke-sized
+    'tiny-avt': dict(variant='avt', model='tiny', r=16, M=3, S=512, B=2, layout='c3', w=1.0),
+}
+DEFAULT_WORKLOAD = 'llama2-7b-avt-m3-r16-s2048'
+
+
+def peak_hbm():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'], 'measured'
+    except Exception:
+        return 6650.0, 'fallback'
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200', '-i', str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except Exception:
+                continue
+            for name, col in (('hw_slowdown', 5), ('hw_thermal_slowdown', 6), ('sw_thermal_slowdown', 7),
+                              ('sw_power_cap', 8)):
+                if len(r) > col and r[col].lower().startswith('active'):
+                    reasons.add(name)
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx, reasons=sorted(reasons),
+                    samples=len(sm))
+
+
+# --------------------------------------------------------------------------- CPU baseline (oracle port)
+def cpu_reference_leg(wl: dict, seconds_budget: float = 25.0, steps: int = 1, warmup: int = 0):
+    """Times the reference's algorithm (oracle/moka_oracle.py *_reference_form: the same op sequence as
+    the reference layers, frozen GEMM included, autograd backward) on the host cores.
+    Sample: the 7 MokaLinear projections of ONE decoder layer on ONE sequence; tokens/s is
+    S / (num_layers * t_layer), i.e. an upper bound on what a whole CPU step could reach
+    (attention, norms, lm_head and the optimizer are left out)."""
+    import torch
+    from oracle import moka_oracle as mo
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    S, r, M = wl['S'], wl['r'], wl['M']
+    variant = mo.VARIANT_AVT if wl['variant'] == 'avt' else mo.VARIANT_VT
+    hidden, inter, layers = {'7b': (4096, 11008, 32), '13b': (5120, 13824, 40), 'tiny': (256, 512, 2)}[wl['model']]
+    shapes = [(hidden, hidden)] * 4 + [(hidden, inter)] * 2 + [(inter, hidden)]
+    masks = mo.layout_masks(variant, 1, S, wl['layout'])
+    gen = torch.Generator().manual_seed(0)
+    dt = torch.float32
+
+    def one_layer():
+        t0 = time.perf_counter()
+        for d_in, d_out in shapes:
+            x = torch.randn(1, S, d_in, generator=gen, dtype=dt).requires_grad_(True)
+            W0 = torch.randn(d_out, d_in, generator=gen, dtype=dt) * 0.02
+            A = [(torch.rand(r, d_in, generator=gen, dtype=dt) - 0.5).requires_grad_(True) for _ in range(M)]
+            Bw = (torch.randn(d_out, r, generator=gen, dtype=dt) * 0.02).requires_grad_(True)
+            t1 = time.perf_counter()
+            if variant == mo.VARIANT_AVT:
+                y = mo.avt_reference_form(x, W0, A, Bw, masks, lora_alpha=16, blc_weight=wl['w'])
+            else:
+                y = mo.vt_reference_form(x, W0, A[0], A[1], Bw, masks[0], masks[1], masks[2], lora_alpha=16,
+                                         attn_weight=wl['w'])
+            y.backward(torch.ones_like(y))
+            one_layer.compute += time.perf_counter() - t1
+        return time.perf_counter() - t0
+
+    one_layer.compute = 0.0
+    for _ in range(warmup):
+        one_layer()
+    times = []
+    for _ in range(max(1, steps)):
+        one_layer.compute = 0.0
+        one_layer()
+        times.append(one_layer.compute)
+        if sum(times) > seconds_budget:
+            break
+    t_layer = statistics.median(times)
+    value = S / (layers * t_layer)
+    sample = (f'7 MokaLinear fwd+bwd (frozen GEMM included) of one decoder layer, 1 sequence of {S} tokens, fp32, '
+              f'{len(times)} repetition(s), median {t_layer:.3f} s/layer; tokens/s = S / ({layers} layers x t_layer) '
+              f'(attention, norms, lm_head, optimizer excluded)')
+    return dict(value=value, unit='tokens/s', cores=threads, kind='port', sample=sample), t_layer
+
+
+# --------------------------------------------------------------------------- main arm
+def build_model(wl, device, ckpt):
+    import torch
+    from moka_b200.config import MokaConfig
+    from moka_b200.inject import PeftMixedModel, get_peft_model
+    from moka_b200.llama import LlamaConfig, LlamaForCausalLM
+    cfg = {'7b': LlamaConfig.llama2_7b, '13b': LlamaConfig.llama2_13b, 'tiny': LlamaConfig.tiny}[wl['model']]()
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)
+    try:
+        with torch.device(device):
+            model = LlamaForCausalLM(cfg)
+    finally:
+        torch.set_default_dtype(prev)
+    if wl['variant'] == 'avt':
+        pm = get_peft_model(model, MokaConfig(variant='avt', r=wl['r'], num_modalities=wl['M'], lora_alpha=16,
+                                              blc_weight=wl['w'], lora_dropout=wl['dropout']))
+    else:
+        c = MokaConfig(variant='vt', r=wl['r'], lora_alpha=16, attn_weight=wl['w'], lora_dropout=wl['dropout'])
+        pm = PeftMixedModel(model, c, 'image')
+        pm.add_adapter('text', c)
+        pm.set_adapter(['image', 'text'])
+    # the reference initialises B to zero; a fine-tune in progress has B != 0 -- use N(0, 0.02^2)
+    g = torch.Generator(device=device).manual_seed(1234)
+    with torch.no_grad():
+        for n, p in pm.named_parameters():
+            if 'lora_B' in n:
+                p.normal_(mean=0.0, std=0.02, generator=g)
+    model.gradient_checkpointing_enable(ckpt)
+    pm.train()
+    return pm, cfg
+
+
+def host_batch(wl, cfg, rank):
+    """Synthetic batch in PINNED host memory: token ids, labels and the reference-shaped masks."""
+    import torch
+    from oracle.moka_oracle import VARIANT_AVT, VARIANT_VT, layout_masks   # span layouts only
+    B, S = wl['B'], wl['S']
+    gen = torch.Generator().manual_seed(1234 + rank)
+    ids = torch.randint(3, cfg.vocab_size, (B, S), generator=gen)
+    labels = ids.clone()
+    variant = VARIANT_AVT if wl['variant'] == 'avt' else VARIANT_VT
+    masks = layout_masks(variant, B, S, wl['layout'])
+    ans = int(S * (1680 if wl['layout'] == 'c3' else 675) / 2048)
+    labels[:, :ans] = -100                          # loss on the answer span only
+    out = dict(input_ids=ids.pin_memory(), labels=labels.pin_memory(), masks=[m.contiguous().pin_memory() for m in masks])
+    return out
+
+
+def to_device(hb, wl, device):
+    ids = hb['input_ids'].to(device, non_blocking=True)
+    labels = hb['labels'].to(device, non_blocking=True)
+    masks = [m.to(device, non_blocking=True) for m in hb['masks']]
+    if wl['variant'] == 'avt':
+        kw = dict(modality_masks=masks)
+    else:
+        kw = dict(my_text_mask=masks[0], my_image_mask=masks[1], question_mask=masks[2])
+    return ids, labels, kw
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='moka', choices=['moka', 'reference'])
+    ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument('--micro-batch', type=int, default=0)
+    ap.add_argument('--zero-stage', type=int, default=1)
+    ap.add_argument('--dropout', type=float, default=0.0)
+    ap.add_argument('--grad-checkpointing', action='store_true')
+    ap.add_argument('--flags', type=int, default=0, help='MokaDesc.flags (1 = force warp-FMA kernels)')
+    ap.add_argument('--skip-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    wl = dict(WORKLOADS[args.workload])
+    wl['dropout'] = args.dropout
+    if args.micro_batch:
+        wl['B'] = args.micro_batch
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    warmup = max(args.warmup, 3) if args.impl == 'moka' else args.warmup
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        base, t_layer = cpu_reference_leg(wl, seconds_budget=120.0, steps=args.steps, warmup=args.warmup)
+        line = dict(metric='tokens/sec Llama-2-7B MokA fine-tune step', value=base['value'], unit='tokens/s',
+                    impl='reference', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=t_layer * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
+                    dtype='f32', data='synthetic',
+                    config=dict(workload=args.workload, lora_dropout=args.dropout, sample=base['sample']),
+                    cpu_baseline=base,
+                    e2e=dict(value=base['value'], unit='tokens/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ this repo's arm (GPU)
+    import torch
+    import torch.distributed as dist
+    from moka_b200 import _cabi
+    from moka_b200 import layer as moka_layer
+    from moka_b200.dp import AdamWConfig, AdapterDataParallel
+    _cabi.load()                                   # no CUDA library -> fail loudly, there is no fallback
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (B200)')
+    torch.cuda.set_device(local_rank)
+    device = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=device)
+    if args.flags:
+        for cls in (moka_layer.MokaLinearAVT, moka_layer.MokaLinearVT):
+            pass
+    pm, cfg = build_model(wl, device, args.grad_checkpointing)
+    if args.flags:
+        for m in pm.moka_layers():
+            m.kernel_flags = args.flags
+    eng = AdapterDataParallel(pm, AdamWConfig(lr=1e-4), zero_stage=args.zero_stage, num_buckets=4)
+    hb = host_batch(wl, cfg, rank)
+    tokens_per_step = wl['B'] * wl['S'] * world
+    h2d = sum(t.numel() * t.element_size() for t in [hb['input_ids'], hb['labels'], *hb['masks']])
+
+    def step(dev_batch=None):
+        ids, labels, kw = dev_batch if dev_batch is not None else to_device(hb, wl, device)
+        loss, _ = pm(input_ids=ids, labels=labels, **kw)
+        loss.backward()
+        eng.step()
+        return loss
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n, resident, collect_events):
+        dev_batch = to_device(hb, wl, device) if resident else None
+        barrier()
+        moka_layer.TIMING['events'].clear()
+        moka_layer.TIMING['enabled'] = collect_events
+        n0 = _cabi.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(n):
+            loss = step(dev_batch)
+            if not resident:
+                last = float(loss)                 # device -> host read of the step's result
+        e1.record()
+        barrier()
+        moka_layer.TIMING['enabled'] = False
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, _cabi.launch_count() - n0, last
+
+    for _ in range(warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches, _ = timed(args.steps, resident=True, collect_events=True)
+    events = list(moka_layer.TIMING['events'])
+    ms_e2e, _, last_loss = timed(args.steps, resident=False, collect_events=False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # roofline of the fused MokaLinear fwd+bwd (algorithmic bytes of SURVEY 8d / DESIGN.md)
+    alg_bytes, dur_ms, per_kind = 0.0, 0.0, {'fwd': [0.0, 0.0], 'bwd': [0.0, 0.0]}
+    for kind, T, d_in, d_out, e, ev in events:
+        b = e * T * ((d_in + 2 * d_out) if kind == 'fwd' else (3 * d_in + d_out))
+        t = ev[0].elapsed_time(ev[1])
+        alg_bytes += b; dur_ms += t
+        per_kind[kind][0] += b; per_kind[kind][1] += t
+    peak, peak_kind = peak_hbm()
+    achieved = alg_bytes / (dur_ms * 1e-3) / 1e9 if dur_ms > 0 else 0.0
+
+    if rank == 0:
+        value = tokens_per_step * args.steps / (ms_dev * 1e-3)
+        e2e_value = tokens_per_step * args.steps / (ms_e2e * 1e-3)
+        uses_tc = None
+        try:
+            lay = pm.moka_layers()[0]
+            uses_tc = 'tcgen05+TMA' if (wl['dropout'] == 0.0 and not (args.flags & 1)) else 'warp-FMA'
+        except Exception:
+            pass
+        line = dict(
+            metric='tokens/sec Llama-2-7B MokA fine-tune step', value=value, unit='tokens/s', n_gpus=world,
+            steps=args.steps, warmup=warmup, ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='weak',
+            vs_baseline=None, dtype='bf16', data='synthetic', impl='moka_b200',
+            config=dict(workload=args.workload, micro_batch_per_gpu=wl['B'], seq_len=wl['S'], rank=wl['r'],
+                        modalities=wl['M'], lora_dropout=wl['dropout'], grad_checkpointing=args.grad_checkpointing,
+                        parallelism=f'dp{world}-zero{args.zero_stage}', kernel_path=uses_tc,
+                        adapted_linears=len(pm.moka_layers()), trainable_params=eng.trainable_numel(),
+                        l2='per-step activations (>1 GB) exceed the 126 MB L2; no explicit flush',
+                        base='frozen random-init Llama-2 (cuBLAS GEMMs + SDPA via PyTorch)'),
+            e2e=dict(value=e2e_value, unit='tokens/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                     ms_per_step=ms_e2e / args.steps, last_loss=last_loss),
+            gpu_launches=int(launches),
+            roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
+                          traffic=None, peak_source=peak_kind,
+                          kernel='fused MokaLinear fwd+bwd (libmoka.so calls, CUDA events per call)',
+                          calls=len(events),
+                          fwd_gbs=per_kind['fwd'][0] / max(per_kind['fwd'][1], 1e-9) / 1e6,
+                          bwd_gbs=per_kind['bwd'][0] / max(per_kind['bwd'][1], 1e-9) / 1e6,
+                          share_of_step=dur_ms / ms_dev),
+            clocks=clocks)
+        if world == 1 and not args.skip_cpu_baseline:
+            base, _ = cpu_reference_leg(wl, seconds_budget=25.0, steps=1, warmup=0)
+            line['cpu_baseline'] = base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())
