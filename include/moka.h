@@ -89,9 +89,9 @@ size_t moka_workspace_bytes(const MokaDesc* desc);
  * every token MOKA_MOD_TEXT and klen == 0 it is the plain-LoRA decode branch
  * (lora.py:373-381, layer.py:672-678).  ``y0`` is the frozen base output W0 x (+bias) and may
  * alias ``y`` (in-place residual add, like layer.py:663).  ``A`` is a HOST array of M device
- * pointers to [r, d_in] matrices, ``Bw`` is [d_out, r].  ``h_stash`` is fp32 [2, B*S, r]: it
- * receives the pre-attention projections h and the post-attention rows g that moka_backward
- * re-uses.
+ * pointers to [r, d_in] matrices, ``Bw`` is [d_out, r].  ``h_stash`` is fp32 [2*B*S*r + B*S]: it
+ * receives the pre-attention projections h [B*S, r], the post-attention rows g [B*S, r] and the
+ * per-token log-sum-exp of the attention scores [B*S] that moka_backward re-uses.
  */
 int moka_forward(const MokaDesc* desc, const void* x, const void* y0, void* y,
                  const void* const* A, const void* Bw,
@@ -143,6 +143,14 @@ int moka_adamw_step(int64_t n, float* master, float* exp_avg, float* exp_avg_sq,
                     const float* grad, void* param_out, int32_t dtype,
                     float lr, float beta1, float beta2, float eps, float weight_decay,
                     int32_t step, float grad_scale, moka_stream_t stream);
+
+/*
+ * Caller-side helper (not part of the adapter path): rotary position embedding of a bf16
+ * [tokens = B*S, H, D] tensor (dst may alias src), HF-Llama half-split convention; backward != 0
+ * applies the inverse rotation (the gradient).  Used by the frozen Llama wrapper of the benchmark.
+ */
+int moka_rope(const void* src, void* dst, int64_t tokens, int32_t S, int32_t H, int32_t D, float theta,
+              int32_t backward, moka_stream_t stream);
 
 /* Number of kernels this library has launched in this process (monotonic). */
 int64_t moka_launch_count(void);

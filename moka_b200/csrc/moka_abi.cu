@@ -86,7 +86,7 @@ extern "C" {
 
 size_t moka_workspace_bytes(const MokaDesc* desc) {
   if (validate(desc) != MOKA_OK) return 0;
-  return ws_dh_bytes(desc) + ws_dk_bytes(desc) + align_up(tc_pack_bytes(desc->B * desc->S, desc->r, desc->M), 256) + 256;
+  return 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc) + align_up(tc_pack_bytes(desc->B * desc->S, desc->r, desc->M), 256) + 256;
 }
 
 int moka_uses_tensor_cores(const MokaDesc* desc) {
@@ -151,10 +151,12 @@ int moka_backward(const MokaDesc* desc, const void* dy, const void* x, const flo
   a.klen_hint = desc->Lk;
   char* ws = static_cast<char*>(workspace);
   a.dh = reinterpret_cast<float*>(ws);
-  a.dK = reinterpret_cast<float*>(ws + ws_dh_bytes(desc));
-  a.pack = ws + ws_dh_bytes(desc) + ws_dk_bytes(desc);
+  a.dh_att = reinterpret_cast<float*>(ws + ws_dh_bytes(desc));
+  a.dK = reinterpret_cast<float*>(ws + 2 * ws_dh_bytes(desc));
+  a.pack = ws + 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  cudaError_t ce = cudaMemsetAsync(a.dK, 0, ws_dk_bytes(desc), st);
+  // one memset covers dh (the tensor-core dgrad reduces into it), dh_att and dK
+  cudaError_t ce = cudaMemsetAsync(a.dh, 0, 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc), st);
   if (ce != cudaSuccess) { set_cuda_error(ce); return MOKA_ECUDA; }
   const int tcs = tc_stages(desc, d) & (kStageDgrad | kStageWgrad);
   if ((desc->flags & MOKA_FLAG_FORCE_TC) && tcs != (kStageDgrad | kStageWgrad)) return MOKA_EUNSUPPORTED;
@@ -195,6 +197,13 @@ int moka_adamw_step(int64_t n, float* master, float* exp_avg, float* exp_avg_sq,
   if (dtype != MOKA_BF16 && dtype != MOKA_F32) return MOKA_EINVAL;
   return launch_adamw(n, master, exp_avg, exp_avg_sq, grad, param_out, dtype, lr, beta1, beta2, eps,
                       weight_decay, step, grad_scale, static_cast<cudaStream_t>(stream));
+}
+
+int moka_rope(const void* src, void* dst, int64_t tokens, int32_t S, int32_t H, int32_t D, float theta,
+              int32_t backward, moka_stream_t stream) {
+  if (!src || !dst || tokens <= 0 || S <= 0 || H <= 0 || D <= 0 || (D % 16) || !aligned16(src) || !aligned16(dst))
+    return MOKA_EINVAL;
+  return launch_rope(src, dst, tokens, S, H, D, theta, backward ? -1.f : 1.f, static_cast<cudaStream_t>(stream));
 }
 
 int64_t moka_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -24,12 +24,14 @@ struct AttnCtx {
   float* dKs;               // smem  [kcap, ks] (backward only)
   int ks;                   // row stride of Ks (r + 1: conflict-free lane<->key reads)
   int kcap;                 // keys that fit in Ks
+  float* lse_out;           // global [T] log2-sum-exp of the scaled scores (forward; may be null)
 };
 
 // ------------------------------------------------------------------ fast path (smem keys)
 template <bool BWD>
 __device__ __forceinline__ void attn_token_fast(const DevDesc& d, const AttnCtx& c, int L,
-                                                const float* hq, float* gq, float* dgq, int lane) {
+                                                const float* hq, float* gq, float* dgq, int lane,
+                                                float* lse = nullptr) {
   const int r = d.r;
   const int nb = (L + 31) >> 5;
   float p[kKeyBlocksMax];
@@ -62,6 +64,7 @@ __device__ __forceinline__ void attn_token_fast(const DevDesc& d, const AttnCtx&
   }
   l = warp_sum(l);
   const float inv = 1.f / l;
+  if (!BWD && lse && lane == 0) *lse = mx + log2f(l);
 #pragma unroll
   for (int kb = 0; kb < kKeyBlocksMax; ++kb) p[kb] *= inv;
 
@@ -139,7 +142,7 @@ __device__ __forceinline__ void attn_token_fast(const DevDesc& d, const AttnCtx&
 // the rescale skipped unless the running max moves.  Used when r <= 32 and the keys fit in smem.
 template <int R>
 __device__ __forceinline__ void attn_thread_fwd(const DevDesc& d, const float* __restrict__ Ks, int L,
-                                                float* row) {
+                                                float* row, float* lse) {
   const int r = d.r;
   float h[R], acc[R];
 #pragma unroll
@@ -173,6 +176,7 @@ __device__ __forceinline__ void attn_thread_fwd(const DevDesc& d, const float* _
     for (int j = 0; j < R; ++j) acc[j] = fmaf(e, kv[j], acc[j]);
   }
   const float sc = d.attn_w / l;
+  if (lse) *lse = m + log2f(l);
 #pragma unroll
   for (int j = 0; j < R; ++j)
     if (j < r) row[j] = fmaf(sc, acc[j], h[j]);
@@ -182,7 +186,8 @@ __device__ __forceinline__ void attn_thread_fwd(const DevDesc& d, const float* _
 // lanes <-> rank index (up to 8 per lane, r <= 256); one key at a time.
 template <bool BWD>
 __device__ __forceinline__ void attn_token_slow(const DevDesc& d, const AttnCtx& c, int b, int L,
-                                                const float* hq, float* gq, float* dgq, int lane) {
+                                                const float* hq, float* gq, float* dgq, int lane,
+                                                float* lse = nullptr) {
   const int r = d.r;
   float hv[8], dav[8], acc[8];
 #pragma unroll
@@ -227,6 +232,7 @@ __device__ __forceinline__ void attn_token_slow(const DevDesc& d, const AttnCtx&
   }
   const float inv = 1.f / l;
   if (!BWD) {
+    if (lse && lane == 0) *lse = mx + log2f(l);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int jj = lane + 32 * i;
@@ -312,9 +318,10 @@ __device__ __forceinline__ void attention_tile(const DevDesc& d, const AttnCtx& 
       for (int tt = lo + tid; tt < hi; tt += nthr) {
         if ((meta_s[tt] & MOKA_MOD_MASK) < MOKA_MOD_VIS) continue;
         float* rowp = gs + (size_t)tt * r;
-        if (r <= 8) attn_thread_fwd<8>(d, c.Ks, L, rowp);
-        else if (r <= 16) attn_thread_fwd<16>(d, c.Ks, L, rowp);
-        else if constexpr (MAXR >= 32) attn_thread_fwd<32>(d, c.Ks, L, rowp);
+        float* lsep = c.lse_out ? c.lse_out + t0 + tt : nullptr;
+        if (r <= 8) attn_thread_fwd<8>(d, c.Ks, L, rowp, lsep);
+        else if (r <= 16) attn_thread_fwd<16>(d, c.Ks, L, rowp, lsep);
+        else if constexpr (MAXR >= 32) attn_thread_fwd<32>(d, c.Ks, L, rowp, lsep);
       }
       g.sync();
       continue;
@@ -324,8 +331,9 @@ __device__ __forceinline__ void attention_tile(const DevDesc& d, const AttnCtx& 
       const float* hq = hs + (size_t)tt * r;
       float* gq = BWD ? nullptr : gs + (size_t)tt * r;
       float* dgq = BWD ? dgs + (size_t)tt * r : nullptr;
-      if (fast) attn_token_fast<BWD>(d, c, L, hq, gq, dgq, lane);
-      else attn_token_slow<BWD>(d, c, b, L, hq, gq, dgq, lane);
+      float* lsep = (!BWD && c.lse_out) ? c.lse_out + t0 + tt : nullptr;
+      if (fast) attn_token_fast<BWD>(d, c, L, hq, gq, dgq, lane, lsep);
+      else attn_token_slow<BWD>(d, c, b, L, hq, gq, dgq, lane, lsep);
     }
     if (fast) {
       g.sync();

@@ -14,6 +14,7 @@ struct SimtArgs {
   const uint8_t* tokmeta; const int32_t* kidx; const int32_t* klen;
   float* h_stash;
   float* dh;        // workspace [T, r]
+  float* dh_att;    // workspace [T, r]: attention-backward contributions, added to dh by the wgrad stage
   float* dK;        // workspace [B, Lk, r]
   void* pack;       // workspace for the packed bf16 dh operands of k_wgrad_tc (tc_pack_bytes)
   int klen_hint;    // upper bound on klen (kidx row stride)
@@ -34,6 +35,8 @@ int launch_build_meta(int variant, int B, int S, int Lk, const void* const* mask
 
 int launch_adamw(int64_t n, float* master, float* m, float* v, const float* grad, void* param_out, int dtype,
                  float lr, float b1, float b2, float eps, float wd, int step, float grad_scale, cudaStream_t st);
+
+int launch_rope(const void* src, void* dst, long long BS, int S, int H, int D, float theta, float sign, cudaStream_t st);
 
 // tensor-core (tcgen05 + TMA) path; returns MOKA_EUNSUPPORTED when the shape does not qualify
 // Returns the mask of stages the tcgen05 path implements for this shape (0 = none).

@@ -42,4 +42,52 @@ int launch_adamw(int64_t n, float* master, float* m, float* v, const float* grad
   return MOKA_OK;
 }
 
+
+// Rotary position embedding applied IN PLACE on a [B, S, H, D] bf16 tensor (half-split
+// convention of HF Llama: pairs (i, i + D/2)).  sign = +1 forward, -1 backward (the transpose of
+// a rotation is the rotation by the opposite angle).  Helper for the frozen Llama caller in
+// moka_b200/llama.py -- the reference does this with eager ops (modeling_llama.py apply_rotary_pos_emb).
+__global__ void __launch_bounds__(256)
+k_rope(const __nv_bfloat16* src, __nv_bfloat16* dst, int S, int H, int D, float log2_theta, float sign, long long npairs8) {
+  const int half = D >> 1;
+  const int gpr = half >> 3;                     // groups of 8 pairs per (token, head)
+  for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < npairs8; g += (long long)gridDim.x * blockDim.x) {
+    const int gi = (int)(g % gpr);
+    const long long th = g / gpr;                // (b*S + s) * H + h
+    const int spos = (int)((th / H) % S);
+    const __nv_bfloat16* sbase = src + th * D + gi * 8;
+    __nv_bfloat16* base = dst + th * D + gi * 8;
+    uint4 lo = *reinterpret_cast<const uint4*>(sbase);
+    uint4 hi = *reinterpret_cast<const uint4*>(sbase + half);
+    uint32_t* lw = reinterpret_cast<uint32_t*>(&lo);
+    uint32_t* hw = reinterpret_cast<uint32_t*>(&hi);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = gi * 8 + e;
+      const float inv = exp2f(-log2_theta * (float)(2 * i) / (float)D);
+      float sn, cs;
+      sincosf((float)spos * inv, &sn, &cs);
+      sn *= sign;
+      const float a = (e & 1) ? bf16hi(lw[e >> 1]) : bf16lo(lw[e >> 1]);
+      const float b = (e & 1) ? bf16hi(hw[e >> 1]) : bf16lo(hw[e >> 1]);
+      const __nv_bfloat16 ra = __float2bfloat16_rn(a * cs - b * sn);
+      const __nv_bfloat16 rb = __float2bfloat16_rn(b * cs + a * sn);
+      reinterpret_cast<__nv_bfloat16*>(lw)[e] = ra;
+      reinterpret_cast<__nv_bfloat16*>(hw)[e] = rb;
+    }
+    *reinterpret_cast<uint4*>(base) = lo;
+    *reinterpret_cast<uint4*>(base + half) = hi;
+  }
+}
+
+int launch_rope(const void* src, void* x, long long BS, int S, int H, int D, float theta, float sign, cudaStream_t st) {
+  const long long npairs8 = BS * H * (D / 16);
+  const int grid = (int)((npairs8 + 255) / 256 < 148 * 16 ? (npairs8 + 255) / 256 : 148 * 16);
+  k_rope<<<grid, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(x), S, H, D, log2f(theta), sign, npairs8);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+  note_launch();
+  return MOKA_OK;
+}
+
 }  // namespace moka

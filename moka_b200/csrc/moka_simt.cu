@@ -163,7 +163,7 @@ k_up(DevDesc d, const T* y0, T* y, const T* __restrict__ Bw,
   const int nchunks = (d.d_out + 255) >> 8;
   const int nrb = (r + RB - 1) / RB;
   const bool inplace = (y0 == y);
-  AttnCtx c{tokmeta, kidx, klen, h_stash, nullptr, Ks, nullptr, r + 1, kcap};
+  AttnCtx c{tokmeta, kidx, klen, h_stash, nullptr, Ks, nullptr, r + 1, kcap, g_out + (size_t)d.T * d.r};
   __shared__ int s_or;
   const SyncGroup grp{(int)threadIdx.x, kThreads, 0, &s_or};
 
@@ -247,7 +247,7 @@ k_dgrad(DevDesc d, const T* __restrict__ dy, const T* __restrict__ Bw,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nchunks = (d.d_out + 255) >> 8;
   const int nrb = (r + RB - 1) / RB;
-  AttnCtx c{tokmeta, kidx, klen, h_stash, dK_glob, Ks, dKs, r + 1, kcap};
+  AttnCtx c{tokmeta, kidx, klen, h_stash, dK_glob, Ks, dKs, r + 1, kcap, nullptr};
   __shared__ int s_or;
   const SyncGroup grp{(int)threadIdx.x, kThreads, 0, &s_or};
 
@@ -339,7 +339,7 @@ template <typename T, int RB>
 __global__ void __launch_bounds__(kThreads, 2)
 k_wgrad(DevDesc d, const T* __restrict__ x, T* dx, APtrs A, GPtrs dA,
         const uint8_t* __restrict__ tokmeta, const int32_t* __restrict__ kidx,
-        const int32_t* __restrict__ klen, const float* __restrict__ dh_in,
+        const int32_t* __restrict__ klen, const float* __restrict__ dh_in, const float* __restrict__ dh_att,
         const float* __restrict__ dK_glob) {
   constexpr int U = 4;
   extern __shared__ __align__(16) float smem[];
@@ -356,7 +356,7 @@ k_wgrad(DevDesc d, const T* __restrict__ x, T* dx, APtrs A, GPtrs dA,
     const int t0 = tile * d.tile_tokens;
     const int nt = min(d.tile_tokens, d.T - t0);
     if (tid == 0) s_present = 0;
-    for (int i = tid; i < nt * r; i += kThreads) dhs[i] = dh_in[(size_t)t0 * r + i];
+    for (int i = tid; i < nt * r; i += kThreads) dhs[i] = dh_in[(size_t)t0 * r + i] + dh_att[(size_t)t0 * r + i];
     __syncthreads();
     for (int i = tid; i < nt; i += kThreads) {
       const uint8_t mb = tokmeta[t0 + i];
@@ -606,7 +606,7 @@ static int launch_backward_t(DevDesc d, const SimtArgs& a, int num_sms, cudaStre
     plan_tiles(dd, 1, 0, num_sms, &smem, &kcap, &grid, 0);
     if (int e = set_smem(k_wgrad<T, RB>, smem)) return e;
     k_wgrad<T, RB><<<grid, kThreads, smem, st>>>(dd, static_cast<const T*>(a.x), static_cast<T*>(a.dx), A, G,
-                                                 a.tokmeta, a.kidx, a.klen, a.dh, a.dK);
+                                                 a.tokmeta, a.kidx, a.klen, a.dh, a.dh_att, a.dK);
     if (int e = check_launch()) return e;
   }
   return MOKA_OK;

@@ -10,6 +10,7 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
 // warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+#include <algorithm>
 #include <mutex>
 
 #include "moka_attn.cuh"
@@ -241,6 +242,34 @@ __device__ __forceinline__ void named_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory");
 }
 
+// Epilogue of the read-modify-write kernels: add the fp32 TMEM accumulator [128 lanes x 128 cols]
+// onto a bf16 tile held in shared memory as two {64 cols x 128 rows} 128B-swizzled TMA boxes.
+// One thread owns one row (TMEM lane).  All shared loads of a half-row are issued before the
+// arithmetic and all stores after it, so nothing waits on a load -> store -> load chain.
+__device__ __forceinline__ void add_acc_to_tile(uint32_t tmem_row_addr, uint32_t tile_smem, uint32_t row) {
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const uint32_t box = tile_smem + (uint32_t)half * 16384u;
+    uint4 yv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) yv[c] = ptx::lds128(box + ptx::sw128_offset(row, (uint32_t)c));
+    float acc[2][32];
+    ptx::tmem_ld32(tmem_row_addr + (uint32_t)(half * 64), acc[0]);
+    ptx::tmem_ld32(tmem_row_addr + (uint32_t)(half * 64 + 32), acc[1]);
+    ptx::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float* a = &acc[c >> 2][(c & 3) * 8];
+      uint4 v = yv[c];
+      v.x = pack_bf16(bf16lo(v.x) + a[0], bf16hi(v.x) + a[1]);
+      v.y = pack_bf16(bf16lo(v.y) + a[2], bf16hi(v.y) + a[3]);
+      v.z = pack_bf16(bf16lo(v.z) + a[4], bf16hi(v.z) + a[5]);
+      v.w = pack_bf16(bf16lo(v.w) + a[6], bf16hi(v.w) + a[7]);
+      ptx::sts128(box + ptx::sw128_offset(row, (uint32_t)c), v);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kTcThreads)
 k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUtensorMap tm_y, DevDesc d,
         UpTcParams p, const __nv_bfloat16* __restrict__ Bw, const uint8_t* __restrict__ tokmeta,
@@ -332,26 +361,45 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
     const int row = q * 32 + lane;                   // token row handled in the epilogue
     const int r = d.r;
     const SyncGroup grp{wt, kWorkers, 1, or_slot};
-    AttnCtx c{tokmeta, kidx, klen, h_stash, nullptr, Ks, nullptr, r + 1, p.kcap};
+    AttnCtx c{tokmeta, kidx, klen, h_stash, nullptr, Ks, nullptr, r + 1, p.kcap,
+              (p.write_g && split == 0) ? g_out + (size_t)d.T * d.r : nullptr};
 
-    // B operand tile of a chunk: rows = 128 output columns, K = rank (bf16, 128B swizzle)
-    auto fill_b = [&](int j, int i) {
-      const int n0 = (c_beg + j) * 128;
-      for (int kb = 0; kb < kblocks; ++kb) {
-        uint8_t* bt = btiles + ((size_t)i * kblocks + kb) * 16384;
-        const int kw = min(64, p.rk - kb * 64);               // K extent of this block
-        const int cpr = kw / 8;                               // 16-byte chunks per row
-        for (int idx = wt; idx < 128 * cpr; idx += kWorkers) {
-          const int n = idx / cpr, ch = idx - n * cpr;
-          const int k = kb * 64 + ch * 8;
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (k < r) v = __ldg(reinterpret_cast<const uint4*>(Bw + (size_t)(n0 + n) * r + k));
-          *reinterpret_cast<uint4*>(bt + ptx::sw128_offset((uint32_t)n, (uint32_t)ch)) = v;
-        }
+    // B operand tile of a chunk: rows = 128 output columns, K = rank (bf16, 128B swizzle).
+    // Split in a global-load half (issued early, results parked in registers) and a
+    // shared-store half, so the L2 latency hides behind the epilogue arithmetic.
+    const int cpr_all = p.rk / 8;                               // 16-byte chunks per B row (all K blocks)
+    const int per_thread = cpr_all;                             // 128 rows * cpr_all chunks / 128 threads
+    constexpr int kMaxPref = 4;
+    uint4 bpre[kMaxPref];
+    auto b_src = [&](int j, int q) -> const uint4* {           // q-th chunk of this thread for chunk j
+      const int idx = wt + q * kWorkers;
+      const int n = idx / cpr_all, ch = idx - n * cpr_all;
+      const int k = ch * 8;
+      return (k < r) ? reinterpret_cast<const uint4*>(Bw + (size_t)((c_beg + j) * 128 + n) * r + k) : nullptr;
+    };
+    auto b_dst = [&](int i, int q) -> uint8_t* {
+      const int idx = wt + q * kWorkers;
+      const int n = idx / cpr_all, ch = idx - n * cpr_all;
+      const int kb = ch >> 3, chb = ch & 7;                     // 64-wide K block and chunk inside it
+      return btiles + ((size_t)i * kblocks + kb) * 16384 + ptx::sw128_offset((uint32_t)n, (uint32_t)chb);
+    };
+    auto load_b = [&](int j) {
+#pragma unroll
+      for (int q = 0; q < kMaxPref; ++q)
+        if (q < per_thread) { const uint4* sp = b_src(j, q); bpre[q] = sp ? __ldg(sp) : make_uint4(0, 0, 0, 0); }
+    };
+    auto store_b = [&](int j, int i) {
+#pragma unroll
+      for (int q = 0; q < kMaxPref; ++q)
+        if (q < per_thread) *reinterpret_cast<uint4*>(b_dst(i, q)) = bpre[q];
+      for (int q = kMaxPref; q < per_thread; ++q) {            // large ranks: no prefetch for the rest
+        const uint4* sp = b_src(j, q);
+        *reinterpret_cast<uint4*>(b_dst(i, q)) = sp ? __ldg(sp) : make_uint4(0, 0, 0, 0);
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&b_full[i]);
     };
+    auto fill_b = [&](int j, int i) { load_b(j); store_b(j, i); };
 
     if (wt < nt) meta_s[wt] = tokmeta[t0 + wt]; else meta_s[wt] = 0;
     for (int i2 = wt; i2 < 128 * r; i2 += kWorkers)
@@ -389,30 +437,12 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
       const uint32_t ph = (uint32_t)(j >> 1) & 1u;
       const int s = j % p.ystages;
       const uint32_t yph = (uint32_t)(j / p.ystages) & 1u;
+      if (j + 2 < nch) load_b(j + 2);                          // L2 loads in flight during the waits + epilogue
       ptx::mbar_wait_or_trap(&t_full[i], ph);
       ptx::mbar_wait_or_trap(&y_full[s], yph);
       ptx::tc_fence_after_sync();
       uint8_t* yt = ytiles + (size_t)s * 32768;
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-#pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16) {
-          float acc[16];
-          ptx::tmem_ld16(lane_base + (uint32_t)(i * 128 + half * 64 + c16 * 16), acc);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint4* pv = reinterpret_cast<uint4*>(yt + half * 16384 + ptx::sw128_offset((uint32_t)row, (uint32_t)(c16 * 2 + hh)));
-            uint4 v = *pv;
-            const float* a = acc + hh * 8;
-            v.x = pack_bf16(bf16lo(v.x) + a[0], bf16hi(v.x) + a[1]);
-            v.y = pack_bf16(bf16lo(v.y) + a[2], bf16hi(v.y) + a[3]);
-            v.z = pack_bf16(bf16lo(v.z) + a[4], bf16hi(v.z) + a[5]);
-            v.w = pack_bf16(bf16lo(v.w) + a[6], bf16hi(v.w) + a[7]);
-            *pv = v;
-          }
-        }
-      }
+      add_acc_to_tile(lane_base + (uint32_t)(i * 128), ptx::smem_u32(yt), (uint32_t)row);
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(&t_empty[i]);
       ptx::fence_proxy_async_smem();
@@ -427,7 +457,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
           ptx::mbar_arrive(&y_empty[(j - 1) % p.ystages]);
         }
       }
-      if (j + 2 < nch) fill_b(j + 2, i);
+      if (j + 2 < nch) store_b(j + 2, i);
     }
     if (wt == 0) ptx::tma_store_wait_all<0>();
   }
@@ -695,7 +725,7 @@ k_attn_bwd(DevDesc d, const uint8_t* __restrict__ tokmeta, const int32_t* __rest
   uint8_t* meta_s = reinterpret_cast<uint8_t*>(dKs + (size_t)kcap * (r + 1));
   __shared__ int s_or;
   const SyncGroup grp{(int)threadIdx.x, 256, 0, &s_or};
-  AttnCtx c{tokmeta, kidx, klen, h_stash, dK_glob, Ks, dKs, r + 1, kcap};
+  AttnCtx c{tokmeta, kidx, klen, h_stash, dK_glob, Ks, dKs, r + 1, kcap, nullptr};
   const int tid = threadIdx.x;
   for (int tile = blockIdx.x; tile < d.num_tiles; tile += gridDim.x) {
     const int t0 = tile * TT;
@@ -717,6 +747,122 @@ k_attn_bwd(DevDesc d, const uint8_t* __restrict__ tokmeta, const int32_t* __rest
   }
 }
 
+// ---------------------------------------------------------------------------- k_attn_bwd_keys
+// Fast attention backward for r <= 32 and <= 256 keys per sample.  A warp owns one 32-key block of
+// one sample (lane <-> key, the key row and its dK accumulator live in registers) and walks a group
+// of 16 consecutive tokens; scores are recomputed from the stashed log-sum-exp, the row constant
+// <p, dp> is dg.(g - h), and the per-token dh contribution (a sum over keys) is reduced across the
+// warp with a 16-shuffle butterfly.  All data is O(T r); the grid has ~T/16 * ceil(Lk/32) warps.
+template <int R>
+__global__ void __launch_bounds__(256)
+k_attn_bwd_keys(DevDesc d, const uint8_t* __restrict__ tokmeta, const int32_t* __restrict__ kidx,
+                const int32_t* __restrict__ klen, const float* __restrict__ h_stash, const float* __restrict__ dh,
+                float* __restrict__ dh_att, float* __restrict__ dK_glob, int kblocks, int groups_per_sample) {
+  constexpr int TG = 4;                                         // tokens per warp (many small work items: latency hiding)
+  const int lane = threadIdx.x & 31;
+  const int r = d.r;
+  const float* g_stash = h_stash + (size_t)d.T * r;
+  const float* lse = g_stash + (size_t)d.T * r;
+  const long long nwork = (long long)d.B * groups_per_sample * kblocks;
+  const float sl = d.sm_scale * kLog2e;
+  for (long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); w < nwork; w += (long long)gridDim.x * 8) {
+    const int kb = (int)(w % kblocks);
+    const long long wg = w / kblocks;
+    const int b = (int)(wg / groups_per_sample);
+    const int s0 = (int)(wg % groups_per_sample) * TG;          // first in-sample position of the group
+    const int L = klen[b];
+    if (kb * 32 >= L) continue;
+    // any query token in the group?
+    uint32_t qmask = 0;
+    if (lane < TG && s0 + lane < d.S) qmask = ((tokmeta[(size_t)b * d.S + s0 + lane] & MOKA_MOD_MASK) >= MOKA_MOD_VIS);
+    qmask = __ballot_sync(0xffffffffu, qmask);
+    if (!qmask) continue;
+    // this lane's key row
+    const int k = kb * 32 + lane;
+    bool kvalid = false;
+    float K[R], dKacc[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) { K[j] = 0.f; dKacc[j] = 0.f; }
+    if (k < L) {
+      const int pos = kidx[(size_t)b * d.Lk + k];
+      const size_t tk = (size_t)b * d.S + pos;
+      kvalid = (tokmeta[tk] & MOKA_KEY_VALID) != 0;
+      if (kvalid) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (j < r) K[j] = h_stash[tk * r + j];
+      }
+    }
+    for (int ti = 0; ti < TG; ++ti) {
+      if (!((qmask >> ti) & 1)) continue;
+      const size_t t = (size_t)b * d.S + s0 + ti;
+      float hq[R], dg[R], gq[R];
+      float Dsum = 0.f;
+      if (r == R) {                                             // full rows: 128-bit broadcast loads
+#pragma unroll
+        for (int j = 0; j < R; j += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(h_stash + t * r + j);
+          const float4 bq = *reinterpret_cast<const float4*>(dh + t * r + j);
+          const float4 cq = *reinterpret_cast<const float4*>(g_stash + t * r + j);
+          hq[j] = a.x; hq[j + 1] = a.y; hq[j + 2] = a.z; hq[j + 3] = a.w;
+          dg[j] = bq.x; dg[j + 1] = bq.y; dg[j + 2] = bq.z; dg[j + 3] = bq.w;
+          gq[j] = cq.x; gq[j + 1] = cq.y; gq[j + 2] = cq.z; gq[j + 3] = cq.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          hq[j] = (j < r) ? h_stash[t * r + j] : 0.f;
+          dg[j] = (j < r) ? dh[t * r + j] : 0.f;
+          gq[j] = (j < r) ? g_stash[t * r + j] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < R; ++j) Dsum = fmaf(dg[j], gq[j] - hq[j], Dsum);   // = <p, dp>
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int j = 0; j < R; ++j) { s = fmaf(hq[j], K[j], s); dp = fmaf(dg[j], K[j], dp); }
+      const float p = (k < L) ? exp2f(s * sl - lse[t]) : 0.f;
+      dp *= d.attn_w;
+      const float ds = p * (dp - Dsum);
+      float part[R];
+      const float pw = p * d.attn_w, dss = ds * d.sm_scale;
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        dKacc[j] = fmaf(pw, dg[j], fmaf(dss, hq[j], dKacc[j]));
+        part[j] = dss * K[j];
+      }
+      // butterfly: R values per lane -> lane (j) holds the sum over the 32 keys of component j
+#pragma unroll
+      for (int half = R / 2, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool upper = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          const float send = upper ? part[i] : part[i + half];
+          const float keep = upper ? part[i + half] : part[i];
+          part[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+      }
+      // R == 32: lane j holds component j.  R == 16: bits 16..2 selected the component, bit 1 remains.
+      // R == 8: bits 16,8,4 selected, bits 2,1 remain.
+      float tot = part[0];
+      if (R <= 16) tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+      if (R <= 8) tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+      const int comp = (R == 32) ? lane : (R == 16 ? (lane >> 1) : (lane >> 2));
+      const bool writer = (R == 32) || (R == 16 && !(lane & 1)) || (R == 8 && !(lane & 3));
+      if (writer && comp < r) red_add_f32(&dh_att[t * r + comp], tot);   // separate buffer: dh stays the pristine dG
+    }
+    if (k < L && kvalid) {
+      float* dst = dK_glob + ((size_t)b * d.Lk + k) * r;
+      if (r == R) {
+#pragma unroll
+        for (int j = 0; j < R; j += 4) red_add_v4_f32(dst + j, dKacc[j], dKacc[j + 1], dKacc[j + 2], dKacc[j + 3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) if (j < r) red_add_f32(dst + j, dKacc[j]);
+      }
+    }
+  }
+}
+
 static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st) {
   DgradTcParams p;
   p.T = d.T; p.d_out = d.d_out; p.r = d.r; p.rk = round_up(d.r, 16);
@@ -735,16 +881,24 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   p.tmem_cols = tmem_cols_for((int)dgc + 2 * p.rk);
   CUtensorMap tdy;
   if (!make_tmap(&tdy, a.dy, (uint64_t)d.T, (uint64_t)d.d_out, 128)) return MOKA_EUNSUPPORTED;
-  // dG lives in the dh workspace; zero it when two CTAs reduce into it
-  cudaError_t e = cudaMemsetAsync(a.dh, 0, (size_t)d.T * d.r * sizeof(float), st);
-  if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+  // dG lives in the dh workspace (zeroed by moka_backward: two CTAs may reduce into it)
   const size_t smem = (size_t)p.stages * p.stage_bytes + fixed;
-  e = cudaFuncSetAttribute(k_dgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(k_dgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
   k_dgrad_tc<<<ntiles * p.csplit, kTcThreads, smem, st>>>(tdy, d, p, static_cast<const __nv_bfloat16*>(a.Bw),
                                                            a.tokmeta, a.h_stash + (size_t)d.T * d.r, a.dh, a.dB);
   if (int rc = check_launch_tc()) return rc;
   // attention backward on the small [T, r] tensors
+  if (d.r <= 32 && a.klen_hint <= 32 * kKeyBlocksMax) {
+    const int kblocks = (max(a.klen_hint, 1) + 31) / 32;
+    const int gps = (d.S + 3) / 4;
+    const long long nwork = (long long)d.B * gps * kblocks;
+    const int grid = (int)std::min<long long>((nwork + 7) / 8, (long long)num_sms * 16);
+    if (d.r <= 8) k_attn_bwd_keys<8><<<grid, 256, 0, st>>>(d, a.tokmeta, a.kidx, a.klen, a.h_stash, a.dh, a.dh_att, a.dK, kblocks, gps);
+    else if (d.r <= 16) k_attn_bwd_keys<16><<<grid, 256, 0, st>>>(d, a.tokmeta, a.kidx, a.klen, a.h_stash, a.dh, a.dh_att, a.dK, kblocks, gps);
+    else k_attn_bwd_keys<32><<<grid, 256, 0, st>>>(d, a.tokmeta, a.kidx, a.klen, a.h_stash, a.dh, a.dh_att, a.dK, kblocks, gps);
+    return check_launch_tc();
+  }
   DevDesc dd = d;
   dd.tile_tokens = 32;
   dd.num_tiles = (d.T + 31) / 32;
@@ -796,35 +950,82 @@ __device__ __forceinline__ int find_key_slot(const int32_t* __restrict__ row, in
   return -1;
 }
 
+// One CTA per 64 tokens: rows are gathered into shared memory once (coalesced), then written as
+// dHc rows and as dHcT columns (64 consecutive tokens = 128 contiguous bytes per packed row).
 __global__ void __launch_bounds__(256)
 k_pack_dh(DevDesc d, int rp, int NPW, int KP, const uint8_t* __restrict__ tokmeta,
           const int32_t* __restrict__ kidx, const int32_t* __restrict__ klen, const float* __restrict__ dh,
-          const float* __restrict__ dK, __nv_bfloat16* __restrict__ hc, __nv_bfloat16* __restrict__ hct_hi,
-          __nv_bfloat16* __restrict__ hct_lo, float scale) {
-  const int t = blockIdx.x * 256 + threadIdx.x;
-  if (t >= d.T) return;
-  const int r = d.r;
-  const uint8_t mb = tokmeta[t];
-  const int code = mb & MOKA_MOD_MASK;
-  const int b = t / d.S, pos = t - b * d.S;
-  int slot = -1;
-  if (code && (mb & MOKA_KEY_VALID)) slot = find_key_slot(kidx + (size_t)b * d.Lk, klen[b], pos);
-  const int n_lo = (code - 1) * rp;                           // first row of the token's rank block
-  const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
-  for (int n = 0; n < KP; ++n) {
+          const float* __restrict__ dh_att, const float* __restrict__ dK, __nv_bfloat16* __restrict__ hc,
+          __nv_bfloat16* __restrict__ hct_hi, __nv_bfloat16* __restrict__ hct_lo, float scale) {
+  extern __shared__ __align__(16) float vs[];                    // [64][r + 1]
+  __shared__ int s_base[64];                                     // first packed row of the token's rank block, -1 = none
+  const int r = d.r, tid = threadIdx.x;
+  const int t0 = blockIdx.x * 64;
+  const int nt = min(64, d.T - t0);
+  if (tid < 64) {
+    int base = -1;
+    if (tid < nt) {
+      const int code = tokmeta[t0 + tid] & MOKA_MOD_MASK;
+      if (code) base = (code - 1) * rp;
+    }
+    s_base[tid] = base;
+  }
+  for (int i = tid; i < 64 * r; i += 256) {
+    const int tt = i / r, j = i - tt * r;
     float v = 0.f;
-    const int j = n - n_lo;
-    if (code && j >= 0 && j < r) {
-      v = dh[(size_t)t * r + j];
-      if (slot >= 0) v += dK[((size_t)b * d.Lk + slot) * r + j];
-      v *= scale;
+    if (tt < nt) {
+      const size_t t = (size_t)t0 + tt;
+      v = dh[t * r + j] + dh_att[t * r + j];
     }
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-    hc[(size_t)t * KP + n] = hi;
-    if (n < NPW) {
-      hct_hi[(size_t)n * d.T + t] = hi;
-      hct_lo[(size_t)n * d.T + t] = (v != 0.f) ? __float2bfloat16_rn(v - __bfloat162float(hi)) : zero;
+    vs[tt * (r + 1) + j] = v;
+  }
+  __syncthreads();
+  // fold dK onto the key tokens of this tile
+  if (tid < nt) {
+    const int t = t0 + tid;
+    const uint8_t mb = tokmeta[t];
+    if ((mb & MOKA_KEY_VALID) && (mb & MOKA_MOD_MASK)) {
+      const int b = t / d.S, pos = t - b * d.S;
+      const int slot = find_key_slot(kidx + (size_t)b * d.Lk, klen[b], pos);
+      if (slot >= 0)
+        for (int j = 0; j < r; ++j) vs[tid * (r + 1) + j] += dK[((size_t)b * d.Lk + slot) * r + j];
     }
+  }
+  __syncthreads();
+  // dHc rows
+  const int cpr = KP / 8;
+  for (int i = tid; i < nt * cpr; i += 256) {
+    const int tt = i / cpr, n0 = (i - tt * cpr) * 8;
+    const int base = s_base[tt];
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = n0 + e - base;
+      v[e] = (base >= 0 && j >= 0 && j < r) ? vs[tt * (r + 1) + j] * scale : 0.f;
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(hc + ((size_t)t0 + tt) * KP + n0) = o;
+  }
+  // dHcT columns (hi + lo); T % 8 == 0 so 8-token chunks never straddle the end
+  const int tch = (nt + 7) / 8;
+  for (int i = tid; i < NPW * tch; i += 256) {
+    const int n = i / tch, c = i - n * tch;
+    float hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int tt = c * 8 + e;
+      const int base = (tt < nt) ? s_base[tt] : -1;
+      const int j = n - base;
+      const float v = (base >= 0 && j >= 0 && j < r) ? vs[tt * (r + 1) + j] * scale : 0.f;
+      hi[e] = __bfloat162float(__float2bfloat16_rn(v));
+      lo[e] = v - hi[e];
+    }
+    uint4 o;
+    o.x = pack_bf16(hi[0], hi[1]); o.y = pack_bf16(hi[2], hi[3]); o.z = pack_bf16(hi[4], hi[5]); o.w = pack_bf16(hi[6], hi[7]);
+    *reinterpret_cast<uint4*>(hct_hi + (size_t)n * d.T + t0 + c * 8) = o;
+    o.x = pack_bf16(lo[0], lo[1]); o.y = pack_bf16(lo[2], lo[3]); o.z = pack_bf16(lo[4], lo[5]); o.w = pack_bf16(lo[6], lo[7]);
+    *reinterpret_cast<uint4*>(hct_lo + (size_t)n * d.T + t0 + c * 8) = o;
   }
 }
 
@@ -999,26 +1200,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         ptx::mbar_wait_or_trap(&d_full[s], dph);
         ptx::tc_fence_after_sync();
         uint8_t* dt = dring + (size_t)s * 32768;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-#pragma unroll
-          for (int c16 = 0; c16 < 4; ++c16) {
-            float acc[16];
-            ptx::tmem_ld16(lane_base + (uint32_t)(i * 128 + half * 64 + c16 * 16), acc);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              uint4* pv = reinterpret_cast<uint4*>(dt + half * 16384 + ptx::sw128_offset((uint32_t)row, (uint32_t)(c16 * 2 + hh)));
-              uint4 v = *pv;
-              const float* a = acc + hh * 8;
-              v.x = pack_bf16(bf16lo(v.x) + a[0], bf16hi(v.x) + a[1]);
-              v.y = pack_bf16(bf16lo(v.y) + a[2], bf16hi(v.y) + a[3]);
-              v.z = pack_bf16(bf16lo(v.z) + a[4], bf16hi(v.z) + a[5]);
-              v.w = pack_bf16(bf16lo(v.w) + a[6], bf16hi(v.w) + a[7]);
-              *pv = v;
-            }
-          }
-        }
+        add_acc_to_tile(lane_base + (uint32_t)(i * 128), ptx::smem_u32(dt), (uint32_t)row);
         ptx::tc_fence_before_sync();
         ptx::mbar_arrive(&t_empty[i]);
         ptx::fence_proxy_async_smem();
@@ -1089,8 +1271,9 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   __nv_bfloat16* hc = reinterpret_cast<__nv_bfloat16*>(pk);
   __nv_bfloat16* hct_hi = reinterpret_cast<__nv_bfloat16*>(pk + L.hc_bytes);
   __nv_bfloat16* hct_lo = reinterpret_cast<__nv_bfloat16*>(pk + L.hc_bytes + L.hct_bytes);
-  k_pack_dh<<<(d.T + 255) / 256, 256, 0, st>>>(d, L.rp, L.NPW, L.KP, a.tokmeta, a.kidx, a.klen, a.dh, a.dK, hc,
-                                               hct_hi, hct_lo, d.pre * d.drop_scale);
+  k_pack_dh<<<(d.T + 63) / 64, 256, (size_t)64 * (d.r + 1) * 4, st>>>(d, L.rp, L.NPW, L.KP, a.tokmeta, a.kidx, a.klen, a.dh,
+                                                                     a.dh_att, a.dK, hc, hct_hi, hct_lo,
+                                                                     d.pre * d.drop_scale);
   if (int rc = check_launch_tc()) return rc;
   CUtensorMap tx, tdx, ta[3], thc, thh, thl;
   if (!make_tmap(&tx, a.x, (uint64_t)d.T, (uint64_t)d.d_in, 128)) return MOKA_EUNSUPPORTED;

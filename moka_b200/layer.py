@@ -86,8 +86,10 @@ class _MokaFn(torch.autograd.Function):
         x2 = x.reshape(B * S, d_in)
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        y = F.linear(x2, weight, bias)                      # frozen base, cuBLAS; adapter added in place
-        h = torch.empty(2, B * S, r, dtype=torch.float32, device=x.device)
+        # frozen base, cuBLAS; the adapter is added in place.  Computed in the caller's shape so the
+        # returned tensor is not a view made inside this Function (callers may modify it in place).
+        y = F.linear(x2.view(shp), weight, bias)
+        h = torch.empty(2 * B * S * r + B * S, dtype=torch.float32, device=x.device)   # h, g, lse
         seed = offset = 0
         if sc.p > 0.0:
             # CPU generator draws are restored by torch.utils.checkpoint, so a recomputed forward
@@ -115,7 +117,7 @@ class _MokaFn(torch.autograd.Function):
         ctx.meta, ctx.sc, ctx.flags, ctx.seed, ctx.offset = meta, sc, flags, seed, offset
         ctx.x_shape = shp
         ctx.param_refs = (Bw, A)
-        return y.view(*shp[:-1], d_out)
+        return y
 
     @staticmethod
     def backward(ctx, dy):

@@ -81,7 +81,7 @@ def _rope_tables(S: int, head_dim: int, theta: float, device, dtype):
     t = torch.arange(S, device=device, dtype=torch.float32)
     fr = torch.outer(t, inv)
     emb = torch.cat((fr, fr), dim=-1)
-    return emb.cos().to(dtype)[None, None], emb.sin().to(dtype)[None, None]
+    return emb.cos().to(dtype)[None, :, None, :], emb.sin().to(dtype)[None, :, None, :]
 
 
 def _rotate_half(x):
@@ -89,11 +89,47 @@ def _rotate_half(x):
     return torch.cat((-x2, x1), dim=-1)
 
 
+class _RopeInplace(torch.autograd.Function):
+    """Rotary embedding in place on a contiguous bf16 [B, S, H, D] tensor (libmoka.so helper
+    kernel); the backward is the inverse rotation of the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, x, theta):
+        from . import _cabi
+        B, S, H, D = x.shape
+        ctx.dims, ctx.theta = (B, S, H, D), theta
+        _cabi.check(_cabi.load().moka_rope(x.data_ptr(), x.data_ptr(), B * S, S, H, D, theta, 0,
+                                           torch.cuda.current_stream(x.device).cuda_stream), 'moka_rope')
+        ctx.mark_dirty(x)
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _cabi
+        B, S, H, D = ctx.dims
+        g = g.contiguous()
+        out = torch.empty_like(g)                  # the incoming gradient is not ours to overwrite
+        _cabi.check(_cabi.load().moka_rope(g.data_ptr(), out.data_ptr(), B * S, S, H, D, ctx.theta, 1,
+                                           torch.cuda.current_stream(g.device).cuda_stream), 'moka_rope')
+        return out, None
+
+
+def apply_rope(x: torch.Tensor, rope, theta: float) -> torch.Tensor:
+    """x: [B, S, H, D].  CUDA bf16 takes the fused in-place kernel; anything else the eager form."""
+    if x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.shape[-1] % 16 == 0:
+        if x.requires_grad and x.is_leaf:
+            x = x.clone()
+        return _RopeInplace.apply(x, theta)
+    cos, sin = rope
+    return x * cos + _rotate_half(x) * sin
+
+
 class LlamaAttention(nn.Module):
     def __init__(self, cfg: LlamaConfig):
         super().__init__()
         self.num_heads = cfg.num_attention_heads
         self.head_dim = cfg.hidden_size // cfg.num_attention_heads
+        self.rope_theta = cfg.rope_theta
         d = cfg.hidden_size
         self.q_proj = nn.Linear(d, d, bias=False)
         self.k_proj = nn.Linear(d, d, bias=False)
@@ -102,14 +138,13 @@ class LlamaAttention(nn.Module):
 
     def forward(self, h, rope, mask_args):
         B, S, _ = h.shape
-        q = _proj(self.q_proj, h, mask_args).view(B, S, self.num_heads, self.head_dim).transpose(1, 2)
-        k = _proj(self.k_proj, h, mask_args).view(B, S, self.num_heads, self.head_dim).transpose(1, 2)
-        v = _proj(self.v_proj, h, mask_args).view(B, S, self.num_heads, self.head_dim).transpose(1, 2)
-        cos, sin = rope
-        q = q * cos + _rotate_half(q) * sin
-        k = k * cos + _rotate_half(k) * sin
-        o = F.scaled_dot_product_attention(q, k, v, is_causal=True)
-        o = o.transpose(1, 2).reshape(B, S, -1)
+        H, D = self.num_heads, self.head_dim
+        # keep the [B, S, H, D] memory layout of the projections; SDPA gets transposed views
+        q = apply_rope(_proj(self.q_proj, h, mask_args).view(B, S, H, D), rope, self.rope_theta)
+        k = apply_rope(_proj(self.k_proj, h, mask_args).view(B, S, H, D), rope, self.rope_theta)
+        v = _proj(self.v_proj, h, mask_args).view(B, S, H, D)
+        o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True)
+        o = o.transpose(1, 2).reshape(B, S, H * D)
         return _proj(self.o_proj, o, mask_args)
 
 

@@ -32,7 +32,7 @@ def abi_forward(meta: TokenMeta, x, y0, A, Bw, sc: FusedScalars, flags=0, seed=0
     y0c = y0.reshape(B * S, d_out).contiguous()
     y = y0c.clone() if inplace else torch.empty_like(y0c)
     src = y if inplace else y0c
-    h = torch.full((2, B * S, r), float('nan'), dtype=torch.float32, device=x.device)
+    h = torch.full((2 * B * S * r + B * S,), float('nan'), dtype=torch.float32, device=x.device)
     desc = _make_desc(x2.shape, B, S, d_out, r, len(A), x.dtype, meta.Lk, sc, flags)
     code = lib.moka_forward(desc, x2.data_ptr(), src.data_ptr(), y.data_ptr(),
                             _cabi.ptr_array([a.data_ptr() for a in A]), Bw.data_ptr(),

@@ -188,3 +188,19 @@ def test_checkpointed_forward_with_dropout_is_consistent():
     assert grads[0].keys() == grads[1].keys() and len(grads[0]) > 0
     for n in grads[0]:
         assert mo.rel_l2(grads[1][n].cpu(), grads[0][n].cpu()) <= 2e-2, n
+
+
+def test_fused_rope_matches_eager():
+    from moka_b200.llama import _rope_tables, _rotate_half, apply_rope
+    B, S, H, D = 2, 300, 4, 128
+    g = torch.Generator(device=DEV).manual_seed(0)
+    x = torch.randn(B, S, H, D, device=DEV, generator=g).to(torch.bfloat16)
+    cos, sin = _rope_tables(S, D, 10000.0, DEV, torch.float32)
+    ref = x.float() * cos + _rotate_half(x.float()) * sin
+    xr = x.clone().requires_grad_(True)
+    y = apply_rope(xr * 1.0, (cos, sin), 10000.0)
+    assert mo.rel_l2(y.detach().cpu(), ref.cpu()) <= 4e-3          # bf16 output rounding
+    dy = torch.randn(B, S, H, D, device=DEV, generator=g).to(torch.bfloat16)
+    y.backward(dy)
+    gref = dy.float() * cos - _rotate_half(dy.float() * sin)       # transpose of the rotation
+    assert mo.rel_l2(xr.grad.cpu(), gref.cpu()) <= 4e-3

@@ -35,7 +35,7 @@ def _run_case(g, x, W0, A, Bw, dy, dtype, flags=0):
     y0d, dx0d = to(y0), to(dx0)
     y, h = gu.abi_forward(meta, to(x), y0d, [to(a) for a in A], to(Bw), sc, flags)
     dx, dA, dB = gu.abi_backward(meta, to(x), to(dy), h, [to(a) for a in A], to(Bw), sc, dx0=dx0d, flags=flags)
-    return dict(y=y.cpu(), dx=dx.cpu(), dA=[a.cpu() for a in dA], dB=dB.cpu(), h=h[0].cpu(),
+    return dict(y=y.cpu(), dx=dx.cpu(), dA=[a.cpu() for a in dA], dB=dB.cpu(), h=h[:x.shape[0] * x.shape[1] * g['r']].cpu(),
                 y0=y0d.cpu().double(), dx0=dx0d.cpu().double(), y0_exact=y0, dx0_exact=dx0)
 
 
@@ -114,7 +114,7 @@ def _oracle_case(variant, B, S, d_in, d_out, r, M, layout, alpha, w, dtype, seed
                                  flags=flags, seed=rng[0], offset=rng[1])
     ty, th = mo.fused_forward(ometa, x, y0, A, Bw, osc, keep, p)
     tdxa, tdA, tdB, _ = mo.fused_backward(ometa, x, dy, th, A, Bw, osc, keep, p)
-    return dict(y=y.cpu(), dx=dx.cpu(), dA=[a.cpu() for a in dA], dB=dB.cpu(), h=h[0].view(B, S, r).cpu(), g=h[1].view(B, S, r).cpu(),
+    return dict(y=y.cpu(), dx=dx.cpu(), dA=[a.cpu() for a in dA], dB=dB.cpu(), h=h[:B * S * r].view(B, S, r).cpu(), g=h[B * S * r:2 * B * S * r].view(B, S, r).cpu(),
                 ty=ty, tdx=dx0 + tdxa, tdA=tdA, tdB=tdB, th=th, y0=y0, dx0=dx0, keep=keep, ometa=ometa)
 
 

@@ -44,7 +44,7 @@ def run_point(variant, B, S, d_in, d_out, r, dtype, flags, iters, warmup, p=0.0,
     Bw = (torch.randn(d_out, r, device=dev) * 0.02).to(dtype)
     dA = [torch.zeros(r, d_in, device=dev) for _ in range(M)]
     dB = torch.zeros(d_out, r, device=dev)
-    h = torch.empty(2, T, r, device=dev)
+    h = torch.empty(2 * T * r + T, device=dev)
     desc = _make_desc((T, d_in), B, S, d_out, r, M, dtype, meta.Lk, sc, flags)
     ws = torch.empty(int(lib.moka_workspace_bytes(desc)), dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream().cuda_stream
