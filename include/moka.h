@@ -152,6 +152,9 @@ int moka_adamw_step(int64_t n, float* master, float* exp_avg, float* exp_avg_sq,
 int moka_rope(const void* src, void* dst, int64_t tokens, int32_t S, int32_t H, int32_t D, float theta,
               int32_t backward, moka_stream_t stream);
 
+/* Tuning aid: copies the in-kernel cycle stamps recorded when MOKA_DEBUG_TIMING=1 (host buffer). */
+int moka_debug_read(unsigned long long* host, int32_t n);
+
 /* Number of kernels this library has launched in this process (monotonic). */
 int64_t moka_launch_count(void);
 

@@ -206,6 +206,11 @@ int moka_rope(const void* src, void* dst, int64_t tokens, int32_t S, int32_t H, 
   return launch_rope(src, dst, tokens, S, H, D, theta, backward ? -1.f : 1.f, static_cast<cudaStream_t>(stream));
 }
 
+int moka_debug_read(unsigned long long* host, int32_t n) {
+  if (!host || n <= 0) return MOKA_EINVAL;
+  return debug_read(host, n);
+}
+
 int64_t moka_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 const char* moka_strerror(int code) {

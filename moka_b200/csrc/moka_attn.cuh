@@ -149,31 +149,55 @@ __device__ __forceinline__ void attn_thread_fwd(const DevDesc& d, const float* _
   for (int j = 0; j < R; ++j) { h[j] = (j < r) ? row[j] : 0.f; acc[j] = 0.f; }
   const float sl = d.sm_scale * kLog2e;
   float m = -INFINITY, l = 0.f;
-  for (int k = 0; k < L; ++k) {
-    const float* Kr = Ks + k * r;
-    float kv[R];
+  const uint32_t ks_addr = static_cast<uint32_t>(__cvta_generic_to_shared(Ks));
+  constexpr int KB = 4;                         // keys per step: one rescale and four exps per step
+  for (int k0 = 0; k0 < L; k0 += KB) {
+    float kv[KB][R];
+    float s[KB];
 #pragma unroll
-    for (int j = 0; j < R; ++j) kv[j] = (j < r) ? Kr[j] : 0.f;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int u = 0; u < KB; ++u) {
+      const int k = min(k0 + u, L - 1);         // clamp: the duplicate of the last key is masked below
+      if (r == R) {
 #pragma unroll
-    for (int j = 0; j < R; j += 4) {
-      s0 = fmaf(h[j], kv[j], s0);
-      s1 = fmaf(h[j + 1], kv[j + 1], s1);
-      s2 = fmaf(h[j + 2], kv[j + 2], s2);
-      s3 = fmaf(h[j + 3], kv[j + 3], s3);
+        for (int j = 0; j < R; j += 4) {
+          float4 v;
+          asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                       : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ks_addr + (uint32_t)(k * r + j) * 4u));
+          kv[u][j] = v.x; kv[u][j + 1] = v.y; kv[u][j + 2] = v.z; kv[u][j + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) kv[u][j] = (j < r) ? Ks[k * r + j] : 0.f;
+      }
     }
-    const float s = ((s0 + s1) + (s2 + s3)) * sl;
-    if (s > m) {
-      const float corr = exp2f(m - s);
+    float smax = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < KB; ++u) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int j = 0; j < R; j += 4) {
+        s0 = fmaf(h[j], kv[u][j], s0);
+        s1 = fmaf(h[j + 1], kv[u][j + 1], s1);
+        s2 = fmaf(h[j + 2], kv[u][j + 2], s2);
+        s3 = fmaf(h[j + 3], kv[u][j + 3], s3);
+      }
+      s[u] = (k0 + u < L) ? ((s0 + s1) + (s2 + s3)) * sl : -INFINITY;
+      smax = fmaxf(smax, s[u]);
+    }
+    if (smax > m) {
+      const float corr = exp2f(m - smax);
       l *= corr;
 #pragma unroll
       for (int j = 0; j < R; ++j) acc[j] *= corr;
-      m = s;
+      m = smax;
     }
-    const float e = exp2f(s - m);
-    l += e;
 #pragma unroll
-    for (int j = 0; j < R; ++j) acc[j] = fmaf(e, kv[j], acc[j]);
+    for (int u = 0; u < KB; ++u) {
+      const float e = exp2f(s[u] - m);          // exp2(-inf) = 0 for the masked tail
+      l += e;
+#pragma unroll
+      for (int j = 0; j < R; ++j) acc[j] = fmaf(e, kv[u][j], acc[j]);
+    }
   }
   const float sc = d.attn_w / l;
   if (lse) *lse = m + log2f(l);
@@ -304,13 +328,23 @@ __device__ __forceinline__ void attention_tile(const DevDesc& d, const AttnCtx& 
     const bool per_thread = !BWD && fast && r <= MAXR;
     const int ks = per_thread ? r : c.ks;
     if (fast) {
-      for (int idx = tid; idx < L * r; idx += nthr) {
-        const int k = idx / r, j = idx - k * r;
+      // one thread per key row: the index / validity lookups (two dependent global loads) happen
+      // once per key, then the row is copied with independent loads
+      for (int k = tid; k < L; k += nthr) {
         const int pos = c.kidx[(size_t)b * d.Lk + k];
         const size_t t = (size_t)b * d.S + pos;
         const bool valid = (c.tokmeta[t] & MOKA_KEY_VALID) != 0;
-        c.Ks[k * ks + j] = valid ? c.h_stash[t * r + j] : 0.f;
-        if (BWD) c.dKs[k * ks + j] = 0.f;
+        const float* src = c.h_stash + t * r;
+        float* dst = c.Ks + k * ks;
+        if ((r & 3) == 0 && (ks & 3) == 0) {
+          for (int j = 0; j < r; j += 4) {
+            const float4 v = valid ? *reinterpret_cast<const float4*>(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(dst + j) = v;
+          }
+        } else {
+          for (int j = 0; j < r; ++j) dst[j] = valid ? src[j] : 0.f;
+        }
+        if (BWD) for (int j = 0; j < r; ++j) c.dKs[k * ks + j] = 0.f;
       }
       g.sync();
     }

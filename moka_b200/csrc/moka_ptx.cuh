@@ -26,20 +26,21 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 // Bounded wait: returns false if the barrier never flipped (a lost arrival would otherwise hang
-// the GPU box); callers trap so the failure is loud.
+// the GPU box); callers trap so the failure is loud.  Non-blocking test_wait probes in a spin
+// loop: measured on B200, a thread suspended inside try_wait resumes ~1-2k cycles after the
+// phase completes (and ~1 us later with a suspend-time hint), which dominated every hand-off.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
-  // ~2 s worst case: 2^21 probes, each allowed to sleep up to ~1 us in hardware
 #pragma unroll 1
-  for (uint32_t it = 0; it < (1u << 21); ++it) {
+  for (uint32_t it = 0; it < (1u << 26); ++it) {
     uint32_t done;
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
-        : "=r"(done) : "r"(addr), "r"(parity), "r"(1000u) : "memory");
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     if (done) return true;
   }
   return false;
@@ -137,6 +138,13 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+// Ampere-style 16-byte async copy global -> shared (no register staging); zero-fills when !valid.
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(smem_dst), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ UMMA descriptors

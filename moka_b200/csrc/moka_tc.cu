@@ -11,6 +11,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
 // warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "moka_attn.cuh"
@@ -60,6 +61,22 @@ static inline uint32_t tmem_cols_for(int n) {
 }
 
 constexpr int kTcThreads = 192;
+
+// Optional in-kernel timestamps (cycle counter of the SM) for tuning: slot layout is per kernel.
+// Written only when MOKA_DEBUG_TIMING=1; read back through moka_debug_read().
+__device__ unsigned long long g_dbg[148 * 2 * 64];
+__device__ __forceinline__ void dbg_stamp(int enabled, int cta, int slot) {
+  if (enabled && cta < 148 * 2 && slot < 64) g_dbg[cta * 64 + slot] = clock64();
+}
+static int dbg_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MOKA_DEBUG_TIMING"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v;
+}
+int debug_read(unsigned long long* host, int n) {
+  if (n > 148 * 2 * 64) n = 148 * 2 * 64;
+  return cudaMemcpyFromSymbol(host, g_dbg, (size_t)n * 8) == cudaSuccess ? MOKA_OK : MOKA_ECUDA;
+}
 
 // ---------------------------------------------------------------------------- k_down_tc
 struct DownTcParams {
@@ -234,6 +251,7 @@ struct UpTcParams {
   int nsplit, chunks;              // chunks = d_out / 128, split across nsplit CTAs per token tile
   int ystages, kcap;
   int write_g;
+  int dbg;
 };
 
 constexpr int kWorkers = 128;
@@ -246,7 +264,8 @@ __device__ __forceinline__ void named_sync(int id, int n) {
 // onto a bf16 tile held in shared memory as two {64 cols x 128 rows} 128B-swizzled TMA boxes.
 // One thread owns one row (TMEM lane).  All shared loads of a half-row are issued before the
 // arithmetic and all stores after it, so nothing waits on a load -> store -> load chain.
-__device__ __forceinline__ void add_acc_to_tile(uint32_t tmem_row_addr, uint32_t tile_smem, uint32_t row) {
+__device__ __forceinline__ void add_acc_to_tile(uint32_t tmem_row_addr, uint32_t tile_smem, uint32_t row,
+                                                uint64_t* tmem_free = nullptr) {
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const uint32_t box = tile_smem + (uint32_t)half * 16384u;
@@ -257,6 +276,10 @@ __device__ __forceinline__ void add_acc_to_tile(uint32_t tmem_row_addr, uint32_t
     ptx::tmem_ld32(tmem_row_addr + (uint32_t)(half * 64), acc[0]);
     ptx::tmem_ld32(tmem_row_addr + (uint32_t)(half * 64 + 32), acc[1]);
     ptx::tmem_ld_wait();
+    if (half == 1 && tmem_free) {              // accumulator fully read: hand the TMEM buffer back early
+      ptx::tc_fence_before_sync();
+      ptx::mbar_arrive(tmem_free);
+    }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const float* a = &acc[c >> 2][(c & 3) * 8];
@@ -270,7 +293,9 @@ __device__ __forceinline__ void add_acc_to_tile(uint32_t tmem_row_addr, uint32_t
   }
 }
 
-__global__ void __launch_bounds__(kTcThreads)
+constexpr int kUpThreads = 352;        // warps 2..9: two worker groups (even / odd chunks); warp 10: TMA store issuer
+
+__global__ void __launch_bounds__(kUpThreads)
 k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUtensorMap tm_y, DevDesc d,
         UpTcParams p, const __nv_bfloat16* __restrict__ Bw, const uint8_t* __restrict__ tokmeta,
         const int32_t* __restrict__ kidx, const int32_t* __restrict__ klen, const float* __restrict__ h_stash,
@@ -280,16 +305,18 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
   const int kblocks = (p.rk + 63) / 64;                       // 64-wide K blocks of the operand tiles
   uint8_t* ytiles = base;                                     // [ystages][2 boxes][128 x 128 B]
   uint8_t* gtile = ytiles + (size_t)p.ystages * 32768;        // [kblocks][128 x 128 B]  A operand
-  uint8_t* btiles = gtile + (size_t)kblocks * 16384;          // [2][kblocks][128 x 128 B] B operand
-  float* gs = reinterpret_cast<float*>(btiles + (size_t)2 * kblocks * 16384);   // [128, r]
+  uint8_t* btiles = gtile + (size_t)kblocks * 16384;          // [4][kblocks][128 x 128 B] B operand
+  float* gs = reinterpret_cast<float*>(btiles + (size_t)4 * kblocks * 16384);   // [128, r]
   float* Ks = gs + 128 * d.r;                                 // [kcap, r+1]
   uint64_t* bars = reinterpret_cast<uint64_t*>(Ks + (size_t)p.kcap * (d.r + 1) + ((p.kcap * (d.r + 1)) & 1));
   uint64_t* y_full = bars;                                    // [ystages]
   uint64_t* y_empty = y_full + p.ystages;                     // [ystages]
-  uint64_t* b_full = y_empty + p.ystages;                     // [2]
-  uint64_t* t_full = b_full + 2;                              // [2]
-  uint64_t* t_empty = t_full + 2;                             // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* b_full = y_empty + p.ystages;                     // [4]
+  uint64_t* t_full = b_full + 4;                              // [4]
+  uint64_t* t_empty = t_full + 4;                             // [4]
+  uint64_t* g_full = t_empty + 4;                             // [1] A operand (post*g) staged
+  uint64_t* y_done = g_full + 1;                              // [ystages] tile updated in smem, ready to store
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_done + p.ystages);
   int* or_slot = reinterpret_cast<int*>(tmem_slot + 1);
   uint8_t* meta_s = reinterpret_cast<uint8_t*>(or_slot + 1);  // [128]
 
@@ -302,14 +329,17 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
   const int nch = c_end - c_beg;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.ystages; ++s) { ptx::mbar_init(&y_full[s], 1); ptx::mbar_init(&y_empty[s], 1); }
-    for (int i = 0; i < 2; ++i) {
+    for (int s = 0; s < p.ystages; ++s) {
+      ptx::mbar_init(&y_full[s], 1); ptx::mbar_init(&y_empty[s], 1); ptx::mbar_init(&y_done[s], kWorkers);
+    }
+    for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(&b_full[i], kWorkers); ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], kWorkers);
     }
+    ptx::mbar_init(g_full, 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tm_y0); ptx::prefetch_tmap(&tm_y);
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_slot, 256);
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, 512);
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -335,11 +365,15 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
     if (lane == 0) {
       const uint32_t idesc = ptx::idesc_bf16(128, 128, 0, 0);
       const uint32_t ga = ptx::smem_u32(gtile);
+      ptx::mbar_wait_or_trap(g_full, 0);
       for (int j = 0; j < nch; ++j) {
-        const int i = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        // chunk j belongs to worker group (j & 1); each group rotates over two accumulator / B buffers
+        const int i = (j & 1) * 2 + ((j >> 1) & 1);
+        const uint32_t ph = (uint32_t)(j >> 2) & 1u;
         ptx::mbar_wait_or_trap(&b_full[i], ph);
+        if (j < 6) dbg_stamp(p.dbg, blockIdx.x, 32 + j * 3);
         ptx::mbar_wait_or_trap(&t_empty[i], ph ^ 1u);
+        if (j < 6) dbg_stamp(p.dbg, blockIdx.x, 33 + j * 3);
         ptx::tc_fence_after_sync();
         const uint32_t ba = ptx::smem_u32(btiles + (size_t)i * kblocks * 16384);
         int kdone = 0;
@@ -352,15 +386,39 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
           }
         }
         ptx::umma_commit(&t_full[i]);
+        if (j < 6) dbg_stamp(p.dbg, blockIdx.x, 34 + j * 3);
       }
     }
+  } else if (warp == 10) {
+    // ================= TMA store issuer: tile j leaves as soon as the workers have updated it
+    if (lane == 0) {
+      for (int j = 0; j < nch; ++j) {
+        const int s = j % p.ystages;
+        const uint32_t ph = (uint32_t)(j / p.ystages) & 1u;
+        ptx::mbar_wait_or_trap(&y_done[s], ph);
+        uint8_t* yt = ytiles + (size_t)s * 32768;
+        const int col = (c_beg + j) * 128;
+        ptx::tma_store_2d(&tm_y, yt, col, t0);
+        ptx::tma_store_2d(&tm_y, yt + 16384, col + 64, t0);
+        ptx::tma_store_commit();
+        if (j > 0) {
+          ptx::tma_store_wait_read<1>();                       // store j-1 has finished reading smem
+          ptx::mbar_arrive(&y_empty[(j - 1) % p.ystages]);
+        }
+      }
+      ptx::tma_store_wait_all<0>();
+    }
   } else {
-    // ================= workers: attention, operand staging, epilogue
-    const int wt = threadIdx.x - 64;                 // 0..127
+    // ================= workers: attention, operand staging, epilogue.  Two groups of 128 threads;
+    // group g owns the chunks j = g (mod 2), TMEM accumulator g and B-tile buffer g, so the epilogue
+    // of one chunk overlaps the waits / staging of the next.
+    const int wt = threadIdx.x - 64;                 // 0..255
+    const int grp_id = wt >> 7;                      // worker group
+    const int wl = wt & 127;                         // thread within the group
     const int q = warp & 3;                          // TMEM lane quadrant of this warp
     const int row = q * 32 + lane;                   // token row handled in the epilogue
     const int r = d.r;
-    const SyncGroup grp{wt, kWorkers, 1, or_slot};
+    const SyncGroup grp{wt, 2 * kWorkers, 1, or_slot};
     AttnCtx c{tokmeta, kidx, klen, h_stash, nullptr, Ks, nullptr, r + 1, p.kcap,
               (p.write_g && split == 0) ? g_out + (size_t)d.T * d.r : nullptr};
 
@@ -369,51 +427,46 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
     // shared-store half, so the L2 latency hides behind the epilogue arithmetic.
     const int cpr_all = p.rk / 8;                               // 16-byte chunks per B row (all K blocks)
     const int per_thread = cpr_all;                             // 128 rows * cpr_all chunks / 128 threads
-    constexpr int kMaxPref = 4;
-    uint4 bpre[kMaxPref];
-    auto b_src = [&](int j, int q) -> const uint4* {           // q-th chunk of this thread for chunk j
-      const int idx = wt + q * kWorkers;
-      const int n = idx / cpr_all, ch = idx - n * cpr_all;
-      const int k = ch * 8;
-      return (k < r) ? reinterpret_cast<const uint4*>(Bw + (size_t)((c_beg + j) * 128 + n) * r + k) : nullptr;
-    };
-    auto b_dst = [&](int i, int q) -> uint8_t* {
-      const int idx = wt + q * kWorkers;
-      const int n = idx / cpr_all, ch = idx - n * cpr_all;
-      const int kb = ch >> 3, chb = ch & 7;                     // 64-wide K block and chunk inside it
-      return btiles + ((size_t)i * kblocks + kb) * 16384 + ptx::sw128_offset((uint32_t)n, (uint32_t)chb);
-    };
-    auto load_b = [&](int j) {
-#pragma unroll
-      for (int q = 0; q < kMaxPref; ++q)
-        if (q < per_thread) { const uint4* sp = b_src(j, q); bpre[q] = sp ? __ldg(sp) : make_uint4(0, 0, 0, 0); }
-    };
-    auto store_b = [&](int j, int i) {
-#pragma unroll
-      for (int q = 0; q < kMaxPref; ++q)
-        if (q < per_thread) *reinterpret_cast<uint4*>(b_dst(i, q)) = bpre[q];
-      for (int q = kMaxPref; q < per_thread; ++q) {            // large ranks: no prefetch for the rest
-        const uint4* sp = b_src(j, q);
-        *reinterpret_cast<uint4*>(b_dst(i, q)) = sp ? __ldg(sp) : make_uint4(0, 0, 0, 0);
+    // load_b: cp.async straight into the swizzled tile (no registers, latency hidden behind the
+    // epilogue); store_b: wait for the copies, publish the tile to the tensor core
+    auto load_b = [&](int j, int i) {
+      for (int qq = 0; qq < per_thread; ++qq) {
+        const int idx = wl + qq * kWorkers;
+        const int n = idx / cpr_all, ch = idx - n * cpr_all;
+        const int k = ch * 8;
+        const int kb = ch >> 3, chb = ch & 7;                   // 64-wide K block and chunk inside it
+        uint8_t* dst = btiles + ((size_t)i * kblocks + kb) * 16384 + ptx::sw128_offset((uint32_t)n, (uint32_t)chb);
+        const __nv_bfloat16* src = Bw + (size_t)((c_beg + j) * 128 + n) * r + (k < r ? k : 0);
+        ptx::cp_async16(ptx::smem_u32(dst), src, k < r);
       }
+      ptx::cp_async_commit();
+    };
+    auto store_b = [&](int i) {
+      ptx::cp_async_wait_all();
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&b_full[i]);
     };
-    auto fill_b = [&](int j, int i) { load_b(j); store_b(j, i); };
 
-    if (wt < nt) meta_s[wt] = tokmeta[t0 + wt]; else meta_s[wt] = 0;
-    for (int i2 = wt; i2 < 128 * r; i2 += kWorkers)
+    if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 0);
+    if (grp_id < nch) load_b(grp_id, grp_id * 2);               // first two B tiles of each group, in flight early
+    if (grp_id + 2 < nch) load_b(grp_id + 2, grp_id * 2 + 1);
+    if (wt < 128) meta_s[wt] = (wt < nt) ? tokmeta[t0 + wt] : 0;
+    for (int i2 = wt; i2 < 128 * r; i2 += 2 * kWorkers)
       gs[i2] = (i2 < nt * r) ? h_stash[(size_t)t0 * r + i2] : 0.f;
     grp.sync();
+    if (grp_id < nch) store_b(grp_id * 2);
+    if (grp_id + 2 < nch) store_b(grp_id * 2 + 1);
+    if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 1);
     attention_tile<false, 32>(d, c, grp, t0, nt, meta_s, gs, gs, nullptr);
     grp.sync();
+    if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 2);
     if (p.write_g && split == 0)
-      for (int i2 = wt; i2 < nt * r; i2 += kWorkers) g_out[(size_t)t0 * r + i2] = gs[i2];
+      for (int i2 = wt; i2 < nt * r; i2 += 2 * kWorkers) g_out[(size_t)t0 * r + i2] = gs[i2];
     // A operand tile: post_m * g, bf16, rows = tokens
     for (int kb = 0; kb < kblocks; ++kb) {
       const int kw = min(64, p.rk - kb * 64);
       const int cpr = kw / 8;
-      for (int idx = wt; idx < 128 * cpr; idx += kWorkers) {
+      for (int idx = wt; idx < 128 * cpr; idx += 2 * kWorkers) {
         const int n = idx / cpr, ch = idx - n * cpr;
         const int k = kb * 64 + ch * 8;
         const int code = meta_s[n] & MOKA_MOD_MASK;
@@ -428,42 +481,37 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
       }
     }
     ptx::fence_proxy_async_smem();
-    if (nch > 0) fill_b(0, 0);
-    if (nch > 1) fill_b(1, 1);
+    named_sync(2, 2 * kWorkers);
+    if (wt == 0) ptx::mbar_arrive(g_full);
+    if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 3);
 
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int j = 0; j < nch; ++j) {
-      const int i = j & 1;
-      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+    for (int j = grp_id; j < nch; j += 2) {
+      const int n = j >> 1;                                      // this group's chunk counter
+      const int i = grp_id * 2 + (n & 1);                        // accumulator / B buffer
+      const uint32_t ph = (uint32_t)(n >> 1) & 1u;
       const int s = j % p.ystages;
       const uint32_t yph = (uint32_t)(j / p.ystages) & 1u;
-      if (j + 2 < nch) load_b(j + 2);                          // L2 loads in flight during the waits + epilogue
       ptx::mbar_wait_or_trap(&t_full[i], ph);
+      if (wl == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 8 + j * 4);
+      // MMA j has consumed B buffer i: restage it right away (async copies fly during the epilogue)
+      if (j + 4 < nch) load_b(j + 4, i);
       ptx::mbar_wait_or_trap(&y_full[s], yph);
+      if (wl == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 4);
       ptx::tc_fence_after_sync();
       uint8_t* yt = ytiles + (size_t)s * 32768;
-      add_acc_to_tile(lane_base + (uint32_t)(i * 128), ptx::smem_u32(yt), (uint32_t)row);
-      ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&t_empty[i]);
-      ptx::fence_proxy_async_smem();
-      named_sync(2, kWorkers);
-      if (wt == 0) {
-        const int col = (c_beg + j) * 128;
-        ptx::tma_store_2d(&tm_y, yt, col, t0);
-        ptx::tma_store_2d(&tm_y, yt + 16384, col + 64, t0);
-        ptx::tma_store_commit();
-        if (j > 0) {
-          ptx::tma_store_wait_read<1>();                       // store j-1 has finished reading smem
-          ptx::mbar_arrive(&y_empty[(j - 1) % p.ystages]);
-        }
-      }
-      if (j + 2 < nch) store_b(j + 2, i);
+      add_acc_to_tile(lane_base + (uint32_t)(i * 128), ptx::smem_u32(yt), (uint32_t)row, &t_empty[i]);
+      if (wl == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 10 + j * 4);
+      ptx::fence_proxy_async_smem();                            // generic writes -> visible to the TMA store
+      ptx::mbar_arrive(&y_done[s]);
+      if (j + 4 < nch) store_b(i);
+      if (wl == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 11 + j * 4);
     }
-    if (wt == 0) ptx::tma_store_wait_all<0>();
+    if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 4);
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 256);
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st) {
@@ -475,21 +523,22 @@ static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaSt
   while (ntiles * p.nsplit * 2 <= num_sms + num_sms / 4 && p.chunks / (p.nsplit * 2) >= 4) p.nsplit *= 2;
   const int kblocks = (p.rk + 63) / 64;
   p.kcap = min(max(a.klen_hint, 1), 32 * kKeyBlocksMax);
-  const size_t fixed = (size_t)3 * kblocks * 16384 + (size_t)128 * d.r * 4 + 1024 + 512;
-  const size_t limit = 220 * 1024;
+  const size_t fixed = (size_t)5 * kblocks * 16384 + (size_t)128 * d.r * 4 + 1024 + 512;
+  const size_t limit = 224 * 1024;
   while (p.kcap > 1 && fixed + (size_t)p.kcap * (d.r + 1) * 4 + 2 * 32768 > limit) p.kcap /= 2;
   const size_t key_bytes = ((size_t)p.kcap * (d.r + 1) + 1) * 4;
   p.ystages = (int)((limit - fixed - key_bytes) / 32768);
   if (p.ystages > 4) p.ystages = 4;
   if (p.ystages < 2) return MOKA_EUNSUPPORTED;
   p.write_g = 1;
+  p.dbg = dbg_enabled();
   CUtensorMap ty0, ty;
   if (!make_tmap(&ty0, a.y0, (uint64_t)d.T, (uint64_t)d.d_out, 128)) return MOKA_EUNSUPPORTED;
   if (!make_tmap(&ty, a.y, (uint64_t)d.T, (uint64_t)d.d_out, 128)) return MOKA_EUNSUPPORTED;
   const size_t smem = (size_t)p.ystages * 32768 + fixed + key_bytes;
   cudaError_t e = cudaFuncSetAttribute(k_up_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
-  k_up_tc<<<ntiles * p.nsplit, kTcThreads, smem, st>>>(ty0, ty, d, p, static_cast<const __nv_bfloat16*>(a.Bw),
+  k_up_tc<<<ntiles * p.nsplit, kUpThreads, smem, st>>>(ty0, ty, d, p, static_cast<const __nv_bfloat16*>(a.Bw),
                                                         a.tokmeta, a.kidx, a.klen, a.h_stash,
                                                         a.h_stash + (size_t)d.T * d.r);
   return check_launch_tc();
