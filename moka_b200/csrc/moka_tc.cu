@@ -401,10 +401,8 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
         ptx::tma_store_2d(&tm_y, yt, col, t0);
         ptx::tma_store_2d(&tm_y, yt + 16384, col + 64, t0);
         ptx::tma_store_commit();
-        if (j > 0) {
-          ptx::tma_store_wait_read<1>();                       // store j-1 has finished reading smem
-          ptx::mbar_arrive(&y_empty[(j - 1) % p.ystages]);
-        }
+        ptx::tma_store_wait_read<0>();                         // smem read out: the slot can take the next load now
+        ptx::mbar_arrive(&y_empty[s]);
       }
       ptx::tma_store_wait_all<0>();
     }
@@ -803,7 +801,7 @@ k_attn_bwd(DevDesc d, const uint8_t* __restrict__ tokmeta, const int32_t* __rest
 // <p, dp> is dg.(g - h), and the per-token dh contribution (a sum over keys) is reduced across the
 // warp with a 16-shuffle butterfly.  All data is O(T r); the grid has ~T/16 * ceil(Lk/32) warps.
 template <int R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (R <= 16) ? 2 : 1)
 k_attn_bwd_keys(DevDesc d, const uint8_t* __restrict__ tokmeta, const int32_t* __restrict__ kidx,
                 const int32_t* __restrict__ klen, const float* __restrict__ h_stash, const float* __restrict__ dh,
                 float* __restrict__ dh_att, float* __restrict__ dK_glob, int kblocks, int groups_per_sample) {
@@ -1087,14 +1085,16 @@ k_pack_dh(DevDesc d, int rp, int NPW, int KP, const uint8_t* __restrict__ tokmet
 struct WgradTcParams {
   int T, d_in, r, rp, M, NPW, KP;
   int tsplit, ntiles;
-  int xs, ds;                      // ring depths: X pairs / dX pairs (32 KB slots)
-  int has_dx;
+  int xs, ds, nop;                 // ring depths: X pairs / dX pairs (32 KB slots), operand buffers
+  int has_dx, dbg;
   uint32_t w_box_bytes;            // one 64-column box of the weight slice: NPW x 128 B
   uint32_t op_bytes;               // operand buffer: dHc tile + dHcT hi/lo tiles
   uint32_t tmem_cols;
 };
 
-__global__ void __launch_bounds__(kTcThreads)
+constexpr int kWgradThreads = 224;                              // + warp 6: TMA store issuer
+
+__global__ void __launch_bounds__(kWgradThreads)
 k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dx,
            const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
            const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_hc,
@@ -1107,17 +1107,16 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   uint8_t* xring = base;                                      // [xs][2 boxes][128 x 128 B]
   uint8_t* dring = xring + (size_t)p.xs * 32768;              // [ds][2 boxes][128 x 128 B]
   uint8_t* wtile = dring + (size_t)p.ds * 32768;              // [2 boxes][NPW x 128 B]  weights (MN-major B operand)
-  uint8_t* op = wtile + 2 * p.w_box_bytes;                    // dHc [kbx][128x128B], dHcT hi [2][blk], lo [2][blk]
-  uint8_t* hc_t = op;
-  uint8_t* hct_t = op + (size_t)kbx * 16384;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(op + p.op_bytes);
+  uint8_t* op = wtile + 2 * p.w_box_bytes;                    // [nop] x { dHc [kbx][128x128B], dHcT hi [2][blk], lo [2][blk] }
+  uint64_t* bars = reinterpret_cast<uint64_t*>(op + (size_t)p.nop * p.op_bytes);
   uint64_t* x_full = bars;                     // [xs]
   uint64_t* x_empty = x_full + p.xs;           // [xs]
-  uint64_t* d_full = x_empty + p.xs;           // [ds]
-  uint64_t* d_empty = d_full + p.ds;           // [ds]
-  uint64_t* op_full = d_empty + p.ds;          // [1]
-  uint64_t* op_empty = op_full + 1;            // [1]
-  uint64_t* w_full = op_empty + 1;             // [1]
+  uint64_t* d_full = x_empty + p.xs;           // [ds]  dx tile landed
+  uint64_t* d_empty = d_full + p.ds;           // [ds]  dx tile stored, slot reusable
+  uint64_t* d_done = d_empty + p.ds;           // [ds]  dx tile updated by the workers
+  uint64_t* op_full = d_done + p.ds;           // [2]
+  uint64_t* op_empty = op_full + 2;            // [2]
+  uint64_t* w_full = op_empty + 2;             // [1]
   uint64_t* t_full = w_full + 1;               // [2] dx accumulator ready
   uint64_t* t_empty = t_full + 2;              // [2]
   uint64_t* a_full = t_empty + 2;              // [1] dA accumulator final
@@ -1131,13 +1130,18 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   const int ntt = tt_end - tt_beg;
 
   // weight rows that TMA never writes (padding of the rank blocks) must read as zero
-  for (uint32_t i = threadIdx.x; i < 2 * p.w_box_bytes / 16; i += kTcThreads)
+  for (uint32_t i = threadIdx.x; i < 2 * p.w_box_bytes / 16; i += kWgradThreads)
     reinterpret_cast<uint4*>(wtile)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.xs; ++s) { ptx::mbar_init(&x_full[s], 1); ptx::mbar_init(&x_empty[s], 1); }
-    for (int s = 0; s < p.ds; ++s) { ptx::mbar_init(&d_full[s], 1); ptx::mbar_init(&d_empty[s], 1); }
-    ptx::mbar_init(op_full, 1); ptx::mbar_init(op_empty, 1); ptx::mbar_init(w_full, 1);
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], kWorkers); }
+    for (int s = 0; s < p.ds; ++s) {
+      ptx::mbar_init(&d_full[s], 1); ptx::mbar_init(&d_empty[s], 1); ptx::mbar_init(&d_done[s], kWorkers);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&op_full[i], 1); ptx::mbar_init(&op_empty[i], 1);
+      ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], kWorkers);
+    }
+    ptx::mbar_init(w_full, 1);
     ptx::mbar_init(a_full, 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tm_x); ptx::prefetch_tmap(&tm_dx); ptx::prefetch_tmap(&tm_hc);
@@ -1163,15 +1167,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       const uint32_t op_tx = (uint32_t)kbx * 16384u + 4u * hct_blk;
       for (int j = 0; j < ntt; ++j) {
         const int t0 = (tt_beg + j) * 128;
-        // operands of tile j (single buffer: wait until the MMAs of tile j-1 are done with it)
-        ptx::mbar_wait_or_trap(op_empty, ((uint32_t)j & 1u) ^ 1u);
-        ptx::mbar_arrive_expect_tx(op_full, op_tx);
-        for (int kb = 0; kb < kbx; ++kb) ptx::tma_load_2d(hc_t + (size_t)kb * 16384, &tm_hc, op_full, kb * 64, t0, ptx::kEvictLast);
-        for (int kb = 0; kb < 2; ++kb) {
-          ptx::tma_load_2d(hct_t + (size_t)kb * hct_blk, &tm_hct_hi, op_full, t0 + kb * 64, 0, ptx::kEvictLast);
-          ptx::tma_load_2d(hct_t + (size_t)(2 + kb) * hct_blk, &tm_hct_lo, op_full, t0 + kb * 64, 0, ptx::kEvictLast);
-        }
-        {
+        {   // the big streams first: they have their own ring slots and must never wait on the MMAs
           const int s = j % p.xs;
           const uint32_t ph = (uint32_t)(j / p.xs) & 1u;
           ptx::mbar_wait_or_trap(&x_empty[s], ph ^ 1u);
@@ -1189,6 +1185,18 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
           ptx::tma_load_2d(dt, &tm_dx, &d_full[s], col0, t0, ptx::kEvictFirst);
           ptx::tma_load_2d(dt + 16384, &tm_dx, &d_full[s], col0 + 64, t0, ptx::kEvictFirst);
         }
+        {   // packed dh operands of tile j (L2-resident; nop buffers, recycled when their MMAs retire)
+          const int ob = j % p.nop;
+          uint8_t* hc_t = op + (size_t)ob * p.op_bytes;
+          uint8_t* hct_t = hc_t + (size_t)kbx * 16384;
+          ptx::mbar_wait_or_trap(&op_empty[ob], ((uint32_t)(j / p.nop) & 1u) ^ 1u);
+          ptx::mbar_arrive_expect_tx(&op_full[ob], op_tx);
+          for (int kb = 0; kb < kbx; ++kb) ptx::tma_load_2d(hc_t + (size_t)kb * 16384, &tm_hc, &op_full[ob], kb * 64, t0, ptx::kEvictLast);
+          for (int kb = 0; kb < 2; ++kb) {
+            ptx::tma_load_2d(hct_t + (size_t)kb * hct_blk, &tm_hct_hi, &op_full[ob], t0 + kb * 64, 0, ptx::kEvictLast);
+            ptx::tma_load_2d(hct_t + (size_t)(2 + kb) * hct_blk, &tm_hct_lo, &op_full[ob], t0 + kb * 64, 0, ptx::kEvictLast);
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -1196,19 +1204,33 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       const uint32_t idesc_a = ptx::idesc_bf16(128, (uint32_t)p.NPW, 1, 0);   // X^T (MN-major) . dHcT (K-major)
       const uint32_t idesc_x = ptx::idesc_bf16(128, 128, 0, 1);               // dHc (K-major) . Acat (MN-major)
       const uint32_t wa = ptx::smem_u32(wtile);
-      const uint32_t hca = ptx::smem_u32(hc_t);
-      const uint32_t hcta = ptx::smem_u32(hct_t);
       ptx::mbar_wait_or_trap(w_full, 0);
       for (int j = 0; j < ntt; ++j) {
         const int s = j % p.xs;
         const uint32_t ph = (uint32_t)(j / p.xs) & 1u;
         const int i = j & 1;
         const uint32_t ph2 = (uint32_t)(j >> 1) & 1u;
-        ptx::mbar_wait_or_trap(op_full, (uint32_t)j & 1u);
+        const int ob = j % p.nop;
+        const uint32_t hca = ptx::smem_u32(op + (size_t)ob * p.op_bytes);
+        const uint32_t hcta = hca + (uint32_t)kbx * 16384u;
+        ptx::mbar_wait_or_trap(&op_full[ob], (uint32_t)(j / p.nop) & 1u);
+        if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 40 + j * 3);
         ptx::mbar_wait_or_trap(&x_full[s], ph);
+        if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 41 + j * 3);
         if (p.has_dx) ptx::mbar_wait_or_trap(&t_empty[i], ph2 ^ 1u);
+        if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 42 + j * 3);
         ptx::tc_fence_after_sync();
         const uint32_t xa = ptx::smem_u32(xring + (size_t)s * 32768);
+        if (p.has_dx) {
+          // MMA-X first (the epilogue is waiting for it): K = NPW rank rows in steps of 16
+          const int ksteps = p.NPW / 16;
+          for (int k = 0; k < ksteps; ++k) {
+            const uint64_t adesc = ptx::smem_desc_sw128(hca + (uint32_t)(k >> 2) * 16384u + (k & 3) * 32, 1024, 0);
+            const uint64_t bdesc = ptx::smem_desc_sw128(wa + (uint32_t)k * 2048u, 1024, p.w_box_bytes);
+            ptx::umma_bf16(tmem_base + (uint32_t)i * 128u, adesc, bdesc, idesc_x, k > 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&t_full[i]);
+        }
         // MMA-A: K = 128 tokens (8 steps), hi then lo
 #pragma unroll
         for (int part = 0; part < 2; ++part)
@@ -1219,22 +1241,28 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
             ptx::umma_bf16(tmem_base + d1_col, adesc, bdesc, idesc_a, (j > 0 || part > 0 || k > 0) ? 1u : 0u);
           }
         ptx::umma_commit(&x_empty[s]);
-        if (p.has_dx) {
-          // MMA-X: K = NPW rank rows in steps of 16 (K block kb of the dHc tile, 16 weight rows = 2048 B)
-          const int ksteps = p.NPW / 16;
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc = ptx::smem_desc_sw128(hca + (uint32_t)(k >> 2) * 16384u + (k & 3) * 32, 1024, 0);
-            const uint64_t bdesc = ptx::smem_desc_sw128(wa + (uint32_t)k * 2048u, 1024, p.w_box_bytes);
-            ptx::umma_bf16(tmem_base + (uint32_t)i * 128u, adesc, bdesc, idesc_x, k > 0 ? 1u : 0u);
-          }
-          ptx::umma_commit(&t_full[i]);
-        }
-        ptx::umma_commit(op_empty);
+        ptx::umma_commit(&op_empty[ob]);
       }
       ptx::umma_commit(a_full);
     }
+  } else if (warp == 6) {
+    // TMA store issuer for the updated dx tiles
+    if (lane == 0 && p.has_dx) {
+      for (int j = 0; j < ntt; ++j) {
+        const int s = j % p.ds;
+        const uint32_t ph = (uint32_t)(j / p.ds) & 1u;
+        const int t0 = (tt_beg + j) * 128;
+        ptx::mbar_wait_or_trap(&d_done[s], ph);
+        uint8_t* dt = dring + (size_t)s * 32768;
+        ptx::tma_store_2d(&tm_dx, dt, col0, t0);
+        ptx::tma_store_2d(&tm_dx, dt + 16384, col0 + 64, t0);
+        ptx::tma_store_commit();
+        ptx::tma_store_wait_read<0>();                         // smem read out: the slot can take the next load now
+        ptx::mbar_arrive(&d_empty[s]);
+      }
+      ptx::tma_store_wait_all<0>();
+    }
   } else {
-    const int wt = threadIdx.x - 64;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -1244,46 +1272,48 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         const uint32_t ph2 = (uint32_t)(j >> 1) & 1u;
         const int s = j % p.ds;
         const uint32_t dph = (uint32_t)(j / p.ds) & 1u;
-        const int t0 = (tt_beg + j) * 128;
+        const bool st = (threadIdx.x == 64) && j < 8;
+        if (st && j == 0) dbg_stamp(p.dbg, blockIdx.x, 0);
         ptx::mbar_wait_or_trap(&t_full[i], ph2);
+        if (st) dbg_stamp(p.dbg, blockIdx.x, 8 + j * 4);
         ptx::mbar_wait_or_trap(&d_full[s], dph);
+        if (st) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 4);
         ptx::tc_fence_after_sync();
         uint8_t* dt = dring + (size_t)s * 32768;
-        add_acc_to_tile(lane_base + (uint32_t)(i * 128), ptx::smem_u32(dt), (uint32_t)row);
-        ptx::tc_fence_before_sync();
-        ptx::mbar_arrive(&t_empty[i]);
+        add_acc_to_tile(lane_base + (uint32_t)(i * 128), ptx::smem_u32(dt), (uint32_t)row, &t_empty[i]);
+        if (st) dbg_stamp(p.dbg, blockIdx.x, 10 + j * 4);
         ptx::fence_proxy_async_smem();
-        named_sync(2, kWorkers);
-        if (wt == 0) {
-          ptx::tma_store_2d(&tm_dx, dt, col0, t0);
-          ptx::tma_store_2d(&tm_dx, dt + 16384, col0 + 64, t0);
-          ptx::tma_store_commit();
-          if (j > 0) {
-            ptx::tma_store_wait_read<1>();
-            ptx::mbar_arrive(&d_empty[(j - 1) % p.ds]);
-          }
-        }
+        ptx::mbar_arrive(&d_done[s]);
+        if (st) dbg_stamp(p.dbg, blockIdx.x, 11 + j * 4);
       }
-      if (wt == 0) ptx::tma_store_wait_all<0>();
     }
     // ---- dA of this column slice: TMEM lane <-> column, TMEM column <-> (modality, rank index)
+    if (threadIdx.x == 64) dbg_stamp(p.dbg, blockIdx.x, 4);
     ptx::mbar_wait_or_trap(a_full, 0);
+    if (threadIdx.x == 64) dbg_stamp(p.dbg, blockIdx.x, 5);
     ptx::tc_fence_after_sync();
-    const int col = col0 + row;
+    // stage the accumulator as [NPW][128 cols] fp32 in the (now idle) X ring so that each thread can
+    // reduce four consecutive columns of one (modality, rank) row with a single red.v4
+    float* stage = reinterpret_cast<float*>(xring);
     for (int n8 = 0; n8 < p.NPW; n8 += 8) {
       float v[8];
       ptx::tmem_ld8(lane_base + d1_col + (uint32_t)n8, v);
       ptx::tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int n = n8 + e;
-        const int m = n / p.rp, jj = n - m * p.rp;
-        if (m < p.M && jj < p.r) {
-          float* dAm = m == 0 ? dA0 : (m == 1 ? dA1 : dA2);
-          red_add_f32(dAm + (size_t)jj * p.d_in + col, v[e]);
-        }
+      for (int e = 0; e < 8; ++e) stage[(n8 + e) * 128 + row] = v[e];
+    }
+    named_sync(2, kWorkers);
+    const int wtid = threadIdx.x - 64;
+    for (int idx = wtid; idx < p.NPW * 32; idx += kWorkers) {
+      const int n = idx >> 5, c4 = (idx & 31) * 4;
+      const int m = n / p.rp, jj = n - m * p.rp;
+      if (m < p.M && jj < p.r) {
+        float* dAm = m == 0 ? dA0 : (m == 1 ? dA1 : dA2);
+        const float4 v = *reinterpret_cast<const float4*>(stage + n * 128 + c4);
+        red_add_v4_f32(dAm + (size_t)jj * p.d_in + col0 + c4, v.x, v.y, v.z, v.w);
       }
     }
+    if (threadIdx.x == 64) dbg_stamp(p.dbg, blockIdx.x, 6);
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -1301,17 +1331,21 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   const int slices = d.d_in / 128;
   p.tsplit = max(1, min(p.ntiles, num_sms / slices));
   p.has_dx = a.dx != nullptr;
+  p.dbg = dbg_enabled();
   p.w_box_bytes = (uint32_t)p.NPW * 128u;
   p.op_bytes = (uint32_t)(p.KP / 64) * 16384u + 4u * p.w_box_bytes;
   p.tmem_cols = 512;
-  const size_t fixed = (size_t)2 * p.w_box_bytes + p.op_bytes + 1024 + 512;
-  const size_t limit = 224 * 1024;
+  const size_t limit = 226 * 1024;
+  // prefer two operand buffers (breaks the MMA -> reload -> MMA chain); the dx ring then gets 2 slots
+  p.nop = 2;
+  size_t fixed = (size_t)2 * p.w_box_bytes + (size_t)p.nop * p.op_bytes + 1024 + 512;
+  if (fixed + 4 * 32768 > limit) { p.nop = 1; fixed -= p.op_bytes; }
   if (fixed + 3 * 32768 > limit) return MOKA_EUNSUPPORTED;
   int slots = (int)((limit - fixed) / 32768);
   if (p.has_dx) {
-    p.ds = min(3, max(2, slots / 2 + (slots & 1)));
-    p.xs = min(2, slots - p.ds);
-    if (p.xs < 1) { p.xs = 1; p.ds = slots - 1; }
+    p.xs = 2;
+    p.ds = min(3, slots - p.xs);
+    if (p.ds < 2) { p.xs = 1; p.ds = slots - 1; }
     if (p.ds < 2) return MOKA_EUNSUPPORTED;
   } else {
     p.xs = min(4, slots); p.ds = 0;
@@ -1335,7 +1369,7 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   const size_t smem = (size_t)(p.xs + p.ds) * 32768 + fixed;
   cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
-  k_wgrad_tc<<<slices * p.tsplit, kTcThreads, smem, st>>>(tx, tdx, ta[0], ta[1], ta[2], thc, thh, thl, p,
+  k_wgrad_tc<<<slices * p.tsplit, kWgradThreads, smem, st>>>(tx, tdx, ta[0], ta[1], ta[2], thc, thh, thl, p,
                                                            a.dA[0], a.dA[d.M > 1 ? 1 : 0], a.dA[d.M > 2 ? 2 : 0]);
   return check_launch_tc();
 }
