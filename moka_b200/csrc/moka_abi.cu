@@ -86,7 +86,11 @@ extern "C" {
 
 size_t moka_workspace_bytes(const MokaDesc* desc) {
   if (validate(desc) != MOKA_OK) return 0;
-  return 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc) + align_up(tc_pack_bytes(desc->B * desc->S, desc->r, desc->M), 256) + 256;
+  // the packed-operand region is shared by B^T [rk, d_out] (dgrad) and the dh operands (wgrad)
+  size_t pack = tc_pack_bytes(desc->B * desc->S, desc->r, desc->M);
+  const size_t bt = (size_t)((desc->r + 15) / 16 * 16) * desc->d_out * 2;
+  if (bt > pack) pack = bt;
+  return 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc) + align_up(pack, 256) + 256;
 }
 
 int moka_uses_tensor_cores(const MokaDesc* desc) {

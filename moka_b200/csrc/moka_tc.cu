@@ -217,9 +217,11 @@ static int launch_down_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cuda
   p.ksplit = (ntiles * 2 <= num_sms * 2 && p.kblocks >= 8 && ntiles < num_sms) ? 2 : 1;
   p.w_bytes = (uint32_t)p.NP * 128u;
   p.stage_bytes = 16384u + p.w_bytes;
-  const size_t budget = 100 * 1024;
+  // one CTA per SM when the grid does not exceed the SM count: spend the whole shared memory on the
+  // ring (tcgen05.commit frees a stage ~1.5k cycles after issue, so >= 6 stages keep HBM busy)
+  const size_t budget = (ntiles * p.ksplit <= num_sms) ? 200 * 1024 : 100 * 1024;
   p.stages = (int)(budget / p.stage_bytes);
-  if (p.stages > 8) p.stages = 8;
+  if (p.stages > 10) p.stages = 10;
   if (p.stages < 2) p.stages = 2;
   p.tmem_cols = tmem_cols_for(p.NP);
   p.scale = d.pre * d.drop_scale;
@@ -554,12 +556,13 @@ struct DgradTcParams {
   int csplit, pairs;               // pairs = d_out / 128 column pairs, split across csplit CTAs
   int stages;
   uint32_t stage_bytes, bt_bytes;  // stage = [box0 16K][box1 16K][Bt kb0][Bt kb1]
+  int dbg;
   uint32_t tmem_cols, d2_col;      // D2 buffers start at column d2_col
 };
 
 __global__ void __launch_bounds__(kTcThreads)
-k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, DevDesc d, DgradTcParams p,
-           const __nv_bfloat16* __restrict__ Bw, const uint8_t* __restrict__ tokmeta,
+k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_bt, DevDesc d,
+           DgradTcParams p, const uint8_t* __restrict__ tokmeta,
            const float* __restrict__ g_stash, float* __restrict__ dG, float* __restrict__ dB) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -585,12 +588,12 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, DevDesc d, DgradTcParams p
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      ptx::mbar_init(&full[s], 1); ptx::mbar_init(&wfull[s], kWorkers); ptx::mbar_init(&empty[s], 1);
+      ptx::mbar_init(&full[s], 1); ptx::mbar_init(&wfull[s], 1); ptx::mbar_init(&empty[s], 1);
     }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&d2_full[i], 1); ptx::mbar_init(&d2_empty[i], kWorkers); }
     ptx::mbar_init(dg_full, 1);
     ptx::fence_mbar_init();
-    ptx::prefetch_tmap(&tm_dy);
+    ptx::prefetch_tmap(&tm_dy); ptx::prefetch_tmap(&tm_bt);
   }
   if (warp == 1) ptx::tmem_alloc(tmem_slot, p.tmem_cols);
   ptx::fence_proxy_async_smem();
@@ -606,10 +609,13 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, DevDesc d, DgradTcParams p
         const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
         ptx::mbar_wait_or_trap(&empty[s], ph ^ 1u);
         uint8_t* st = ring + (size_t)s * p.stage_bytes;
-        ptx::mbar_arrive_expect_tx(&full[s], 32768u);
+        ptx::mbar_arrive_expect_tx(&full[s], 32768u + p.bt_bytes);
         const int col = (p_beg + j) * 128;
         ptx::tma_load_2d(st, &tm_dy, &full[s], col, t0, ptx::kEvictFirst);
         ptx::tma_load_2d(st + 16384, &tm_dy, &full[s], col + 64, t0, ptx::kEvictFirst);
+        // B^T blocks [rk rows x 64 cols] of the pre-transposed copy (L2-resident)
+        ptx::tma_load_2d(st + 32768, &tm_bt, &full[s], col, 0, ptx::kEvictLast);
+        ptx::tma_load_2d(st + 32768 + gt_block, &tm_bt, &full[s], col + 64, 0, ptx::kEvictLast);
       }
     }
   } else if (warp == 1) {
@@ -617,13 +623,13 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, DevDesc d, DgradTcParams p
       const uint32_t idesc1 = ptx::idesc_bf16(128, (uint32_t)p.rk, 0, 0);     // dG: A K-major, B K-major
       const uint32_t idesc2 = ptx::idesc_bf16(128, (uint32_t)p.rk, 1, 0);     // dB: A MN-major (transposed view)
       const uint32_t gta = ptx::smem_u32(gt);
+      ptx::mbar_wait_or_trap(&wfull[0], 0);
       for (int j = 0; j < np; ++j) {
         const int s = j % p.stages;
         const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
         const int i = j & 1;
         const uint32_t ph2 = (uint32_t)(j >> 1) & 1u;
         ptx::mbar_wait_or_trap(&full[s], ph);
-        ptx::mbar_wait_or_trap(&wfull[s], ph);
         ptx::mbar_wait_or_trap(&d2_empty[i], ph2 ^ 1u);
         ptx::tc_fence_after_sync();
         const uint32_t sa = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
@@ -657,29 +663,6 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, DevDesc d, DgradTcParams p
     const int wt = threadIdx.x - 64;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    // B^T block of a column pair: rows = rank index, K = 64 columns per block (two blocks)
-    auto fill_bt = [&](int j) {
-      const int s = j % p.stages;
-      uint8_t* bt = ring + (size_t)s * p.stage_bytes + 32768;
-      const int n0 = (p_beg + j) * 128;
-      const int cpr = p.rk / 8;                              // 16-byte chunks of one B row
-      for (int idx = wt; idx < 128 * cpr; idx += kWorkers) {
-        const int n = idx / cpr, ch = idx - n * cpr;         // n = column within the pair
-        const int k0 = ch * 8;
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (k0 < r) v = __ldg(reinterpret_cast<const uint4*>(Bw + (size_t)(n0 + n) * r + k0));
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        uint8_t* blk = bt + (size_t)(n >> 6) * gt_block;     // K block (64 columns each)
-        const int kk = n & 63;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const uint16_t val = (uint16_t)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
-          *reinterpret_cast<uint16_t*>(blk + ptx::sw128_offset((uint32_t)(k0 + e), (uint32_t)(kk >> 3)) + (kk & 7) * 2) = val;
-        }
-      }
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&wfull[s]);
-    };
     // G^T operand (post_m * g as hi + lo bf16): rows = rank index, K = tokens
     {
       const int t = t0 + row;
@@ -695,8 +678,8 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, DevDesc d, DgradTcParams p
       }
     }
     ptx::fence_proxy_async_smem();
-    const int pre_n = min(np, p.stages);
-    for (int j = 0; j < pre_n; ++j) fill_bt(j);
+    named_sync(2, kWorkers);
+    if (wt == 0) ptx::mbar_arrive(&wfull[0]);                  // G^T staged: the MMA thread may start
 
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int j = 0; j < np; ++j) {
@@ -717,13 +700,6 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, DevDesc d, DgradTcParams p
       }
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(&d2_empty[i]);
-      // the stage that pair j occupied is recycled for pair j + stages
-      if (j + p.stages < np) {
-        const int s = j % p.stages;
-        const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
-        ptx::mbar_wait_or_trap(&empty[s], ph);               // MMAs of pair j have drained the stage
-        fill_bt(j + p.stages);
-      }
     }
     // dG partial of this CTA
     ptx::mbar_wait_or_trap(dg_full, 0);
@@ -794,90 +770,111 @@ k_attn_bwd(DevDesc d, const uint8_t* __restrict__ tokmeta, const int32_t* __rest
   }
 }
 
-// ---------------------------------------------------------------------------- k_attn_bwd_keys
-// Fast attention backward for r <= 32 and <= 256 keys per sample.  A warp owns one 32-key block of
-// one sample (lane <-> key, the key row and its dK accumulator live in registers) and walks a group
-// of 16 consecutive tokens; scores are recomputed from the stashed log-sum-exp, the row constant
-// <p, dp> is dg.(g - h), and the per-token dh contribution (a sum over keys) is reduced across the
-// warp with a 16-shuffle butterfly.  All data is O(T r); the grid has ~T/16 * ceil(Lk/32) warps.
-template <int R>
-__global__ void __launch_bounds__(256, (R <= 16) ? 2 : 1)
-k_attn_bwd_keys(DevDesc d, const uint8_t* __restrict__ tokmeta, const int32_t* __restrict__ kidx,
-                const int32_t* __restrict__ klen, const float* __restrict__ h_stash, const float* __restrict__ dh,
-                float* __restrict__ dh_att, float* __restrict__ dK_glob, int kblocks, int groups_per_sample) {
-  constexpr int TG = 4;                                         // tokens per warp (many small work items: latency hiding)
-  const int lane = threadIdx.x & 31;
+// ---------------------------------------------------------------------------- k_attn_bwd_tile
+// Fast attention backward for r <= 32 and <= 128 keys per sample.  A CTA owns 32 consecutive tokens
+// of one sample: their h / g / dG rows and all key rows of the sample are staged in shared memory
+// with coalesced loads; a warp takes 4 tokens and, per 32-key block, maps lane <-> key.  Scores are
+// recomputed from the stashed log-sum-exp, <p, dp> is dg.(g - h), the per-token dh contribution is
+// reduced over the keys with a shuffle butterfly and written back IN PLACE (the CTA owns the rows),
+// the per-key dK sums live in registers across the warp's tokens, are combined across warps in
+// shared memory and leave with one reduction per (key, rank) element per CTA.
+template <int R, int KB>
+__global__ void __launch_bounds__(256)
+k_attn_bwd_tile(DevDesc d, const uint8_t* __restrict__ tokmeta, const int32_t* __restrict__ kidx,
+                const int32_t* __restrict__ klen, const float* __restrict__ h_stash, float* __restrict__ dh,
+                float* __restrict__ dK_glob, int groups_per_sample) {
+  constexpr int TT = 32;
+  extern __shared__ __align__(16) float sm[];
   const int r = d.r;
+  constexpr int RS = R + 1;                         // odd row stride: lane <-> key reads are conflict-free
+  float* Ks = sm;                                   // [KB*32][RS]   (zero rows for invalid keys)
+  float* dKs = Ks + KB * 32 * RS;                   // [KB*32][RS]
+  float* hs = dKs + KB * 32 * RS;                   // [TT][R]
+  float* gs = hs + TT * R;
+  float* dgs = gs + TT * R;
+  __shared__ int s_code[TT];
+  __shared__ float s_lse[TT];
+  __shared__ int s_anyq;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / groups_per_sample;
+  const int s0 = (blockIdx.x % groups_per_sample) * TT;
+  const int nt = min(TT, d.S - s0);
+  const size_t tbase = (size_t)b * d.S + s0;
   const float* g_stash = h_stash + (size_t)d.T * r;
   const float* lse = g_stash + (size_t)d.T * r;
-  const long long nwork = (long long)d.B * groups_per_sample * kblocks;
-  const float sl = d.sm_scale * kLog2e;
-  for (long long w = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); w < nwork; w += (long long)gridDim.x * 8) {
-    const int kb = (int)(w % kblocks);
-    const long long wg = w / kblocks;
-    const int b = (int)(wg / groups_per_sample);
-    const int s0 = (int)(wg % groups_per_sample) * TG;          // first in-sample position of the group
-    const int L = klen[b];
-    if (kb * 32 >= L) continue;
-    // any query token in the group?
-    uint32_t qmask = 0;
-    if (lane < TG && s0 + lane < d.S) qmask = ((tokmeta[(size_t)b * d.S + s0 + lane] & MOKA_MOD_MASK) >= MOKA_MOD_VIS);
-    qmask = __ballot_sync(0xffffffffu, qmask);
-    if (!qmask) continue;
-    // this lane's key row
-    const int k = kb * 32 + lane;
-    bool kvalid = false;
-    float K[R], dKacc[R];
-#pragma unroll
-    for (int j = 0; j < R; ++j) { K[j] = 0.f; dKacc[j] = 0.f; }
+  const int L = klen[b];
+  if (tid == 0) s_anyq = 0;
+  __syncthreads();
+  if (tid < TT) {
+    const int code = (tid < nt) ? (tokmeta[tbase + tid] & MOKA_MOD_MASK) : 0;
+    s_code[tid] = code;
+    s_lse[tid] = (tid < nt && code >= MOKA_MOD_VIS) ? lse[tbase + tid] : 0.f;
+    if (code >= MOKA_MOD_VIS) s_anyq = 1;
+  }
+  __syncthreads();
+  if (!s_anyq || L <= 0) return;                    // no query token here: dh == dG already
+  // stage rows (coalesced) and keys
+  for (int i = tid; i < TT * R; i += 256) {
+    const int tt = i / R, j = i - tt * R;
+    const bool ok = tt < nt && j < r;
+    hs[i] = ok ? h_stash[(tbase + tt) * r + j] : 0.f;
+    gs[i] = ok ? g_stash[(tbase + tt) * r + j] : 0.f;
+    dgs[i] = ok ? dh[(tbase + tt) * r + j] : 0.f;
+  }
+  for (int k = tid; k < KB * 32; k += 256) {
+    bool valid = false;
+    size_t tk = 0;
     if (k < L) {
       const int pos = kidx[(size_t)b * d.Lk + k];
-      const size_t tk = (size_t)b * d.S + pos;
-      kvalid = (tokmeta[tk] & MOKA_KEY_VALID) != 0;
-      if (kvalid) {
-#pragma unroll
-        for (int j = 0; j < R; ++j) if (j < r) K[j] = h_stash[tk * r + j];
-      }
+      tk = (size_t)b * d.S + pos;
+      valid = (tokmeta[tk] & MOKA_KEY_VALID) != 0;
     }
-    for (int ti = 0; ti < TG; ++ti) {
-      if (!((qmask >> ti) & 1)) continue;
-      const size_t t = (size_t)b * d.S + s0 + ti;
-      float hq[R], dg[R], gq[R];
-      float Dsum = 0.f;
-      if (r == R) {                                             // full rows: 128-bit broadcast loads
+    for (int j = 0; j < R; ++j) {
+      Ks[k * RS + j] = (valid && j < r) ? h_stash[tk * r + j] : 0.f;
+      dKs[k * RS + j] = 0.f;
+    }
+  }
+  __syncthreads();
+  const float sl = d.sm_scale * kLog2e;
+  float dKacc[KB][R];
 #pragma unroll
-        for (int j = 0; j < R; j += 4) {
-          const float4 a = *reinterpret_cast<const float4*>(h_stash + t * r + j);
-          const float4 bq = *reinterpret_cast<const float4*>(dh + t * r + j);
-          const float4 cq = *reinterpret_cast<const float4*>(g_stash + t * r + j);
-          hq[j] = a.x; hq[j + 1] = a.y; hq[j + 2] = a.z; hq[j + 3] = a.w;
-          dg[j] = bq.x; dg[j + 1] = bq.y; dg[j + 2] = bq.z; dg[j + 3] = bq.w;
-          gq[j] = cq.x; gq[j + 1] = cq.y; gq[j + 2] = cq.z; gq[j + 3] = cq.w;
-        }
-      } else {
+  for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-          hq[j] = (j < r) ? h_stash[t * r + j] : 0.f;
-          dg[j] = (j < r) ? dh[t * r + j] : 0.f;
-          gq[j] = (j < r) ? g_stash[t * r + j] : 0.f;
-        }
-      }
+    for (int j = 0; j < R; ++j) dKacc[kb][j] = 0.f;
+  const int comp = (R == 32) ? lane : (R == 16 ? (lane >> 1) : (lane >> 2));
+  const bool writer = (R == 32) || (R == 16 && !(lane & 1)) || (R == 8 && !(lane & 3));
+  for (int ti = 0; ti < 4; ++ti) {
+    const int tt = warp * 4 + ti;
+    if (s_code[tt] < MOKA_MOD_VIS) continue;        // warp-uniform
+    float hq[R], dg[R];
+    float Dsum = 0.f;
 #pragma unroll
-      for (int j = 0; j < R; ++j) Dsum = fmaf(dg[j], gq[j] - hq[j], Dsum);   // = <p, dp>
-      float s = 0.f, dp = 0.f;
+    for (int j = 0; j < R; ++j) {
+      hq[j] = hs[tt * R + j];
+      dg[j] = dgs[tt * R + j];
+      Dsum = fmaf(dg[j], gs[tt * R + j] - hq[j], Dsum);
+    }
+    const float lse_t = s_lse[tt];
+    float dh_tot = 0.f;                             // component `comp` of the dh contribution (writer lanes)
 #pragma unroll
-      for (int j = 0; j < R; ++j) { s = fmaf(hq[j], K[j], s); dp = fmaf(dg[j], K[j], dp); }
-      const float p = (k < L) ? exp2f(s * sl - lse[t]) : 0.f;
+    for (int kb = 0; kb < KB; ++kb) {
+      if (kb * 32 >= L) break;                      // uniform
+      const int k = kb * 32 + lane;
+      const float* Kr = Ks + k * RS;
+      float Kv[R];
+      float sc = 0.f, dp = 0.f;
+#pragma unroll
+      for (int j = 0; j < R; ++j) { Kv[j] = Kr[j]; sc = fmaf(hq[j], Kv[j], sc); dp = fmaf(dg[j], Kv[j], dp); }
+      const float p = (k < L) ? exp2f(sc * sl - lse_t) : 0.f;
       dp *= d.attn_w;
       const float ds = p * (dp - Dsum);
-      float part[R];
       const float pw = p * d.attn_w, dss = ds * d.sm_scale;
+      float part[R];
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-        dKacc[j] = fmaf(pw, dg[j], fmaf(dss, hq[j], dKacc[j]));
-        part[j] = dss * K[j];
+        dKacc[kb][j] = fmaf(pw, dg[j], fmaf(dss, hq[j], dKacc[kb][j]));
+        part[j] = dss * Kv[j];
       }
-      // butterfly: R values per lane -> lane (j) holds the sum over the 32 keys of component j
 #pragma unroll
       for (int half = R / 2, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
         const bool upper = (lane & bit) != 0;
@@ -888,25 +885,45 @@ k_attn_bwd_keys(DevDesc d, const uint8_t* __restrict__ tokmeta, const int32_t* _
           part[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
         }
       }
-      // R == 32: lane j holds component j.  R == 16: bits 16..2 selected the component, bit 1 remains.
-      // R == 8: bits 16,8,4 selected, bits 2,1 remain.
       float tot = part[0];
       if (R <= 16) tot += __shfl_xor_sync(0xffffffffu, tot, 1);
       if (R <= 8) tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-      const int comp = (R == 32) ? lane : (R == 16 ? (lane >> 1) : (lane >> 2));
-      const bool writer = (R == 32) || (R == 16 && !(lane & 1)) || (R == 8 && !(lane & 3));
-      if (writer && comp < r) red_add_f32(&dh_att[t * r + comp], tot);   // separate buffer: dh stays the pristine dG
+      dh_tot += tot;
     }
-    if (k < L && kvalid) {
-      float* dst = dK_glob + ((size_t)b * d.Lk + k) * r;
-      if (r == R) {
+    if (writer && comp < r) dh[(tbase + tt) * r + comp] = dgs[tt * R + comp] + dh_tot;   // in place: rows are ours
+  }
+  // combine the per-warp dK partials in shared memory, then one reduction per element
 #pragma unroll
-        for (int j = 0; j < R; j += 4) red_add_v4_f32(dst + j, dKacc[j], dKacc[j + 1], dKacc[j + 2], dKacc[j + 3]);
-      } else {
+  for (int kb = 0; kb < KB; ++kb) {
+    if (kb * 32 >= L) break;
+    const int k = kb * 32 + lane;
 #pragma unroll
-        for (int j = 0; j < R; ++j) if (j < r) red_add_f32(dst + j, dKacc[j]);
-      }
+    for (int j = 0; j < R; ++j) atomicAdd(&dKs[k * RS + j], dKacc[kb][j]);
+  }
+  __syncthreads();
+  for (int i = tid; i < L * R; i += 256) {
+    const int k = i / R, j = i - k * R;
+    if (j < r) {
+      const float v = dKs[k * RS + j];
+      if (v != 0.f) red_add_f32(&dK_glob[((size_t)b * d.Lk + k) * r + j], v);
     }
+  }
+}
+
+// B [d_out, r] -> B^T [rk, d_out] bf16 (rows r..rk zero): the K-major operand of dG = dY . B that
+// k_dgrad_tc TMA-loads.  64 K elements; one launch per backward call.
+__global__ void __launch_bounds__(256)
+k_transpose_b(const __nv_bfloat16* __restrict__ Bw, __nv_bfloat16* __restrict__ Bt, int d_out, int r, int rk) {
+  __shared__ __nv_bfloat16 tile[64][136];                        // 64 columns x up to 128 ranks (+pad)
+  const int c0 = blockIdx.x * 64;
+  for (int idx = threadIdx.x; idx < 64 * r; idx += 256) {
+    const int c = idx / r, j = idx - c * r;
+    tile[c][j] = (c0 + c < d_out) ? Bw[(size_t)(c0 + c) * r + j] : __float2bfloat16_rn(0.f);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < rk * 64; idx += 256) {
+    const int j = idx >> 6, c = idx & 63;
+    if (c0 + c < d_out) Bt[(size_t)j * d_out + c0 + c] = (j < r) ? tile[c][j] : __float2bfloat16_rn(0.f);
   }
 }
 
@@ -926,24 +943,37 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   const uint32_t dgc = tmem_cols_for(p.rk);
   p.d2_col = dgc;
   p.tmem_cols = tmem_cols_for((int)dgc + 2 * p.rk);
-  CUtensorMap tdy;
+  // pre-transposed B in the (otherwise unused until k_pack_dh) packed-operand workspace
+  __nv_bfloat16* Bt = static_cast<__nv_bfloat16*>(a.pack);
+  k_transpose_b<<<(d.d_out + 63) / 64, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(a.Bw), Bt, d.d_out, d.r, p.rk);
+  if (int rc = check_launch_tc()) return rc;
+  CUtensorMap tdy, tbt;
   if (!make_tmap(&tdy, a.dy, (uint64_t)d.T, (uint64_t)d.d_out, 128)) return MOKA_EUNSUPPORTED;
+  if (!make_tmap(&tbt, Bt, (uint64_t)p.rk, (uint64_t)d.d_out, (uint32_t)p.rk)) return MOKA_EUNSUPPORTED;
   // dG lives in the dh workspace (zeroed by moka_backward: two CTAs may reduce into it)
   const size_t smem = (size_t)p.stages * p.stage_bytes + fixed;
   cudaError_t e = cudaFuncSetAttribute(k_dgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
-  k_dgrad_tc<<<ntiles * p.csplit, kTcThreads, smem, st>>>(tdy, d, p, static_cast<const __nv_bfloat16*>(a.Bw),
-                                                           a.tokmeta, a.h_stash + (size_t)d.T * d.r, a.dh, a.dB);
+  k_dgrad_tc<<<ntiles * p.csplit, kTcThreads, smem, st>>>(tdy, tbt, d, p, a.tokmeta, a.h_stash + (size_t)d.T * d.r,
+                                                           a.dh, a.dB);
   if (int rc = check_launch_tc()) return rc;
   // attention backward on the small [T, r] tensors
-  if (d.r <= 32 && a.klen_hint <= 32 * kKeyBlocksMax) {
+  if (d.r <= 32 && a.klen_hint <= 128 && (d.r <= 16 || a.klen_hint <= 64)) {
     const int kblocks = (max(a.klen_hint, 1) + 31) / 32;
-    const int gps = (d.S + 3) / 4;
-    const long long nwork = (long long)d.B * gps * kblocks;
-    const int grid = (int)std::min<long long>((nwork + 7) / 8, (long long)num_sms * 16);
-    if (d.r <= 8) k_attn_bwd_keys<8><<<grid, 256, 0, st>>>(d, a.tokmeta, a.kidx, a.klen, a.h_stash, a.dh, a.dh_att, a.dK, kblocks, gps);
-    else if (d.r <= 16) k_attn_bwd_keys<16><<<grid, 256, 0, st>>>(d, a.tokmeta, a.kidx, a.klen, a.h_stash, a.dh, a.dh_att, a.dK, kblocks, gps);
-    else k_attn_bwd_keys<32><<<grid, 256, 0, st>>>(d, a.tokmeta, a.kidx, a.klen, a.h_stash, a.dh, a.dh_att, a.dK, kblocks, gps);
+    const int gps = (d.S + 31) / 32;
+    const int grid = d.B * gps;
+    const int R = d.r <= 8 ? 8 : (d.r <= 16 ? 16 : 32);
+    const int KBs = kblocks <= 1 ? 1 : (kblocks <= 2 ? 2 : 4);
+    const size_t sm = ((size_t)2 * KBs * 32 * (R + 1) + 3 * 32 * R) * 4;
+#define MOKA_LAUNCH_ATTN_BWD(RR, KK)                                                                     \
+    do {                                                                                                \
+      if (sm > 48 * 1024) cudaFuncSetAttribute(k_attn_bwd_tile<RR, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+      k_attn_bwd_tile<RR, KK><<<grid, 256, sm, st>>>(d, a.tokmeta, a.kidx, a.klen, a.h_stash, a.dh, a.dK, gps); \
+    } while (0)
+    if (R == 8) { if (KBs == 1) MOKA_LAUNCH_ATTN_BWD(8, 1); else if (KBs == 2) MOKA_LAUNCH_ATTN_BWD(8, 2); else MOKA_LAUNCH_ATTN_BWD(8, 4); }
+    else if (R == 16) { if (KBs == 1) MOKA_LAUNCH_ATTN_BWD(16, 1); else if (KBs == 2) MOKA_LAUNCH_ATTN_BWD(16, 2); else MOKA_LAUNCH_ATTN_BWD(16, 4); }
+    else { if (KBs == 1) MOKA_LAUNCH_ATTN_BWD(32, 1); else MOKA_LAUNCH_ATTN_BWD(32, 2); }
+#undef MOKA_LAUNCH_ATTN_BWD
     return check_launch_tc();
   }
   DevDesc dd = d;
@@ -983,7 +1013,7 @@ static PackLayout pack_layout(int T, int r, int M) {
 }
 size_t tc_pack_bytes(int T, int r, int M) {
   PackLayout L = pack_layout(T, r, M);
-  return L.hc_bytes + 2 * L.hct_bytes;
+  return L.hc_bytes + 2 * L.hct_bytes;                           // also hosts B^T [rk, d_out] (see moka_workspace_bytes)
 }
 
 __device__ __forceinline__ int find_key_slot(const int32_t* __restrict__ row, int L, int pos) {
