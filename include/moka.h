@@ -54,7 +54,11 @@ enum {
   MOKA_FLAG_FORCE_TC = 2,     /* fail with MOKA_EUNSUPPORTED instead of falling back to warp-FMA */
   /* per-stage vetoes of the tcgen05 path (debugging / A-B measurements) */
   MOKA_FLAG_NO_TC_DOWN = 1 << 8, MOKA_FLAG_NO_TC_UP = 1 << 9,
-  MOKA_FLAG_NO_TC_DGRAD = 1 << 10, MOKA_FLAG_NO_TC_WGRAD = 1 << 11
+  MOKA_FLAG_NO_TC_DGRAD = 1 << 10, MOKA_FLAG_NO_TC_WGRAD = 1 << 11,
+  /* timing aid (results are NOT valid): bits 16.. skip individual kernels of the tensor-core path:
+     +0 down, +1 up, +2 backward prep, +3 dgrad, +4 attention backward / pack, +5 wgrad,
+     +6 forward attention */
+  MOKA_FLAG_DBG_SKIP_SHIFT = 16
 };
 
 /* status words written by moka_build_token_meta (int32 status[4]) */
@@ -80,7 +84,8 @@ typedef struct MokaDesc {
   int32_t flags;        /* MOKA_FLAG_* */
 } MokaDesc;
 
-/* Bytes of scratch the forward/backward of this shape need (16-byte aligned base). */
+/* Bytes of scratch moka_forward / moka_backward of this shape need (16-byte aligned base; the
+ * same buffer may serve both calls and every layer of the same shape on one stream). */
 size_t moka_workspace_bytes(const MokaDesc* desc);
 
 /*

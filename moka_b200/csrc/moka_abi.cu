@@ -72,6 +72,8 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 static size_t ws_dh_bytes(const MokaDesc* m) { return align_up((size_t)m->B * m->S * m->r * 4, 256); }
 static size_t ws_dk_bytes(const MokaDesc* m) { return align_up((size_t)m->B * (m->Lk > 0 ? m->Lk : 1) * m->r * 4, 256); }
 
+static size_t ws_cnt_bytes(const MokaDesc* m) { return align_up((size_t)m->B * 4, 256); }
+
 // stages the tcgen05 path takes for this call (flags bits 8..11 veto individual stages)
 static int tc_stages(const MokaDesc* m, const DevDesc& d) {
   if (m->flags & MOKA_FLAG_FORCE_SIMT) return 0;
@@ -90,7 +92,8 @@ size_t moka_workspace_bytes(const MokaDesc* desc) {
   size_t pack = tc_pack_bytes(desc->B * desc->S, desc->r, desc->M);
   const size_t bt = (size_t)((desc->r + 15) / 16 * 16) * desc->d_out * 2;
   if (bt > pack) pack = bt;
-  return 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc) + align_up(pack, 256) + 256;
+  // [dh | dh_att | dK | counters | pack]; the forward uses the first 2 T r floats for the partial h
+  return 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc) + ws_cnt_bytes(desc) + align_up(pack, 256) + 256;
 }
 
 int moka_uses_tensor_cores(const MokaDesc* desc) {
@@ -110,18 +113,30 @@ int moka_forward(const MokaDesc* desc, const void* x, const void* y0, void* y,
   for (int m = 0; m < desc->M; ++m) if (!A[m]) return MOKA_EINVAL;
   if (!aligned16(x) || !aligned16(y0) || !aligned16(y) || !aligned16(Bw) || !aligned16(h_stash)) return MOKA_EALIGN;
   for (int m = 0; m < desc->M; ++m) if (!aligned16(A[m])) return MOKA_EALIGN;
-  (void)workspace; (void)workspace_bytes;
+  if (!workspace || !aligned16(workspace)) return workspace ? MOKA_EALIGN : MOKA_EWORKSPACE;
+  if (workspace_bytes < moka_workspace_bytes(desc)) return MOKA_EWORKSPACE;
   DevDesc d = make_dev(desc, seed, offset);
   SimtArgs a;
   memset(&a, 0, sizeof(a));
   a.x = x; a.y0 = y0; a.y = y; a.Bw = Bw;
   for (int m = 0; m < desc->M; ++m) a.A[m] = A[m];
   a.tokmeta = tokmeta; a.kidx = kidx; a.klen = klen; a.h_stash = h_stash; a.klen_hint = desc->Lk;
+  a.hpart = static_cast<float*>(workspace);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int tcs = tc_stages(desc, d) & (kStageDown | kStageUp);
   if ((desc->flags & MOKA_FLAG_FORCE_TC) && tcs != (kStageDown | kStageUp)) return MOKA_EUNSUPPORTED;
-  // stage order matters: down (h) before up (y)
   const bool force = (desc->flags & MOKA_FLAG_FORCE_TC) != 0;
+  const int skip = (desc->flags >> MOKA_FLAG_DBG_SKIP_SHIFT) & 0xff;     // timing aid only
+  d.dbg_skip = skip;
+  if (tcs == (kStageDown | kStageUp)) {
+    // both stages on the tensor-core path: one call so that they can agree on the split-reduction layout
+    int e = tc_forward(d, a, num_sms(), st, tcs);
+    if (e != MOKA_EUNSUPPORTED || force) return e;
+    // a shape the tensor-core kernels cannot tile (shared-memory budget): redo stage by stage below
+    // (the down-projection is idempotent)
+  }
+  a.hpart = nullptr;
+  // stage order matters: down (h) before up (y)
   for (int stage : {kStageDown, kStageUp}) {
     int e = MOKA_EUNSUPPORTED;
     if (tcs & stage) e = tc_forward(d, a, num_sms(), st, stage);
@@ -157,17 +172,26 @@ int moka_backward(const MokaDesc* desc, const void* dy, const void* x, const flo
   a.dh = reinterpret_cast<float*>(ws);
   a.dh_att = reinterpret_cast<float*>(ws + ws_dh_bytes(desc));
   a.dK = reinterpret_cast<float*>(ws + 2 * ws_dh_bytes(desc));
-  a.pack = ws + 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc);
+  a.counters = reinterpret_cast<int*>(ws + 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc));
+  a.pack = ws + 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc) + ws_cnt_bytes(desc);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // one memset covers dh (the tensor-core dgrad reduces into it), dh_att and dK
-  cudaError_t ce = cudaMemsetAsync(a.dh, 0, 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc), st);
-  if (ce != cudaSuccess) { set_cuda_error(ce); return MOKA_ECUDA; }
   const int tcs = tc_stages(desc, d) & (kStageDgrad | kStageWgrad);
   if ((desc->flags & MOKA_FLAG_FORCE_TC) && tcs != (kStageDgrad | kStageWgrad)) return MOKA_EUNSUPPORTED;
   const bool force = (desc->flags & MOKA_FLAG_FORCE_TC) != 0;
+  d.dbg_skip = (desc->flags >> MOKA_FLAG_DBG_SKIP_SHIFT) & 0xff;          // timing aid only
+  if (tcs == (kStageDgrad | kStageWgrad) && tc_backward_fused_ok(d, desc->Lk, dx != nullptr)) {
+    // whole backward on the tensor-core path: four kernels chained by programmatic dependent launch,
+    // the first of which zero-fills what needs it (no memset node in the chain)
+    // (tc_backward_fused_ok has already checked that every stage can tile this shape)
+    return tc_backward(d, a, num_sms(), st, tcs, true);
+  }
+  (void)force;
+  // one memset covers dh (the tensor-core dgrad reduces into it), dh_att and dK
+  cudaError_t ce = cudaMemsetAsync(a.dh, 0, 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc) + ws_cnt_bytes(desc), st);
+  if (ce != cudaSuccess) { set_cuda_error(ce); return MOKA_ECUDA; }
   for (int stage : {kStageDgrad, kStageWgrad}) {
     int e = MOKA_EUNSUPPORTED;
-    if (tcs & stage) e = tc_backward(d, a, num_sms(), st, stage);
+    if (tcs & stage) e = tc_backward(d, a, num_sms(), st, stage, false);
     if (e == MOKA_EUNSUPPORTED && !force) e = simt_backward(d, desc->dtype, a, num_sms(), st, stage);
     if (e) return e;
   }

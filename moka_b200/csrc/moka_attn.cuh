@@ -25,6 +25,7 @@ struct AttnCtx {
   int ks;                   // row stride of Ks (r + 1: conflict-free lane<->key reads)
   int kcap;                 // keys that fit in Ks
   float* lse_out;           // global [T] log2-sum-exp of the scaled scores (forward; may be null)
+  const float* h_stash2 = nullptr;   // optional second partial of h (added to h_stash rows when loading keys)
 };
 
 // ------------------------------------------------------------------ fast path (smem keys)
@@ -229,7 +230,7 @@ __device__ __forceinline__ void attn_token_slow(const DevDesc& d, const AttnCtx&
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int jj = lane + 32 * i;
-      kv[i] = (valid && jj < r) ? c.h_stash[t * r + jj] : 0.f;
+      kv[i] = (valid && jj < r) ? (c.h_stash[t * r + jj] + (c.h_stash2 ? c.h_stash2[t * r + jj] : 0.f)) : 0.f;
     }
     return valid;
   };
@@ -335,14 +336,19 @@ __device__ __forceinline__ void attention_tile(const DevDesc& d, const AttnCtx& 
         const size_t t = (size_t)b * d.S + pos;
         const bool valid = (c.tokmeta[t] & MOKA_KEY_VALID) != 0;
         const float* src = c.h_stash + t * r;
+        const float* src2 = c.h_stash2 ? c.h_stash2 + t * r : nullptr;
         float* dst = c.Ks + k * ks;
         if ((r & 3) == 0 && (ks & 3) == 0) {
           for (int j = 0; j < r; j += 4) {
-            const float4 v = valid ? *reinterpret_cast<const float4*>(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 v = valid ? *reinterpret_cast<const float4*>(src + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid && src2) {
+              const float4 w = *reinterpret_cast<const float4*>(src2 + j);
+              v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+            }
             *reinterpret_cast<float4*>(dst + j) = v;
           }
         } else {
-          for (int j = 0; j < r; ++j) dst[j] = valid ? src[j] : 0.f;
+          for (int j = 0; j < r; ++j) dst[j] = valid ? (src[j] + (src2 ? src2[j] : 0.f)) : 0.f;
         }
         if (BWD) for (int j = 0; j < r; ++j) c.dKs[k * ks + j] = 0.f;
       }

@@ -25,6 +25,7 @@ struct DevDesc {            // by-value kernel argument (POD)
   unsigned long long seed, offset;
   int tile_tokens;          // tokens per CTA tile
   int num_tiles;
+  int dbg_skip;             // MOKA_FLAG_DBG_SKIP bits (timing aid)
 };
 
 // ---------------------------------------------------------------------------- vectors

@@ -13,6 +13,8 @@ struct SimtArgs {
   float* dA[3]; float* dB;
   const uint8_t* tokmeta; const int32_t* kidx; const int32_t* klen;
   float* h_stash;
+  float* hpart;     // forward workspace [2, T, r]: partial h of a split down-projection (null: none)
+  int* counters;    // backward workspace [B]: per-sample arrival counters of k_attn_pack (zeroed by k_bwd_prep)
   float* dh;        // workspace [T, r]
   float* dh_att;    // workspace [T, r]: attention-backward contributions, added to dh by the wgrad stage
   float* dK;        // workspace [B, Lk, r]
@@ -44,6 +46,7 @@ int debug_read(unsigned long long* host, int n);
 // Returns the mask of stages the tcgen05 path implements for this shape (0 = none).
 int tc_stage_mask(const DevDesc& d, int dtype);
 int tc_forward(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, int stages);
-int tc_backward(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, int stages);
+int tc_backward(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, int stages, bool fused);
+bool tc_backward_fused_ok(const DevDesc& d, int klen_hint, bool has_dx);
 
 }  // namespace moka

@@ -49,6 +49,16 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity
   if (!mbar_wait(bar, parity)) asm volatile("trap;");
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// Every kernel of a moka_forward / moka_backward call is launched with the programmatic stream
+// serialization attribute: its prologue (barrier init, TMEM alloc, tensor-map prefetch, loads of
+// tensors no kernel of the call writes) overlaps the tail of the previous kernel.  Rule used
+// throughout: pdl_wait() before the first access to memory an earlier kernel of the chain writes,
+// and pdl_trigger() only AFTER pdl_wait() - so when a kernel starts, everything older than its
+// direct predecessor has completed.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -12,6 +12,7 @@
 // warps 2..5 = epilogue (TMEM lane quadrant = warp % 4).
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "moka_attn.cuh"
@@ -62,11 +63,42 @@ static inline uint32_t tmem_cols_for(int n) {
 
 constexpr int kTcThreads = 192;
 
+// Launch with programmatic stream serialization (see moka_ptx.cuh: pdl_wait / pdl_trigger).
+// MOKA_NO_PDL=1 falls back to plain stream order (A/B measurements).
+static int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MOKA_NO_PDL"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v;
+}
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+  if (e != cudaSuccess) (void)cudaGetLastError();               // reported through the return value: do not leave it behind
+  return e;
+}
+
 // Optional in-kernel timestamps (cycle counter of the SM) for tuning: slot layout is per kernel.
 // Written only when MOKA_DEBUG_TIMING=1; read back through moka_debug_read().
 __device__ unsigned long long g_dbg[148 * 2 * 64];
 __device__ __forceinline__ void dbg_stamp(int enabled, int cta, int slot) {
   if (enabled && cta < 148 * 2 && slot < 64) g_dbg[cta * 64 + slot] = clock64();
+}
+// wall-clock (globaltimer, ns) stamps: comparable across CTAs; slots 60 (entry) / 61 (exit) by convention
+__device__ __forceinline__ void dbg_stamp_g(int enabled, int cta, int slot) {
+  if (enabled && cta < 148 * 2 && slot < 64) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_dbg[cta * 64 + slot] = t;
+  }
 }
 static int dbg_enabled() {
   static int v = -1;
@@ -81,16 +113,19 @@ int debug_read(unsigned long long* host, int n) {
 // ---------------------------------------------------------------------------- k_down_tc
 struct DownTcParams {
   int T, d_in, r, rp, M, NP;       // rp = r rounded to 8 (rows per modality block), NP = padded N
-  int ksplit, kblocks;             // split of the d_in reduction across CTAs; kblocks = d_in / 64
+  int ksplit, kblocks;             // split of the d_in reduction across CTAs; kblocks = d_in / (64 kbox)
+  int kbox;                        // 64-column TMA boxes per pipeline stage (1 or 2)
   int stages;
   uint32_t stage_bytes, w_bytes, tmem_cols;
   float scale;                     // pre * dropout scale
+  int dbg;
 };
 
 __global__ void __launch_bounds__(kTcThreads)
 k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_a0,
           const __grid_constant__ CUtensorMap tm_a1, const __grid_constant__ CUtensorMap tm_a2,
-          DownTcParams p, const uint8_t* __restrict__ tokmeta, float* __restrict__ h_out) {
+          DownTcParams p, const uint8_t* __restrict__ tokmeta, float* __restrict__ h_out0,
+          float* __restrict__ h_out1) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.stages * p.stage_bytes);
@@ -102,13 +137,15 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x / p.ksplit, split = blockIdx.x % p.ksplit;
   const int t0 = tile * 128;
+  if (threadIdx.x == 0) { dbg_stamp_g(p.dbg, blockIdx.x, 60); dbg_stamp(p.dbg, blockIdx.x, 0); }
   const int kb0 = (int)((long long)split * p.kblocks / p.ksplit);
   const int kb1 = (int)((long long)(split + 1) * p.kblocks / p.ksplit);
 
   // rows of the weight tiles that TMA never writes (padding between modality blocks) must be 0
+  const uint32_t xbytes = 16384u * (uint32_t)p.kbox;
   for (int s = 0; s < p.stages; ++s) {
-    uint4* w = reinterpret_cast<uint4*>(ring + (size_t)s * p.stage_bytes + 16384);
-    for (uint32_t i = threadIdx.x; i < p.w_bytes / 16; i += kTcThreads) w[i] = make_uint4(0, 0, 0, 0);
+    uint4* w = reinterpret_cast<uint4*>(ring + (size_t)s * p.stage_bytes + xbytes);
+    for (uint32_t i = threadIdx.x; i < p.w_bytes * p.kbox / 16; i += kTcThreads) w[i] = make_uint4(0, 0, 0, 0);
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
@@ -122,21 +159,29 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) dbg_stamp(p.dbg, blockIdx.x, 1);
+  // x may come straight from the kernel launched before this one: wait, then let k_up_tc start
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
+  if (threadIdx.x == 0) dbg_stamp(p.dbg, blockIdx.x, 2);
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t tx = 16384u + (uint32_t)p.M * (uint32_t)p.r * 128u;
+      const uint32_t tx = (16384u + (uint32_t)p.M * (uint32_t)p.r * 128u) * (uint32_t)p.kbox;
       for (int kb = kb0; kb < kb1; ++kb) {
         const int it = kb - kb0, s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         ptx::mbar_wait_or_trap(&empty[s], ph ^ 1u);
         uint8_t* xs = ring + (size_t)s * p.stage_bytes;
-        uint8_t* ws = xs + 16384;
         ptx::mbar_arrive_expect_tx(&full[s], tx);
-        ptx::tma_load_2d(xs, &tm_x, &full[s], kb * 64, t0, ptx::kEvictFirst);
-        ptx::tma_load_2d(ws, &tm_a0, &full[s], kb * 64, 0, ptx::kEvictLast);
-        if (p.M > 1) ptx::tma_load_2d(ws + (size_t)p.rp * 128, &tm_a1, &full[s], kb * 64, 0, ptx::kEvictLast);
-        if (p.M > 2) ptx::tma_load_2d(ws + (size_t)2 * p.rp * 128, &tm_a2, &full[s], kb * 64, 0, ptx::kEvictLast);
+        for (int bx = 0; bx < p.kbox; ++bx) {
+          const int col = (kb * p.kbox + bx) * 64;
+          uint8_t* ws = xs + xbytes + (size_t)bx * p.w_bytes;
+          ptx::tma_load_2d(xs + (size_t)bx * 16384, &tm_x, &full[s], col, t0, ptx::kEvictFirst);
+          ptx::tma_load_2d(ws, &tm_a0, &full[s], col, 0, ptx::kEvictLast);
+          if (p.M > 1) ptx::tma_load_2d(ws + (size_t)p.rp * 128, &tm_a1, &full[s], col, 0, ptx::kEvictLast);
+          if (p.M > 2) ptx::tma_load_2d(ws + (size_t)2 * p.rp * 128, &tm_a2, &full[s], col, 0, ptx::kEvictLast);
+        }
       }
     }
   } else if (warp == 1) {
@@ -149,20 +194,25 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         const int it = kb - kb0, s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         ptx::mbar_wait_or_trap(&full[s], ph);
+        if (it == 0) dbg_stamp(p.dbg, blockIdx.x, 3);
         ptx::tc_fence_after_sync();
-        const uint32_t xa = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
-        const uint32_t wa = xa + 16384u;
+        const uint32_t xa0 = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
+        for (int bx = 0; bx < p.kbox; ++bx) {
+          const uint32_t xa = xa0 + (uint32_t)bx * 16384u;
+          const uint32_t wa = xa0 + xbytes + (uint32_t)bx * p.w_bytes;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint64_t adesc = ptx::smem_desc_sw128(xa + k * 32, 1024, 0);
-          for (int part = 0; part < nparts; ++part) {
-            const uint64_t bdesc = ptx::smem_desc_sw128(wa + (uint32_t)part * npart * 128u + k * 32, 1024, 0);
-            ptx::umma_bf16(tmem_base + (uint32_t)part * npart, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t adesc = ptx::smem_desc_sw128(xa + k * 32, 1024, 0);
+            for (int part = 0; part < nparts; ++part) {
+              const uint64_t bdesc = ptx::smem_desc_sw128(wa + (uint32_t)part * npart * 128u + k * 32, 1024, 0);
+              ptx::umma_bf16(tmem_base + (uint32_t)part * npart, adesc, bdesc, idesc, (it > 0 || bx > 0 || k > 0) ? 1u : 0u);
+            }
           }
         }
         ptx::umma_commit(&empty[s]);
       }
       ptx::umma_commit(tmem_full);
+      dbg_stamp(p.dbg, blockIdx.x, 4);
     }
   } else {
     // ---- epilogue: thread <-> token row (TMEM lane); pick the columns of the token's modality
@@ -171,8 +221,12 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     const int t = t0 + row;
     const int code = (t < p.T) ? (tokmeta[t] & MOKA_MOD_MASK) : -1;
     ptx::mbar_wait_or_trap(tmem_full, 0);
+    if (threadIdx.x == 64) dbg_stamp(p.dbg, blockIdx.x, 5);
     ptx::tc_fence_after_sync();
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    // each split of the d_in reduction writes its own partial buffer with plain stores (the consumer,
+    // k_up_tc, adds the two): no zero-fill, no atomics, bit-reproducible
+    float* h_out = split == 0 ? h_out0 : h_out1;
     for (int m = 0; m < p.M; ++m) {
       for (int c8 = 0; c8 < p.rp; c8 += 8) {
         float v[8];
@@ -180,23 +234,23 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         ptx::tmem_ld_wait();
         if (code == m + 1) {
           float* dst = h_out + (size_t)t * p.r + c8;
-          if (p.ksplit == 1) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (c8 + i < p.r) dst[i] = v[i] * p.scale;
+          if (c8 + 8 <= p.r) {
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0] * p.scale, v[1] * p.scale, v[2] * p.scale, v[3] * p.scale);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4] * p.scale, v[5] * p.scale, v[6] * p.scale, v[7] * p.scale);
           } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              if (c8 + i < p.r) red_add_f32(dst + i, v[i] * p.scale);
+              if (c8 + i < p.r) dst[i] = v[i] * p.scale;
           }
         }
       }
     }
-    if (code == 0 && p.ksplit == 1)
+    if (code == 0)
       for (int j = 0; j < p.r; ++j) h_out[(size_t)t * p.r + j] = 0.f;
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) { dbg_stamp(p.dbg, blockIdx.x, 6); dbg_stamp_g(p.dbg, blockIdx.x, 61); }
   if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
@@ -207,39 +261,297 @@ static int check_launch_tc() {
   return MOKA_OK;
 }
 
-static int launch_down_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st) {
+// Split of the d_in reduction of k_down_tc across two CTAs (when the token tiles alone do not fill the
+// SMs).  k_up_tc must agree: with a split it reads two partial buffers.
+static int down_ksplit(const DevDesc& d, int num_sms, bool allow_partials) {
+  const int ntiles = (d.T + 127) / 128;
+  return (allow_partials && ntiles < num_sms && d.d_in / 128 >= 8) ? 2 : 1;
+}
+
+static int launch_down_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, bool allow_partials) {
   DownTcParams p;
   p.T = d.T; p.d_in = d.d_in; p.r = d.r; p.rp = round_up(d.r, 8); p.M = d.M;
   p.NP = round_up(p.M * p.rp, 16);
   if (p.NP > 256) p.NP = round_up(p.NP, 32);
-  p.kblocks = d.d_in / 64;
+  static int kbox_env = -1;
+  if (kbox_env < 0) { const char* e = getenv("MOKA_DOWN_KBOX"); kbox_env = e ? atoi(e) : 2; }
   const int ntiles = (d.T + 127) / 128;
-  p.ksplit = (ntiles * 2 <= num_sms * 2 && p.kblocks >= 8 && ntiles < num_sms) ? 2 : 1;
+  p.ksplit = down_ksplit(d, num_sms, allow_partials && a.hpart != nullptr);
   p.w_bytes = (uint32_t)p.NP * 128u;
-  p.stage_bytes = 16384u + p.w_bytes;
+  // two 64-column boxes per stage (256 contiguous bytes per token row and request: measured faster
+  // than one) as long as the ring still holds >= 4 stages
+  const size_t budget0 = (ntiles * p.ksplit <= num_sms) ? 200 * 1024 : 100 * 1024;
+  p.kbox = (kbox_env == 2 && d.d_in % 128 == 0 && budget0 / ((16384u + p.w_bytes) * 2u) >= 4) ? 2 : 1;
+  p.kblocks = d.d_in / (64 * p.kbox);
+  p.stage_bytes = (16384u + p.w_bytes) * (uint32_t)p.kbox;
   // one CTA per SM when the grid does not exceed the SM count: spend the whole shared memory on the
   // ring (tcgen05.commit frees a stage ~1.5k cycles after issue, so >= 6 stages keep HBM busy)
   const size_t budget = (ntiles * p.ksplit <= num_sms) ? 200 * 1024 : 100 * 1024;
   p.stages = (int)(budget / p.stage_bytes);
   if (p.stages > 10) p.stages = 10;
   if (p.stages < 2) p.stages = 2;
+  if ((size_t)p.stages * p.stage_bytes + 1024 + 256 > 227 * 1024) return MOKA_EUNSUPPORTED;
   p.tmem_cols = tmem_cols_for(p.NP);
   p.scale = d.pre * d.drop_scale;
+  p.dbg = dbg_enabled();
   CUtensorMap tx, ta[3];
   if (!make_tmap(&tx, a.x, (uint64_t)d.T, (uint64_t)d.d_in, 128)) return MOKA_EUNSUPPORTED;
   for (int m = 0; m < 3; ++m) {
     const void* base = a.A[m < d.M ? m : 0];
     if (!make_tmap(&ta[m], base, (uint64_t)d.r, (uint64_t)d.d_in, (uint32_t)d.r)) return MOKA_EUNSUPPORTED;
   }
-  if (p.ksplit > 1) {
-    cudaError_t e = cudaMemsetAsync(a.h_stash, 0, (size_t)d.T * d.r * sizeof(float), st);
-    if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
-  }
+  // split reduction: partials go to the forward workspace (hpart0 / hpart1), k_up_tc adds them and
+  // writes the final h into the stash; unsplit: straight into the stash
+  float* h0 = p.ksplit > 1 ? a.hpart : a.h_stash;
+  float* h1 = p.ksplit > 1 ? a.hpart + (size_t)d.T * d.r : nullptr;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 256;
   cudaError_t e = cudaFuncSetAttribute(k_down_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
-  k_down_tc<<<ntiles * p.ksplit, kTcThreads, smem, st>>>(tx, ta[0], ta[1], ta[2], p, a.tokmeta, a.h_stash);
+  e = launch_pdl(k_down_tc, dim3(ntiles * p.ksplit), dim3(kTcThreads), smem, st, tx, ta[0], ta[1], ta[2], p,
+                 a.tokmeta, h0, h1);
+  if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
   return check_launch_tc();
+}
+
+// ---------------------------------------------------------------------------- k_attn_fwd
+// Rank-r cross-modal attention of the forward, between k_down_tc and k_up_tc.  Inside k_up_tc the
+// attention sat on the critical path of every streaming CTA (measured: ~10 us of a ~36 us kernel
+// during which only the 4-slot y0 ring was in flight, and twice per tile when the columns are split
+// over two CTAs).  As its own small kernel it runs once per token on all SMs while k_up_tc - launched
+// early by programmatic dependent launch - already prefetches its y0 tiles.
+// A CTA owns 32 tokens of one sample: sums the partial h buffers of a split down-projection, writes
+// the final h, g (= h for tokens that are not queries) and the per-token log-sum-exp.  One warp per
+// query token, lane <-> key for the scores, lane <-> rank index for the weighted sum.
+__global__ void __launch_bounds__(256)
+k_attn_fwd(DevDesc d, int kcap, int gps, const uint8_t* __restrict__ tokmeta, const int32_t* __restrict__ kidx,
+           const int32_t* __restrict__ klen, const float* __restrict__ h0, const float* __restrict__ h1,
+           float* __restrict__ h_final, float* __restrict__ g_out, float* __restrict__ lse_out) {
+  constexpr int TT = 32;
+  extern __shared__ __align__(16) float sm_af[];
+  const int r = d.r, ks = r + 1;
+  float* Ks = sm_af;                                 // [kcap][r + 1]
+  float* hs = Ks + (size_t)kcap * ks + ((kcap * ks) & 1 ? 1 : 0) + 2;
+  hs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(hs) + 15) & ~uintptr_t(15));   // [TT][r]
+  float* gs = hs + TT * r;                           // [TT][r]
+  __shared__ int s_code[TT];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / gps;
+  const int s0 = (blockIdx.x % gps) * TT;
+  const int nt = min(TT, d.S - s0);
+  const size_t tbase = (size_t)b * d.S + s0;
+  const int L = min(klen[b], kcap);
+  int myq = 0;
+  if (tid < TT) {
+    const int code = (tid < nt) ? (tokmeta[tbase + tid] & MOKA_MOD_MASK) : 0;
+    s_code[tid] = code;
+    myq = code >= MOKA_MOD_VIS;
+  }
+  const int anyq = __syncthreads_or(myq) && L > 0;
+  ptx::pdl_wait();                                   // h comes from k_down_tc
+  ptx::pdl_trigger();
+  const int r4 = r >> 2;                             // r % 4 == 0 on this path
+  for (int i = tid; i < nt * r4; i += 256) {
+    float4 v = reinterpret_cast<const float4*>(h0 + tbase * r)[i];
+    if (h1) {
+      const float4 w = reinterpret_cast<const float4*>(h1 + tbase * r)[i];
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    reinterpret_cast<float4*>(hs)[i] = v;
+    reinterpret_cast<float4*>(gs)[i] = v;
+    if (h_final) reinterpret_cast<float4*>(h_final + tbase * r)[i] = v;
+  }
+  if (anyq) {
+    for (int idx = tid; idx < L * r4; idx += 256) {
+      const int k = idx / r4, j = (idx - k * r4) * 4;
+      const int pos = kidx[(size_t)b * d.Lk + k];
+      const size_t t = (size_t)b * d.S + pos;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tokmeta[t] & MOKA_KEY_VALID) {
+        v = *reinterpret_cast<const float4*>(h0 + t * r + j);
+        if (h1) {
+          const float4 w = *reinterpret_cast<const float4*>(h1 + t * r + j);
+          v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+      }
+      float* dst = Ks + k * ks + j;
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+  }
+  __syncthreads();
+  if (anyq) {
+    AttnCtx c{tokmeta, kidx, klen, h0, nullptr, Ks, nullptr, ks, kcap, nullptr};
+    for (int ti = 0; ti < TT / 8; ++ti) {
+      const int tt = warp * (TT / 8) + ti;
+      if (tt >= nt || s_code[tt] < MOKA_MOD_VIS) continue;       // warp-uniform
+      attn_token_fast<false>(d, c, L, hs + tt * r, gs + tt * r, nullptr, lane, lse_out + tbase + tt);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < nt * r4; i += 256) reinterpret_cast<float4*>(g_out + tbase * r)[i] = reinterpret_cast<float4*>(gs)[i];
+}
+
+// k_attn_fwd_split: the fast form for r <= 32.  Eight threads share one query token: thread `sub`
+// takes the keys k = sub (mod 8) with an online softmax over its share (two keys per step, h and
+// the running sum in registers, key rows read as 128-bit shared loads: row stride r + 4 floats puts
+// the eight rows a warp touches per load on disjoint banks), then the eight partial (max, sum,
+// weighted-sum) triples are merged with three xor-shuffle rounds.  32 tokens per CTA, 256 threads.
+template <int R>
+__global__ void __launch_bounds__(256)
+k_attn_fwd_split(DevDesc d, int kcap, int gps, const uint8_t* __restrict__ tokmeta, const int32_t* __restrict__ kidx,
+                 const int32_t* __restrict__ klen, const float* __restrict__ h0, const float* __restrict__ h1,
+                 float* __restrict__ h_final, float* __restrict__ g_out, float* __restrict__ lse_out) {
+  constexpr int TT = 32, SUB = 8, KS = R + 4;
+  extern __shared__ __align__(16) float sm_af[];
+  const int r = d.r;
+  float* Ks = sm_af;                                 // [kcap][KS]
+  float* hs = Ks + (size_t)kcap * KS;                // [TT][R]  (h in, g out)
+  __shared__ int s_code[TT];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / gps;
+  const int s0 = (blockIdx.x % gps) * TT;
+  const int nt = min(TT, d.S - s0);
+  const size_t tbase = (size_t)b * d.S + s0;
+  const int L = min(klen[b], kcap);
+  int myq = 0;
+  if (tid < TT) {
+    const int code = (tid < nt) ? (tokmeta[tbase + tid] & MOKA_MOD_MASK) : 0;
+    s_code[tid] = code;
+    myq = code >= MOKA_MOD_VIS;
+  }
+  const int anyq = __syncthreads_or(myq) && L > 0;
+  // key positions / validity do not depend on the previous kernel: look them up before the wait
+  constexpr int R4 = R / 4;
+  const int r4 = r >> 2;
+  int kpos[2] = {-1, -1};
+  if (anyq) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int idx = tid + u * 256;
+      const int k = idx / R4;
+      if (k < L) {
+        const int pos = kidx[(size_t)b * d.Lk + k];
+        if (tokmeta[(size_t)b * d.S + pos] & MOKA_KEY_VALID) kpos[u] = pos;
+      }
+    }
+  }
+  ptx::pdl_wait();                                   // h comes from k_down_tc
+  ptx::pdl_trigger();
+  for (int i = tid; i < TT * R4; i += 256) {
+    const int tt = i / R4, j4 = i - tt * R4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tt < nt && j4 < r4) {
+      const size_t off = (tbase + tt) * r + j4 * 4;
+      v = *reinterpret_cast<const float4*>(h0 + off);
+      if (h1) {
+        const float4 w = *reinterpret_cast<const float4*>(h1 + off);
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+      }
+      if (h_final) *reinterpret_cast<float4*>(h_final + off) = v;
+    }
+    reinterpret_cast<float4*>(hs)[i] = v;
+  }
+  if (anyq) {
+    // kcap * R4 <= 512 items is guaranteed by the launcher for the first two rounds; the rest loops
+    for (int u = 0, idx = tid; idx < L * R4; idx += 256, ++u) {
+      const int k = idx / R4, j4 = idx - k * R4;
+      int pos;
+      if (u < 2) pos = kpos[u];
+      else {
+        pos = kidx[(size_t)b * d.Lk + k];
+        if (!(tokmeta[(size_t)b * d.S + pos] & MOKA_KEY_VALID)) pos = -1;
+      }
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pos >= 0 && j4 < r4) {
+        const size_t off = ((size_t)b * d.S + pos) * r + j4 * 4;
+        v = *reinterpret_cast<const float4*>(h0 + off);
+        if (h1) {
+          const float4 w = *reinterpret_cast<const float4*>(h1 + off);
+          v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+      }
+      *reinterpret_cast<float4*>(Ks + k * KS + j4 * 4) = v;
+    }
+  }
+  __syncthreads();
+  if (anyq) {
+    const int tt = warp * 4 + (lane >> 3), sub = lane & 7;
+    const bool isq = tt < nt && s_code[tt] >= MOKA_MOD_VIS;
+    const int Lq = isq ? L : 0;
+    float h[R], acc[R];
+#pragma unroll
+    for (int j = 0; j < R; j += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(hs + tt * R + j);
+      h[j] = v.x; h[j + 1] = v.y; h[j + 2] = v.z; h[j + 3] = v.w;
+      acc[j] = acc[j + 1] = acc[j + 2] = acc[j + 3] = 0.f;
+    }
+    const float sl = d.sm_scale * kLog2e;
+    float m = -INFINITY, l = 0.f;
+    const uint32_t ks_addr = static_cast<uint32_t>(__cvta_generic_to_shared(Ks));
+    for (int k0 = sub; k0 < Lq; k0 += 2 * SUB) {
+      const int k1 = k0 + SUB;
+      const bool has1 = k1 < Lq;
+      float kv0[R], kv1[R];
+#pragma unroll
+      for (int j = 0; j < R; j += 4) {
+        float4 a, c2;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(ks_addr + (uint32_t)(k0 * KS + j) * 4u));
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(c2.x), "=f"(c2.y), "=f"(c2.z), "=f"(c2.w)
+                     : "r"(ks_addr + (uint32_t)((has1 ? k1 : k0) * KS + j) * 4u));
+        kv0[j] = a.x; kv0[j + 1] = a.y; kv0[j + 2] = a.z; kv0[j + 3] = a.w;
+        kv1[j] = c2.x; kv1[j + 1] = c2.y; kv1[j + 2] = c2.z; kv1[j + 3] = c2.w;
+      }
+      float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < R; j += 2) {
+        a0 = fmaf(h[j], kv0[j], a0); a1 = fmaf(h[j + 1], kv0[j + 1], a1);
+        b0 = fmaf(h[j], kv1[j], b0); b1 = fmaf(h[j + 1], kv1[j + 1], b1);
+      }
+      const float sc0 = (a0 + a1) * sl;
+      const float sc1 = has1 ? (b0 + b1) * sl : -INFINITY;
+      const float smax = fmaxf(sc0, sc1);
+      if (smax > m) {
+        const float corr = exp2f(m - smax);
+        l *= corr;
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[j] *= corr;
+        m = smax;
+      }
+      const float e0 = exp2f(sc0 - m), e1 = exp2f(sc1 - m);
+      l += e0 + e1;
+#pragma unroll
+      for (int j = 0; j < R; ++j) acc[j] = fmaf(e0, kv0[j], fmaf(e1, kv1[j], acc[j]));
+    }
+    // merge the eight partials of a token (lanes differing in bits 0..2)
+#pragma unroll
+    for (int bit = 1; bit < SUB; bit <<= 1) {
+      const float mo = __shfl_xor_sync(0xffffffffu, m, bit);
+      const float lo = __shfl_xor_sync(0xffffffffu, l, bit);
+      const float mn = fmaxf(m, mo);
+      const float ca = (m == -INFINITY) ? 0.f : exp2f(m - mn);
+      const float cb = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
+      l = l * ca + lo * cb;
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const float ao = __shfl_xor_sync(0xffffffffu, acc[j], bit);
+        acc[j] = acc[j] * ca + ao * cb;
+      }
+      m = mn;
+    }
+    if (isq && sub == 0) {
+      const float sc = d.attn_w / l;
+      lse_out[tbase + tt] = m + log2f(l);
+#pragma unroll
+      for (int j = 0; j < R; ++j) hs[tt * R + j] = fmaf(sc, acc[j], h[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < TT * R4; i += 256) {
+    const int tt = i / R4, j4 = i - tt * R4;
+    if (tt < nt && j4 < r4)
+      *reinterpret_cast<float4*>(g_out + (tbase + tt) * r + j4 * 4) = reinterpret_cast<const float4*>(hs)[i];
+  }
 }
 
 // ---------------------------------------------------------------------------- k_up_tc
@@ -253,6 +565,7 @@ struct UpTcParams {
   int nsplit, chunks;              // chunks = d_out / 128, split across nsplit CTAs per token tile
   int ystages, kcap;
   int write_g;
+  int attn_in_kernel;              // 0: g rows come precomputed from k_attn_fwd (h_in0 = g)
   int dbg;
 };
 
@@ -300,8 +613,10 @@ constexpr int kUpThreads = 352;        // warps 2..9: two worker groups (even / 
 __global__ void __launch_bounds__(kUpThreads)
 k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUtensorMap tm_y, DevDesc d,
         UpTcParams p, const __nv_bfloat16* __restrict__ Bw, const uint8_t* __restrict__ tokmeta,
-        const int32_t* __restrict__ kidx, const int32_t* __restrict__ klen, const float* __restrict__ h_stash,
-        float* __restrict__ g_out) {
+        const int32_t* __restrict__ kidx, const int32_t* __restrict__ klen, const float* __restrict__ h_in0,
+        const float* __restrict__ h_in1, float* __restrict__ h_final, float* __restrict__ g_out) {
+  // h_in0 (+ h_in1 when k_down_tc split its reduction) = pre-attention rows; h_final: where the summed
+  // rows are written for the backward (null when h_in0 already is the stash)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int kblocks = (p.rk + 63) / 64;                       // 64-wide K blocks of the operand tiles
@@ -329,6 +644,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
   const int c_beg = (int)((long long)split * p.chunks / p.nsplit);
   const int c_end = (int)((long long)(split + 1) * p.chunks / p.nsplit);
   const int nch = c_end - c_beg;
+  if (threadIdx.x == 0) dbg_stamp_g(p.dbg, blockIdx.x, 60);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.ystages; ++s) {
@@ -419,8 +735,8 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
     const int row = q * 32 + lane;                   // token row handled in the epilogue
     const int r = d.r;
     const SyncGroup grp{wt, 2 * kWorkers, 1, or_slot};
-    AttnCtx c{tokmeta, kidx, klen, h_stash, nullptr, Ks, nullptr, r + 1, p.kcap,
-              (p.write_g && split == 0) ? g_out + (size_t)d.T * d.r : nullptr};
+    AttnCtx c{tokmeta, kidx, klen, h_in0, nullptr, Ks, nullptr, r + 1, p.kcap,
+              (p.write_g && split == 0) ? g_out + (size_t)d.T * d.r : nullptr, h_in1};
 
     // B operand tile of a chunk: rows = 128 output columns, K = rank (bf16, 128B swizzle).
     // Split in a global-load half (issued early, results parked in registers) and a
@@ -451,17 +767,29 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
     if (grp_id < nch) load_b(grp_id, grp_id * 2);               // first two B tiles of each group, in flight early
     if (grp_id + 2 < nch) load_b(grp_id + 2, grp_id * 2 + 1);
     if (wt < 128) meta_s[wt] = (wt < nt) ? tokmeta[t0 + wt] : 0;
-    for (int i2 = wt; i2 < 128 * r; i2 += 2 * kWorkers)
-      gs[i2] = (i2 < nt * r) ? h_stash[(size_t)t0 * r + i2] : 0.f;
+    ptx::pdl_wait();                                             // h comes from k_down_tc
+    ptx::pdl_trigger();
+    if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 6);
+    for (int i2 = wt; i2 < 128 * r; i2 += 2 * kWorkers) {
+      float v = 0.f;
+      if (i2 < nt * r) {
+        v = h_in0[(size_t)t0 * r + i2];
+        if (h_in1) v += h_in1[(size_t)t0 * r + i2];
+        if (h_final && split == 0) h_final[(size_t)t0 * r + i2] = v;
+      }
+      gs[i2] = v;
+    }
     grp.sync();
     if (grp_id < nch) store_b(grp_id * 2);
     if (grp_id + 2 < nch) store_b(grp_id * 2 + 1);
     if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 1);
-    attention_tile<false, 32>(d, c, grp, t0, nt, meta_s, gs, gs, nullptr);
-    grp.sync();
+    if (p.attn_in_kernel) {
+      attention_tile<false, 32>(d, c, grp, t0, nt, meta_s, gs, gs, nullptr);
+      grp.sync();
+      if (p.write_g && split == 0)
+        for (int i2 = wt; i2 < nt * r; i2 += 2 * kWorkers) g_out[(size_t)t0 * r + i2] = gs[i2];
+    }
     if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 2);
-    if (p.write_g && split == 0)
-      for (int i2 = wt; i2 < nt * r; i2 += 2 * kWorkers) g_out[(size_t)t0 * r + i2] = gs[i2];
     // A operand tile: post_m * g, bf16, rows = tokens
     for (int kb = 0; kb < kblocks; ++kb) {
       const int kw = min(64, p.rk - kb * 64);
@@ -511,10 +839,11 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) { dbg_stamp(p.dbg, blockIdx.x, 5); dbg_stamp_g(p.dbg, blockIdx.x, 61); }
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st) {
+static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, bool partials) {
   UpTcParams p;
   p.T = d.T; p.d_out = d.d_out; p.r = d.r; p.rk = round_up(d.r, 16);
   p.chunks = d.d_out / 128;
@@ -523,6 +852,14 @@ static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaSt
   while (ntiles * p.nsplit * 2 <= num_sms + num_sms / 4 && p.chunks / (p.nsplit * 2) >= 4) p.nsplit *= 2;
   const int kblocks = (p.rk + 63) / 64;
   p.kcap = min(max(a.klen_hint, 1), 32 * kKeyBlocksMax);
+  // attention as its own kernel (k_attn_fwd) whenever the sample's keys fit its shared memory
+  const size_t attn_smem = ((size_t)p.kcap * (d.r + 1) + 8 + 2 * 32 * d.r) * 4 + 32;
+  static int sep_env = -1;
+  if (sep_env < 0) { const char* e = getenv("MOKA_ATTN_IN_UP"); sep_env = (e && e[0] == '1') ? 0 : 1; }
+  const bool sep_attn = sep_env && a.klen_hint <= 32 * kKeyBlocksMax && attn_smem <= 160 * 1024 && d.r % 4 == 0;
+  p.attn_in_kernel = sep_attn ? 0 : 1;
+  if (sep_attn) p.kcap = 1;
+  const int attn_kcap = min(max(a.klen_hint, 1), 32 * kKeyBlocksMax);
   const size_t fixed = (size_t)5 * kblocks * 16384 + (size_t)128 * d.r * 4 + 1024 + 512;
   const size_t limit = 224 * 1024;
   while (p.kcap > 1 && fixed + (size_t)p.kcap * (d.r + 1) * 4 + 2 * 32768 > limit) p.kcap /= 2;
@@ -538,9 +875,41 @@ static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaSt
   const size_t smem = (size_t)p.ystages * 32768 + fixed + key_bytes;
   cudaError_t e = cudaFuncSetAttribute(k_up_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
-  k_up_tc<<<ntiles * p.nsplit, kUpThreads, smem, st>>>(ty0, ty, d, p, static_cast<const __nv_bfloat16*>(a.Bw),
-                                                        a.tokmeta, a.kidx, a.klen, a.h_stash,
-                                                        a.h_stash + (size_t)d.T * d.r);
+  const float* h0 = partials ? a.hpart : a.h_stash;
+  const float* h1 = partials ? a.hpart + (size_t)d.T * d.r : nullptr;
+  float* g_stash = a.h_stash + (size_t)d.T * d.r;
+  if (sep_attn) {
+    if (!(d.dbg_skip & 64)) {
+      if (attn_smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem);
+        if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+      }
+      const int gps = (d.S + 31) / 32;
+      float* hfin = partials ? a.h_stash : (float*)nullptr;
+      float* lse = g_stash + (size_t)d.T * d.r;
+      if (d.r <= 32) {
+        const int R = d.r <= 8 ? 8 : (d.r <= 16 ? 16 : 32);
+        const size_t sm2 = ((size_t)attn_kcap * (R + 4) + 32 * R) * 4;
+        if (R == 8) e = launch_pdl(k_attn_fwd_split<8>, dim3(d.B * gps), dim3(256), sm2, st, d, attn_kcap, gps, a.tokmeta, a.kidx, a.klen, h0, h1, hfin, g_stash, lse);
+        else if (R == 16) e = launch_pdl(k_attn_fwd_split<16>, dim3(d.B * gps), dim3(256), sm2, st, d, attn_kcap, gps, a.tokmeta, a.kidx, a.klen, h0, h1, hfin, g_stash, lse);
+        else e = launch_pdl(k_attn_fwd_split<32>, dim3(d.B * gps), dim3(256), sm2, st, d, attn_kcap, gps, a.tokmeta, a.kidx, a.klen, h0, h1, hfin, g_stash, lse);
+      } else
+      e = launch_pdl(k_attn_fwd, dim3(d.B * gps), dim3(256), attn_smem, st, d, attn_kcap, gps, a.tokmeta, a.kidx, a.klen,
+                     h0, h1, hfin, g_stash, lse);
+      if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+      if (int rc = check_launch_tc()) return rc;
+    }
+    if (d.dbg_skip & 2) return MOKA_OK;
+    e = launch_pdl(k_up_tc, dim3(ntiles * p.nsplit), dim3(kUpThreads), smem, st, ty0, ty, d, p,
+                   static_cast<const __nv_bfloat16*>(a.Bw), a.tokmeta, a.kidx, a.klen, (const float*)g_stash,
+                   (const float*)nullptr, (float*)nullptr, g_stash);
+  } else {
+    if (d.dbg_skip & 2) return MOKA_OK;
+    e = launch_pdl(k_up_tc, dim3(ntiles * p.nsplit), dim3(kUpThreads), smem, st, ty0, ty, d, p,
+                   static_cast<const __nv_bfloat16*>(a.Bw), a.tokmeta, a.kidx, a.klen, h0, h1,
+                   partials ? a.h_stash : (float*)nullptr, g_stash);
+  }
+  if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
   return check_launch_tc();
 }
 
@@ -557,13 +926,15 @@ struct DgradTcParams {
   int stages;
   uint32_t stage_bytes, bt_bytes;  // stage = [box0 16K][box1 16K][Bt kb0][Bt kb1]
   int dbg;
+  int dg_mode;                     // 0 plain store (csplit == 1), 1 one partial buffer per split, 2 reduce into zeroed dG
   uint32_t tmem_cols, d2_col;      // D2 buffers start at column d2_col
 };
 
 __global__ void __launch_bounds__(kTcThreads)
 k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_bt, DevDesc d,
            DgradTcParams p, const uint8_t* __restrict__ tokmeta,
-           const float* __restrict__ g_stash, float* __restrict__ dG, float* __restrict__ dB) {
+           const float* __restrict__ g_stash, float* __restrict__ dG0, float* __restrict__ dG1,
+           float* __restrict__ dB) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t gt_block = (uint32_t)p.rk * 128u;            // one 64-token K block of G^T
@@ -604,7 +975,24 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int j = 0; j < np; ++j) {
+      // dy is older than this call's first kernel (k_bwd_prep waited for it): its tiles stream in
+      // right away; the B^T blocks are written by k_bwd_prep, so they follow the dependency wait
+      const int npre = min(np, p.stages);
+      for (int j = 0; j < npre; ++j) {
+        uint8_t* st = ring + (size_t)j * p.stage_bytes;
+        ptx::mbar_arrive_expect_tx(&full[j], 32768u + p.bt_bytes);
+        const int col = (p_beg + j) * 128;
+        ptx::tma_load_2d(st, &tm_dy, &full[j], col, t0, ptx::kEvictFirst);
+        ptx::tma_load_2d(st + 16384, &tm_dy, &full[j], col + 64, t0, ptx::kEvictFirst);
+      }
+      ptx::pdl_wait();
+      for (int j = 0; j < npre; ++j) {
+        uint8_t* st = ring + (size_t)j * p.stage_bytes;
+        const int col = (p_beg + j) * 128;
+        ptx::tma_load_2d(st + 32768, &tm_bt, &full[j], col, 0, ptx::kEvictLast);
+        ptx::tma_load_2d(st + 32768 + gt_block, &tm_bt, &full[j], col + 64, 0, ptx::kEvictLast);
+      }
+      for (int j = npre; j < np; ++j) {
         const int s = j % p.stages;
         const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
         ptx::mbar_wait_or_trap(&empty[s], ph ^ 1u);
@@ -680,6 +1068,10 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
     ptx::fence_proxy_async_smem();
     named_sync(2, kWorkers);
     if (wt == 0) ptx::mbar_arrive(&wfull[0]);                  // G^T staged: the MMA thread may start
+    // dB / dG are written below: everything older than k_bwd_prep (zero-fills, earlier calls that
+    // shared the workspace) must be complete
+    ptx::pdl_wait();
+    ptx::pdl_trigger();
 
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int j = 0; j < np; ++j) {
@@ -713,14 +1105,18 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
         float v[8];
         ptx::tmem_ld8(lane_base + (uint32_t)c8, v);
         ptx::tmem_ld_wait();
-        if (c8 < r && code) {
-          float* dst = dG + (size_t)t * r + c8;
-          if (p.csplit == 1) {
+        if (c8 < r && row < nt) {
+          if (p.dg_mode == 2) {
+            if (code) {
+              float* dst = dG0 + (size_t)t * r + c8;
+              red_add_v4_f32(dst, v[0] * ps, v[1] * ps, v[2] * ps, v[3] * ps);
+              red_add_v4_f32(dst + 4, v[4] * ps, v[5] * ps, v[6] * ps, v[7] * ps);
+            }
+          } else {
+            // plain stores (zeros for tokens in no mask): nothing has to be zero-filled beforehand
+            float* dst = (split == 0 ? dG0 : dG1) + (size_t)t * r + c8;
             *reinterpret_cast<float4*>(dst) = make_float4(v[0] * ps, v[1] * ps, v[2] * ps, v[3] * ps);
             *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4] * ps, v[5] * ps, v[6] * ps, v[7] * ps);
-          } else {
-            red_add_v4_f32(dst, v[0] * ps, v[1] * ps, v[2] * ps, v[3] * ps);
-            red_add_v4_f32(dst + 4, v[4] * ps, v[5] * ps, v[6] * ps, v[7] * ps);
           }
         }
       }
@@ -910,11 +1306,17 @@ k_attn_bwd_tile(DevDesc d, const uint8_t* __restrict__ tokmeta, const int32_t* _
   }
 }
 
-// B [d_out, r] -> B^T [rk, d_out] bf16 (rows r..rk zero): the K-major operand of dG = dY . B that
-// k_dgrad_tc TMA-loads.  64 K elements; one launch per backward call.
+// First kernel of a backward call: B [d_out, r] -> B^T [rk, d_out] bf16 (rows r..rk zero), the K-major
+// operand of dG = dY . B that k_dgrad_tc TMA-loads, plus the zero-fill of the small reduction targets
+// (per-sample dK, arrival counters).  Replaces a cudaMemsetAsync + transpose pair; being a kernel it
+// can chain with programmatic dependent launch.
 __global__ void __launch_bounds__(256)
-k_transpose_b(const __nv_bfloat16* __restrict__ Bw, __nv_bfloat16* __restrict__ Bt, int d_out, int r, int rk) {
+k_bwd_prep(const __nv_bfloat16* __restrict__ Bw, __nv_bfloat16* __restrict__ Bt, int d_out, int r, int rk,
+           uint32_t* __restrict__ zero_ptr, int zero_words) {
   __shared__ __nv_bfloat16 tile[64][136];                        // 64 columns x up to 128 ranks (+pad)
+  ptx::pdl_wait();                                               // B (optimizer), workspace (earlier calls)
+  ptx::pdl_trigger();
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < zero_words; i += gridDim.x * 256) zero_ptr[i] = 0u;
   const int c0 = blockIdx.x * 64;
   for (int idx = threadIdx.x; idx < 64 * r; idx += 256) {
     const int c = idx / r, j = idx - c * r;
@@ -927,12 +1329,15 @@ k_transpose_b(const __nv_bfloat16* __restrict__ Bw, __nv_bfloat16* __restrict__ 
   }
 }
 
-static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st) {
+// fused = the merged attention-backward + pack kernel follows (partial dG buffers, nothing zero-filled
+// but dK and the counters); otherwise the legacy kernels run on a complete dG in a.dh.
+static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, bool fused) {
   DgradTcParams p;
   p.T = d.T; p.d_out = d.d_out; p.r = d.r; p.rk = round_up(d.r, 16);
   p.pairs = d.d_out / 128;
   const int ntiles = (d.T + 127) / 128;
   p.csplit = (ntiles < num_sms && ntiles * 2 <= num_sms + num_sms / 4 && p.pairs >= 8) ? 2 : 1;
+  p.dg_mode = p.csplit == 1 ? 0 : (fused ? 1 : 2);
   p.bt_bytes = 2u * (uint32_t)p.rk * 128u;
   p.stage_bytes = 32768u + p.bt_bytes;
   const size_t fixed = (size_t)4 * p.rk * 128 + 1024 + 512;
@@ -940,24 +1345,35 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   p.stages = (int)((limit - fixed) / p.stage_bytes);
   if (p.stages > 5) p.stages = 5;
   if (p.stages < 2) return MOKA_EUNSUPPORTED;
+  p.dbg = dbg_enabled();
   const uint32_t dgc = tmem_cols_for(p.rk);
   p.d2_col = dgc;
   p.tmem_cols = tmem_cols_for((int)dgc + 2 * p.rk);
-  // pre-transposed B in the (otherwise unused until k_pack_dh) packed-operand workspace
+  // pre-transposed B in the (otherwise unused until the pack step) packed-operand workspace
   __nv_bfloat16* Bt = static_cast<__nv_bfloat16*>(a.pack);
-  k_transpose_b<<<(d.d_out + 63) / 64, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(a.Bw), Bt, d.d_out, d.r, p.rk);
-  if (int rc = check_launch_tc()) return rc;
   CUtensorMap tdy, tbt;
   if (!make_tmap(&tdy, a.dy, (uint64_t)d.T, (uint64_t)d.d_out, 128)) return MOKA_EUNSUPPORTED;
   if (!make_tmap(&tbt, Bt, (uint64_t)p.rk, (uint64_t)d.d_out, (uint32_t)p.rk)) return MOKA_EUNSUPPORTED;
-  // dG lives in the dh workspace (zeroed by moka_backward: two CTAs may reduce into it)
   const size_t smem = (size_t)p.stages * p.stage_bytes + fixed;
   cudaError_t e = cudaFuncSetAttribute(k_dgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
-  k_dgrad_tc<<<ntiles * p.csplit, kTcThreads, smem, st>>>(tdy, tbt, d, p, a.tokmeta, a.h_stash + (size_t)d.T * d.r,
-                                                           a.dh, a.dB);
-  if (int rc = check_launch_tc()) return rc;
-  // attention backward on the small [T, r] tensors
+  if (!(d.dbg_skip & 4)) {
+    // fused: dK [B, Lk, r] and the counters [B] sit next to each other in the workspace
+    uint32_t* zp = fused ? reinterpret_cast<uint32_t*>(a.dK) : nullptr;
+    const int zw = fused ? (int)((reinterpret_cast<char*>(a.counters) - reinterpret_cast<char*>(a.dK)) / 4) + d.B : 0;
+    e = launch_pdl(k_bwd_prep, dim3((d.d_out + 63) / 64), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(a.Bw), Bt,
+                   d.d_out, d.r, p.rk, zp, zw);
+    if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+    if (int rc = check_launch_tc()) return rc;
+  }
+  if (!(d.dbg_skip & 8)) {
+    e = launch_pdl(k_dgrad_tc, dim3(ntiles * p.csplit), dim3(kTcThreads), smem, st, tdy, tbt, d, p, a.tokmeta,
+                   a.h_stash + (size_t)d.T * d.r, a.dh, a.dh_att, a.dB);
+    if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+    if (int rc = check_launch_tc()) return rc;
+  }
+  if (fused) return MOKA_OK;
+  // legacy: attention backward on the small [T, r] tensors, in place in a.dh
   if (d.r <= 32 && a.klen_hint <= 128 && (d.r <= 16 || a.klen_hint <= 64)) {
     const int kblocks = (max(a.klen_hint, 1) + 31) / 32;
     const int gps = (d.S + 31) / 32;
@@ -1106,6 +1522,273 @@ k_pack_dh(DevDesc d, int rp, int NPW, int KP, const uint8_t* __restrict__ tokmet
   }
 }
 
+// ---------------------------------------------------------------------------- k_attn_pack
+// Attention backward + operand packing in one kernel (r <= 32, <= 128 keys per sample).
+// A CTA owns 64 consecutive tokens of one sample (16 warps x 4 tokens):
+//   1. dG rows (the two partial buffers of k_dgrad_tc summed) -> shared memory; for tiles with query
+//      tokens the attention backward of k_attn_bwd_tile runs on them in place (dh), the per-sample dK
+//      sums leave through one reduction per element per CTA;
+//   2. tiles WITHOUT key tokens are packed straight from shared memory into the bf16 operands of
+//      k_wgrad_tc (dHc, dHcT hi/lo) - dh never goes back to HBM as fp32;
+//   3. tiles WITH key tokens need the finished dK of their sample: they park their dh rows in the dG
+//      buffer, every CTA bumps the sample's arrival counter, and the CTA that arrives last packs the
+//      parked tiles with dK folded onto the key rows (threadfence + counter: the classic last-block
+//      pattern, no second launch and no grid-wide barrier).
+struct AttnPackParams {
+  int rp, NPW, KP, bps;             // bps = 64-token blocks per sample
+  float scale;
+};
+
+template <int R>
+__device__ __forceinline__ void pack_rows64(const DevDesc& d, const AttnPackParams& p, const float* __restrict__ vs,
+                                            const int* __restrict__ s_base, size_t tbase, int nt,
+                                            __nv_bfloat16* __restrict__ hc, __nv_bfloat16* __restrict__ hct_hi,
+                                            __nv_bfloat16* __restrict__ hct_lo, int tid, int nthr) {
+  constexpr int VS = R + 1;
+  const int r = d.r;
+  const int cpr = p.KP / 8;
+  for (int i = tid; i < nt * cpr; i += nthr) {
+    const int tt = i / cpr, n0 = (i - tt * cpr) * 8;
+    const int base = s_base[tt];
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = n0 + e - base;
+      v[e] = (base >= 0 && j >= 0 && j < r) ? vs[tt * VS + j] * p.scale : 0.f;
+    }
+    uint4 o;
+    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+    *reinterpret_cast<uint4*>(hc + (tbase + tt) * p.KP + n0) = o;
+  }
+  const int tch = (nt + 7) / 8;                     // S % 8 == 0: 8-token chunks never straddle a sample
+  for (int i = tid; i < p.NPW * tch; i += nthr) {
+    const int n = i / tch, c = i - n * tch;
+    float hi[8], lo[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int tt = c * 8 + e;
+      const int base = (tt < nt) ? s_base[tt] : -1;
+      const int j = n - base;
+      const float v = (base >= 0 && j >= 0 && j < r) ? vs[tt * VS + j] * p.scale : 0.f;
+      hi[e] = __bfloat162float(__float2bfloat16_rn(v));
+      lo[e] = v - hi[e];
+    }
+    uint4 o;
+    o.x = pack_bf16(hi[0], hi[1]); o.y = pack_bf16(hi[2], hi[3]); o.z = pack_bf16(hi[4], hi[5]); o.w = pack_bf16(hi[6], hi[7]);
+    *reinterpret_cast<uint4*>(hct_hi + (size_t)n * d.T + tbase + c * 8) = o;
+    o.x = pack_bf16(lo[0], lo[1]); o.y = pack_bf16(lo[2], lo[3]); o.z = pack_bf16(lo[4], lo[5]); o.w = pack_bf16(lo[6], lo[7]);
+    *reinterpret_cast<uint4*>(hct_lo + (size_t)n * d.T + tbase + c * 8) = o;
+  }
+}
+
+template <int R, int KB, int NT>
+__global__ void __launch_bounds__(NT)
+k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, const int32_t* __restrict__ kidx,
+            const int32_t* __restrict__ klen, const float* __restrict__ h_stash, float* __restrict__ dG0,
+            const float* __restrict__ dG1, float* __restrict__ dK_glob, int* __restrict__ counters,
+            __nv_bfloat16* __restrict__ hc, __nv_bfloat16* __restrict__ hct_hi, __nv_bfloat16* __restrict__ hct_lo) {
+  constexpr int TT = 64;
+  constexpr int TPW = TT / (NT / 32);               // tokens per warp
+  constexpr int RS = R + 1;                         // odd row stride: lane <-> key reads are conflict-free
+  extern __shared__ __align__(16) float sm[];
+  const int r = d.r;
+  float* Ks = sm;                                   // [KB*32][RS]   (zero rows for invalid keys)
+  float* dKs = Ks + KB * 32 * RS;                   // [KB*32][RS]
+  float* hs = dKs + KB * 32 * RS;                   // [TT][R]
+  float* gs = hs + TT * R;
+  float* dgs = gs + TT * R;                         // dG rows in, dh rows out
+  float* vs = dgs + TT * R;                         // [TT][RS] staging of the pack step
+  __shared__ int s_code[TT];
+  __shared__ int s_base[TT];
+  __shared__ float s_lse[TT];
+  __shared__ uint32_t s_blkmask[32];
+  __shared__ int s_last;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / p.bps;
+  const int s0 = (blockIdx.x % p.bps) * TT;
+  const int nt = min(TT, d.S - s0);
+  const size_t tbase = (size_t)b * d.S + s0;
+  const float* g_stash = h_stash + (size_t)d.T * r;
+  const float* lse = g_stash + (size_t)d.T * r;
+  const int L = klen[b];
+  int myq = 0, mykey = 0;
+  if (tid < TT) {
+    const uint8_t mb = (tid < nt) ? tokmeta[tbase + tid] : (uint8_t)0;
+    const int code = mb & MOKA_MOD_MASK;
+    s_code[tid] = code;
+    s_base[tid] = code ? (code - 1) * p.rp : -1;
+    s_lse[tid] = (code >= MOKA_MOD_VIS) ? lse[tbase + tid] : 0.f;
+    myq = code >= MOKA_MOD_VIS;
+    mykey = (mb & MOKA_KEY_VALID) && code;
+  }
+  const int anyq = __syncthreads_or(myq) && L > 0;
+  const int anykey = __syncthreads_or(mykey);
+  if (anyq) {
+    // h, g rows and the sample's keys come from the forward: older than this call
+    for (int i = tid; i < TT * R; i += NT) {
+      const int tt = i / R, j = i - tt * R;
+      const bool ok = tt < nt && j < r;
+      hs[i] = ok ? h_stash[(tbase + tt) * r + j] : 0.f;
+      gs[i] = ok ? g_stash[(tbase + tt) * r + j] : 0.f;
+    }
+    for (int k = tid; k < KB * 32; k += NT) {
+      bool valid = false;
+      size_t tk = 0;
+      if (k < L) {
+        const int pos = kidx[(size_t)b * d.Lk + k];
+        tk = (size_t)b * d.S + pos;
+        valid = (tokmeta[tk] & MOKA_KEY_VALID) != 0;
+      }
+      for (int j = 0; j < R; ++j) {
+        Ks[k * RS + j] = (valid && j < r) ? h_stash[tk * r + j] : 0.f;
+        dKs[k * RS + j] = 0.f;
+      }
+    }
+  }
+  ptx::pdl_wait();                                  // dG from k_dgrad_tc, zeroed dK / counters from k_bwd_prep
+  ptx::pdl_trigger();
+  for (int i = tid; i < TT * R; i += NT) {
+    const int tt = i / R, j = i - tt * R;
+    float v = 0.f;
+    if (tt < nt && j < r) {
+      v = dG0[(tbase + tt) * r + j];
+      if (dG1) v += dG1[(tbase + tt) * r + j];
+    }
+    dgs[i] = v;
+  }
+  __syncthreads();
+  if (anyq) {
+    const float sl = d.sm_scale * kLog2e;
+    float dKacc[KB][R];
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+      for (int j = 0; j < R; ++j) dKacc[kb][j] = 0.f;
+    const int comp = (R == 32) ? lane : (R == 16 ? (lane >> 1) : (lane >> 2));
+    const bool writer = (R == 32) || (R == 16 && !(lane & 1)) || (R == 8 && !(lane & 3));
+    bool any_tok = false;
+    for (int ti = 0; ti < TPW; ++ti) {
+      const int tt = warp * TPW + ti;
+      if (s_code[tt] < MOKA_MOD_VIS) continue;        // warp-uniform
+      any_tok = true;
+      float hq[R], dg[R];
+      float Dsum = 0.f;
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        hq[j] = hs[tt * R + j];
+        dg[j] = dgs[tt * R + j];
+        Dsum = fmaf(dg[j], gs[tt * R + j] - hq[j], Dsum);
+      }
+      const float lse_t = s_lse[tt];
+      float dh_tot = 0.f;                             // component `comp` of the dh contribution (writer lanes)
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        if (kb * 32 >= L) break;                      // uniform
+        const int k = kb * 32 + lane;
+        const float* Kr = Ks + k * RS;
+        float Kv[R];
+        float sc = 0.f, dp = 0.f;
+#pragma unroll
+        for (int j = 0; j < R; ++j) { Kv[j] = Kr[j]; sc = fmaf(hq[j], Kv[j], sc); dp = fmaf(dg[j], Kv[j], dp); }
+        const float pr = (k < L) ? exp2f(sc * sl - lse_t) : 0.f;
+        dp *= d.attn_w;
+        const float ds = pr * (dp - Dsum);
+        const float pw = pr * d.attn_w, dss = ds * d.sm_scale;
+        float part[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          dKacc[kb][j] = fmaf(pw, dg[j], fmaf(dss, hq[j], dKacc[kb][j]));
+          part[j] = dss * Kv[j];
+        }
+#pragma unroll
+        for (int half = R / 2, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+          const bool upper = (lane & bit) != 0;
+#pragma unroll
+          for (int i = 0; i < half; ++i) {
+            const float send = upper ? part[i] : part[i + half];
+            const float keep = upper ? part[i + half] : part[i];
+            part[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+          }
+        }
+        float tot = part[0];
+        if (R <= 16) tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+        if (R <= 8) tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+        dh_tot += tot;
+      }
+      __syncwarp();
+      if (writer && comp < r) dgs[tt * R + comp] += dh_tot;       // in place: the row belongs to this warp
+    }
+    // combine the per-warp dK partials in shared memory, then one reduction per element
+    if (any_tok) {
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        if (kb * 32 >= L) break;
+        const int k = kb * 32 + lane;
+#pragma unroll
+        for (int j = 0; j < R; ++j) atomicAdd(&dKs[k * RS + j], dKacc[kb][j]);
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < L * R; i += NT) {
+      const int k = i / R, j = i - k * R;
+      if (j < r) {
+        const float v = dKs[k * RS + j];
+        if (v != 0.f) red_add_f32(&dK_glob[((size_t)b * d.Lk + k) * r + j], v);
+      }
+    }
+  }
+  if (!anykey) {
+    for (int i = tid; i < TT * R; i += NT) { const int tt = i / R, j = i - tt * R; vs[tt * RS + j] = dgs[i]; }
+    __syncthreads();
+    pack_rows64<R>(d, p, vs, s_base, tbase, nt, hc, hct_hi, hct_lo, tid, NT);
+  } else {
+    // parked: the finisher of this sample reads these rows back (L2) once dK is complete
+    for (int i = tid; i < nt * R; i += NT) {
+      const int tt = i / R, j = i - tt * R;
+      if (j < r) dG0[(tbase + tt) * r + j] = dgs[i];
+    }
+  }
+  // ---- arrival: the last CTA of the sample packs the parked tiles
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&counters[b], 1) == p.bps - 1);
+  if (tid < 32) s_blkmask[tid] = 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = tid; i < d.S; i += NT) {
+    const uint8_t mb = tokmeta[(size_t)b * d.S + i];
+    if ((mb & MOKA_KEY_VALID) && (mb & MOKA_MOD_MASK)) atomicOr(&s_blkmask[(i >> 6) >> 5], 1u << ((i >> 6) & 31));
+  }
+  __syncthreads();
+  for (int blk = 0; blk < p.bps; ++blk) {
+    if (!((s_blkmask[blk >> 5] >> (blk & 31)) & 1u)) continue;        // uniform
+    const int q0 = blk * TT;
+    const int qn = min(TT, d.S - q0);
+    const size_t qbase = (size_t)b * d.S + q0;
+    __syncthreads();                                                  // previous round done with vs / s_base
+    if (tid < TT) {
+      const int code = (tid < qn) ? (tokmeta[qbase + tid] & MOKA_MOD_MASK) : 0;
+      s_base[tid] = code ? (code - 1) * p.rp : -1;
+    }
+    for (int i = tid; i < TT * R; i += NT) {
+      const int tt = i / R, j = i - tt * R;
+      vs[tt * RS + j] = (tt < qn && j < r) ? __ldcg(&dG0[(qbase + tt) * r + j]) : 0.f;
+    }
+    __syncthreads();
+    if (tid < qn) {
+      const uint8_t mb = tokmeta[qbase + tid];
+      if ((mb & MOKA_KEY_VALID) && (mb & MOKA_MOD_MASK)) {
+        const int slot = find_key_slot(kidx + (size_t)b * d.Lk, L, q0 + tid);
+        if (slot >= 0)
+          for (int j = 0; j < r; ++j) vs[tid * RS + j] += __ldcg(&dK_glob[((size_t)b * d.Lk + slot) * r + j]);
+      }
+    }
+    __syncthreads();
+    pack_rows64<R>(d, p, vs, s_base, qbase, qn, hc, hct_hi, hct_lo, tid, NT);
+  }
+}
+
 // ---------------------------------------------------------------------------- k_wgrad_tc
 // A CTA owns 128 columns of d_in and walks token tiles:
 //   MMA-A  dAcat[128 cols, NPW] += X^T[128 cols, 128 tok] . dHc[128 tok, NPW]   (X tile MN-major,
@@ -1195,9 +1878,26 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         if (p.M > 2) ptx::tma_load_2d(wb + (size_t)2 * p.rp * 128, &tm_a2, w_full, col0 + box * 64, 0, ptx::kEvictLast);
       }
       const uint32_t op_tx = (uint32_t)kbx * 16384u + 4u * hct_blk;
+      // x and dx are older than this call (the first kernel of the call waited for them): fill their
+      // rings before the dependency wait; the packed dh operands come from the kernel just before
+      const int npre_x = min(ntt, p.xs), npre_d = p.has_dx ? min(ntt, p.ds) : 0;
+      for (int j = 0; j < npre_x; ++j) {
+        uint8_t* xt = xring + (size_t)j * 32768;
+        ptx::mbar_arrive_expect_tx(&x_full[j], 32768u);
+        ptx::tma_load_2d(xt, &tm_x, &x_full[j], col0, (tt_beg + j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d(xt + 16384, &tm_x, &x_full[j], col0 + 64, (tt_beg + j) * 128, ptx::kEvictFirst);
+      }
+      for (int j = 0; j < npre_d; ++j) {
+        uint8_t* dt = dring + (size_t)j * 32768;
+        ptx::mbar_arrive_expect_tx(&d_full[j], 32768u);
+        ptx::tma_load_2d(dt, &tm_dx, &d_full[j], col0, (tt_beg + j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d(dt + 16384, &tm_dx, &d_full[j], col0 + 64, (tt_beg + j) * 128, ptx::kEvictFirst);
+      }
+      ptx::pdl_wait();
+      ptx::pdl_trigger();
       for (int j = 0; j < ntt; ++j) {
         const int t0 = (tt_beg + j) * 128;
-        {   // the big streams first: they have their own ring slots and must never wait on the MMAs
+        if (j >= npre_x) {   // the big streams first: they have their own ring slots and must never wait on the MMAs
           const int s = j % p.xs;
           const uint32_t ph = (uint32_t)(j / p.xs) & 1u;
           ptx::mbar_wait_or_trap(&x_empty[s], ph ^ 1u);
@@ -1206,7 +1906,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
           ptx::tma_load_2d(xt, &tm_x, &x_full[s], col0, t0, ptx::kEvictFirst);
           ptx::tma_load_2d(xt + 16384, &tm_x, &x_full[s], col0 + 64, t0, ptx::kEvictFirst);
         }
-        if (p.has_dx) {
+        if (p.has_dx && j >= npre_d) {
           const int s = j % p.ds;
           const uint32_t ph = (uint32_t)(j / p.ds) & 1u;
           ptx::mbar_wait_or_trap(&d_empty[s], ph ^ 1u);
@@ -1351,16 +2051,53 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
 }
 
 // Tensor map over a row-major bf16 matrix with an explicit box (cols multiple of 8 elements).
-static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st) {
-  if (d.T % 8) return MOKA_EUNSUPPORTED;                      // transposed operand rows must be 16-byte multiples
-  PackLayout L = pack_layout(d.T, d.r, d.M);
-  if (L.NPW > 256) return MOKA_EUNSUPPORTED;
+// Can the merged attention-backward + pack kernel (k_attn_pack) serve this call?
+static bool wgrad_plan(const DevDesc& d, bool has_dx, int num_sms, WgradTcParams& p, PackLayout& L, size_t& fixed);
+
+bool tc_backward_fused_ok(const DevDesc& d, int klen_hint, bool has_dx) {
   WgradTcParams p;
+  PackLayout L;
+  size_t fixed;
+  return d.r <= 32 && klen_hint <= 128 && (d.r <= 16 || klen_hint <= 64) && d.S % 8 == 0 && d.S <= 65536 &&
+         wgrad_plan(d, has_dx, 148, p, L, fixed);
+}
+
+static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayout& L, int dg_partials,
+                            __nv_bfloat16* hc, __nv_bfloat16* hct_hi, __nv_bfloat16* hct_lo, cudaStream_t st) {
+  AttnPackParams p;
+  p.rp = L.rp; p.NPW = L.NPW; p.KP = L.KP; p.bps = (d.S + 63) / 64;
+  p.scale = d.pre * d.drop_scale;
+  const int kblocks = (max(a.klen_hint, 1) + 31) / 32;
+  const int R = d.r <= 8 ? 8 : (d.r <= 16 ? 16 : 32);
+  const int KBs = kblocks <= 1 ? 1 : (kblocks <= 2 ? 2 : 4);
+  const size_t sm = ((size_t)2 * KBs * 32 * (R + 1) + 3 * 64 * R + 64 * (R + 1)) * 4;
+  const float* dG1 = dg_partials ? a.dh_att : nullptr;
+  cudaError_t e = cudaSuccess;
+#define MOKA_LAUNCH_ATTN_PACK(RR, KK, NN)                                                                    \
+  do {                                                                                                       \
+    if (sm > 48 * 1024)                                                                                      \
+      cudaFuncSetAttribute(k_attn_pack<RR, KK, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);    \
+    e = launch_pdl(k_attn_pack<RR, KK, NN>, dim3(d.B * p.bps), dim3(NN), sm, st, d, p, a.tokmeta, a.kidx, a.klen, \
+                   (const float*)a.h_stash, a.dh, dG1, a.dK, a.counters, hc, hct_hi, hct_lo);                  \
+  } while (0)
+  if (R == 8) { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK(8, 1, 512); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK(8, 2, 512); else MOKA_LAUNCH_ATTN_PACK(8, 4, 512); }
+  else if (R == 16) { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK(16, 1, 512); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK(16, 2, 512); else MOKA_LAUNCH_ATTN_PACK(16, 4, 512); }
+  else { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK(32, 1, 256); else MOKA_LAUNCH_ATTN_PACK(32, 2, 256); }
+#undef MOKA_LAUNCH_ATTN_PACK
+  if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+  return check_launch_tc();
+}
+
+// Shape checks and ring sizing of k_wgrad_tc (false: the kernel cannot tile this shape).
+static bool wgrad_plan(const DevDesc& d, bool has_dx, int num_sms, WgradTcParams& p, PackLayout& L, size_t& fixed) {
+  if (d.T % 8) return false;                                  // transposed operand rows must be 16-byte multiples
+  L = pack_layout(d.T, d.r, d.M);
+  if (L.NPW > 256) return false;
   p.T = d.T; p.d_in = d.d_in; p.r = d.r; p.rp = L.rp; p.M = d.M; p.NPW = L.NPW; p.KP = L.KP;
   p.ntiles = (d.T + 127) / 128;
   const int slices = d.d_in / 128;
   p.tsplit = max(1, min(p.ntiles, num_sms / slices));
-  p.has_dx = a.dx != nullptr;
+  p.has_dx = has_dx;
   p.dbg = dbg_enabled();
   p.w_box_bytes = (uint32_t)p.NPW * 128u;
   p.op_bytes = (uint32_t)(p.KP / 64) * 16384u + 4u * p.w_box_bytes;
@@ -1368,26 +2105,44 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   const size_t limit = 226 * 1024;
   // prefer two operand buffers (breaks the MMA -> reload -> MMA chain); the dx ring then gets 2 slots
   p.nop = 2;
-  size_t fixed = (size_t)2 * p.w_box_bytes + (size_t)p.nop * p.op_bytes + 1024 + 512;
+  fixed = (size_t)2 * p.w_box_bytes + (size_t)p.nop * p.op_bytes + 1024 + 512;
   if (fixed + 4 * 32768 > limit) { p.nop = 1; fixed -= p.op_bytes; }
-  if (fixed + 3 * 32768 > limit) return MOKA_EUNSUPPORTED;
+  if (fixed + 3 * 32768 > limit) return false;
   int slots = (int)((limit - fixed) / 32768);
   if (p.has_dx) {
     p.xs = 2;
     p.ds = min(3, slots - p.xs);
     if (p.ds < 2) { p.xs = 1; p.ds = slots - 1; }
-    if (p.ds < 2) return MOKA_EUNSUPPORTED;
+    if (p.ds < 2) return false;
   } else {
     p.xs = min(4, slots); p.ds = 0;
   }
+  return true;
+}
+
+static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, bool fused) {
+  WgradTcParams p;
+  PackLayout L;
+  size_t fixed;
+  if (!wgrad_plan(d, a.dx != nullptr, num_sms, p, L, fixed)) return MOKA_EUNSUPPORTED;
+  const int slices = d.d_in / 128;
   char* pk = static_cast<char*>(a.pack);
   __nv_bfloat16* hc = reinterpret_cast<__nv_bfloat16*>(pk);
   __nv_bfloat16* hct_hi = reinterpret_cast<__nv_bfloat16*>(pk + L.hc_bytes);
   __nv_bfloat16* hct_lo = reinterpret_cast<__nv_bfloat16*>(pk + L.hc_bytes + L.hct_bytes);
-  k_pack_dh<<<(d.T + 63) / 64, 256, (size_t)64 * (d.r + 1) * 4, st>>>(d, L.rp, L.NPW, L.KP, a.tokmeta, a.kidx, a.klen, a.dh,
-                                                                     a.dh_att, a.dK, hc, hct_hi, hct_lo,
-                                                                     d.pre * d.drop_scale);
-  if (int rc = check_launch_tc()) return rc;
+  if (fused) {
+    if (!(d.dbg_skip & 16)) {
+      const int ntiles128 = (d.T + 127) / 128;
+      const int csplit = (ntiles128 < num_sms && ntiles128 * 2 <= num_sms + num_sms / 4 && d.d_out / 128 >= 8) ? 2 : 1;
+      if (int rc = launch_attn_pack(d, a, L, csplit > 1, hc, hct_hi, hct_lo, st)) return rc;
+    }
+  } else {
+    k_pack_dh<<<(d.T + 63) / 64, 256, (size_t)64 * (d.r + 1) * 4, st>>>(d, L.rp, L.NPW, L.KP, a.tokmeta, a.kidx, a.klen, a.dh,
+                                                                       a.dh_att, a.dK, hc, hct_hi, hct_lo,
+                                                                       d.pre * d.drop_scale);
+    if (int rc = check_launch_tc()) return rc;
+  }
+  if (d.dbg_skip & 32) return MOKA_OK;
   CUtensorMap tx, tdx, ta[3], thc, thh, thl;
   if (!make_tmap(&tx, a.x, (uint64_t)d.T, (uint64_t)d.d_in, 128)) return MOKA_EUNSUPPORTED;
   if (!make_tmap(&tdx, p.has_dx ? a.dx : a.x, (uint64_t)d.T, (uint64_t)d.d_in, 128)) return MOKA_EUNSUPPORTED;
@@ -1399,8 +2154,9 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   const size_t smem = (size_t)(p.xs + p.ds) * 32768 + fixed;
   cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
-  k_wgrad_tc<<<slices * p.tsplit, kWgradThreads, smem, st>>>(tx, tdx, ta[0], ta[1], ta[2], thc, thh, thl, p,
-                                                           a.dA[0], a.dA[d.M > 1 ? 1 : 0], a.dA[d.M > 2 ? 2 : 0]);
+  e = launch_pdl(k_wgrad_tc, dim3(slices * p.tsplit), dim3(kWgradThreads), smem, st, tx, tdx, ta[0], ta[1], ta[2], thc,
+                 thh, thl, p, a.dA[0], a.dA[d.M > 1 ? 1 : 0], a.dA[d.M > 2 ? 2 : 0]);
+  if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
   return check_launch_tc();
 }
 
@@ -1418,21 +2174,25 @@ int tc_stage_mask(const DevDesc& d, int dtype) {
 }
 
 int tc_forward(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, int stages) {
-  if (stages & kStageDown) {
-    if (int e = launch_down_tc(d, a, num_sms, st)) return e;
+  // the split down-projection hands two partial buffers to k_up_tc: only when both stages run here
+  const bool both = (stages & kStageDown) && (stages & kStageUp) && a.hpart != nullptr;
+  if ((stages & kStageDown) && !(d.dbg_skip & 1)) {
+    if (int e = launch_down_tc(d, a, num_sms, st, both)) return e;
   }
-  if (stages & kStageUp) {
-    if (int e = launch_up_tc(d, a, num_sms, st)) return e;
+  if ((stages & kStageUp) && (d.dbg_skip & (2 | 64)) != (2 | 64)) {
+    if (int e = launch_up_tc(d, a, num_sms, st, both && down_ksplit(d, num_sms, true) > 1)) return e;
   }
   return MOKA_OK;
 }
 
-int tc_backward(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, int stages) {
+int tc_backward(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, int stages, bool fused) {
+  // fused (both stages here, k_attn_pack applicable): prep -> dgrad -> attn+pack -> wgrad, all chained
+  // with programmatic dependent launch; nothing but dK and the counters is zero-filled
   if (stages & kStageDgrad) {
-    if (int e = launch_dgrad_tc(d, a, num_sms, st)) return e;
+    if (int e = launch_dgrad_tc(d, a, num_sms, st, fused)) return e;
   }
   if (stages & kStageWgrad) {
-    if (int e = launch_wgrad_tc(d, a, num_sms, st)) return e;
+    if (int e = launch_wgrad_tc(d, a, num_sms, st, fused)) return e;
   }
   return MOKA_OK;
 }

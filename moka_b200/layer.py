@@ -99,6 +99,7 @@ class _MokaFn(torch.autograd.Function):
         Ac = [a if a.is_contiguous() else a.contiguous() for a in A]
         Bc = Bw if Bw.is_contiguous() else Bw.contiguous()
         desc = _make_desc(x2.shape, B, S, d_out, r, len(A), x.dtype, meta.Lk, sc, flags)
+        ws = _workspace(x.device, int(lib.moka_workspace_bytes(desc)))
         stream = torch.cuda.current_stream(x.device).cuda_stream
         ev = None
         if TIMING['enabled']:
@@ -108,7 +109,7 @@ class _MokaFn(torch.autograd.Function):
             code = lib.moka_forward(desc, x2.data_ptr(), y.data_ptr(), y.data_ptr(),
                                     _cabi.ptr_array([a.data_ptr() for a in Ac]), Bc.data_ptr(),
                                     meta.tokmeta.data_ptr(), meta.kidx.data_ptr(), meta.klen.data_ptr(),
-                                    h.data_ptr(), seed, offset, None, 0, stream)
+                                    h.data_ptr(), seed, offset, ws.data_ptr(), ws.numel(), stream)
         _cabi.check(code, 'moka_forward')
         if ev is not None:
             ev[1].record()

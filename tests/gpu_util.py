@@ -34,10 +34,12 @@ def abi_forward(meta: TokenMeta, x, y0, A, Bw, sc: FusedScalars, flags=0, seed=0
     src = y if inplace else y0c
     h = torch.full((2 * B * S * r + B * S,), float('nan'), dtype=torch.float32, device=x.device)
     desc = _make_desc(x2.shape, B, S, d_out, r, len(A), x.dtype, meta.Lk, sc, flags)
+    ws = torch.empty(int(lib.moka_workspace_bytes(desc)), dtype=torch.uint8, device=x.device)
     code = lib.moka_forward(desc, x2.data_ptr(), src.data_ptr(), y.data_ptr(),
                             _cabi.ptr_array([a.data_ptr() for a in A]), Bw.data_ptr(),
                             meta.tokmeta.data_ptr(), meta.kidx.data_ptr(), meta.klen.data_ptr(),
-                            h.data_ptr(), seed, offset, None, 0, torch.cuda.current_stream().cuda_stream)
+                            h.data_ptr(), seed, offset, ws.data_ptr(), ws.numel(),
+                            torch.cuda.current_stream().cuda_stream)
     _cabi.check(code, 'moka_forward')
     torch.cuda.synchronize()
     return y.view(B, S, d_out), h

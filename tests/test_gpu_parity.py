@@ -305,7 +305,7 @@ def test_full_size_properties_c2():
     y0 = torch.zeros(B, S, d, device=gu.DEV, dtype=bf)
     n0 = _cabi.launch_count()
     y1, h1 = gu.abi_forward(meta, x, y0, A, Bw, sc)
-    assert _cabi.launch_count() - n0 == 2
+    assert _cabi.launch_count() - n0 == 3          # down-projection, attention, up-projection
     y2, _ = gu.abi_forward(meta, x, y0, A, (Bw.float() * 2).to(bf), sc)
     none = ((meta.tokmeta & 7) == 0)
     assert int(none.sum()) == B * 100

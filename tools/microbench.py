@@ -21,7 +21,7 @@ except Exception:
     pass
 
 
-def run_point(variant, B, S, d_in, d_out, r, dtype, flags, iters, warmup, p=0.0, nbuf=3):
+def run_point(variant, B, S, d_in, d_out, r, dtype, flags, iters, warmup, p=0.0, nbuf=3, isolate=False):
     lib = _cabi.load()
     dev = 'cuda:0'
     M = 3 if variant == VARIANT_AVT else 2
@@ -55,7 +55,7 @@ def run_point(variant, B, S, d_in, d_out, r, dtype, flags, iters, warmup, p=0.0,
         x, y, dy, dx = bufs[i % nbuf]
         _cabi.check(lib.moka_forward(desc, x.data_ptr(), y.data_ptr(), y.data_ptr(), Ap, Bw.data_ptr(),
                                      meta.tokmeta.data_ptr(), meta.kidx.data_ptr(), meta.klen.data_ptr(),
-                                     h.data_ptr(), 1, i, None, 0, st), 'fwd')
+                                     h.data_ptr(), 1, i, ws.data_ptr(), ws.numel(), st), 'fwd')
 
     def bwd(i):
         x, y, dy, dx = bufs[i % nbuf]
@@ -76,6 +76,36 @@ def run_point(variant, B, S, d_in, d_out, r, dtype, flags, iters, warmup, p=0.0,
         e1.record()
         torch.cuda.synchronize()
         res[name] = e0.elapsed_time(e1) / iters * 1e3       # us
+    iso = {}
+    if isolate:
+        # per-kernel hot times: run the call with every other kernel of the tensor-core chain skipped
+        # (MOKA_FLAG_DBG_SKIP bits; results are garbage, timings are what we want)
+        names = ['down', 'up', 'prep', 'dgrad', 'attn_pack', 'wgrad', 'attn_fwd']
+        for k, nm in enumerate(names):
+            mask = (0x7f & ~(1 << k)) << 16
+            desc_k = _make_desc((T, d_in), B, S, d_out, r, M, dtype, meta.Lk, sc, flags | mask)
+            is_fwd = k < 2 or k == 6
+
+            def call(i, desc_k=desc_k, is_fwd=is_fwd):
+                x, y, dy, dx = bufs[i % nbuf]
+                if is_fwd:
+                    lib.moka_forward(desc_k, x.data_ptr(), y.data_ptr(), y.data_ptr(), Ap, Bw.data_ptr(),
+                                     meta.tokmeta.data_ptr(), meta.kidx.data_ptr(), meta.klen.data_ptr(),
+                                     h.data_ptr(), 1, i, ws.data_ptr(), ws.numel(), st)
+                else:
+                    lib.moka_backward(desc_k, dy.data_ptr(), x.data_ptr(), h.data_ptr(), Ap, Bw.data_ptr(),
+                                      meta.tokmeta.data_ptr(), meta.kidx.data_ptr(), meta.klen.data_ptr(),
+                                      dx.data_ptr(), dAp, dB.data_ptr(), 1, i, ws.data_ptr(), ws.numel(), st)
+            for i in range(3):
+                call(i)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(iters):
+                call(i)
+            e1.record()
+            torch.cuda.synchronize()
+            iso[nm] = round(e0.elapsed_time(e1) / iters * 1e3, 2)
     bytes_f = e * (d_in + 2 * d_out) * T
     bytes_b = e * (3 * d_in + d_out) * T
     out = dict(variant='avt' if variant == VARIANT_AVT else 'vt', T=T, d_in=d_in, d_out=d_out, r=r,
@@ -84,6 +114,8 @@ def run_point(variant, B, S, d_in, d_out, r, dtype, flags, iters, warmup, p=0.0,
                fwd_gbs=round(bytes_f / res['fwd'] / 1e3, 1), bwd_gbs=round(bytes_b / res['bwd'] / 1e3, 1),
                both_gbs=round((bytes_f + bytes_b) / res['fwd+bwd'] / 1e3, 1))
     out['frac'] = round(out['both_gbs'] / PEAK, 4)
+    if iso:
+        out['isolated_us'] = iso
     return out
 
 
@@ -99,6 +131,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--flags', type=int, default=0)
     ap.add_argument('--dropout', type=float, default=0.0)
+    ap.add_argument('--isolate', action='store_true')
     ap.add_argument('--out', default='')
     a = ap.parse_args()
     dtype = torch.bfloat16 if a.dtype == 'bf16' else torch.float32
@@ -107,7 +140,7 @@ def main():
         for d in [int(t) for t in a.dims.split(',')]:
             for r in [int(t) for t in a.ranks.split(',')]:
                 row = run_point(VARIANT_AVT if v == 'avt' else VARIANT_VT, a.B, a.S, d, d, r, dtype, a.flags,
-                                a.iters, a.warmup, a.dropout)
+                                a.iters, a.warmup, a.dropout, isolate=a.isolate)
                 print(json.dumps(row), flush=True)
                 rows.append(row)
     if a.out:
