@@ -128,6 +128,7 @@ int moka_forward(const MokaDesc* desc, const void* x, const void* y0, void* y,
   const bool force = (desc->flags & MOKA_FLAG_FORCE_TC) != 0;
   const int skip = (desc->flags >> MOKA_FLAG_DBG_SKIP_SHIFT) & 0xff;     // timing aid only
   d.dbg_skip = skip;
+  d.dbg = tc_dbg_enabled();
   if (tcs == (kStageDown | kStageUp)) {
     // both stages on the tensor-core path: one call so that they can agree on the split-reduction layout
     int e = tc_forward(d, a, num_sms(), st, tcs);
@@ -179,6 +180,7 @@ int moka_backward(const MokaDesc* desc, const void* dy, const void* x, const flo
   if ((desc->flags & MOKA_FLAG_FORCE_TC) && tcs != (kStageDgrad | kStageWgrad)) return MOKA_EUNSUPPORTED;
   const bool force = (desc->flags & MOKA_FLAG_FORCE_TC) != 0;
   d.dbg_skip = (desc->flags >> MOKA_FLAG_DBG_SKIP_SHIFT) & 0xff;          // timing aid only
+  d.dbg = tc_dbg_enabled();
   if (tcs == (kStageDgrad | kStageWgrad) && tc_backward_fused_ok(d, desc->Lk, dx != nullptr)) {
     // whole backward on the tensor-core path: four kernels chained by programmatic dependent launch,
     // the first of which zero-fills what needs it (no memset node in the chain)

@@ -26,6 +26,7 @@ struct DevDesc {            // by-value kernel argument (POD)
   int tile_tokens;          // tokens per CTA tile
   int num_tiles;
   int dbg_skip;             // MOKA_FLAG_DBG_SKIP bits (timing aid)
+  int dbg;                  // in-kernel time stamps enabled (MOKA_DEBUG_TIMING=1)
 };
 
 // ---------------------------------------------------------------------------- vectors

@@ -41,6 +41,7 @@ int launch_adamw(int64_t n, float* master, float* m, float* v, const float* grad
 int launch_rope(const void* src, void* dst, long long BS, int S, int H, int D, float theta, float sign, cudaStream_t st);
 
 int debug_read(unsigned long long* host, int n);
+int tc_dbg_enabled();
 
 // tensor-core (tcgen05 + TMA) path; returns MOKA_EUNSUPPORTED when the shape does not qualify
 // Returns the mask of stages the tcgen05 path implements for this shape (0 = none).

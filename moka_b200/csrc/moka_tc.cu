@@ -88,16 +88,17 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 // Optional in-kernel timestamps (cycle counter of the SM) for tuning: slot layout is per kernel.
 // Written only when MOKA_DEBUG_TIMING=1; read back through moka_debug_read().
-__device__ unsigned long long g_dbg[148 * 2 * 64];
+constexpr int kDbgSlots = 128;                                  // per CTA: 0..63 cycle stamps, 100.. wall-clock timeline
+__device__ unsigned long long g_dbg[148 * 2 * kDbgSlots];
 __device__ __forceinline__ void dbg_stamp(int enabled, int cta, int slot) {
-  if (enabled && cta < 148 * 2 && slot < 64) g_dbg[cta * 64 + slot] = clock64();
+  if (enabled && cta < 148 * 2 && slot < 64) g_dbg[cta * kDbgSlots + slot] = clock64();
 }
 // wall-clock (globaltimer, ns) stamps: comparable across CTAs; slots 60 (entry) / 61 (exit) by convention
 __device__ __forceinline__ void dbg_stamp_g(int enabled, int cta, int slot) {
-  if (enabled && cta < 148 * 2 && slot < 64) {
+  if (enabled && cta < 148 * 2 && slot < kDbgSlots) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_dbg[cta * 64 + slot] = t;
+    g_dbg[cta * kDbgSlots + slot] = t;
   }
 }
 static int dbg_enabled() {
@@ -105,8 +106,9 @@ static int dbg_enabled() {
   if (v < 0) { const char* e = getenv("MOKA_DEBUG_TIMING"); v = (e && e[0] == '1') ? 1 : 0; }
   return v;
 }
+int tc_dbg_enabled() { return dbg_enabled(); }
 int debug_read(unsigned long long* host, int n) {
-  if (n > 148 * 2 * 64) n = 148 * 2 * 64;
+  if (n > 148 * 2 * kDbgSlots) n = 148 * 2 * kDbgSlots;
   return cudaMemcpyFromSymbol(host, g_dbg, (size_t)n * 8) == cudaSuccess ? MOKA_OK : MOKA_ECUDA;
 }
 
@@ -137,7 +139,7 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x / p.ksplit, split = blockIdx.x % p.ksplit;
   const int t0 = tile * 128;
-  if (threadIdx.x == 0) { dbg_stamp_g(p.dbg, blockIdx.x, 60); dbg_stamp(p.dbg, blockIdx.x, 0); }
+  if (threadIdx.x == 0) { dbg_stamp_g(p.dbg, blockIdx.x, 100); dbg_stamp(p.dbg, blockIdx.x, 0); }
   const int kb0 = (int)((long long)split * p.kblocks / p.ksplit);
   const int kb1 = (int)((long long)(split + 1) * p.kblocks / p.ksplit);
 
@@ -250,7 +252,7 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (threadIdx.x == 0) { dbg_stamp(p.dbg, blockIdx.x, 6); dbg_stamp_g(p.dbg, blockIdx.x, 61); }
+  if (threadIdx.x == 0) { dbg_stamp(p.dbg, blockIdx.x, 6); dbg_stamp_g(p.dbg, blockIdx.x, 101); }
   if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
@@ -347,8 +349,8 @@ k_attn_fwd(DevDesc d, int kcap, int gps, const uint8_t* __restrict__ tokmeta, co
     myq = code >= MOKA_MOD_VIS;
   }
   const int anyq = __syncthreads_or(myq) && L > 0;
+  ptx::pdl_trigger();                                // (see k_attn_fwd_split)
   ptx::pdl_wait();                                   // h comes from k_down_tc
-  ptx::pdl_trigger();
   const int r4 = r >> 2;                             // r % 4 == 0 on this path
   for (int i = tid; i < nt * r4; i += 256) {
     float4 v = reinterpret_cast<const float4*>(h0 + tbase * r)[i];
@@ -412,6 +414,7 @@ k_attn_fwd_split(DevDesc d, int kcap, int gps, const uint8_t* __restrict__ tokme
   const int nt = min(TT, d.S - s0);
   const size_t tbase = (size_t)b * d.S + s0;
   const int L = min(klen[b], kcap);
+  if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 102);
   int myq = 0;
   if (tid < TT) {
     const int code = (tid < nt) ? (tokmeta[tbase + tid] & MOKA_MOD_MASK) : 0;
@@ -434,8 +437,10 @@ k_attn_fwd_split(DevDesc d, int kcap, int gps, const uint8_t* __restrict__ tokme
       }
     }
   }
-  ptx::pdl_wait();                                   // h comes from k_down_tc
+  // k_up_tc may start right away: before its own wait it only touches tensors older than this call
+  // (y0 tiles, B, token metadata) - and k_down_tc, which triggered after ITS wait, vouches for those
   ptx::pdl_trigger();
+  ptx::pdl_wait();                                   // h comes from k_down_tc
   for (int i = tid; i < TT * R4; i += 256) {
     const int tt = i / R4, j4 = i - tt * R4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -552,6 +557,7 @@ k_attn_fwd_split(DevDesc d, int kcap, int gps, const uint8_t* __restrict__ tokme
     if (tt < nt && j4 < r4)
       *reinterpret_cast<float4*>(g_out + (tbase + tt) * r + j4 * 4) = reinterpret_cast<const float4*>(hs)[i];
   }
+  if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 103);
 }
 
 // ---------------------------------------------------------------------------- k_up_tc
@@ -644,7 +650,10 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
   const int c_beg = (int)((long long)split * p.chunks / p.nsplit);
   const int c_end = (int)((long long)(split + 1) * p.chunks / p.nsplit);
   const int nch = c_end - c_beg;
-  if (threadIdx.x == 0) dbg_stamp_g(p.dbg, blockIdx.x, 60);
+  if (threadIdx.x == 0) dbg_stamp_g(p.dbg, blockIdx.x, 104);
+  // last kernel of the forward chain: whatever follows (the first kernel of the next libmoka call waits
+  // before it touches memory; anything else is a normal stream-ordered launch) may start its prologue now
+  if (threadIdx.x == 0) ptx::pdl_trigger();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.ystages; ++s) {
@@ -766,9 +775,54 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
     if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 0);
     if (grp_id < nch) load_b(grp_id, grp_id * 2);               // first two B tiles of each group, in flight early
     if (grp_id + 2 < nch) load_b(grp_id + 2, grp_id * 2 + 1);
+    if (!p.attn_in_kernel) {
+      // g rows come finished from k_attn_fwd: build the A operand (post_m * g, bf16) straight from global
+      // memory - every load of a thread is issued before its first use, so the prologue costs one memory
+      // round trip instead of a chain of them
+      const int cpr_t = p.rk / 8;                                // 16-byte chunks per token row
+      constexpr int kMaxItems = 4;                               // 128 * cpr_t / 256 items per thread (rk <= 64)
+      int codes[kMaxItems];
+#pragma unroll
+      for (int u = 0; u < kMaxItems; ++u) {
+        const int idx = wt + u * 2 * kWorkers;
+        const int n = idx / cpr_t;
+        codes[u] = (idx < 128 * cpr_t && n < nt) ? (tokmeta[t0 + n] & MOKA_MOD_MASK) : 0;
+      }
+      ptx::pdl_wait();                                           // g comes from k_attn_fwd
+      if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 6);
+      for (int base = 0; base < 128 * cpr_t; base += kMaxItems * 2 * kWorkers) {
+        float4 ga[kMaxItems], gb[kMaxItems];
+#pragma unroll
+        for (int u = 0; u < kMaxItems; ++u) {
+          const int idx = base + wt + u * 2 * kWorkers;
+          const int n = idx / cpr_t, k = (idx - n * cpr_t) * 8;
+          ga[u] = gb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (idx < 128 * cpr_t && n < nt) {
+            if (k < r) ga[u] = *reinterpret_cast<const float4*>(h_in0 + (size_t)(t0 + n) * r + k);
+            if (k + 4 < r) gb[u] = *reinterpret_cast<const float4*>(h_in0 + (size_t)(t0 + n) * r + k + 4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kMaxItems; ++u) {
+          const int idx = base + wt + u * 2 * kWorkers;
+          if (idx >= 128 * cpr_t) continue;
+          const int n = idx / cpr_t, chf = idx - n * cpr_t;      // chunk over the full rank
+          const int kb = chf >> 3, ch = chf & 7;
+          int code = codes[u];
+          if (base > 0) code = (n < nt) ? (tokmeta[t0 + n] & MOKA_MOD_MASK) : 0;
+          const float ps = code ? d.post[code] : 0.f;
+          uint4 v;
+          v.x = pack_bf16(ga[u].x * ps, ga[u].y * ps); v.y = pack_bf16(ga[u].z * ps, ga[u].w * ps);
+          v.z = pack_bf16(gb[u].x * ps, gb[u].y * ps); v.w = pack_bf16(gb[u].z * ps, gb[u].w * ps);
+          *reinterpret_cast<uint4*>(gtile + (size_t)kb * 16384 + ptx::sw128_offset((uint32_t)n, (uint32_t)ch)) = v;
+        }
+      }
+      if (grp_id < nch) store_b(grp_id * 2);
+      if (grp_id + 2 < nch) store_b(grp_id * 2 + 1);
+      if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 2);
+    } else {
     if (wt < 128) meta_s[wt] = (wt < nt) ? tokmeta[t0 + wt] : 0;
     ptx::pdl_wait();                                             // h comes from k_down_tc
-    ptx::pdl_trigger();
     if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 6);
     for (int i2 = wt; i2 < 128 * r; i2 += 2 * kWorkers) {
       float v = 0.f;
@@ -808,6 +862,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
         *reinterpret_cast<uint4*>(gtile + (size_t)kb * 16384 + ptx::sw128_offset((uint32_t)n, (uint32_t)ch)) = v;
       }
     }
+    }
     ptx::fence_proxy_async_smem();
     named_sync(2, 2 * kWorkers);
     if (wt == 0) ptx::mbar_arrive(g_full);
@@ -839,7 +894,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (threadIdx.x == 0) { dbg_stamp(p.dbg, blockIdx.x, 5); dbg_stamp_g(p.dbg, blockIdx.x, 61); }
+  if (threadIdx.x == 0) { dbg_stamp(p.dbg, blockIdx.x, 5); dbg_stamp_g(p.dbg, blockIdx.x, 105); }
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
@@ -927,6 +982,7 @@ struct DgradTcParams {
   uint32_t stage_bytes, bt_bytes;  // stage = [box0 16K][box1 16K][Bt kb0][Bt kb1]
   int dbg;
   int dg_mode;                     // 0 plain store (csplit == 1), 1 one partial buffer per split, 2 reduce into zeroed dG
+  int nbuf;                        // dB accumulators in TMEM (2, or 1 when rk = 128)
   uint32_t tmem_cols, d2_col;      // D2 buffers start at column d2_col
 };
 
@@ -937,9 +993,10 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
            float* __restrict__ dB) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t gt_block = (uint32_t)p.rk * 128u;            // one 64-token K block of G^T
-  uint8_t* gt = ring + (size_t)p.stages * p.stage_bytes;      // [hi/lo][2 kblocks][rk x 128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(gt + 4 * gt_block);
+  const uint32_t gt_block = (uint32_t)p.rk * 128u;            // one 64-column K block of B^T (rk rows)
+  const uint32_t g2_block = 2u * gt_block;                    // one 64-token K block of [G^T hi ; G^T lo] (2 rk rows)
+  uint8_t* gt = ring + (size_t)p.stages * p.stage_bytes;      // [2 kblocks][2 rk x 128 B]: rows 0..rk-1 hi, rk..2rk-1 lo
+  uint64_t* bars = reinterpret_cast<uint64_t*>(gt + 2 * g2_block);
   uint64_t* full = bars;                       // TMA landed            [stages]
   uint64_t* wfull = full + p.stages;           // B^T block staged      [stages]
   uint64_t* empty = wfull + p.stages;          // MMAs done with stage  [stages]
@@ -956,6 +1013,7 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
   const int p_end = (int)((long long)(split + 1) * p.pairs / p.csplit);
   const int np = p_end - p_beg;
   const int r = p.r;
+  if (threadIdx.x == 0) { dbg_stamp_g(p.dbg, blockIdx.x, 108); dbg_stamp(p.dbg, blockIdx.x, 0); }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -972,6 +1030,9 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // successors may start early: before their waits they only read the forward's stash, the token
+  // metadata, x / dx and the adapter weights - all older than k_bwd_prep, which triggered after its wait
+  if (threadIdx.x == 0) ptx::pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1009,43 +1070,53 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc1 = ptx::idesc_bf16(128, (uint32_t)p.rk, 0, 0);     // dG: A K-major, B K-major
-      const uint32_t idesc2 = ptx::idesc_bf16(128, (uint32_t)p.rk, 1, 0);     // dB: A MN-major (transposed view)
+      // dB: A MN-major (transposed view of the dY tile); hi and lo halves of g stacked along N, so one
+      // pass over the tile yields both products (the epilogue adds them)
+      const uint32_t idesc2 = ptx::idesc_bf16(128, 2u * (uint32_t)p.rk, 1, 0);
       const uint32_t gta = ptx::smem_u32(gt);
+      // descriptors differ only in their 14-bit start-address field: build once, add offsets (>> 4)
+      const uint64_t a1_base = ptx::smem_desc_sw128(0, 1024, 0);
+      const uint64_t a2_base = ptx::smem_desc_sw128(0, 1024, 16384);
+      uint64_t g_desc[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        g_desc[k] = ptx::smem_desc_sw128(gta + (uint32_t)(k >> 2) * g2_block + (k & 3) * 32, 1024, 0);
       ptx::mbar_wait_or_trap(&wfull[0], 0);
+      dbg_stamp(p.dbg, blockIdx.x, 2);
       for (int j = 0; j < np; ++j) {
         const int s = j % p.stages;
         const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
-        const int i = j & 1;
-        const uint32_t ph2 = (uint32_t)(j >> 1) & 1u;
+        const int i = p.nbuf == 2 ? (j & 1) : 0;
+        const uint32_t ph2 = (uint32_t)(p.nbuf == 2 ? (j >> 1) : j) & 1u;
         ptx::mbar_wait_or_trap(&full[s], ph);
+        if (j == 0) dbg_stamp(p.dbg, blockIdx.x, 3);
+        if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 8 + j * 3);
         ptx::mbar_wait_or_trap(&d2_empty[i], ph2 ^ 1u);
+        if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 3);
         ptx::tc_fence_after_sync();
         const uint32_t sa = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
         const uint32_t bta = sa + 32768u;
         // MMA1: K = 128 columns of this pair (two boxes, four 16-wide steps each)
+        const uint64_t a1 = a1_base + (uint64_t)(sa >> 4);
+        const uint64_t b1 = a1_base + (uint64_t)(bta >> 4);
+        const uint64_t a2 = a2_base + (uint64_t)(sa >> 4);
 #pragma unroll
         for (int box = 0; box < 2; ++box)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = ptx::smem_desc_sw128(sa + box * 16384 + k * 32, 1024, 0);
-            const uint64_t bdesc = ptx::smem_desc_sw128(bta + box * gt_block + k * 32, 1024, 0);
-            ptx::umma_bf16(tmem_base, adesc, bdesc, idesc1, (j > 0 || box > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16(tmem_base, a1 + (uint64_t)((box * 16384 + k * 32) >> 4),
+                           b1 + (uint64_t)((box * gt_block + k * 32) >> 4), idesc1, (j > 0 || box > 0 || k > 0) ? 1u : 0u);
         // MMA2: M = 128 columns (two 64-wide atoms 16 KB apart), K = 128 tokens in 8 steps of 16
+        const uint32_t d2 = tmem_base + p.d2_col + (uint32_t)i * 2u * (uint32_t)p.rk;
 #pragma unroll
-        for (int part = 0; part < 2; ++part)           // g = hi + lo
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t adesc = ptx::smem_desc_sw128(sa + k * 2048, 1024, 16384);
-            const uint64_t bdesc = ptx::smem_desc_sw128(gta + (uint32_t)part * 2u * gt_block +
-                                                        (uint32_t)(k >> 2) * gt_block + (k & 3) * 32, 1024, 0);
-            ptx::umma_bf16(tmem_base + p.d2_col + (uint32_t)i * p.rk, adesc, bdesc, idesc2,
-                           (part > 0 || k > 0) ? 1u : 0u);
-          }
+        for (int k = 0; k < 8; ++k)
+          ptx::umma_bf16(d2, a2 + (uint64_t)((k * 2048) >> 4), g_desc[k], idesc2, k > 0 ? 1u : 0u);
         ptx::umma_commit(&empty[s]);
         ptx::umma_commit(&d2_full[i]);
+        if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 10 + j * 3);
       }
       ptx::umma_commit(dg_full);
+      dbg_stamp(p.dbg, blockIdx.x, 4);
     }
   } else {
     const int wt = threadIdx.x - 64;
@@ -1054,15 +1125,27 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
     // G^T operand (post_m * g as hi + lo bf16): rows = rank index, K = tokens
     {
       const int t = t0 + row;
-      const int code = (row < nt) ? (tokmeta[t] & MOKA_MOD_MASK) : 0;
-      const float ps = code ? d.post[code] : 0.f;
-      for (int jj = 0; jj < p.rk; ++jj) {
-        const float gv = (code && jj < r) ? g_stash[(size_t)t * r + jj] * ps : 0.f;
-        const __nv_bfloat16 hi = __float2bfloat16_rn(gv);
-        const __nv_bfloat16 lo = __float2bfloat16_rn(gv - __bfloat162float(hi));
-        const uint32_t off = (uint32_t)(row >> 6) * gt_block + ptx::sw128_offset((uint32_t)jj, (uint32_t)((row & 63) >> 3)) + (row & 7) * 2;
-        *reinterpret_cast<__nv_bfloat16*>(gt + off) = hi;
-        *reinterpret_cast<__nv_bfloat16*>(gt + 2 * gt_block + off) = lo;
+      const uint8_t mb = (row < nt) ? tokmeta[t] : (uint8_t)0;  // issued together with the first g loads below
+      const uint32_t kblk = (uint32_t)(row >> 6) * g2_block, ch = (uint32_t)((row & 63) >> 3), in = (row & 7) * 2;
+      for (int j0 = 0; j0 < p.rk; j0 += 16) {
+        float4 gq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          gq[u] = (row < nt && j0 + 4 * u < r) ? *reinterpret_cast<const float4*>(g_stash + (size_t)t * r + j0 + 4 * u)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int code = mb & MOKA_MOD_MASK;
+        const float ps = code ? d.post[code] : 0.f;
+        const float gvals[16] = {gq[0].x, gq[0].y, gq[0].z, gq[0].w, gq[1].x, gq[1].y, gq[1].z, gq[1].w,
+                                 gq[2].x, gq[2].y, gq[2].z, gq[2].w, gq[3].x, gq[3].y, gq[3].z, gq[3].w};
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int jj = j0 + u;
+          const float gv = gvals[u] * ps;
+          const __nv_bfloat16 hi = __float2bfloat16_rn(gv);
+          const __nv_bfloat16 lo = __float2bfloat16_rn(gv - __bfloat162float(hi));
+          *reinterpret_cast<__nv_bfloat16*>(gt + kblk + ptx::sw128_offset((uint32_t)jj, ch) + in) = hi;
+          *reinterpret_cast<__nv_bfloat16*>(gt + kblk + ptx::sw128_offset((uint32_t)(p.rk + jj), ch) + in) = lo;
+        }
       }
     }
     ptx::fence_proxy_async_smem();
@@ -1071,30 +1154,31 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
     // dB / dG are written below: everything older than k_bwd_prep (zero-fills, earlier calls that
     // shared the workspace) must be complete
     ptx::pdl_wait();
-    ptx::pdl_trigger();
 
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int j = 0; j < np; ++j) {
-      const int i = j & 1;
-      const uint32_t ph2 = (uint32_t)(j >> 1) & 1u;
+      const int i = p.nbuf == 2 ? (j & 1) : 0;
+      const uint32_t ph2 = (uint32_t)(p.nbuf == 2 ? (j >> 1) : j) & 1u;
       ptx::mbar_wait_or_trap(&d2_full[i], ph2);
+      if (wt == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 32 + j * 2);
       ptx::tc_fence_after_sync();
       const int col = (p_beg + j) * 128 + row;               // TMEM lane <-> output column
       float* dst = dB + (size_t)col * r;
-      for (int c8 = 0; c8 < p.rk; c8 += 8) {
-        float v[8];
-        ptx::tmem_ld8(lane_base + p.d2_col + (uint32_t)(i * p.rk + c8), v);
+      for (int c8 = 0; c8 < r; c8 += 8) {                       // r % 8 == 0 on this path
+        float v[8], w[8];
+        ptx::tmem_ld8(lane_base + p.d2_col + (uint32_t)(i * 2 * p.rk + c8), v);          // hi product
+        ptx::tmem_ld8(lane_base + p.d2_col + (uint32_t)(i * 2 * p.rk + p.rk + c8), w);   // lo product
         ptx::tmem_ld_wait();
-        if (c8 < r) {                                        // r % 8 == 0 on this path
-          red_add_v4_f32(dst + c8, v[0], v[1], v[2], v[3]);
-          red_add_v4_f32(dst + c8 + 4, v[4], v[5], v[6], v[7]);
-        }
+        red_add_v4_f32(dst + c8, v[0] + w[0], v[1] + w[1], v[2] + w[2], v[3] + w[3]);
+        red_add_v4_f32(dst + c8 + 4, v[4] + w[4], v[5] + w[5], v[6] + w[6], v[7] + w[7]);
       }
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(&d2_empty[i]);
+      if (wt == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 33 + j * 2);
     }
     // dG partial of this CTA
     ptx::mbar_wait_or_trap(dg_full, 0);
+    if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 5);
     ptx::tc_fence_after_sync();
     {
       // tcgen05.ld is warp-collective: every lane issues it, only live token rows store
@@ -1124,6 +1208,7 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) { dbg_stamp(p.dbg, blockIdx.x, 6); dbg_stamp_g(p.dbg, blockIdx.x, 109); }
   if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
@@ -1312,10 +1397,12 @@ k_attn_bwd_tile(DevDesc d, const uint8_t* __restrict__ tokmeta, const int32_t* _
 // can chain with programmatic dependent launch.
 __global__ void __launch_bounds__(256)
 k_bwd_prep(const __nv_bfloat16* __restrict__ Bw, __nv_bfloat16* __restrict__ Bt, int d_out, int r, int rk,
-           uint32_t* __restrict__ zero_ptr, int zero_words) {
+           uint32_t* __restrict__ zero_ptr, int zero_words, int dbg) {
   __shared__ __nv_bfloat16 tile[64][136];                        // 64 columns x up to 128 ranks (+pad)
+  if (threadIdx.x == 0) dbg_stamp_g(dbg, blockIdx.x, 106);
   ptx::pdl_wait();                                               // B (optimizer), workspace (earlier calls)
   ptx::pdl_trigger();
+  if (threadIdx.x == 0) dbg_stamp_g(dbg, blockIdx.x, 99);
   for (int i = blockIdx.x * 256 + threadIdx.x; i < zero_words; i += gridDim.x * 256) zero_ptr[i] = 0u;
   const int c0 = blockIdx.x * 64;
   for (int idx = threadIdx.x; idx < 64 * r; idx += 256) {
@@ -1327,6 +1414,7 @@ k_bwd_prep(const __nv_bfloat16* __restrict__ Bw, __nv_bfloat16* __restrict__ Bt,
     const int j = idx >> 6, c = idx & 63;
     if (c0 + c < d_out) Bt[(size_t)j * d_out + c0 + c] = (j < r) ? tile[c][j] : __float2bfloat16_rn(0.f);
   }
+  if (threadIdx.x == 0) dbg_stamp_g(dbg, blockIdx.x, 107);
 }
 
 // fused = the merged attention-backward + pack kernel follows (partial dG buffers, nothing zero-filled
@@ -1341,14 +1429,20 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   p.bt_bytes = 2u * (uint32_t)p.rk * 128u;
   p.stage_bytes = 32768u + p.bt_bytes;
   const size_t fixed = (size_t)4 * p.rk * 128 + 1024 + 512;
-  const size_t limit = 200 * 1024;
+  // fused chain: leave ~56 KB of the SM's shared memory to an early-launched k_attn_pack CTA, whose
+  // staging of the forward's stash then overlaps this kernel
+  static int dg_stages_env = -1;
+  if (dg_stages_env < 0) { const char* e = getenv("MOKA_DGRAD_STAGES"); dg_stages_env = e ? atoi(e) : 0; }
+  const size_t limit = (fused && !dg_stages_env ? 168 : 200) * 1024;
   p.stages = (int)((limit - fixed) / p.stage_bytes);
   if (p.stages > 5) p.stages = 5;
+  if (dg_stages_env > 0 && p.stages > dg_stages_env) p.stages = dg_stages_env;
   if (p.stages < 2) return MOKA_EUNSUPPORTED;
   p.dbg = dbg_enabled();
   const uint32_t dgc = tmem_cols_for(p.rk);
   p.d2_col = dgc;
-  p.tmem_cols = tmem_cols_for((int)dgc + 2 * p.rk);
+  p.nbuf = (dgc + 4 * p.rk <= 512) ? 2 : 1;                  // [128 x 2 rk] dB accumulators next to dG in TMEM
+  p.tmem_cols = tmem_cols_for((int)dgc + p.nbuf * 2 * p.rk);
   // pre-transposed B in the (otherwise unused until the pack step) packed-operand workspace
   __nv_bfloat16* Bt = static_cast<__nv_bfloat16*>(a.pack);
   CUtensorMap tdy, tbt;
@@ -1362,7 +1456,7 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
     uint32_t* zp = fused ? reinterpret_cast<uint32_t*>(a.dK) : nullptr;
     const int zw = fused ? (int)((reinterpret_cast<char*>(a.counters) - reinterpret_cast<char*>(a.dK)) / 4) + d.B : 0;
     e = launch_pdl(k_bwd_prep, dim3((d.d_out + 63) / 64), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(a.Bw), Bt,
-                   d.d_out, d.r, p.rk, zp, zw);
+                   d.d_out, d.r, p.rk, zp, zw, p.dbg);
     if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
     if (int rc = check_launch_tc()) return rc;
   }
@@ -1539,11 +1633,11 @@ struct AttnPackParams {
   float scale;
 };
 
-template <int R>
-__device__ __forceinline__ void pack_rows64(const DevDesc& d, const AttnPackParams& p, const float* __restrict__ vs,
-                                            const int* __restrict__ s_base, size_t tbase, int nt,
-                                            __nv_bfloat16* __restrict__ hc, __nv_bfloat16* __restrict__ hct_hi,
-                                            __nv_bfloat16* __restrict__ hct_lo, int tid, int nthr) {
+template <int R, int TT>
+__device__ __forceinline__ void pack_rows(const DevDesc& d, const AttnPackParams& p, const float* __restrict__ vs,
+                                          const int* __restrict__ s_base, size_t tbase, int nt,
+                                          __nv_bfloat16* __restrict__ hc, __nv_bfloat16* __restrict__ hct_hi,
+                                          __nv_bfloat16* __restrict__ hct_lo, int tid, int nthr) {
   constexpr int VS = R + 1;
   const int r = d.r;
   const int cpr = p.KP / 8;
@@ -1581,27 +1675,38 @@ __device__ __forceinline__ void pack_rows64(const DevDesc& d, const AttnPackPara
   }
 }
 
+// R: padded rank (8/16/32); KB: 32-key blocks; NT threads; a CTA owns TT = 32 tokens, a warp TT/(NT/32).
+//   phase A  warp <-> tokens, lane <-> key: scores from the stashed log-sum-exp, ds, the dh update of the
+//            query rows (butterfly over keys), and the per-(token, key) factors p w and ds/sqrt(r) to smem;
+//   phase B  thread <-> (key, 4 rank indices): dK[k] = sum_t (p w)[t,k] dg_t + (ds/sqrt r)[t,k] h_t as an
+//            outer-product accumulation over the CTA's tokens - every dK element has one owner, so there is
+//            no cross-warp reduction (shared-memory float atomics are CAS loops on this hardware).
 template <int R, int KB, int NT>
 __global__ void __launch_bounds__(NT)
 k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, const int32_t* __restrict__ kidx,
             const int32_t* __restrict__ klen, const float* __restrict__ h_stash, float* __restrict__ dG0,
             const float* __restrict__ dG1, float* __restrict__ dK_glob, int* __restrict__ counters,
             __nv_bfloat16* __restrict__ hc, __nv_bfloat16* __restrict__ hct_hi, __nv_bfloat16* __restrict__ hct_lo) {
-  constexpr int TT = 64;
+  constexpr int TT = 32;
   constexpr int TPW = TT / (NT / 32);               // tokens per warp
   constexpr int RS = R + 1;                         // odd row stride: lane <-> key reads are conflict-free
+  constexpr int KP32 = KB * 32;
+  constexpr int R4 = R / 4;
   extern __shared__ __align__(16) float sm[];
   const int r = d.r;
-  float* Ks = sm;                                   // [KB*32][RS]   (zero rows for invalid keys)
-  float* dKs = Ks + KB * 32 * RS;                   // [KB*32][RS]
-  float* hs = dKs + KB * 32 * RS;                   // [TT][R]
+  float* hs = sm;                                   // [TT][R]
   float* gs = hs + TT * R;
-  float* dgs = gs + TT * R;                         // dG rows in, dh rows out
-  float* vs = dgs + TT * R;                         // [TT][RS] staging of the pack step
+  float* dgs = gs + TT * R;                         // dG rows (kept: phase B needs the original dg)
+  float* dhs = dgs + TT * R;                        // dh rows: dG + the attention-backward update of query rows
+  float* pws = dhs + TT * R;                        // [TT][KP32]  p * w
+  float* dss = pws + TT * KP32;                     // [TT][KP32]  ds / sqrt(r)
+  float* Ks = dss + TT * KP32;                      // [KP32][RS]   (zero rows for invalid keys)
+  float* vs = Ks + KP32 * RS;                       // [TT][RS] staging of the pack step
   __shared__ int s_code[TT];
   __shared__ int s_base[TT];
   __shared__ float s_lse[TT];
   __shared__ uint32_t s_blkmask[32];
+  __shared__ int s_kidx[KP32];                      // the sample's key positions (finisher)
   __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / p.bps;
@@ -1611,7 +1716,10 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
   const float* g_stash = h_stash + (size_t)d.T * r;
   const float* lse = g_stash + (size_t)d.T * r;
   const int L = klen[b];
+  if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 110);
+  ptx::pdl_trigger();                               // k_wgrad_tc: prologue + x / dx prefetch may start (see k_dgrad_tc)
   int myq = 0, mykey = 0;
+  if (tid < 32) s_blkmask[tid] = 0u;
   if (tid < TT) {
     const uint8_t mb = (tid < nt) ? tokmeta[tbase + tid] : (uint8_t)0;
     const int code = mb & MOKA_MOD_MASK;
@@ -1625,52 +1733,62 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
   const int anykey = __syncthreads_or(mykey);
   if (anyq) {
     // h, g rows and the sample's keys come from the forward: older than this call
-    for (int i = tid; i < TT * R; i += NT) {
-      const int tt = i / R, j = i - tt * R;
-      const bool ok = tt < nt && j < r;
-      hs[i] = ok ? h_stash[(tbase + tt) * r + j] : 0.f;
-      gs[i] = ok ? g_stash[(tbase + tt) * r + j] : 0.f;
+    for (int i = tid; i < TT * R4; i += NT) {
+      const int tt = i / R4, j = (i - tt * R4) * 4;
+      float4 hv = make_float4(0.f, 0.f, 0.f, 0.f), gv = hv;
+      if (tt < nt && j < r) {
+        hv = *reinterpret_cast<const float4*>(h_stash + (tbase + tt) * r + j);
+        gv = *reinterpret_cast<const float4*>(g_stash + (tbase + tt) * r + j);
+      }
+      reinterpret_cast<float4*>(hs)[i] = hv;
+      reinterpret_cast<float4*>(gs)[i] = gv;
     }
-    for (int k = tid; k < KB * 32; k += NT) {
-      bool valid = false;
-      size_t tk = 0;
-      if (k < L) {
+    for (int idx = tid; idx < KP32 * R4; idx += NT) {
+      const int k = idx / R4, j = (idx - k * R4) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < L && j < r) {
         const int pos = kidx[(size_t)b * d.Lk + k];
-        tk = (size_t)b * d.S + pos;
-        valid = (tokmeta[tk] & MOKA_KEY_VALID) != 0;
+        const size_t tk = (size_t)b * d.S + pos;
+        if (j == 0) {                                 // for the finisher: key positions + candidate-tile mask
+          s_kidx[k] = pos;
+          atomicOr(&s_blkmask[(pos >> 5) >> 5], 1u << ((pos >> 5) & 31));
+        }
+        if (tokmeta[tk] & MOKA_KEY_VALID) v = *reinterpret_cast<const float4*>(h_stash + tk * r + j);
       }
-      for (int j = 0; j < R; ++j) {
-        Ks[k * RS + j] = (valid && j < r) ? h_stash[tk * r + j] : 0.f;
-        dKs[k * RS + j] = 0.f;
-      }
+      float* dst = Ks + k * RS + j;
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
     }
   }
+  if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 114);
   ptx::pdl_wait();                                  // dG from k_dgrad_tc, zeroed dK / counters from k_bwd_prep
-  ptx::pdl_trigger();
-  for (int i = tid; i < TT * R; i += NT) {
-    const int tt = i / R, j = i - tt * R;
-    float v = 0.f;
+  if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 115);
+  for (int i = tid; i < TT * R4; i += NT) {
+    const int tt = i / R4, j = (i - tt * R4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tt < nt && j < r) {
-      v = dG0[(tbase + tt) * r + j];
-      if (dG1) v += dG1[(tbase + tt) * r + j];
+      v = *reinterpret_cast<const float4*>(dG0 + (tbase + tt) * r + j);
+      if (dG1) {
+        const float4 w = *reinterpret_cast<const float4*>(dG1 + (tbase + tt) * r + j);
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+      }
     }
-    dgs[i] = v;
+    reinterpret_cast<float4*>(dgs)[i] = v;
+    reinterpret_cast<float4*>(dhs)[i] = v;
   }
   __syncthreads();
   if (anyq) {
+    // ---- phase A
     const float sl = d.sm_scale * kLog2e;
-    float dKacc[KB][R];
-#pragma unroll
-    for (int kb = 0; kb < KB; ++kb)
-#pragma unroll
-      for (int j = 0; j < R; ++j) dKacc[kb][j] = 0.f;
     const int comp = (R == 32) ? lane : (R == 16 ? (lane >> 1) : (lane >> 2));
     const bool writer = (R == 32) || (R == 16 && !(lane & 1)) || (R == 8 && !(lane & 3));
-    bool any_tok = false;
+#pragma unroll 1
     for (int ti = 0; ti < TPW; ++ti) {
       const int tt = warp * TPW + ti;
-      if (s_code[tt] < MOKA_MOD_VIS) continue;        // warp-uniform
-      any_tok = true;
+      if (s_code[tt] < MOKA_MOD_VIS) {                // warp-uniform: not a query, contributes nothing to dK
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) { pws[tt * KP32 + kb * 32 + lane] = 0.f; dss[tt * KP32 + kb * 32 + lane] = 0.f; }
+        continue;
+      }
       float hq[R], dg[R];
       float Dsum = 0.f;
 #pragma unroll
@@ -1683,110 +1801,221 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
       float dh_tot = 0.f;                             // component `comp` of the dh contribution (writer lanes)
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
-        if (kb * 32 >= L) break;                      // uniform
         const int k = kb * 32 + lane;
-        const float* Kr = Ks + k * RS;
-        float Kv[R];
-        float sc = 0.f, dp = 0.f;
+        float pw = 0.f, dsv = 0.f;
+        if (kb * 32 < L) {                            // uniform
+          const float* Kr = Ks + k * RS;
+          float Kv[R];
+          float sc = 0.f, dp = 0.f;
 #pragma unroll
-        for (int j = 0; j < R; ++j) { Kv[j] = Kr[j]; sc = fmaf(hq[j], Kv[j], sc); dp = fmaf(dg[j], Kv[j], dp); }
-        const float pr = (k < L) ? exp2f(sc * sl - lse_t) : 0.f;
-        dp *= d.attn_w;
-        const float ds = pr * (dp - Dsum);
-        const float pw = pr * d.attn_w, dss = ds * d.sm_scale;
-        float part[R];
+          for (int j = 0; j < R; ++j) { Kv[j] = Kr[j]; sc = fmaf(hq[j], Kv[j], sc); dp = fmaf(dg[j], Kv[j], dp); }
+          const float pr = (k < L) ? exp2f(sc * sl - lse_t) : 0.f;
+          dp *= d.attn_w;
+          const float ds = pr * (dp - Dsum);
+          pw = pr * d.attn_w;
+          dsv = ds * d.sm_scale;
+          float part[R];
 #pragma unroll
-        for (int j = 0; j < R; ++j) {
-          dKacc[kb][j] = fmaf(pw, dg[j], fmaf(dss, hq[j], dKacc[kb][j]));
-          part[j] = dss * Kv[j];
-        }
+          for (int j = 0; j < R; ++j) part[j] = dsv * Kv[j];
 #pragma unroll
-        for (int half = R / 2, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
-          const bool upper = (lane & bit) != 0;
+          for (int half = R / 2, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+            const bool upper = (lane & bit) != 0;
 #pragma unroll
-          for (int i = 0; i < half; ++i) {
-            const float send = upper ? part[i] : part[i + half];
-            const float keep = upper ? part[i + half] : part[i];
-            part[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+            for (int i = 0; i < half; ++i) {
+              const float send = upper ? part[i] : part[i + half];
+              const float keep = upper ? part[i + half] : part[i];
+              part[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+            }
           }
+          float tot = part[0];
+          if (R <= 16) tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+          if (R <= 8) tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+          dh_tot += tot;
         }
-        float tot = part[0];
-        if (R <= 16) tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-        if (R <= 8) tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-        dh_tot += tot;
+        pws[tt * KP32 + k] = pw;
+        dss[tt * KP32 + k] = dsv;
       }
-      __syncwarp();
-      if (writer && comp < r) dgs[tt * R + comp] += dh_tot;       // in place: the row belongs to this warp
-    }
-    // combine the per-warp dK partials in shared memory, then one reduction per element
-    if (any_tok) {
-#pragma unroll
-      for (int kb = 0; kb < KB; ++kb) {
-        if (kb * 32 >= L) break;
-        const int k = kb * 32 + lane;
-#pragma unroll
-        for (int j = 0; j < R; ++j) atomicAdd(&dKs[k * RS + j], dKacc[kb][j]);
-      }
+      if (writer && comp < r) dhs[tt * R + comp] += dh_tot;
     }
     __syncthreads();
-    for (int i = tid; i < L * R; i += NT) {
-      const int k = i / R, j = i - k * R;
-      if (j < r) {
-        const float v = dKs[k * RS + j];
-        if (v != 0.f) red_add_f32(&dK_glob[((size_t)b * d.Lk + k) * r + j], v);
+    if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 116);
+    // ---- phase B: dK[k, 4 jq..] = sum over the CTA's tokens, one owner per element
+    for (int idx = tid; idx < L * R4; idx += NT) {
+      const int k = idx / R4, j = (idx - k * R4) * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+      for (int tt = 0; tt < TT; ++tt) {
+        const float pw = pws[tt * KP32 + k], dsv = dss[tt * KP32 + k];
+        const float4 dgv = *reinterpret_cast<const float4*>(dgs + tt * R + j);
+        const float4 hv = *reinterpret_cast<const float4*>(hs + tt * R + j);
+        acc.x = fmaf(pw, dgv.x, fmaf(dsv, hv.x, acc.x));
+        acc.y = fmaf(pw, dgv.y, fmaf(dsv, hv.y, acc.y));
+        acc.z = fmaf(pw, dgv.z, fmaf(dsv, hv.z, acc.z));
+        acc.w = fmaf(pw, dgv.w, fmaf(dsv, hv.w, acc.w));
       }
+      if (j < r && (acc.x != 0.f || acc.y != 0.f || acc.z != 0.f || acc.w != 0.f))
+        red_add_v4_f32(&dK_glob[((size_t)b * d.Lk + k) * r + j], acc.x, acc.y, acc.z, acc.w);
     }
   }
+  if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 117);
   if (!anykey) {
-    for (int i = tid; i < TT * R; i += NT) { const int tt = i / R, j = i - tt * R; vs[tt * RS + j] = dgs[i]; }
+    for (int i = tid; i < TT * R; i += NT) { const int tt = i / R, j = i - tt * R; vs[tt * RS + j] = dhs[i]; }
     __syncthreads();
-    pack_rows64<R>(d, p, vs, s_base, tbase, nt, hc, hct_hi, hct_lo, tid, NT);
+    pack_rows<R, TT>(d, p, vs, s_base, tbase, nt, hc, hct_hi, hct_lo, tid, NT);
   } else {
     // parked: the finisher of this sample reads these rows back (L2) once dK is complete
     for (int i = tid; i < nt * R; i += NT) {
       const int tt = i / R, j = i - tt * R;
-      if (j < r) dG0[(tbase + tt) * r + j] = dgs[i];
+      if (j < r) dG0[(tbase + tt) * r + j] = dhs[i];
     }
   }
   // ---- arrival: the last CTA of the sample packs the parked tiles
+  if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 118);
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(&counters[b], 1) == p.bps - 1);
-  if (tid < 32) s_blkmask[tid] = 0u;
   __syncthreads();
-  if (!s_last) return;
+  if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 119);
+  if (!s_last) { if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 111); return; }
   __threadfence();
-  for (int i = tid; i < d.S; i += NT) {
-    const uint8_t mb = tokmeta[(size_t)b * d.S + i];
-    if ((mb & MOKA_KEY_VALID) && (mb & MOKA_MOD_MASK)) atomicOr(&s_blkmask[(i >> 6) >> 5], 1u << ((i >> 6) & 31));
-  }
-  __syncthreads();
-  for (int blk = 0; blk < p.bps; ++blk) {
-    if (!((s_blkmask[blk >> 5] >> (blk & 31)) & 1u)) continue;        // uniform
-    const int q0 = blk * TT;
-    const int qn = min(TT, d.S - q0);
-    const size_t qbase = (size_t)b * d.S + q0;
-    __syncthreads();                                                  // previous round done with vs / s_base
-    if (tid < TT) {
-      const int code = (tid < qn) ? (tokmeta[qbase + tid] & MOKA_MOD_MASK) : 0;
-      s_base[tid] = code ? (code - 1) * p.rp : -1;
-    }
-    for (int i = tid; i < TT * R; i += NT) {
-      const int tt = i / R, j = i - tt * R;
-      vs[tt * RS + j] = (tt < qn && j < r) ? __ldcg(&dG0[(qbase + tt) * r + j]) : 0.f;
+  // ---- finisher.  The key index row and the mask of candidate tiles (tiles holding a key position) were
+  // built while staging the keys (CTAs without queries fetch them now); the finished dK rows and the
+  // parked tiles' dh rows / token codes then arrive in ONE round of independent loads, and folding and
+  // packing run out of shared memory, all tiles of a round at once.
+  constexpr int kSmFloats = 4 * TT * R + 2 * TT * KP32 + KP32 * RS + TT * RS;
+  constexpr int kPBfit = (kSmFloats - KP32 * R) / (TT * RS);
+  constexpr int PB = kPBfit < 6 ? kPBfit : 6;       // parked tiles per round
+  static_assert(PB >= 1, "finisher scratch does not fit");
+  float* dKs = sm;                                  // [L][R]   (the whole dynamic shared memory is free again)
+  float* vs_all = sm + KP32 * R;                    // [PB][TT][RS]
+  __shared__ int s_codes[PB * TT];
+  __shared__ int s_base_all[PB * TT];
+  __shared__ int s_list[PB];
+  __shared__ int s_parked[PB];
+  __shared__ int s_nlist;
+  if (!anyq) {
+    for (int i = tid; i < L; i += NT) {
+      const int pos = kidx[(size_t)b * d.Lk + i];
+      s_kidx[i] = pos;
+      if (pos >= 0) atomicOr(&s_blkmask[(pos >> 5) >> 5], 1u << ((pos >> 5) & 31));
     }
     __syncthreads();
-    if (tid < qn) {
-      const uint8_t mb = tokmeta[qbase + tid];
-      if ((mb & MOKA_KEY_VALID) && (mb & MOKA_MOD_MASK)) {
-        const int slot = find_key_slot(kidx + (size_t)b * d.Lk, L, q0 + tid);
-        if (slot >= 0)
-          for (int j = 0; j < r; ++j) vs[tid * RS + j] += __ldcg(&dK_glob[((size_t)b * d.Lk + slot) * r + j]);
+  }
+  if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 120);
+  int word = 0;                                      // candidate tiles are walked 32 at a time
+  uint32_t bits = s_blkmask[0];
+  bool first_round = true;
+  while (true) {
+    __syncthreads();                                 // previous round done with the scratch
+    if (tid == 0) {
+      int n = 0, w = word;
+      uint32_t m = bits;
+      while (n < PB) {
+        if (m == 0u) { if (++w >= 32) break; m = s_blkmask[w]; continue; }
+        const int bit = __ffs(m) - 1;
+        m &= m - 1u;
+        s_list[n] = w * 32 + bit;
+        s_parked[n] = 0;
+        ++n;
+      }
+      s_nlist = n;
+      s_last = w;                                    // resume point (word) ...
+      s_blkmask[w < 32 ? w : 31] = (w < 32) ? m : 0u;   // ... and the bits still to do in it
+    }
+    __syncthreads();
+    const int nl = s_nlist;
+    word = s_last;
+    bits = (word < 32) ? s_blkmask[word] : 0u;
+    if (nl == 0) break;
+    if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 121);
+    if (first_round) {
+      for (int i = tid; i < L * R4; i += NT) {
+        const int k = i / R4, j = (i - k * R4) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < r) v = __ldcg(reinterpret_cast<const float4*>(&dK_glob[((size_t)b * d.Lk + k) * r + j]));
+        *reinterpret_cast<float4*>(dKs + k * R + j) = v;
+      }
+      first_round = false;
+    }
+    for (int i = tid; i < nl * TT; i += NT) {
+      const int q = i / TT, tt = i - q * TT;
+      const int pos = s_list[q] * TT + tt;
+      const int mb = (pos < d.S) ? tokmeta[(size_t)b * d.S + pos] : 0;
+      const int code = mb & MOKA_MOD_MASK;
+      s_codes[i] = mb;
+      s_base_all[i] = code ? (code - 1) * p.rp : -1;
+      if ((mb & MOKA_KEY_VALID) && code) s_parked[q] = 1;        // benign race: every writer stores 1
+    }
+    for (int i = tid; i < nl * TT * R4; i += NT) {
+      const int q = i / (TT * R4), rem = i - q * TT * R4;
+      const int tt = rem / R4, j = (rem - tt * R4) * 4;
+      const int pos = s_list[q] * TT + tt;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (pos < d.S && j < r) v = __ldcg(reinterpret_cast<const float4*>(&dG0[((size_t)b * d.S + pos) * r + j]));
+      float* dst = vs_all + (q * TT + tt) * RS + j;
+      dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    __syncthreads();
+    if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 122);
+    // fold dK onto the key rows: thread <-> (parked row, 4 rank indices)
+    for (int i = tid; i < nl * TT * R4; i += NT) {
+      const int q = i / (TT * R4), rem = i - q * TT * R4;
+      const int tt = rem / R4, j = (rem - tt * R4) * 4;
+      const int mb = s_codes[q * TT + tt];
+      if ((mb & MOKA_KEY_VALID) && (mb & MOKA_MOD_MASK) && j < r) {
+        const int slot = find_key_slot(s_kidx, L, s_list[q] * TT + tt);
+        if (slot >= 0) {
+          float* dst = vs_all + (q * TT + tt) * RS + j;
+          const float4 v = *reinterpret_cast<const float4*>(dKs + slot * R + j);
+          dst[0] += v.x; dst[1] += v.y; dst[2] += v.z; dst[3] += v.w;
+        }
       }
     }
     __syncthreads();
-    pack_rows64<R>(d, p, vs, s_base, qbase, qn, hc, hct_hi, hct_lo, tid, NT);
+    if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 123);
+    // pack every parked tile of the round (a candidate without a valid key was packed by its own CTA)
+    const int cpr = p.KP / 8;
+    for (int i = tid; i < nl * TT * cpr; i += NT) {
+      const int q = i / (TT * cpr), rem = i - q * TT * cpr;
+      const int tt = rem / cpr, n0 = (rem - tt * cpr) * 8;
+      const int pos = s_list[q] * TT + tt;
+      if (!s_parked[q] || pos >= d.S) continue;
+      const int base = s_base_all[q * TT + tt];
+      const float* row = vs_all + (q * TT + tt) * RS;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int j = n0 + e - base;
+        v[e] = (base >= 0 && j >= 0 && j < r) ? row[j] * p.scale : 0.f;
+      }
+      uint4 o;
+      o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
+      *reinterpret_cast<uint4*>(hc + ((size_t)b * d.S + pos) * p.KP + n0) = o;
+    }
+    constexpr int TCH = TT / 8;
+    for (int i = tid; i < nl * p.NPW * TCH; i += NT) {
+      const int q = i / (p.NPW * TCH), rem = i - q * p.NPW * TCH;
+      const int n = rem / TCH, c = rem - n * TCH;
+      const int pos0 = s_list[q] * TT + c * 8;
+      if (!s_parked[q] || pos0 >= d.S) continue;      // S % 8 == 0: a chunk is inside the sample or outside
+      float hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int tt = c * 8 + e;
+        const int base = s_base_all[q * TT + tt];
+        const int j = n - base;
+        const float v = (base >= 0 && j >= 0 && j < r) ? vs_all[(q * TT + tt) * RS + j] * p.scale : 0.f;
+        hi[e] = __bfloat162float(__float2bfloat16_rn(v));
+        lo[e] = v - hi[e];
+      }
+      uint4 o;
+      o.x = pack_bf16(hi[0], hi[1]); o.y = pack_bf16(hi[2], hi[3]); o.z = pack_bf16(hi[4], hi[5]); o.w = pack_bf16(hi[6], hi[7]);
+      *reinterpret_cast<uint4*>(hct_hi + (size_t)n * d.T + (size_t)b * d.S + pos0) = o;
+      o.x = pack_bf16(lo[0], lo[1]); o.y = pack_bf16(lo[2], lo[3]); o.z = pack_bf16(lo[4], lo[5]); o.w = pack_bf16(lo[6], lo[7]);
+      *reinterpret_cast<uint4*>(hct_lo + (size_t)n * d.T + (size_t)b * d.S + pos0) = o;
+    }
   }
+  if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 111);
 }
 
 // ---------------------------------------------------------------------------- k_wgrad_tc
@@ -1841,6 +2070,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   const int tt_beg = (int)((long long)split * p.ntiles / p.tsplit);
   const int tt_end = (int)((long long)(split + 1) * p.ntiles / p.tsplit);
   const int ntt = tt_end - tt_beg;
+  if (threadIdx.x == 0) { dbg_stamp_g(p.dbg, blockIdx.x, 112); dbg_stamp(p.dbg, blockIdx.x, 1); }
+  if (threadIdx.x == 0) ptx::pdl_trigger();                   // last kernel of the backward chain (see k_up_tc)
 
   // weight rows that TMA never writes (padding of the rank blocks) must read as zero
   for (uint32_t i = threadIdx.x; i < 2 * p.w_box_bytes / 16; i += kWgradThreads)
@@ -1894,7 +2125,6 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         ptx::tma_load_2d(dt + 16384, &tm_dx, &d_full[j], col0 + 64, (tt_beg + j) * 128, ptx::kEvictFirst);
       }
       ptx::pdl_wait();
-      ptx::pdl_trigger();
       for (int j = 0; j < ntt; ++j) {
         const int t0 = (tt_beg + j) * 128;
         if (j >= npre_x) {   // the big streams first: they have their own ring slots and must never wait on the MMAs
@@ -2047,6 +2277,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) { dbg_stamp(p.dbg, blockIdx.x, 7); dbg_stamp_g(p.dbg, blockIdx.x, 113); }
   if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
@@ -2058,19 +2289,19 @@ bool tc_backward_fused_ok(const DevDesc& d, int klen_hint, bool has_dx) {
   WgradTcParams p;
   PackLayout L;
   size_t fixed;
-  return d.r <= 32 && klen_hint <= 128 && (d.r <= 16 || klen_hint <= 64) && d.S % 8 == 0 && d.S <= 65536 &&
+  return d.r <= 32 && klen_hint <= 128 && (d.r <= 16 || klen_hint <= 64) && d.S % 8 == 0 && d.S <= 32768 &&
          wgrad_plan(d, has_dx, 148, p, L, fixed);
 }
 
 static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayout& L, int dg_partials,
                             __nv_bfloat16* hc, __nv_bfloat16* hct_hi, __nv_bfloat16* hct_lo, cudaStream_t st) {
   AttnPackParams p;
-  p.rp = L.rp; p.NPW = L.NPW; p.KP = L.KP; p.bps = (d.S + 63) / 64;
+  p.rp = L.rp; p.NPW = L.NPW; p.KP = L.KP; p.bps = (d.S + 31) / 32;
   p.scale = d.pre * d.drop_scale;
   const int kblocks = (max(a.klen_hint, 1) + 31) / 32;
   const int R = d.r <= 8 ? 8 : (d.r <= 16 ? 16 : 32);
   const int KBs = kblocks <= 1 ? 1 : (kblocks <= 2 ? 2 : 4);
-  const size_t sm = ((size_t)2 * KBs * 32 * (R + 1) + 3 * 64 * R + 64 * (R + 1)) * 4;
+  const size_t sm = ((size_t)4 * 32 * R + 2 * 32 * KBs * 32 + (size_t)KBs * 32 * (R + 1) + 32 * (R + 1)) * 4;
   const float* dG1 = dg_partials ? a.dh_att : nullptr;
   cudaError_t e = cudaSuccess;
 #define MOKA_LAUNCH_ATTN_PACK(RR, KK, NN)                                                                    \
@@ -2081,7 +2312,8 @@ static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayou
                    (const float*)a.h_stash, a.dh, dG1, a.dK, a.counters, hc, hct_hi, hct_lo);                  \
   } while (0)
   if (R == 8) { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK(8, 1, 512); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK(8, 2, 512); else MOKA_LAUNCH_ATTN_PACK(8, 4, 512); }
-  else if (R == 16) { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK(16, 1, 512); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK(16, 2, 512); else MOKA_LAUNCH_ATTN_PACK(16, 4, 512); }
+  // (R = 16 at 512 threads needs 128 registers: one CTA per SM and a second wave; 256 threads fit two)
+  else if (R == 16) { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK(16, 1, 256); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK(16, 2, 256); else MOKA_LAUNCH_ATTN_PACK(16, 4, 256); }
   else { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK(32, 1, 256); else MOKA_LAUNCH_ATTN_PACK(32, 2, 256); }
 #undef MOKA_LAUNCH_ATTN_PACK
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }

@@ -17,10 +17,11 @@ from oracle.moka_oracle import VARIANT_AVT, VARIANT_VT, layout_masks
 kern = sys.argv[1] if len(sys.argv) > 1 else 'up'
 variant = VARIANT_VT if (len(sys.argv) > 2 and sys.argv[2] == 'vt') else VARIANT_AVT
 r = int(sys.argv[3]) if len(sys.argv) > 3 else 16
+BARG = int(sys.argv[4]) if len(sys.argv) > 4 else 4
 KID = {'down': 0, 'up': 1, 'prep': 2, 'dgrad': 3, 'attn_pack': 4, 'wgrad': 5, 'attn_fwd': 6}[kern]
 lib = _cabi.load()
 dev = 'cuda:0'
-B, S, d = 4, 2048, 4096
+B, S, d = BARG, 2048, 4096
 T = B * S
 M = 3 if variant == VARIANT_AVT else 2
 masks = [m.to(dev) for m in layout_masks(variant, B, S, 'c3' if variant == VARIANT_AVT else 'c2')]
@@ -64,23 +65,25 @@ for _ in range(2):
     torch.cuda.synchronize()
     run(only)
     torch.cuda.synchronize()
-n = 148 * 2 * 64
+n = 148 * 2 * 128
 buf = (ctypes.c_ulonglong * n)()
 _cabi.check(lib.moka_debug_read(buf, n), 'debug_read')
-a = np.frombuffer(buf, dtype=np.uint64).reshape(-1, 64).astype(np.int64)
-a = a[a[:, 60] > 0] if (a[:, 60] > 0).any() else a[a[:, 0] > 0]
+a = np.frombuffer(buf, dtype=np.uint64).reshape(-1, 128).astype(np.int64)
+ES = {'down': 100, 'attn_fwd': 102, 'up': 104, 'prep': 106, 'dgrad': 108, 'attn_pack': 110, 'wgrad': 112}[kern]
+a = a[a[:, ES] > 0] if (a[:, ES] > 0).any() else a[a[:, 0] > 0]
 print(kern, 'CTAs', len(a))
-if (a[:, 60] > 0).any():
-    t0 = a[:, 60].min()
-    ent = a[:, 60] - t0
-    ext = a[:, 61] - t0
+if (a[:, ES] > 0).any():
+    t0 = a[:, ES].min()
+    ent = a[:, ES] - t0
+    ext = a[:, ES + 1] - t0
     print('globaltimer ns: entry min/med/max %d %d %d | exit min/med/max %d %d %d' %
           (ent.min(), np.median(ent), ent.max(), ext.min(), np.median(ext), ext.max()))
 rel = a - a[:, :1]
 names = {
     'down': {1: 'prologue done', 2: 'after pdl_wait', 3: 'first stage landed', 4: 'last mma issued', 5: 'tmem_full seen', 6: 'exit'},
     'up': {6: 'after pdl_wait (rel worker start)', 1: 'B/h staged', 2: 'attention done', 3: 'A operand staged', 4: 'loop end', 5: 'exit'},
-    'wgrad': {4: 'loop end', 5: 'a_full', 6: 'dA flushed'},
+    'wgrad': {1: 'entry (rel worker loop start)', 4: 'loop end', 5: 'a_full', 6: 'dA flushed', 7: 'exit'},
+    'dgrad': {2: 'G^T staged (mma thread)', 3: 'first stage landed', 4: 'last mma issued', 5: 'dg_full seen', 6: 'exit'},
 }.get(kern, {})
 for slot, nm in names.items():
     v = rel[:, slot]
@@ -95,3 +98,8 @@ if kern == 'wgrad':
         b = 8 + j * 4
         m = lambda i: rel[:, i].mean()
         print(f'tile {j}: t_full {m(b):8.0f} d_full {m(b+1):8.0f} epilogue {m(b+2):8.0f} done {m(b+3):8.0f} | mma op_full {m(40+j*3):8.0f} x_full {m(41+j*3):8.0f} t_empty {m(42+j*3):8.0f}')
+
+if kern == 'dgrad':
+    for j in range(8):
+        m = lambda i: rel[:, i].mean()
+        print(f'stage {j}: mma full {m(8+j*3):8.0f} d2_empty {m(9+j*3):8.0f} issued {m(10+j*3):8.0f} | workers d2_full {m(32+j*2):8.0f} epilogue done {m(33+j*2):8.0f}')

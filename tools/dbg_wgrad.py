@@ -13,11 +13,11 @@ from oracle.moka_oracle import VARIANT_AVT
 row = run_point(VARIANT_AVT, 4, 2048, 4096, 4096, 16, torch.bfloat16, 0, 2, 1)   # last timed pass is fwd+bwd: wgrad stamps win
 print(row)
 lib = _cabi.load()
-n = 148 * 2 * 64
+n = 148 * 2 * 128
 buf = (ctypes.c_ulonglong * n)()
 torch.cuda.synchronize()
 _cabi.check(lib.moka_debug_read(buf, n), 'debug_read')
-a = np.frombuffer(buf, dtype=np.uint64).reshape(-1, 64).astype(np.int64)
+a = np.frombuffer(buf, dtype=np.uint64).reshape(-1, 128).astype(np.int64)
 a = a[a[:, 0] > 0][:128]
 rel = a - a[:, :1]
 m = lambda i: rel[:, i].mean()
