@@ -26,7 +26,9 @@ if ROOT not in sys.path:
 
 WORKLOADS = {
     # BASELINE.json configs[2] shape (per GPU): the metric's "Llama-2-7B MokA r=16", 3 modalities
-    'llama2-7b-avt-m3-r16-s2048': dict(variant='avt', model='7b', r=16, M=3, S=2048, B=4, layout='c3', w=1.0),
+    # micro-batch 16 x 2048 tokens per GPU (fits without gradient checkpointing; measured round 1: the step rate
+    # is flat from 4 to 16 sequences, the per-call launch ramps of the adapter kernels amortise better)
+    'llama2-7b-avt-m3-r16-s2048': dict(variant='avt', model='7b', r=16, M=3, S=2048, B=16, layout='c3', w=1.0),
     # BASELINE.json configs[1]
     'llama2-7b-vt-m2-r8-s2048': dict(variant='vt', model='7b', r=8, M=2, S=2048, B=4, layout='c2', w=0.05),
     # BASELINE.json configs[3] (13B, r=64, seq 4096)
@@ -343,8 +345,12 @@ def main():
             e2e=dict(value=e2e_value, unit='tokens/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                      ms_per_step=ms_e2e / args.steps, last_loss=last_loss),
             gpu_launches=int(launches),
+            # traffic: dram__bytes_read + dram__bytes_write of one forward + backward chain from the ncu --set
+            # full capture in profiles/r01_ncu_chain_r16.md (T = 8192, 4096 -> 4096, r = 16; algorithmic
+            # 469.8 MB, of which the writes still resident in the 126 MB L2 at kernel end are not counted)
             roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
-                          traffic=None, peak_source=peak_kind,
+                          traffic=372.8e6, traffic_shape='one fwd+bwd call pair, T=8192 d=4096->4096 r=16 (ncu)',
+                          peak_source=peak_kind,
                           kernel='fused MokaLinear fwd+bwd (libmoka.so calls, CUDA events per call)',
                           calls=len(events),
                           fwd_gbs=per_kind['fwd'][0] / max(per_kind['fwd'][1], 1e-9) / 1e6,

@@ -560,6 +560,126 @@ k_attn_fwd_split(DevDesc d, int kcap, int gps, const uint8_t* __restrict__ tokme
   if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 103);
 }
 
+// k_attn_fwd_rank: forward attention for 32 < r <= 128.  One warp per query token, lane <-> C = R/32
+// consecutive rank indices (h and the running weighted sum in registers, key rows read as aligned
+// vectors), the score of a key is a warp reduction; two keys per step.  Same tile / staging scheme as
+// k_attn_fwd_split.
+template <int C>
+__global__ void __launch_bounds__(256)
+k_attn_fwd_rank(DevDesc d, int kcap, int gps, const uint8_t* __restrict__ tokmeta, const int32_t* __restrict__ kidx,
+                const int32_t* __restrict__ klen, const float* __restrict__ h0, const float* __restrict__ h1,
+                float* __restrict__ h_final, float* __restrict__ g_out, float* __restrict__ lse_out) {
+  constexpr int TT = 32, R = 32 * C, R4 = R / 4;
+  extern __shared__ __align__(16) float sm_af[];
+  const int r = d.r;
+  const int kcap2 = (kcap + 1) & ~1;                 // rows are read in pairs
+  float* Ks = sm_af;                                 // [kcap2][R]
+  float* hs = Ks + (size_t)kcap2 * R;                // [TT][R]  (h in, g out)
+  __shared__ int s_code[TT];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / gps;
+  const int s0 = (blockIdx.x % gps) * TT;
+  const int nt = min(TT, d.S - s0);
+  const size_t tbase = (size_t)b * d.S + s0;
+  const int L = min(klen[b], kcap);
+  if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 102);
+  int myq = 0;
+  if (tid < TT) {
+    const int code = (tid < nt) ? (tokmeta[tbase + tid] & MOKA_MOD_MASK) : 0;
+    s_code[tid] = code;
+    myq = code >= MOKA_MOD_VIS;
+  }
+  const int anyq = __syncthreads_or(myq) && L > 0;
+  ptx::pdl_trigger();                                // (see k_attn_fwd_split)
+  ptx::pdl_wait();                                   // h comes from k_down_tc
+  const int r4 = r >> 2;
+  for (int i = tid; i < TT * R4; i += 256) {
+    const int tt = i / R4, j4 = i - tt * R4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tt < nt && j4 < r4) {
+      const size_t off = (tbase + tt) * r + j4 * 4;
+      v = *reinterpret_cast<const float4*>(h0 + off);
+      if (h1) {
+        const float4 w = *reinterpret_cast<const float4*>(h1 + off);
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+      }
+      if (h_final) *reinterpret_cast<float4*>(h_final + off) = v;
+    }
+    reinterpret_cast<float4*>(hs)[i] = v;
+  }
+  if (anyq) {
+    for (int idx = tid; idx < kcap2 * R4; idx += 256) {
+      const int k = idx / R4, j4 = idx - k * R4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k < L && j4 < r4) {
+        const int pos = kidx[(size_t)b * d.Lk + k];
+        const size_t t = (size_t)b * d.S + pos;
+        if (tokmeta[t] & MOKA_KEY_VALID) {
+          v = *reinterpret_cast<const float4*>(h0 + t * r + j4 * 4);
+          if (h1) {
+            const float4 w = *reinterpret_cast<const float4*>(h1 + t * r + j4 * 4);
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+          }
+        }
+      }
+      reinterpret_cast<float4*>(Ks)[idx] = v;
+    }
+  }
+  __syncthreads();
+  if (anyq) {
+    const float sl = d.sm_scale * kLog2e;
+    for (int ti = 0; ti < TT / 8; ++ti) {
+      const int tt = warp * (TT / 8) + ti;
+      if (tt >= nt || s_code[tt] < MOKA_MOD_VIS) continue;       // warp-uniform
+      float h[C], acc[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) { h[c] = hs[tt * R + lane * C + c]; acc[c] = 0.f; }
+      float m = -INFINITY, l = 0.f;
+      for (int k0 = 0; k0 < L; k0 += 2) {
+        float K0[C], K1[C];
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          K0[c] = Ks[k0 * R + lane * C + c];
+          K1[c] = Ks[(k0 + 1) * R + lane * C + c];
+          a0 = fmaf(h[c], K0[c], a0);
+          a1 = fmaf(h[c], K1[c], a1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        }
+        const float sc0 = a0 * sl;
+        const float sc1 = (k0 + 1 < L) ? a1 * sl : -INFINITY;
+        const float smax = fmaxf(sc0, sc1);
+        if (smax > m) {                                // uniform
+          const float corr = exp2f(m - smax);
+          l *= corr;
+#pragma unroll
+          for (int c = 0; c < C; ++c) acc[c] *= corr;
+          m = smax;
+        }
+        const float e0 = exp2f(sc0 - m), e1 = exp2f(sc1 - m);
+        l += e0 + e1;
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[c] = fmaf(e0, K0[c], fmaf(e1, K1[c], acc[c]));
+      }
+      const float scw = d.attn_w / l;
+      if (lane == 0) lse_out[tbase + tt] = m + log2f(l);
+#pragma unroll
+      for (int c = 0; c < C; ++c) hs[tt * R + lane * C + c] = fmaf(scw, acc[c], h[c]);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < TT * R4; i += 256) {
+    const int tt = i / R4, j4 = i - tt * R4;
+    if (tt < nt && j4 < r4)
+      *reinterpret_cast<float4*>(g_out + (tbase + tt) * r + j4 * 4) = reinterpret_cast<const float4*>(hs)[i];
+  }
+  if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 103);
+}
+
 // ---------------------------------------------------------------------------- k_up_tc
 //   Y[128 tok, 128 cols] = Y0 + (post_m g)[128 tok, r] . B[128 cols, r]^T   per column chunk
 // Warp 0 streams the y0 tiles in with TMA, the 128 worker threads (warps 2..5) run the rank-r
@@ -948,6 +1068,15 @@ static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaSt
         if (R == 8) e = launch_pdl(k_attn_fwd_split<8>, dim3(d.B * gps), dim3(256), sm2, st, d, attn_kcap, gps, a.tokmeta, a.kidx, a.klen, h0, h1, hfin, g_stash, lse);
         else if (R == 16) e = launch_pdl(k_attn_fwd_split<16>, dim3(d.B * gps), dim3(256), sm2, st, d, attn_kcap, gps, a.tokmeta, a.kidx, a.klen, h0, h1, hfin, g_stash, lse);
         else e = launch_pdl(k_attn_fwd_split<32>, dim3(d.B * gps), dim3(256), sm2, st, d, attn_kcap, gps, a.tokmeta, a.kidx, a.klen, h0, h1, hfin, g_stash, lse);
+      } else if (d.r <= 128) {
+        const int C = d.r <= 64 ? 2 : 4;
+        const size_t sm3 = ((size_t)((attn_kcap + 1) & ~1) * 32 * C + 32 * 32 * C) * 4;
+        if (sm3 > 48 * 1024) {
+          cudaFuncSetAttribute(k_attn_fwd_rank<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
+          cudaFuncSetAttribute(k_attn_fwd_rank<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
+        }
+        if (C == 2) e = launch_pdl(k_attn_fwd_rank<2>, dim3(d.B * gps), dim3(256), sm3, st, d, attn_kcap, gps, a.tokmeta, a.kidx, a.klen, h0, h1, hfin, g_stash, lse);
+        else e = launch_pdl(k_attn_fwd_rank<4>, dim3(d.B * gps), dim3(256), sm3, st, d, attn_kcap, gps, a.tokmeta, a.kidx, a.klen, h0, h1, hfin, g_stash, lse);
       } else
       e = launch_pdl(k_attn_fwd, dim3(d.B * gps), dim3(256), attn_smem, st, d, attn_kcap, gps, a.tokmeta, a.kidx, a.klen,
                      h0, h1, hfin, g_stash, lse);
@@ -1689,7 +1818,8 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
             __nv_bfloat16* __restrict__ hc, __nv_bfloat16* __restrict__ hct_hi, __nv_bfloat16* __restrict__ hct_lo) {
   constexpr int TT = 32;
   constexpr int TPW = TT / (NT / 32);               // tokens per warp
-  constexpr int RS = R + 1;                         // odd row stride: lane <-> key reads are conflict-free
+  constexpr int RS = R + 1;                         // odd row stride of the pack staging rows
+  constexpr int KS = R <= 32 ? R + 1 : R;           // key rows: odd stride for lane <-> key reads, aligned for lane <-> rank
   constexpr int KP32 = KB * 32;
   constexpr int R4 = R / 4;
   extern __shared__ __align__(16) float sm[];
@@ -1700,8 +1830,8 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
   float* dhs = dgs + TT * R;                        // dh rows: dG + the attention-backward update of query rows
   float* pws = dhs + TT * R;                        // [TT][KP32]  p * w
   float* dss = pws + TT * KP32;                     // [TT][KP32]  ds / sqrt(r)
-  float* Ks = dss + TT * KP32;                      // [KP32][RS]   (zero rows for invalid keys)
-  float* vs = Ks + KP32 * RS;                       // [TT][RS] staging of the pack step
+  float* Ks = dss + TT * KP32;                      // [KP32][KS]   (zero rows for invalid keys)
+  float* vs = Ks + KP32 * KS;                       // [TT][RS] staging of the pack step
   __shared__ int s_code[TT];
   __shared__ int s_base[TT];
   __shared__ float s_lse[TT];
@@ -1755,7 +1885,7 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
         }
         if (tokmeta[tk] & MOKA_KEY_VALID) v = *reinterpret_cast<const float4*>(h_stash + tk * r + j);
       }
-      float* dst = Ks + k * RS + j;
+      float* dst = Ks + k * KS + j;
       dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
     }
   }
@@ -1776,7 +1906,68 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
     reinterpret_cast<float4*>(dhs)[i] = v;
   }
   __syncthreads();
-  if (anyq) {
+  if (anyq && R > 32) {
+    // ---- phase A, rank-parallel form (R = 64 / 128): lane <-> R/32 consecutive rank indices, the dot
+    // products over the rank are warp reductions, one key at a time (two in flight)
+    if constexpr (R > 32) {
+      constexpr int C = R / 32;
+      const float sl = d.sm_scale * kLog2e;
+#pragma unroll 1
+      for (int ti = 0; ti < TPW; ++ti) {
+        const int tt = warp * TPW + ti;
+        if (s_code[tt] < MOKA_MOD_VIS) {              // warp-uniform
+#pragma unroll
+          for (int kb = 0; kb < KB; ++kb) { pws[tt * KP32 + kb * 32 + lane] = 0.f; dss[tt * KP32 + kb * 32 + lane] = 0.f; }
+          continue;
+        }
+        float hq[C], dg[C], dacc[C];
+        float Dsum = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          hq[c] = hs[tt * R + lane * C + c];
+          dg[c] = dgs[tt * R + lane * C + c];
+          dacc[c] = 0.f;
+          Dsum = fmaf(dg[c], gs[tt * R + lane * C + c] - hq[c], Dsum);
+        }
+        Dsum = warp_sum(Dsum);
+        const float lse_t = s_lse[tt];
+        for (int k0 = 0; k0 < KP32; k0 += 2) {
+          if (k0 >= L) {                              // uniform: beyond the key list
+            if (lane < 2) { pws[tt * KP32 + k0 + lane] = 0.f; dss[tt * KP32 + k0 + lane] = 0.f; }
+            continue;
+          }
+          float K0[C], K1[C];
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            K0[c] = Ks[k0 * KS + lane * C + c];
+            K1[c] = Ks[(k0 + 1) * KS + lane * C + c];          // KP32 is even: row k0 + 1 exists (zero beyond L)
+            a0 = fmaf(hq[c], K0[c], a0); b0 = fmaf(dg[c], K0[c], b0);
+            a1 = fmaf(hq[c], K1[c], a1); b1 = fmaf(dg[c], K1[c], b1);
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o); b0 += __shfl_xor_sync(0xffffffffu, b0, o);
+            a1 += __shfl_xor_sync(0xffffffffu, a1, o); b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+          }
+          const float p0 = exp2f(a0 * sl - lse_t);
+          const float p1 = (k0 + 1 < L) ? exp2f(a1 * sl - lse_t) : 0.f;
+          const float ds0 = p0 * (b0 * d.attn_w - Dsum) * d.sm_scale;
+          const float ds1 = p1 * (b1 * d.attn_w - Dsum) * d.sm_scale;
+#pragma unroll
+          for (int c = 0; c < C; ++c) dacc[c] = fmaf(ds0, K0[c], fmaf(ds1, K1[c], dacc[c]));
+          if (lane == 0) {
+            pws[tt * KP32 + k0] = p0 * d.attn_w; pws[tt * KP32 + k0 + 1] = p1 * d.attn_w;
+            dss[tt * KP32 + k0] = ds0; dss[tt * KP32 + k0 + 1] = ds1;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < C; ++c)
+          if (lane * C + c < r) dhs[tt * R + lane * C + c] += dacc[c];
+      }
+    }
+  }
+  if (anyq && R <= 32) {
     // ---- phase A
     const float sl = d.sm_scale * kLog2e;
     const int comp = (R == 32) ? lane : (R == 16 ? (lane >> 1) : (lane >> 2));
@@ -1798,13 +1989,15 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
         Dsum = fmaf(dg[j], gs[tt * R + j] - hq[j], Dsum);
       }
       const float lse_t = s_lse[tt];
-      float dh_tot = 0.f;                             // component `comp` of the dh contribution (writer lanes)
+      float part[R];                                  // this lane's keys' share of the dh update: sum_k ds_k K_k
+#pragma unroll
+      for (int j = 0; j < R; ++j) part[j] = 0.f;
 #pragma unroll
       for (int kb = 0; kb < KB; ++kb) {
         const int k = kb * 32 + lane;
         float pw = 0.f, dsv = 0.f;
         if (kb * 32 < L) {                            // uniform
-          const float* Kr = Ks + k * RS;
+          const float* Kr = Ks + k * KS;
           float Kv[R];
           float sc = 0.f, dp = 0.f;
 #pragma unroll
@@ -1814,29 +2007,30 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
           const float ds = pr * (dp - Dsum);
           pw = pr * d.attn_w;
           dsv = ds * d.sm_scale;
-          float part[R];
 #pragma unroll
-          for (int j = 0; j < R; ++j) part[j] = dsv * Kv[j];
-#pragma unroll
-          for (int half = R / 2, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
-            const bool upper = (lane & bit) != 0;
-#pragma unroll
-            for (int i = 0; i < half; ++i) {
-              const float send = upper ? part[i] : part[i + half];
-              const float keep = upper ? part[i + half] : part[i];
-              part[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
-            }
-          }
-          float tot = part[0];
-          if (R <= 16) tot += __shfl_xor_sync(0xffffffffu, tot, 1);
-          if (R <= 8) tot += __shfl_xor_sync(0xffffffffu, tot, 2);
-          dh_tot += tot;
+          for (int j = 0; j < R; ++j) part[j] = fmaf(dsv, Kv[j], part[j]);
         }
         pws[tt * KP32 + k] = pw;
         dss[tt * KP32 + k] = dsv;
       }
+      // one butterfly per token: lane <-> key partials -> lane <-> rank index
+#pragma unroll
+      for (int half = R / 2, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+        const bool upper = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          const float send = upper ? part[i] : part[i + half];
+          const float keep = upper ? part[i + half] : part[i];
+          part[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+      }
+      float dh_tot = part[0];
+      if (R <= 16) dh_tot += __shfl_xor_sync(0xffffffffu, dh_tot, 1);
+      if (R <= 8) dh_tot += __shfl_xor_sync(0xffffffffu, dh_tot, 2);
       if (writer && comp < r) dhs[tt * R + comp] += dh_tot;
     }
+  }
+  if (anyq) {
     __syncthreads();
     if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 116);
     // ---- phase B: dK[k, 4 jq..] = sum over the CTA's tokens, one owner per element
@@ -1882,7 +2076,7 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
   // built while staging the keys (CTAs without queries fetch them now); the finished dK rows and the
   // parked tiles' dh rows / token codes then arrive in ONE round of independent loads, and folding and
   // packing run out of shared memory, all tiles of a round at once.
-  constexpr int kSmFloats = 4 * TT * R + 2 * TT * KP32 + KP32 * RS + TT * RS;
+  constexpr int kSmFloats = 4 * TT * R + 2 * TT * KP32 + KP32 * KS + TT * RS;
   constexpr int kPBfit = (kSmFloats - KP32 * R) / (TT * RS);
   constexpr int PB = kPBfit < 6 ? kPBfit : 6;       // parked tiles per round
   static_assert(PB >= 1, "finisher scratch does not fit");
@@ -2289,8 +2483,7 @@ bool tc_backward_fused_ok(const DevDesc& d, int klen_hint, bool has_dx) {
   WgradTcParams p;
   PackLayout L;
   size_t fixed;
-  return d.r <= 32 && klen_hint <= 128 && (d.r <= 16 || klen_hint <= 64) && d.S % 8 == 0 && d.S <= 32768 &&
-         wgrad_plan(d, has_dx, 148, p, L, fixed);
+  return d.r <= 128 && klen_hint <= 128 && d.S % 8 == 0 && d.S <= 32768 && wgrad_plan(d, has_dx, 148, p, L, fixed);
 }
 
 static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayout& L, int dg_partials,
@@ -2299,9 +2492,10 @@ static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayou
   p.rp = L.rp; p.NPW = L.NPW; p.KP = L.KP; p.bps = (d.S + 31) / 32;
   p.scale = d.pre * d.drop_scale;
   const int kblocks = (max(a.klen_hint, 1) + 31) / 32;
-  const int R = d.r <= 8 ? 8 : (d.r <= 16 ? 16 : 32);
+  const int R = d.r <= 8 ? 8 : (d.r <= 16 ? 16 : (d.r <= 32 ? 32 : (d.r <= 64 ? 64 : 128)));
   const int KBs = kblocks <= 1 ? 1 : (kblocks <= 2 ? 2 : 4);
-  const size_t sm = ((size_t)4 * 32 * R + 2 * 32 * KBs * 32 + (size_t)KBs * 32 * (R + 1) + 32 * (R + 1)) * 4;
+  const int KS = R <= 32 ? R + 1 : R;
+  const size_t sm = ((size_t)4 * 32 * R + 2 * 32 * KBs * 32 + (size_t)KBs * 32 * KS + 32 * (R + 1)) * 4;
   const float* dG1 = dg_partials ? a.dh_att : nullptr;
   cudaError_t e = cudaSuccess;
 #define MOKA_LAUNCH_ATTN_PACK(RR, KK, NN)                                                                    \
@@ -2314,7 +2508,9 @@ static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayou
   if (R == 8) { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK(8, 1, 512); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK(8, 2, 512); else MOKA_LAUNCH_ATTN_PACK(8, 4, 512); }
   // (R = 16 at 512 threads needs 128 registers: one CTA per SM and a second wave; 256 threads fit two)
   else if (R == 16) { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK(16, 1, 256); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK(16, 2, 256); else MOKA_LAUNCH_ATTN_PACK(16, 4, 256); }
-  else { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK(32, 1, 256); else MOKA_LAUNCH_ATTN_PACK(32, 2, 256); }
+  else if (R == 32) { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK(32, 1, 256); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK(32, 2, 256); else MOKA_LAUNCH_ATTN_PACK(32, 4, 256); }
+  else if (R == 64) { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK(64, 1, 256); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK(64, 2, 256); else MOKA_LAUNCH_ATTN_PACK(64, 4, 256); }
+  else { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK(128, 1, 256); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK(128, 2, 256); else MOKA_LAUNCH_ATTN_PACK(128, 4, 256); }
 #undef MOKA_LAUNCH_ATTN_PACK
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
   return check_launch_tc();

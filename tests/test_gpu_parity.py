@@ -367,3 +367,137 @@ def test_forward_is_bit_reproducible():
         b = _oracle_case(mo.VARIANT_AVT, 2, 2048, 1024, 512, 16, 3, 'c3', 16, 1.0, torch.bfloat16, flags=flags)
         assert torch.equal(a['h'], b['h'])
         assert torch.equal(a['y'], b['y'])
+
+
+def test_back_to_back_calls_with_dependent_launch_are_race_free():
+    """The kernels of consecutive calls overlap through programmatic dependent launch and share one
+    workspace: 20 forward+backward pairs issued back to back (no synchronisation in between, three
+    rotating input sets) must reproduce the results of the same calls issued one at a time."""
+    from moka_b200 import _cabi
+    from moka_b200.layer import _make_desc
+    from tests import gpu_util as gu
+    lib = _cabi.load()
+    variant, B, S, d, r, M = mo.VARIANT_AVT, 2, 2048, 1024, 16, 3
+    masks = mo.layout_masks(variant, B, S, 'c3')
+    meta = gu.gpu_meta(variant, masks)
+    sc, _ = gu.scalars_for(variant, 16, r, 1.0)
+    T = B * S
+    bf = torch.bfloat16
+    gen = torch.Generator(device=gu.DEV).manual_seed(11)
+    sets = []
+    for _ in range(3):
+        sets.append(dict(x=torch.randn(T, d, generator=gen, device=gu.DEV).to(bf),
+                         y0=torch.randn(T, d, generator=gen, device=gu.DEV).to(bf),
+                         dy=torch.randn(T, d, generator=gen, device=gu.DEV).to(bf),
+                         dx0=torch.randn(T, d, generator=gen, device=gu.DEV).to(bf)))
+    A = [(torch.rand(r, d, generator=gen, device=gu.DEV) * 2 - 1).mul_(d ** -0.5).to(bf) for _ in range(M)]
+    Bw = (torch.randn(d, r, generator=gen, device=gu.DEV) * 0.02).to(bf)
+    desc = _make_desc((T, d), B, S, d, r, M, bf, meta.Lk, sc, 0)
+    ws = torch.empty(int(lib.moka_workspace_bytes(desc)), dtype=torch.uint8, device=gu.DEV)
+    Ap = _cabi.ptr_array([a.data_ptr() for a in A])
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run(n, sync_each):
+        outs = []
+        for i in range(n):
+            s_ = sets[i % 3]
+            y = s_['y0'].clone(); dx = s_['dx0'].clone()
+            h = torch.empty(2 * T * r + T, device=gu.DEV)
+            dA = [torch.zeros(r, d, device=gu.DEV) for _ in range(M)]
+            dB = torch.zeros(d, r, device=gu.DEV)
+            outs.append((y, dx, h, dA, dB))
+        torch.cuda.synchronize()
+        for i in range(n):
+            s_ = sets[i % 3]
+            y, dx, h, dA, dB = outs[i]
+            _cabi.check(lib.moka_forward(desc, s_['x'].data_ptr(), y.data_ptr(), y.data_ptr(), Ap, Bw.data_ptr(),
+                                         meta.tokmeta.data_ptr(), meta.kidx.data_ptr(), meta.klen.data_ptr(),
+                                         h.data_ptr(), 0, 0, ws.data_ptr(), ws.numel(), st), 'fwd')
+            _cabi.check(lib.moka_backward(desc, s_['dy'].data_ptr(), s_['x'].data_ptr(), h.data_ptr(), Ap, Bw.data_ptr(),
+                                          meta.tokmeta.data_ptr(), meta.kidx.data_ptr(), meta.klen.data_ptr(),
+                                          dx.data_ptr(), _cabi.ptr_array([g.data_ptr() for g in dA]), dB.data_ptr(),
+                                          0, 0, ws.data_ptr(), ws.numel(), st), 'bwd')
+            if sync_each:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        return outs
+
+    ref = run(3, True)
+    got = run(21, False)
+    for i, (y, dx, h, dA, dB) in enumerate(got):
+        ry, rdx, rh, rdA, rdB = ref[i % 3]
+        assert torch.equal(y, ry), f'y differs in call {i}'
+        assert torch.equal(h[:2 * T * r], rh[:2 * T * r]), f'h/g stash differs in call {i}'
+        # key rows of dx see dK, an fp32 reduction in arbitrary order: allow last-bit flips there
+        assert mo.rel_l2(dx, rdx) <= 1e-4, f'dx differs in call {i}'
+        # weight gradients are accumulated with fp32 reductions in arbitrary order
+        assert mo.rel_l2(dB, rdB) <= 1e-5
+        for m in range(M):
+            assert mo.rel_l2(dA[m], rdA[m]) <= 1e-5
+
+
+def test_chain_is_cuda_graph_capturable():
+    """moka_forward + moka_backward record into a CUDA graph (no allocation, memset or sync inside the
+    library; the dependent-launch edges are captured) and the replay reproduces the eager results."""
+    from moka_b200 import _cabi
+    from moka_b200.layer import _make_desc
+    from tests import gpu_util as gu
+    lib = _cabi.load()
+    variant, B, S, d, r, M = mo.VARIANT_VT, 2, 1024, 512, 8, 2
+    masks = mo.layout_masks(variant, B, S, 'c2')
+    meta = gu.gpu_meta(variant, masks)
+    sc, _ = gu.scalars_for(variant, 16, r, 0.05)
+    T = B * S
+    bf = torch.bfloat16
+    gen = torch.Generator(device=gu.DEV).manual_seed(3)
+    x = torch.randn(T, d, generator=gen, device=gu.DEV).to(bf)
+    y0 = torch.randn(T, d, generator=gen, device=gu.DEV).to(bf)
+    dy = torch.randn(T, d, generator=gen, device=gu.DEV).to(bf)
+    dx0 = torch.randn(T, d, generator=gen, device=gu.DEV).to(bf)
+    A = [(torch.rand(r, d, generator=gen, device=gu.DEV) * 2 - 1).mul_(d ** -0.5).to(bf) for _ in range(M)]
+    Bw = (torch.randn(d, r, generator=gen, device=gu.DEV) * 0.02).to(bf)
+    desc = _make_desc((T, d), B, S, d, r, M, bf, meta.Lk, sc, 0)
+    ws = torch.empty(int(lib.moka_workspace_bytes(desc)), dtype=torch.uint8, device=gu.DEV)
+    Ap = _cabi.ptr_array([a.data_ptr() for a in A])
+    y = torch.empty_like(y0); dx = torch.empty_like(dx0)
+    h = torch.empty(2 * T * r + T, device=gu.DEV)
+    dA = [torch.zeros(r, d, device=gu.DEV) for _ in range(M)]
+    dB = torch.zeros(d, r, device=gu.DEV)
+    dAp = _cabi.ptr_array([g.data_ptr() for g in dA])
+
+    def chain(stream):
+        _cabi.check(lib.moka_forward(desc, x.data_ptr(), y.data_ptr(), y.data_ptr(), Ap, Bw.data_ptr(),
+                                     meta.tokmeta.data_ptr(), meta.kidx.data_ptr(), meta.klen.data_ptr(),
+                                     h.data_ptr(), 0, 0, ws.data_ptr(), ws.numel(), stream), 'fwd')
+        _cabi.check(lib.moka_backward(desc, dy.data_ptr(), x.data_ptr(), h.data_ptr(), Ap, Bw.data_ptr(),
+                                      meta.tokmeta.data_ptr(), meta.kidx.data_ptr(), meta.klen.data_ptr(),
+                                      dx.data_ptr(), dAp, dB.data_ptr(), 0, 0, ws.data_ptr(), ws.numel(), stream), 'bwd')
+
+    def reset():
+        y.copy_(y0); dx.copy_(dx0); dB.zero_()
+        for g in dA:
+            g.zero_()
+
+    reset()
+    chain(torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    eager = (y.clone(), dx.clone(), dB.clone(), [g.clone() for g in dA])
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        reset()
+        side.synchronize()
+        with torch.cuda.graph(graph, stream=side):
+            chain(side.cuda_stream)
+    torch.cuda.synchronize()
+    for _ in range(2):
+        reset()
+        torch.cuda.synchronize()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(y, eager[0])
+        assert mo.rel_l2(dx, eager[1]) <= 1e-4
+        assert mo.rel_l2(dB, eager[2]) <= 1e-5
+        for m in range(M):
+            assert mo.rel_l2(dA[m], eager[3][m]) <= 1e-5
