@@ -213,7 +213,8 @@ def main():
     ap.add_argument('--workload', default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument('--micro-batch', type=int, default=0)
     ap.add_argument('--zero-stage', type=int, default=1)
-    ap.add_argument('--dropout', type=float, default=0.0)
+    ap.add_argument('--dropout', type=float, default=0.05,
+                    help='lora_dropout; 0.05 is what both reference launch scripts train with')
     ap.add_argument('--grad-checkpointing', action='store_true')
     ap.add_argument('--flags', type=int, default=0, help='MokaDesc.flags (1 = force warp-FMA kernels)')
     ap.add_argument('--skip-cpu-baseline', action='store_true')
@@ -329,7 +330,7 @@ def main():
         uses_tc = None
         try:
             lay = pm.moka_layers()[0]
-            uses_tc = 'tcgen05+TMA' if (wl['dropout'] == 0.0 and not (args.flags & 1)) else 'warp-FMA'
+            uses_tc = 'tcgen05+TMA' if not (args.flags & 1) else 'warp-FMA'
         except Exception:
             pass
         line = dict(

@@ -55,14 +55,24 @@ static DevDesc make_dev(const MokaDesc* m, uint64_t seed, uint64_t offset) {
   d.sm_scale = 1.0f / sqrtf((float)m->r);
   if (m->dropout_p > 0.f) {
     d.drop_scale = 1.0f / (1.0f - m->dropout_p);
-    long t = lrintf(m->dropout_p * 65536.0f);
+    long t = lrintf(m->dropout_p * 4096.0f);
     if (t < 1) t = 1;
-    if (t > 65535) t = 65535;
+    if (t > 4095) t = 4095;
     d.drop_thresh = (uint32_t)t;
+    for (int i = 0; i < 12; ++i) d.drop_sel[i] = ((t >> i) & 1) ? 0xffffffffu : 0u;
   } else {
     d.drop_scale = 1.0f; d.drop_thresh = 0;
   }
   d.seed = seed; d.offset = offset;
+  {
+    // splitmix64 over (seed, offset) -> the two 32-bit keys of the dropout generator
+    uint64_t z = seed * 0x9E3779B97F4A7C15ull + offset + 0xD1B54A32D192ED03ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    d.key_lo = (uint32_t)z;
+    d.key_odd = (uint32_t)(z >> 32) | 1u;
+  }
   return d;
 }
 

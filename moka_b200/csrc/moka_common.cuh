@@ -21,8 +21,10 @@ struct DevDesc {            // by-value kernel argument (POD)
   float pre, post[4];       // post[code], code 1..3 (post[0] unused)
   float attn_w, sm_scale;   // sm_scale = 1/sqrt(r)
   float drop_scale;         // 1/(1-p) or 1
-  uint32_t drop_thresh;     // keep iff u16 >= thresh ; 0 = dropout off
+  uint32_t drop_thresh;     // drop probability = thresh / 4096 ; 0 = dropout off
+  uint32_t drop_sel[12];    // all-ones where the corresponding bit of drop_thresh is set
   unsigned long long seed, offset;
+  uint32_t key_lo, key_odd; // dropout generator keys (splitmix64 of seed, offset; key_odd is odd)
   int tile_tokens;          // tokens per CTA tile
   int num_tiles;
   int dbg_skip;             // MOKA_FLAG_DBG_SKIP bits (timing aid)
@@ -126,33 +128,58 @@ template <typename T> __device__ __forceinline__ float to_f32(T v);
 template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-// ---------------------------------------------------------------------------- Philox
-// Philox4x32-10 (Salmon et al. 2011), counter = (group index, offset), key = seed.
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int i = 0; i < 10; ++i) {
-    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0; key.y += W1;
-  }
-  return ctr;
+// ---------------------------------------------------------------------------- dropout keep masks
+// Bit-sliced Bernoulli generator: one evaluation yields the 32 drop decisions of a 32-column super-group
+// (token t, columns 32 sg .. 32 sg + 31), each bit set with probability T / 2^12, T = drop_thresh =
+// round(p * 4096).  Twelve pseudo-random words R_i are folded from the least significant bit of T upwards,
+//     x <- bit_i(T) ? (R_i | x) : (R_i & x),
+// which halves-and-shifts the per-bit probability exactly like long division of T by 2^12.  The words are
+// R_i = z_i ^ (z_i >> 15), z_i = (y ^ key_odd) * C_i (odd constants C_i) drawn from one full avalanche
+// y = mix32((idx_lo ^ key_lo) + idx_hi * golden) of the super-group index idx = t * ceil(d_in / 32) + sg
+// (mix32 = the 2-multiply finaliser "lowbias32", C. Wellons); (key_lo, key_odd) come from (seed, offset) by
+// splitmix64 on the host.  ~2 integer ops per element (Philox4x32-10 + compares: ~17), cheap enough to mask
+// the shared-memory tiles of the tensor-core kernels close to HBM rate.  Every kernel and the test hook
+// moka_dropout_keep_mask use these functions, so forward, backward and the oracle see one mask.
+constexpr int kDropBits = 12;
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x21f0aaadu;
+  x ^= x >> 15; x *= 0x735a2d97u;
+  x ^= x >> 15;
+  return x;
 }
-
+// 32 KEEP bits (bit j = column 32 sg + j is kept) of super-group `idx`.
+__device__ __forceinline__ uint32_t dropout_keep32(const DevDesc& d, unsigned long long idx) {
+  constexpr uint32_t C[16] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du,
+                              0xFD7046C5u, 0xB55A4F09u, 0x94D049BBu, 0xBF58476Du, 0x2545F491u, 0x6C8E9CF5u,
+                              0xE7037ED1u, 0x8EBC6AF1u, 0x589965CDu, 0x1D8E4E27u};
+  const uint32_t y = mix32(((uint32_t)idx ^ d.key_lo) + (uint32_t)(idx >> 32) * 0x9E3779B1u) ^ d.key_odd;
+  uint32_t x = 0u;
+#pragma unroll
+  for (int i = 0; i < kDropBits; ++i) {
+    const uint32_t z = y * C[i];
+    const uint32_t R = z ^ (z >> 15);
+    const uint32_t m = d.drop_sel[i];                          // all ones where bit i of T is set (constant bank)
+    x = (R & x) | (m & (R | x));                               // one LOP3: m ? (R | x) : (R & x)
+  }
+  return ~x;
+}
+__device__ __forceinline__ unsigned long long dropout_row_base(const DevDesc& d, long long t) {
+  return (unsigned long long)t * (unsigned long long)((d.d_in + 31) >> 5);
+}
 // keep mask for 8 consecutive columns (group g = col/8) of token t: bit i set = element kept.
 __device__ __forceinline__ uint32_t dropout_keep8(const DevDesc& d, int t, int group) {
-  unsigned long long idx = (unsigned long long)t * (unsigned long long)(d.d_in >> 3) + (unsigned long long)group;
-  uint4 c = make_uint4((uint32_t)idx, (uint32_t)(idx >> 32), (uint32_t)d.offset, (uint32_t)(d.offset >> 32));
-  uint4 o = philox4x32_10(c, make_uint2((uint32_t)d.seed, (uint32_t)(d.seed >> 32)));
-  uint32_t w[4] = {o.x, o.y, o.z, o.w};
-  uint32_t m = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    m |= ((w[i] & 0xffffu) >= d.drop_thresh ? 1u : 0u) << (2 * i);
-    m |= ((w[i] >> 16) >= d.drop_thresh ? 1u : 0u) << (2 * i + 1);
-  }
-  return m;
+  const uint32_t k32 = dropout_keep32(d, dropout_row_base(d, t) + (unsigned long long)(group >> 2));
+  return (k32 >> ((group & 3) * 8)) & 0xffu;
+}
+// 8 keep bits -> AND-masks for the four bf16 pairs of the group (0xFFFF per kept element): a multiply
+// spreads four bits onto the four byte sign positions, prmt with sign replication fills the halfwords.
+__device__ __forceinline__ void dropout_expand8(uint32_t km, uint32_t (&W)[4]) {
+  const uint32_t lo = ((km & 0xfu) * 0x10204080u) & 0x80808080u;
+  const uint32_t hi = ((km >> 4) * 0x10204080u) & 0x80808080u;
+  asm("prmt.b32 %0, %1, %1, 0x9988;" : "=r"(W[0]) : "r"(lo));
+  asm("prmt.b32 %0, %1, %1, 0xBBAA;" : "=r"(W[1]) : "r"(lo));
+  asm("prmt.b32 %0, %1, %1, 0x9988;" : "=r"(W[2]) : "r"(hi));
+  asm("prmt.b32 %0, %1, %1, 0xBBAA;" : "=r"(W[3]) : "r"(hi));
 }
 
 // ---------------------------------------------------------------------------- warp utils

@@ -62,6 +62,7 @@ static inline uint32_t tmem_cols_for(int n) {
 }
 
 constexpr int kTcThreads = 192;
+constexpr int kWorkers = 128;                                   // worker threads of a group (one per TMEM lane)
 
 // Launch with programmatic stream serialization (see moka_ptx.cuh: pdl_wait / pdl_trigger).
 // MOKA_NO_PDL=1 falls back to plain stream order (A/B measurements).
@@ -123,10 +124,15 @@ struct DownTcParams {
   int dbg;
 };
 
-__global__ void __launch_bounds__(kTcThreads)
+// DROP: lora_dropout > 0.  The worker warps (idle until the epilogue otherwise) apply the keep mask to every x
+// tile in shared memory between its TMA arrival (full) and its use by the tensor core (ready): thread <-> token
+// row, one 16-byte chunk = one 8-column group of the generator; the 1/(1-p) factor rides in p.scale.
+constexpr int kDownDropThreads = kTcThreads + 384;              // + 12 warps that only apply the dropout mask
+template <bool DROP>
+__global__ void __launch_bounds__(DROP ? kDownDropThreads : kTcThreads)
 k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_a0,
           const __grid_constant__ CUtensorMap tm_a1, const __grid_constant__ CUtensorMap tm_a2,
-          DownTcParams p, const uint8_t* __restrict__ tokmeta, float* __restrict__ h_out0,
+          DownTcParams p, DevDesc d, const uint8_t* __restrict__ tokmeta, float* __restrict__ h_out0,
           float* __restrict__ h_out1) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -134,7 +140,8 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
   uint64_t* tmem_full = bars + 2 * p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.stages + 1);
+  uint64_t* ready = bars + 2 * p.stages + 1;                  // [stages] tile masked (DROP only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x / p.ksplit, split = blockIdx.x % p.ksplit;
@@ -147,10 +154,12 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   const uint32_t xbytes = 16384u * (uint32_t)p.kbox;
   for (int s = 0; s < p.stages; ++s) {
     uint4* w = reinterpret_cast<uint4*>(ring + (size_t)s * p.stage_bytes + xbytes);
-    for (uint32_t i = threadIdx.x; i < p.w_bytes * p.kbox / 16; i += kTcThreads) w[i] = make_uint4(0, 0, 0, 0);
+    for (uint32_t i = threadIdx.x; i < p.w_bytes * p.kbox / 16; i += blockDim.x) w[i] = make_uint4(0, 0, 0, 0);
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); ptx::mbar_init(&ready[s], 4 * kWorkers);
+    }
     ptx::mbar_init(tmem_full, 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tm_x); ptx::prefetch_tmap(&tm_a0);
@@ -195,7 +204,8 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       for (int kb = kb0; kb < kb1; ++kb) {
         const int it = kb - kb0, s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        ptx::mbar_wait_or_trap(&full[s], ph);
+        ptx::mbar_wait_or_trap(&full[s], ph);                    // weights + x landed
+        if (DROP) ptx::mbar_wait_or_trap(&ready[s], ph);           // ... and x masked
         if (it == 0) dbg_stamp(p.dbg, blockIdx.x, 3);
         ptx::tc_fence_after_sync();
         const uint32_t xa0 = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
@@ -222,6 +232,41 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     const int row = q * 32 + lane;
     const int t = t0 + row;
     const int code = (t < p.T) ? (tokmeta[t] & MOKA_MOD_MASK) : -1;
+    if (DROP) {
+      // dropout on the x tiles, in place in shared memory.  16 warps (the 4 epilogue warps + 12 that only do
+      // this): a single warp per scheduler runs these dependent integer chains at ~5 cycles per instruction,
+      // four of them hide the latencies.  thread <-> (token row, every 4th 32-column super-group of the stage)
+      const int mt = threadIdx.x - 64;                         // 0 .. 511
+      const int mrow = mt & 127, part = mt >> 7;
+      const unsigned long long rowbase = dropout_row_base(d, t0 + mrow);
+      const int nsg = 2 * p.kbox;                              // super-groups per stage
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int it = kb - kb0, s = it % p.stages;
+        const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        ptx::mbar_wait_or_trap(&full[s], ph);
+        const uint32_t xs = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
+        for (int sg = part; sg < nsg; sg += 4) {
+          const uint32_t k32 = dropout_keep32(d, rowbase + (unsigned long long)(kb * nsg + sg));
+          if (k32 == 0xffffffffu) continue;
+          const uint32_t boxaddr = xs + (uint32_t)(sg >> 1) * 16384u;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const uint32_t km = (k32 >> (cc * 8)) & 0xffu;
+            if (km != 0xffu) {                                   // ~1/3 of the chunks at p = 0.05
+              uint32_t W[4];
+              dropout_expand8(km, W);
+              const uint32_t addr = boxaddr + ptx::sw128_offset((uint32_t)mrow, (uint32_t)((sg & 1) * 4 + cc));
+              uint4 v = ptx::lds128(addr);
+              v.x &= W[0]; v.y &= W[1]; v.z &= W[2]; v.w &= W[3];
+              ptx::sts128(addr, v);
+            }
+          }
+        }
+        ptx::fence_proxy_async_smem();                           // generic writes -> visible to the tensor core
+        ptx::mbar_arrive(&ready[s]);
+      }
+    }
+    if (warp < 6) {                                              // (the extra masking warps have no epilogue role)
     ptx::mbar_wait_or_trap(tmem_full, 0);
     if (threadIdx.x == 64) dbg_stamp(p.dbg, blockIdx.x, 5);
     ptx::tc_fence_after_sync();
@@ -249,6 +294,7 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     }
     if (code == 0)
       for (int j = 0; j < p.r; ++j) h_out[(size_t)t * p.r + j] = 0.f;
+    }
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -307,10 +353,18 @@ static int launch_down_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cuda
   float* h0 = p.ksplit > 1 ? a.hpart : a.h_stash;
   float* h1 = p.ksplit > 1 ? a.hpart + (size_t)d.T * d.r : nullptr;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 256;
-  cudaError_t e = cudaFuncSetAttribute(k_down_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
-  e = launch_pdl(k_down_tc, dim3(ntiles * p.ksplit), dim3(kTcThreads), smem, st, tx, ta[0], ta[1], ta[2], p,
-                 a.tokmeta, h0, h1);
+  cudaError_t e;
+  if (d.drop_thresh) {
+    e = cudaFuncSetAttribute(k_down_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+    e = launch_pdl(k_down_tc<true>, dim3(ntiles * p.ksplit), dim3(kDownDropThreads), smem, st, tx, ta[0], ta[1], ta[2], p, d,
+                   a.tokmeta, h0, h1);
+  } else {
+    e = cudaFuncSetAttribute(k_down_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+    e = launch_pdl(k_down_tc<false>, dim3(ntiles * p.ksplit), dim3(kTcThreads), smem, st, tx, ta[0], ta[1], ta[2], p, d,
+                   a.tokmeta, h0, h1);
+  }
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
   return check_launch_tc();
 }
@@ -695,7 +749,6 @@ struct UpTcParams {
   int dbg;
 };
 
-constexpr int kWorkers = 128;
 
 __device__ __forceinline__ void named_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory");
@@ -705,8 +758,12 @@ __device__ __forceinline__ void named_sync(int id, int n) {
 // onto a bf16 tile held in shared memory as two {64 cols x 128 rows} 128B-swizzled TMA boxes.
 // One thread owns one row (TMEM lane).  All shared loads of a half-row are issued before the
 // arithmetic and all stores after it, so nothing waits on a load -> store -> load chain.
+// DROP (k_wgrad_tc with lora_dropout > 0): the accumulator is the gradient with respect to the DROPPED input,
+// so it is masked with the row's keep bits (km16: 16 bytes, one per 8-column chunk of the 128-column tile,
+// produced when the x tile of the same rows was masked) before it is added.
+template <bool DROP = false>
 __device__ __forceinline__ void add_acc_to_tile(uint32_t tmem_row_addr, uint32_t tile_smem, uint32_t row,
-                                                uint64_t* tmem_free = nullptr) {
+                                                uint64_t* tmem_free = nullptr, const uint32_t* km16 = nullptr) {
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     const uint32_t box = tile_smem + (uint32_t)half * 16384u;
@@ -723,7 +780,13 @@ __device__ __forceinline__ void add_acc_to_tile(uint32_t tmem_row_addr, uint32_t
     }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
-      const float* a = &acc[c >> 2][(c & 3) * 8];
+      float* a = &acc[c >> 2][(c & 3) * 8];
+      if (DROP) {
+        const uint32_t km = (km16[half * 2 + (c >> 2)] >> ((c & 3) * 8)) & 0xffu;   // keep bits of chunk (half, c)
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (!((km >> i) & 1u)) a[i] = 0.f;
+      }
       uint4 v = yv[c];
       v.x = pack_bf16(bf16lo(v.x) + a[0], bf16hi(v.x) + a[1]);
       v.y = pack_bf16(bf16lo(v.y) + a[2], bf16hi(v.y) + a[3]);
@@ -2230,12 +2293,17 @@ struct WgradTcParams {
 
 constexpr int kWgradThreads = 224;                              // + warp 6: TMA store issuer
 
-__global__ void __launch_bounds__(kWgradThreads)
+// DROP: lora_dropout > 0.  dA needs u = keep (.) x and dx needs keep (.) (A^T dh): the workers mask every x tile
+// in shared memory before the tensor core reads it (x_ready) and mask the dx accumulator in the epilogue; the
+// 1/(1-p) factor is already in the packed dh operands.
+constexpr int kWgradDropThreads = kWgradThreads + 256;          // + 8 warps that only apply the dropout mask
+template <bool DROP>
+__global__ void __launch_bounds__(DROP ? kWgradDropThreads : kWgradThreads)
 k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_dx,
            const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
            const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_hc,
            const __grid_constant__ CUtensorMap tm_hct_hi, const __grid_constant__ CUtensorMap tm_hct_lo,
-           WgradTcParams p, float* __restrict__ dA0, float* __restrict__ dA1, float* __restrict__ dA2) {
+           WgradTcParams p, DevDesc d, float* __restrict__ dA0, float* __restrict__ dA1, float* __restrict__ dA2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t hct_blk = (uint32_t)p.NPW * 128u;            // [NPW rows x 64 tokens] block
@@ -2256,7 +2324,10 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   uint64_t* t_full = w_full + 1;               // [2] dx accumulator ready
   uint64_t* t_empty = t_full + 2;              // [2]
   uint64_t* a_full = t_empty + 2;              // [1] dA accumulator final
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 1);
+  uint64_t* x_ready = a_full + 1;              // [xs] x tile masked (DROP only)
+  uint64_t* km_free = x_ready + p.xs;          // [xs] keep bits of the slot consumed by the epilogue (DROP only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(km_free + p.xs);
+  uint32_t* km_s = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [xs][128 rows][4 words] (DROP)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int slice = blockIdx.x / p.tsplit, split = blockIdx.x % p.tsplit;
@@ -2268,10 +2339,13 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   if (threadIdx.x == 0) ptx::pdl_trigger();                   // last kernel of the backward chain (see k_up_tc)
 
   // weight rows that TMA never writes (padding of the rank blocks) must read as zero
-  for (uint32_t i = threadIdx.x; i < 2 * p.w_box_bytes / 16; i += kWgradThreads)
+  for (uint32_t i = threadIdx.x; i < 2 * p.w_box_bytes / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(wtile)[i] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.xs; ++s) { ptx::mbar_init(&x_full[s], 1); ptx::mbar_init(&x_empty[s], 1); }
+    for (int s = 0; s < p.xs; ++s) {
+      ptx::mbar_init(&x_full[s], 1); ptx::mbar_init(&x_empty[s], 1);
+      ptx::mbar_init(&x_ready[s], 2 * kWorkers); ptx::mbar_init(&km_free[s], kWorkers);
+    }
     for (int s = 0; s < p.ds; ++s) {
       ptx::mbar_init(&d_full[s], 1); ptx::mbar_init(&d_empty[s], 1); ptx::mbar_init(&d_done[s], kWorkers);
     }
@@ -2370,6 +2444,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         ptx::mbar_wait_or_trap(&op_full[ob], (uint32_t)(j / p.nop) & 1u);
         if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 40 + j * 3);
         ptx::mbar_wait_or_trap(&x_full[s], ph);
+        if (DROP) ptx::mbar_wait_or_trap(&x_ready[s], ph);
         if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 41 + j * 3);
         if (p.has_dx) ptx::mbar_wait_or_trap(&t_empty[i], ph2 ^ 1u);
         if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 42 + j * 3);
@@ -2399,6 +2474,41 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       }
       ptx::umma_commit(a_full);
     }
+  } else if (warp >= 7) {
+    // ================= dropout masking warps (DROP only): thread <-> (token row, 64-column box of the x tile).
+    // Mask the tile in place before the tensor core reads it and leave the keep bits for the dx epilogue.
+    if constexpr (DROP) {
+      const int mt = threadIdx.x - 224;                        // 0 .. 255
+      const int mrow = mt & 127, box = mt >> 7;
+      for (int j = 0; j < ntt; ++j) {
+        const int s = j % p.xs;
+        const uint32_t k = (uint32_t)(j / p.xs);
+        ptx::mbar_wait_or_trap(&x_full[s], k & 1u);
+        if (p.has_dx && k > 0) ptx::mbar_wait_or_trap(&km_free[s], (k - 1u) & 1u);
+        const unsigned long long rowbase = dropout_row_base(d, (long long)(tt_beg + j) * 128 + mrow);
+        const uint32_t boxaddr = ptx::smem_u32(xring + (size_t)s * 32768) + (uint32_t)box * 16384u;
+#pragma unroll
+        for (int hs = 0; hs < 2; ++hs) {                         // a box = two 32-column super-groups
+          const uint32_t k32 = dropout_keep32(d, rowbase + (unsigned long long)((col0 >> 5) + box * 2 + hs));
+          km_s[((size_t)s * 128 + mrow) * 4 + box * 2 + hs] = k32;
+          if (k32 == 0xffffffffu) continue;
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            const uint32_t km = (k32 >> (cc * 8)) & 0xffu;
+            if (km != 0xffu) {
+              uint32_t W[4];
+              dropout_expand8(km, W);
+              const uint32_t addr = boxaddr + ptx::sw128_offset((uint32_t)mrow, (uint32_t)(hs * 4 + cc));
+              uint4 v = ptx::lds128(addr);
+              v.x &= W[0]; v.y &= W[1]; v.z &= W[2]; v.w &= W[3];
+              ptx::sts128(addr, v);
+            }
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&x_ready[s]);
+      }
+    }
   } else if (warp == 6) {
     // TMA store issuer for the updated dx tiles
     if (lane == 0 && p.has_dx) {
@@ -2420,6 +2530,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t km_cur[4] = {0, 0, 0, 0};                           // keep bits of this row in the current tile (DROP)
     if (p.has_dx) {
       for (int j = 0; j < ntt; ++j) {
         const int i = j & 1;
@@ -2429,12 +2540,23 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         const bool st = (threadIdx.x == 64) && j < 8;
         if (st && j == 0) dbg_stamp(p.dbg, blockIdx.x, 0);
         ptx::mbar_wait_or_trap(&t_full[i], ph2);
+        if (DROP) {
+          // the keep bits of tile j were left in shared memory by the masking warps (published by x_ready)
+          const int sx = j % p.xs;
+          ptx::mbar_wait_or_trap(&x_ready[sx], (uint32_t)(j / p.xs) & 1u);
+          const uint4 kv = ptx::lds128(ptx::smem_u32(km_s + ((size_t)sx * 128 + row) * 4));
+          km_cur[0] = kv.x; km_cur[1] = kv.y; km_cur[2] = kv.z; km_cur[3] = kv.w;
+          ptx::mbar_arrive(&km_free[sx]);
+        }
         if (st) dbg_stamp(p.dbg, blockIdx.x, 8 + j * 4);
         ptx::mbar_wait_or_trap(&d_full[s], dph);
         if (st) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 4);
         ptx::tc_fence_after_sync();
         uint8_t* dt = dring + (size_t)s * 32768;
-        add_acc_to_tile(lane_base + (uint32_t)(i * 128), ptx::smem_u32(dt), (uint32_t)row, &t_empty[i]);
+        if (DROP)
+          add_acc_to_tile<true>(lane_base + (uint32_t)(i * 128), ptx::smem_u32(dt), (uint32_t)row, &t_empty[i], km_cur);
+        else
+          add_acc_to_tile(lane_base + (uint32_t)(i * 128), ptx::smem_u32(dt), (uint32_t)row, &t_empty[i]);
         if (st) dbg_stamp(p.dbg, blockIdx.x, 10 + j * 4);
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&d_done[s]);
@@ -2533,7 +2655,9 @@ static bool wgrad_plan(const DevDesc& d, bool has_dx, int num_sms, WgradTcParams
   const size_t limit = 226 * 1024;
   // prefer two operand buffers (breaks the MMA -> reload -> MMA chain); the dx ring then gets 2 slots
   p.nop = 2;
-  fixed = (size_t)2 * p.w_box_bytes + (size_t)p.nop * p.op_bytes + 1024 + 512;
+  // dropout: the masking warps hand the keep bits of each x slot to the epilogue through shared memory
+  const size_t km_bytes = d.drop_thresh ? (size_t)(has_dx ? 2 : 4) * 2048 : 0;
+  fixed = (size_t)2 * p.w_box_bytes + (size_t)p.nop * p.op_bytes + 1024 + 512 + km_bytes;
   if (fixed + 4 * 32768 > limit) { p.nop = 1; fixed -= p.op_bytes; }
   if (fixed + 3 * 32768 > limit) return false;
   int slots = (int)((limit - fixed) / 32768);
@@ -2580,10 +2704,16 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   if (!make_tmap(&thh, hct_hi, (uint64_t)L.NPW, (uint64_t)d.T, (uint32_t)L.NPW)) return MOKA_EUNSUPPORTED;
   if (!make_tmap(&thl, hct_lo, (uint64_t)L.NPW, (uint64_t)d.T, (uint32_t)L.NPW)) return MOKA_EUNSUPPORTED;
   const size_t smem = (size_t)(p.xs + p.ds) * 32768 + fixed;
-  cudaError_t e = cudaFuncSetAttribute(k_wgrad_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = d.drop_thresh
+                      ? cudaFuncSetAttribute(k_wgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                      : cudaFuncSetAttribute(k_wgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
-  e = launch_pdl(k_wgrad_tc, dim3(slices * p.tsplit), dim3(kWgradThreads), smem, st, tx, tdx, ta[0], ta[1], ta[2], thc,
-                 thh, thl, p, a.dA[0], a.dA[d.M > 1 ? 1 : 0], a.dA[d.M > 2 ? 2 : 0]);
+  if (d.drop_thresh)
+    e = launch_pdl(k_wgrad_tc<true>, dim3(slices * p.tsplit), dim3(kWgradDropThreads), smem, st, tx, tdx, ta[0], ta[1], ta[2],
+                   thc, thh, thl, p, d, a.dA[0], a.dA[d.M > 1 ? 1 : 0], a.dA[d.M > 2 ? 2 : 0]);
+  else
+    e = launch_pdl(k_wgrad_tc<false>, dim3(slices * p.tsplit), dim3(kWgradThreads), smem, st, tx, tdx, ta[0], ta[1], ta[2],
+                   thc, thh, thl, p, d, a.dA[0], a.dA[d.M > 1 ? 1 : 0], a.dA[d.M > 2 ? 2 : 0]);
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
   return check_launch_tc();
 }
@@ -2591,7 +2721,6 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
 // ---------------------------------------------------------------------------- dispatch
 int tc_stage_mask(const DevDesc& d, int dtype) {
   if (dtype != MOKA_BF16) return 0;                 // fp32 storage keeps exact fp32 FMA (1e-5 bar)
-  if (d.drop_thresh) return 0;                      // dropout is applied on the warp-FMA path
   if (d.d_in % 64 || d.d_out % 64) return 0;
   if (d.r % 8 || d.r > 128) return 0;
   if (!get_encode_fn()) return 0;

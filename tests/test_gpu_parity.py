@@ -501,3 +501,32 @@ def test_chain_is_cuda_graph_capturable():
         assert mo.rel_l2(dB, eager[2]) <= 1e-5
         for m in range(M):
             assert mo.rel_l2(dA[m], eager[3][m]) <= 1e-5
+
+
+@pytest.mark.parametrize('variant,M,layout,r,d_in,d_out,S,p', [
+    (mo.VARIANT_AVT, 3, 'c3', 16, 1024, 512, 2048, 0.05),
+    (mo.VARIANT_VT, 2, 'c2', 8, 512, 1024, 2048, 0.1),
+    (mo.VARIANT_VT, 2, 'c1', 32, 256, 256, 200, 0.25),          # ragged last token tile
+], ids=['avt_r16_p05', 'vt_r8_p10', 'vt_r32_ragged_p25'])
+def test_dropout_on_tensor_core_path(variant, M, layout, r, d_in, d_out, S, p):
+    """lora_dropout > 0 stays on the tcgen05 kernels (x tiles masked in shared memory in k_down_tc and
+    k_wgrad_tc, the dx accumulator masked in the wgrad epilogue): same mask as the test hook reports, the
+    oracle run on that mask, and the warp-FMA kernels given the same (seed, offset) agree."""
+    from moka_b200 import _cabi
+    from moka_b200.layer import _make_desc
+    from tests import gpu_util as gu
+    w = 1.0 if variant == mo.VARIANT_AVT else 0.05
+    o_tc = _oracle_case(variant, 2, S, d_in, d_out, r, M, layout, 16, w, torch.bfloat16, p=p, rng=(99, 5))
+    sc, _ = gu.scalars_for(variant, 16, r, w, p)
+    desc = _make_desc((2 * S, d_in), 2, S, d_out, r, M, torch.bfloat16, 8, sc, 0)
+    assert _cabi.load().moka_uses_tensor_cores(desc) == 1
+    rate = 1.0 - float(o_tc['keep'].double().mean())
+    assert abs(rate - p) < 0.01
+    _assert_case(o_tc, torch.bfloat16, M)
+    o_fma = _oracle_case(variant, 2, S, d_in, d_out, r, M, layout, 16, w, torch.bfloat16, p=p, rng=(99, 5),
+                         flags=FORCE_SIMT)
+    assert mo.rel_l2(o_tc['h'], o_fma['h']) <= 2e-6
+    assert mo.rel_l2(o_tc['dx'], o_fma['dx']) <= 1e-3
+    for m in range(M):
+        if float(o_fma['dA'][m].norm()) > 0:
+            assert mo.rel_l2(o_tc['dA'][m], o_fma['dA'][m]) <= 1e-4
