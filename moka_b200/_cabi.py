@@ -20,7 +20,8 @@ META_EMPTY_QUESTION, META_OVERLAP, META_KEY_OVERFLOW = 1, 2, 4
 
 EXPORTS = ['moka_workspace_bytes', 'moka_forward', 'moka_backward', 'moka_build_token_meta',
            'moka_dropout_keep_mask', 'moka_adamw_step', 'moka_launch_count',
-           'moka_uses_tensor_cores', 'moka_strerror', 'moka_version', 'moka_rope', 'moka_debug_read']
+           'moka_uses_tensor_cores', 'moka_strerror', 'moka_version', 'moka_rope', 'moka_debug_read',
+           'moka_debug_trap_buffer']
 
 
 class MokaDesc(Structure):
@@ -67,6 +68,8 @@ def load():
                                     c_float, c_float, c_float, c_float, c_float, c_int32, c_float, c_void_p]
     lib.moka_rope.restype = c_int32
     lib.moka_rope.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]
+    lib.moka_debug_trap_buffer.restype = c_int32
+    lib.moka_debug_trap_buffer.argtypes = [c_void_p]
     lib.moka_debug_read.restype = c_int32
     lib.moka_debug_read.argtypes = [c_void_p, c_int32]
     lib.moka_launch_count.restype = c_int64

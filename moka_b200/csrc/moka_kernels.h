@@ -42,6 +42,7 @@ int launch_rope(const void* src, void* dst, long long BS, int S, int H, int D, f
 
 int debug_read(unsigned long long* host, int n);
 int tc_dbg_enabled();
+int debug_set_trap_buffer(unsigned long long* mapped);
 
 // tensor-core (tcgen05 + TMA) path; returns MOKA_EUNSUPPORTED when the shape does not qualify
 // Returns the mask of stages the tcgen05 path implements for this shape (0 = none).

@@ -45,8 +45,25 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   }
   return false;
 }
-__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
-  if (!mbar_wait(bar, parity)) asm volatile("trap;");
+// Optional post-mortem: a host-mapped word (moka_debug_trap_buffer) receives (source line << 32 | block << 12 |
+// thread) of the wait that timed out before the trap kills the context.
+__device__ unsigned long long* g_trap_buf = nullptr;
+__device__ int g_prog[148 * 4 * 8];            // per-CTA role progress counters (written when g_trap_buf is set)
+__device__ __forceinline__ void prog_mark(int role, int v) {
+  if (g_trap_buf && blockIdx.x < 148 * 4) g_prog[blockIdx.x * 8 + role] = v;
+}
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity, int line = 0) {
+  if (!mbar_wait(bar, parity)) {
+    if (g_trap_buf) {
+      g_trap_buf[0] = ((unsigned long long)line << 32) | ((unsigned long long)(blockIdx.x & 0xfffff) << 12) |
+                      (unsigned long long)(threadIdx.x & 0xfff);
+      g_trap_buf[1] = (unsigned long long)parity;
+      if (blockIdx.x < 148 * 4)
+        for (int i = 0; i < 8; ++i) g_trap_buf[2 + i] = (unsigned long long)(unsigned)g_prog[blockIdx.x * 8 + i];
+      __threadfence_system();
+    }
+    asm volatile("trap;");
+  }
 }
 
 // ------------------------------------------------------------------ programmatic dependent launch

@@ -92,11 +92,11 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 constexpr int kDbgSlots = 128;                                  // per CTA: 0..63 cycle stamps, 100.. wall-clock timeline
 __device__ unsigned long long g_dbg[148 * 2 * kDbgSlots];
 __device__ __forceinline__ void dbg_stamp(int enabled, int cta, int slot) {
-  if (enabled && cta < 148 * 2 && slot < 64) g_dbg[cta * kDbgSlots + slot] = clock64();
+  if ((enabled & 1) && cta < 148 * 2 && slot < 64) g_dbg[cta * kDbgSlots + slot] = clock64();
 }
 // wall-clock (globaltimer, ns) stamps: comparable across CTAs; slots 60 (entry) / 61 (exit) by convention
 __device__ __forceinline__ void dbg_stamp_g(int enabled, int cta, int slot) {
-  if (enabled && cta < 148 * 2 && slot < kDbgSlots) {
+  if ((enabled & 1) && cta < 148 * 2 && slot < kDbgSlots) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_dbg[cta * kDbgSlots + slot] = t;
@@ -108,6 +108,9 @@ static int dbg_enabled() {
   return v;
 }
 int tc_dbg_enabled() { return dbg_enabled(); }
+int debug_set_trap_buffer(unsigned long long* mapped) {
+  return cudaMemcpyToSymbol(ptx::g_trap_buf, &mapped, sizeof(mapped)) == cudaSuccess ? MOKA_OK : MOKA_ECUDA;
+}
 int debug_read(unsigned long long* host, int n) {
   if (n > 148 * 2 * kDbgSlots) n = 148 * 2 * kDbgSlots;
   return cudaMemcpyFromSymbol(host, g_dbg, (size_t)n * 8) == cudaSuccess ? MOKA_OK : MOKA_ECUDA;
@@ -182,7 +185,7 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       for (int kb = kb0; kb < kb1; ++kb) {
         const int it = kb - kb0, s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        ptx::mbar_wait_or_trap(&empty[s], ph ^ 1u);
+        ptx::mbar_wait_or_trap(&empty[s], ph ^ 1u, __LINE__);
         uint8_t* xs = ring + (size_t)s * p.stage_bytes;
         ptx::mbar_arrive_expect_tx(&full[s], tx);
         for (int bx = 0; bx < p.kbox; ++bx) {
@@ -204,8 +207,8 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       for (int kb = kb0; kb < kb1; ++kb) {
         const int it = kb - kb0, s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        ptx::mbar_wait_or_trap(&full[s], ph);                    // weights + x landed
-        if (DROP) ptx::mbar_wait_or_trap(&ready[s], ph);           // ... and x masked
+        ptx::mbar_wait_or_trap(&full[s], ph, __LINE__);                    // weights + x landed
+        if (DROP) ptx::mbar_wait_or_trap(&ready[s], ph, __LINE__);           // ... and x masked
         if (it == 0) dbg_stamp(p.dbg, blockIdx.x, 3);
         ptx::tc_fence_after_sync();
         const uint32_t xa0 = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
@@ -243,31 +246,19 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       for (int kb = kb0; kb < kb1; ++kb) {
         const int it = kb - kb0, s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        ptx::mbar_wait_or_trap(&full[s], ph);
+        ptx::mbar_wait_or_trap(&full[s], ph, __LINE__);
         const uint32_t xs = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
         for (int sg = part; sg < nsg; sg += 4) {
           const uint32_t k32 = dropout_keep32(d, rowbase + (unsigned long long)(kb * nsg + sg));
-          if (k32 == 0xffffffffu) continue;
-          const uint32_t boxaddr = xs + (uint32_t)(sg >> 1) * 16384u;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const uint32_t km = (k32 >> (cc * 8)) & 0xffu;
-            if (km != 0xffu) {                                   // ~1/3 of the chunks at p = 0.05
-              uint32_t W[4];
-              dropout_expand8(km, W);
-              const uint32_t addr = boxaddr + ptx::sw128_offset((uint32_t)mrow, (uint32_t)((sg & 1) * 4 + cc));
-              uint4 v = ptx::lds128(addr);
-              v.x &= W[0]; v.y &= W[1]; v.z &= W[2]; v.w &= W[3];
-              ptx::sts128(addr, v);
-            }
-          }
+          dropout_zero_dropped(k32, xs + (uint32_t)(sg >> 1) * 16384u + (uint32_t)mrow * 128u, (uint32_t)mrow & 7u,
+                               (uint32_t)(sg & 1));
         }
         ptx::fence_proxy_async_smem();                           // generic writes -> visible to the tensor core
         ptx::mbar_arrive(&ready[s]);
       }
     }
     if (warp < 6) {                                              // (the extra masking warps have no epilogue role)
-    ptx::mbar_wait_or_trap(tmem_full, 0);
+    ptx::mbar_wait_or_trap(tmem_full, 0, __LINE__);
     if (threadIdx.x == 64) dbg_stamp(p.dbg, blockIdx.x, 5);
     ptx::tc_fence_after_sync();
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -329,7 +320,9 @@ static int launch_down_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cuda
   // two 64-column boxes per stage (256 contiguous bytes per token row and request: measured faster
   // than one) as long as the ring still holds >= 4 stages
   const size_t budget0 = (ntiles * p.ksplit <= num_sms) ? 200 * 1024 : 100 * 1024;
-  p.kbox = (kbox_env == 2 && d.d_in % 128 == 0 && budget0 / ((16384u + p.w_bytes) * 2u) >= 4) ? 2 : 1;
+  // (two CTAs per SM share the SM's in-flight bytes: two stages each are enough there)
+  const size_t min_stages = (ntiles * p.ksplit <= num_sms) ? 4 : 2;
+  p.kbox = (kbox_env == 2 && d.d_in % 128 == 0 && budget0 / ((16384u + p.w_bytes) * 2u) >= min_stages) ? 2 : 1;
   p.kblocks = d.d_in / (64 * p.kbox);
   p.stage_bytes = (16384u + p.w_bytes) * (uint32_t)p.kbox;
   // one CTA per SM when the grid does not exceed the SM count: spend the whole shared memory on the
@@ -812,8 +805,8 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
   uint8_t* ytiles = base;                                     // [ystages][2 boxes][128 x 128 B]
   uint8_t* gtile = ytiles + (size_t)p.ystages * 32768;        // [kblocks][128 x 128 B]  A operand
   uint8_t* btiles = gtile + (size_t)kblocks * 16384;          // [4][kblocks][128 x 128 B] B operand
-  float* gs = reinterpret_cast<float*>(btiles + (size_t)4 * kblocks * 16384);   // [128, r]
-  float* Ks = gs + 128 * d.r;                                 // [kcap, r+1]
+  float* gs = reinterpret_cast<float*>(btiles + (size_t)4 * kblocks * 16384);   // [128, r] (in-kernel attention only)
+  float* Ks = gs + (p.attn_in_kernel ? 128 * d.r : 0);        // [kcap, r+1]
   uint64_t* bars = reinterpret_cast<uint64_t*>(Ks + (size_t)p.kcap * (d.r + 1) + ((p.kcap * (d.r + 1)) & 1));
   uint64_t* y_full = bars;                                    // [ystages]
   uint64_t* y_empty = y_full + p.ystages;                     // [ystages]
@@ -862,12 +855,13 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
       for (int j = 0; j < nch; ++j) {
         const int s = j % p.ystages;
         const uint32_t ph = (uint32_t)(j / p.ystages) & 1u;
-        ptx::mbar_wait_or_trap(&y_empty[s], ph ^ 1u);
+        ptx::mbar_wait_or_trap(&y_empty[s], ph ^ 1u, __LINE__);
         uint8_t* yt = ytiles + (size_t)s * 32768;
         ptx::mbar_arrive_expect_tx(&y_full[s], 32768u);
         const int col = (c_beg + j) * 128;
         ptx::tma_load_2d(yt, &tm_y0, &y_full[s], col, t0, ptx::kEvictFirst);
         ptx::tma_load_2d(yt + 16384, &tm_y0, &y_full[s], col + 64, t0, ptx::kEvictFirst);
+        ptx::prog_mark(0, j + 1);
       }
     }
   } else if (warp == 1) {
@@ -875,14 +869,14 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
     if (lane == 0) {
       const uint32_t idesc = ptx::idesc_bf16(128, 128, 0, 0);
       const uint32_t ga = ptx::smem_u32(gtile);
-      ptx::mbar_wait_or_trap(g_full, 0);
+      ptx::mbar_wait_or_trap(g_full, 0, __LINE__);
       for (int j = 0; j < nch; ++j) {
         // chunk j belongs to worker group (j & 1); each group rotates over two accumulator / B buffers
         const int i = (j & 1) * 2 + ((j >> 1) & 1);
         const uint32_t ph = (uint32_t)(j >> 2) & 1u;
-        ptx::mbar_wait_or_trap(&b_full[i], ph);
+        ptx::mbar_wait_or_trap(&b_full[i], ph, __LINE__);
         if (j < 6) dbg_stamp(p.dbg, blockIdx.x, 32 + j * 3);
-        ptx::mbar_wait_or_trap(&t_empty[i], ph ^ 1u);
+        ptx::mbar_wait_or_trap(&t_empty[i], ph ^ 1u, __LINE__);
         if (j < 6) dbg_stamp(p.dbg, blockIdx.x, 33 + j * 3);
         ptx::tc_fence_after_sync();
         const uint32_t ba = ptx::smem_u32(btiles + (size_t)i * kblocks * 16384);
@@ -896,6 +890,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
           }
         }
         ptx::umma_commit(&t_full[i]);
+        ptx::prog_mark(1, j + 1);
         if (j < 6) dbg_stamp(p.dbg, blockIdx.x, 34 + j * 3);
       }
     }
@@ -905,7 +900,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
       for (int j = 0; j < nch; ++j) {
         const int s = j % p.ystages;
         const uint32_t ph = (uint32_t)(j / p.ystages) & 1u;
-        ptx::mbar_wait_or_trap(&y_done[s], ph);
+        ptx::mbar_wait_or_trap(&y_done[s], ph, __LINE__);
         uint8_t* yt = ytiles + (size_t)s * 32768;
         const int col = (c_beg + j) * 128;
         ptx::tma_store_2d(&tm_y, yt, col, t0);
@@ -913,6 +908,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
         ptx::tma_store_commit();
         ptx::tma_store_wait_read<0>();                         // smem read out: the slot can take the next load now
         ptx::mbar_arrive(&y_empty[s]);
+        ptx::prog_mark(2, j + 1);
       }
       ptx::tma_store_wait_all<0>();
     }
@@ -1058,11 +1054,11 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
       const uint32_t ph = (uint32_t)(n >> 1) & 1u;
       const int s = j % p.ystages;
       const uint32_t yph = (uint32_t)(j / p.ystages) & 1u;
-      ptx::mbar_wait_or_trap(&t_full[i], ph);
+      ptx::mbar_wait_or_trap(&t_full[i], ph, __LINE__);
       if (wl == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 8 + j * 4);
       // MMA j has consumed B buffer i: restage it right away (async copies fly during the epilogue)
       if (j + 4 < nch) load_b(j + 4, i);
-      ptx::mbar_wait_or_trap(&y_full[s], yph);
+      ptx::mbar_wait_or_trap(&y_full[s], yph, __LINE__);
       if (wl == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 4);
       ptx::tc_fence_after_sync();
       uint8_t* yt = ytiles + (size_t)s * 32768;
@@ -1070,7 +1066,9 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
       if (wl == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 10 + j * 4);
       ptx::fence_proxy_async_smem();                            // generic writes -> visible to the TMA store
       ptx::mbar_arrive(&y_done[s]);
+      if (wl == 0) ptx::prog_mark(3 + grp_id, j + 1);
       if (j + 4 < nch) store_b(i);
+      if (wl == 0) ptx::prog_mark(5 + grp_id, j + 1);
       if (wl == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 11 + j * 4);
     }
     if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 4);
@@ -1098,12 +1096,18 @@ static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaSt
   p.attn_in_kernel = sep_attn ? 0 : 1;
   if (sep_attn) p.kcap = 1;
   const int attn_kcap = min(max(a.klen_hint, 1), 32 * kKeyBlocksMax);
-  const size_t fixed = (size_t)5 * kblocks * 16384 + (size_t)128 * d.r * 4 + 1024 + 512;
+  // (the fp32 row staging `gs` is only needed when the attention runs inside this kernel)
+  const size_t gs_bytes = sep_attn ? 0 : (size_t)128 * d.r * 4;
+  const size_t fixed = (size_t)5 * kblocks * 16384 + gs_bytes + 1024 + 512;
   const size_t limit = 224 * 1024;
   while (p.kcap > 1 && fixed + (size_t)p.kcap * (d.r + 1) * 4 + 2 * 32768 > limit) p.kcap /= 2;
   const size_t key_bytes = ((size_t)p.kcap * (d.r + 1) + 1) * 4;
   p.ystages = (int)((limit - fixed - key_bytes) / 32768);
   if (p.ystages > 4) p.ystages = 4;
+  // The two worker groups alternate chunks, so with an EVEN ring every slot (and its y_full / y_done barriers)
+  // belongs to one group.  With 3 slots the groups take turns on a slot and a group can ask for a phase two ahead
+  // of the barrier; mbarrier parity waits cannot tell that from "done" (seen as a rare hang at r = 32 / 64).
+  if (p.ystages == 3) p.ystages = 2;
   if (p.ystages < 2) return MOKA_EUNSUPPORTED;
   p.write_g = 1;
   p.dbg = dbg_enabled();
@@ -1248,7 +1252,7 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
       for (int j = npre; j < np; ++j) {
         const int s = j % p.stages;
         const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
-        ptx::mbar_wait_or_trap(&empty[s], ph ^ 1u);
+        ptx::mbar_wait_or_trap(&empty[s], ph ^ 1u, __LINE__);
         uint8_t* st = ring + (size_t)s * p.stage_bytes;
         ptx::mbar_arrive_expect_tx(&full[s], 32768u + p.bt_bytes);
         const int col = (p_beg + j) * 128;
@@ -1273,17 +1277,17 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
 #pragma unroll
       for (int k = 0; k < 8; ++k)
         g_desc[k] = ptx::smem_desc_sw128(gta + (uint32_t)(k >> 2) * g2_block + (k & 3) * 32, 1024, 0);
-      ptx::mbar_wait_or_trap(&wfull[0], 0);
+      ptx::mbar_wait_or_trap(&wfull[0], 0, __LINE__);
       dbg_stamp(p.dbg, blockIdx.x, 2);
       for (int j = 0; j < np; ++j) {
         const int s = j % p.stages;
         const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
         const int i = p.nbuf == 2 ? (j & 1) : 0;
         const uint32_t ph2 = (uint32_t)(p.nbuf == 2 ? (j >> 1) : j) & 1u;
-        ptx::mbar_wait_or_trap(&full[s], ph);
+        ptx::mbar_wait_or_trap(&full[s], ph, __LINE__);
         if (j == 0) dbg_stamp(p.dbg, blockIdx.x, 3);
         if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 8 + j * 3);
-        ptx::mbar_wait_or_trap(&d2_empty[i], ph2 ^ 1u);
+        ptx::mbar_wait_or_trap(&d2_empty[i], ph2 ^ 1u, __LINE__);
         if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 3);
         ptx::tc_fence_after_sync();
         const uint32_t sa = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
@@ -1292,17 +1296,17 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
         const uint64_t a1 = a1_base + (uint64_t)(sa >> 4);
         const uint64_t b1 = a1_base + (uint64_t)(bta >> 4);
         const uint64_t a2 = a2_base + (uint64_t)(sa >> 4);
-#pragma unroll
-        for (int box = 0; box < 2; ++box)
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16(tmem_base, a1 + (uint64_t)((box * 16384 + k * 32) >> 4),
-                           b1 + (uint64_t)((box * gt_block + k * 32) >> 4), idesc1, (j > 0 || box > 0 || k > 0) ? 1u : 0u);
-        // MMA2: M = 128 columns (two 64-wide atoms 16 KB apart), K = 128 tokens in 8 steps of 16
+        // MMA2: M = 128 columns (two 64-wide atoms 16 KB apart), K = 128 tokens in 8 steps of 16.
+        // The two products accumulate into different TMEM regions: issued alternately, so that consecutive
+        // instructions never wait on the same accumulator.
         const uint32_t d2 = tmem_base + p.d2_col + (uint32_t)i * 2u * (uint32_t)p.rk;
 #pragma unroll
-        for (int k = 0; k < 8; ++k)
+        for (int k = 0; k < 8; ++k) {
+          const int box = k >> 2, kk = k & 3;
+          ptx::umma_bf16(tmem_base, a1 + (uint64_t)((box * 16384 + kk * 32) >> 4),
+                         b1 + (uint64_t)((box * gt_block + kk * 32) >> 4), idesc1, (j > 0 || k > 0) ? 1u : 0u);
           ptx::umma_bf16(d2, a2 + (uint64_t)((k * 2048) >> 4), g_desc[k], idesc2, k > 0 ? 1u : 0u);
+        }
         ptx::umma_commit(&empty[s]);
         ptx::umma_commit(&d2_full[i]);
         if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 10 + j * 3);
@@ -1351,7 +1355,7 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
     for (int j = 0; j < np; ++j) {
       const int i = p.nbuf == 2 ? (j & 1) : 0;
       const uint32_t ph2 = (uint32_t)(p.nbuf == 2 ? (j >> 1) : j) & 1u;
-      ptx::mbar_wait_or_trap(&d2_full[i], ph2);
+      ptx::mbar_wait_or_trap(&d2_full[i], ph2, __LINE__);
       if (wt == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 32 + j * 2);
       ptx::tc_fence_after_sync();
       const int col = (p_beg + j) * 128 + row;               // TMEM lane <-> output column
@@ -1361,6 +1365,7 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
         ptx::tmem_ld8(lane_base + p.d2_col + (uint32_t)(i * 2 * p.rk + c8), v);          // hi product
         ptx::tmem_ld8(lane_base + p.d2_col + (uint32_t)(i * 2 * p.rk + p.rk + c8), w);   // lo product
         ptx::tmem_ld_wait();
+        if (p.dbg & 2) continue;                                // timing experiment: no dB reductions
         red_add_v4_f32(dst + c8, v[0] + w[0], v[1] + w[1], v[2] + w[2], v[3] + w[3]);
         red_add_v4_f32(dst + c8 + 4, v[4] + w[4], v[5] + w[5], v[6] + w[6], v[7] + w[7]);
       }
@@ -1369,7 +1374,7 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
       if (wt == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 33 + j * 2);
     }
     // dG partial of this CTA
-    ptx::mbar_wait_or_trap(dg_full, 0);
+    ptx::mbar_wait_or_trap(dg_full, 0, __LINE__);
     if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 5);
     ptx::tc_fence_after_sync();
     {
@@ -1631,6 +1636,7 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   if (dg_stages_env > 0 && p.stages > dg_stages_env) p.stages = dg_stages_env;
   if (p.stages < 2) return MOKA_EUNSUPPORTED;
   p.dbg = dbg_enabled();
+  { static int nodb = -1; if (nodb < 0) { const char* e = getenv("MOKA_DBG_NO_DB"); nodb = (e && e[0] == '1') ? 2 : 0; } p.dbg |= nodb; }
   const uint32_t dgc = tmem_cols_for(p.rk);
   p.d2_col = dgc;
   p.nbuf = (dgc + 4 * p.rk <= 512) ? 2 : 1;                  // [128 x 2 rk] dB accumulators next to dG in TMEM
@@ -2398,7 +2404,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         if (j >= npre_x) {   // the big streams first: they have their own ring slots and must never wait on the MMAs
           const int s = j % p.xs;
           const uint32_t ph = (uint32_t)(j / p.xs) & 1u;
-          ptx::mbar_wait_or_trap(&x_empty[s], ph ^ 1u);
+          ptx::mbar_wait_or_trap(&x_empty[s], ph ^ 1u, __LINE__);
           uint8_t* xt = xring + (size_t)s * 32768;
           ptx::mbar_arrive_expect_tx(&x_full[s], 32768u);
           ptx::tma_load_2d(xt, &tm_x, &x_full[s], col0, t0, ptx::kEvictFirst);
@@ -2407,7 +2413,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         if (p.has_dx && j >= npre_d) {
           const int s = j % p.ds;
           const uint32_t ph = (uint32_t)(j / p.ds) & 1u;
-          ptx::mbar_wait_or_trap(&d_empty[s], ph ^ 1u);
+          ptx::mbar_wait_or_trap(&d_empty[s], ph ^ 1u, __LINE__);
           uint8_t* dt = dring + (size_t)s * 32768;
           ptx::mbar_arrive_expect_tx(&d_full[s], 32768u);
           ptx::tma_load_2d(dt, &tm_dx, &d_full[s], col0, t0, ptx::kEvictFirst);
@@ -2417,7 +2423,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
           const int ob = j % p.nop;
           uint8_t* hc_t = op + (size_t)ob * p.op_bytes;
           uint8_t* hct_t = hc_t + (size_t)kbx * 16384;
-          ptx::mbar_wait_or_trap(&op_empty[ob], ((uint32_t)(j / p.nop) & 1u) ^ 1u);
+          ptx::mbar_wait_or_trap(&op_empty[ob], ((uint32_t)(j / p.nop) & 1u) ^ 1u, __LINE__);
           ptx::mbar_arrive_expect_tx(&op_full[ob], op_tx);
           for (int kb = 0; kb < kbx; ++kb) ptx::tma_load_2d(hc_t + (size_t)kb * 16384, &tm_hc, &op_full[ob], kb * 64, t0, ptx::kEvictLast);
           for (int kb = 0; kb < 2; ++kb) {
@@ -2432,7 +2438,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       const uint32_t idesc_a = ptx::idesc_bf16(128, (uint32_t)p.NPW, 1, 0);   // X^T (MN-major) . dHcT (K-major)
       const uint32_t idesc_x = ptx::idesc_bf16(128, 128, 0, 1);               // dHc (K-major) . Acat (MN-major)
       const uint32_t wa = ptx::smem_u32(wtile);
-      ptx::mbar_wait_or_trap(w_full, 0);
+      ptx::mbar_wait_or_trap(w_full, 0, __LINE__);
       for (int j = 0; j < ntt; ++j) {
         const int s = j % p.xs;
         const uint32_t ph = (uint32_t)(j / p.xs) & 1u;
@@ -2441,12 +2447,12 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         const int ob = j % p.nop;
         const uint32_t hca = ptx::smem_u32(op + (size_t)ob * p.op_bytes);
         const uint32_t hcta = hca + (uint32_t)kbx * 16384u;
-        ptx::mbar_wait_or_trap(&op_full[ob], (uint32_t)(j / p.nop) & 1u);
+        ptx::mbar_wait_or_trap(&op_full[ob], (uint32_t)(j / p.nop) & 1u, __LINE__);
         if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 40 + j * 3);
-        ptx::mbar_wait_or_trap(&x_full[s], ph);
-        if (DROP) ptx::mbar_wait_or_trap(&x_ready[s], ph);
+        ptx::mbar_wait_or_trap(&x_full[s], ph, __LINE__);
+        if (DROP) ptx::mbar_wait_or_trap(&x_ready[s], ph, __LINE__);
         if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 41 + j * 3);
-        if (p.has_dx) ptx::mbar_wait_or_trap(&t_empty[i], ph2 ^ 1u);
+        if (p.has_dx) ptx::mbar_wait_or_trap(&t_empty[i], ph2 ^ 1u, __LINE__);
         if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 42 + j * 3);
         ptx::tc_fence_after_sync();
         const uint32_t xa = ptx::smem_u32(xring + (size_t)s * 32768);
@@ -2483,27 +2489,15 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       for (int j = 0; j < ntt; ++j) {
         const int s = j % p.xs;
         const uint32_t k = (uint32_t)(j / p.xs);
-        ptx::mbar_wait_or_trap(&x_full[s], k & 1u);
-        if (p.has_dx && k > 0) ptx::mbar_wait_or_trap(&km_free[s], (k - 1u) & 1u);
+        ptx::mbar_wait_or_trap(&x_full[s], k & 1u, __LINE__);
+        if (p.has_dx && k > 0) ptx::mbar_wait_or_trap(&km_free[s], (k - 1u) & 1u, __LINE__);
         const unsigned long long rowbase = dropout_row_base(d, (long long)(tt_beg + j) * 128 + mrow);
         const uint32_t boxaddr = ptx::smem_u32(xring + (size_t)s * 32768) + (uint32_t)box * 16384u;
 #pragma unroll
         for (int hs = 0; hs < 2; ++hs) {                         // a box = two 32-column super-groups
           const uint32_t k32 = dropout_keep32(d, rowbase + (unsigned long long)((col0 >> 5) + box * 2 + hs));
           km_s[((size_t)s * 128 + mrow) * 4 + box * 2 + hs] = k32;
-          if (k32 == 0xffffffffu) continue;
-#pragma unroll
-          for (int cc = 0; cc < 4; ++cc) {
-            const uint32_t km = (k32 >> (cc * 8)) & 0xffu;
-            if (km != 0xffu) {
-              uint32_t W[4];
-              dropout_expand8(km, W);
-              const uint32_t addr = boxaddr + ptx::sw128_offset((uint32_t)mrow, (uint32_t)(hs * 4 + cc));
-              uint4 v = ptx::lds128(addr);
-              v.x &= W[0]; v.y &= W[1]; v.z &= W[2]; v.w &= W[3];
-              ptx::sts128(addr, v);
-            }
-          }
+          dropout_zero_dropped(k32, boxaddr + (uint32_t)mrow * 128u, (uint32_t)mrow & 7u, (uint32_t)hs);
         }
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&x_ready[s]);
@@ -2516,7 +2510,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         const int s = j % p.ds;
         const uint32_t ph = (uint32_t)(j / p.ds) & 1u;
         const int t0 = (tt_beg + j) * 128;
-        ptx::mbar_wait_or_trap(&d_done[s], ph);
+        ptx::mbar_wait_or_trap(&d_done[s], ph, __LINE__);
         uint8_t* dt = dring + (size_t)s * 32768;
         ptx::tma_store_2d(&tm_dx, dt, col0, t0);
         ptx::tma_store_2d(&tm_dx, dt + 16384, col0 + 64, t0);
@@ -2539,17 +2533,17 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         const uint32_t dph = (uint32_t)(j / p.ds) & 1u;
         const bool st = (threadIdx.x == 64) && j < 8;
         if (st && j == 0) dbg_stamp(p.dbg, blockIdx.x, 0);
-        ptx::mbar_wait_or_trap(&t_full[i], ph2);
+        ptx::mbar_wait_or_trap(&t_full[i], ph2, __LINE__);
         if (DROP) {
           // the keep bits of tile j were left in shared memory by the masking warps (published by x_ready)
           const int sx = j % p.xs;
-          ptx::mbar_wait_or_trap(&x_ready[sx], (uint32_t)(j / p.xs) & 1u);
+          ptx::mbar_wait_or_trap(&x_ready[sx], (uint32_t)(j / p.xs) & 1u, __LINE__);
           const uint4 kv = ptx::lds128(ptx::smem_u32(km_s + ((size_t)sx * 128 + row) * 4));
           km_cur[0] = kv.x; km_cur[1] = kv.y; km_cur[2] = kv.z; km_cur[3] = kv.w;
           ptx::mbar_arrive(&km_free[sx]);
         }
         if (st) dbg_stamp(p.dbg, blockIdx.x, 8 + j * 4);
-        ptx::mbar_wait_or_trap(&d_full[s], dph);
+        ptx::mbar_wait_or_trap(&d_full[s], dph, __LINE__);
         if (st) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 4);
         ptx::tc_fence_after_sync();
         uint8_t* dt = dring + (size_t)s * 32768;
@@ -2565,7 +2559,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
     }
     // ---- dA of this column slice: TMEM lane <-> column, TMEM column <-> (modality, rank index)
     if (threadIdx.x == 64) dbg_stamp(p.dbg, blockIdx.x, 4);
-    ptx::mbar_wait_or_trap(a_full, 0);
+    ptx::mbar_wait_or_trap(a_full, 0, __LINE__);
     if (threadIdx.x == 64) dbg_stamp(p.dbg, blockIdx.x, 5);
     ptx::tc_fence_after_sync();
     // stage the accumulator as [NPW][128 cols] fp32 in the (now idle) X ring so that each thread can
@@ -2646,7 +2640,19 @@ static bool wgrad_plan(const DevDesc& d, bool has_dx, int num_sms, WgradTcParams
   p.T = d.T; p.d_in = d.d_in; p.r = d.r; p.rp = L.rp; p.M = d.M; p.NPW = L.NPW; p.KP = L.KP;
   p.ntiles = (d.T + 127) / 128;
   const int slices = d.d_in / 128;
-  p.tsplit = max(1, min(p.ntiles, num_sms / slices));
+  // token split: a CTA owns (column slice, token range).  Pick the split that minimises the makespan in tile
+  // steps: waves of CTAs (one CTA per SM) x (tiles per CTA + ~1.2 tile-equivalents of ramp and dA flush).
+  // (4096 columns, 64 tiles -> 4; 11008 columns, 256 tiles -> 5 instead of the 86-CTA single wave.)
+  {
+    int best = 1;
+    double best_cost = 1e30;
+    for (int ts = 1; ts <= min(p.ntiles, 24); ++ts) {
+      const int waves = (slices * ts + num_sms - 1) / num_sms;
+      const double cost = waves * ((p.ntiles + ts - 1) / ts + 1.2);
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = ts; }
+    }
+    p.tsplit = best;
+  }
   p.has_dx = has_dx;
   p.dbg = dbg_enabled();
   p.w_box_bytes = (uint32_t)p.NPW * 128u;
