@@ -54,6 +54,21 @@ static bool make_tmap(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t
   return r == CUDA_SUCCESS;
 }
 
+// Same for a column window of a wider matrix: `cols` columns starting at `base`, rows `row_stride` elements apart.
+static bool make_tmap_strided(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride,
+                              uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {row_stride * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 static inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 static inline uint32_t tmem_cols_for(int n) {
   uint32_t c = 32;
@@ -739,6 +754,7 @@ struct UpTcParams {
   int ystages, kcap;
   int write_g;
   int attn_in_kernel;              // 0: g rows come precomputed from k_attn_fwd (h_in0 = g)
+  int bpg;                         // B-tile buffers / TMEM accumulators per worker group: 2, or 1 when r > 64
   int dbg;
 };
 
@@ -805,7 +821,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
   uint8_t* ytiles = base;                                     // [ystages][2 boxes][128 x 128 B]
   uint8_t* gtile = ytiles + (size_t)p.ystages * 32768;        // [kblocks][128 x 128 B]  A operand
   uint8_t* btiles = gtile + (size_t)kblocks * 16384;          // [4][kblocks][128 x 128 B] B operand
-  float* gs = reinterpret_cast<float*>(btiles + (size_t)4 * kblocks * 16384);   // [128, r] (in-kernel attention only)
+  float* gs = reinterpret_cast<float*>(btiles + (size_t)2 * p.bpg * kblocks * 16384);   // [128, r] (in-kernel attention only)
   float* Ks = gs + (p.attn_in_kernel ? 128 * d.r : 0);        // [kcap, r+1]
   uint64_t* bars = reinterpret_cast<uint64_t*>(Ks + (size_t)p.kcap * (d.r + 1) + ((p.kcap * (d.r + 1)) & 1));
   uint64_t* y_full = bars;                                    // [ystages]
@@ -872,14 +888,14 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
       ptx::mbar_wait_or_trap(g_full, 0, __LINE__);
       for (int j = 0; j < nch; ++j) {
         // chunk j belongs to worker group (j & 1); each group rotates over two accumulator / B buffers
-        const int i = (j & 1) * 2 + ((j >> 1) & 1);
-        const uint32_t ph = (uint32_t)(j >> 2) & 1u;
+        const int i = (j & 1) * 2 + ((j >> 1) & (p.bpg - 1));
+        const uint32_t ph = (uint32_t)((j >> 1) / p.bpg) & 1u;
         ptx::mbar_wait_or_trap(&b_full[i], ph, __LINE__);
         if (j < 6) dbg_stamp(p.dbg, blockIdx.x, 32 + j * 3);
         ptx::mbar_wait_or_trap(&t_empty[i], ph ^ 1u, __LINE__);
         if (j < 6) dbg_stamp(p.dbg, blockIdx.x, 33 + j * 3);
         ptx::tc_fence_after_sync();
-        const uint32_t ba = ptx::smem_u32(btiles + (size_t)i * kblocks * 16384);
+        const uint32_t ba = ptx::smem_u32(btiles + (size_t)((j & 1) * p.bpg + ((j >> 1) & (p.bpg - 1))) * kblocks * 16384);
         int kdone = 0;
         for (int kb = 0; kb < kblocks; ++kb) {
           const int ksteps = min(4, (p.rk - kb * 64) / 16);
@@ -939,7 +955,8 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
         const int n = idx / cpr_all, ch = idx - n * cpr_all;
         const int k = ch * 8;
         const int kb = ch >> 3, chb = ch & 7;                   // 64-wide K block and chunk inside it
-        uint8_t* dst = btiles + ((size_t)i * kblocks + kb) * 16384 + ptx::sw128_offset((uint32_t)n, (uint32_t)chb);
+        const int slot = (i >> 1) * p.bpg + (i & 1);              // barrier index i = group * 2 + buffer -> smem slot
+        uint8_t* dst = btiles + ((size_t)slot * kblocks + kb) * 16384 + ptx::sw128_offset((uint32_t)n, (uint32_t)chb);
         const __nv_bfloat16* src = Bw + (size_t)((c_beg + j) * 128 + n) * r + (k < r ? k : 0);
         ptx::cp_async16(ptx::smem_u32(dst), src, k < r);
       }
@@ -953,7 +970,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
 
     if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 0);
     if (grp_id < nch) load_b(grp_id, grp_id * 2);               // first two B tiles of each group, in flight early
-    if (grp_id + 2 < nch) load_b(grp_id + 2, grp_id * 2 + 1);
+    if (p.bpg == 2 && grp_id + 2 < nch) load_b(grp_id + 2, grp_id * 2 + 1);
     if (!p.attn_in_kernel) {
       // g rows come finished from k_attn_fwd: build the A operand (post_m * g, bf16) straight from global
       // memory - every load of a thread is issued before its first use, so the prologue costs one memory
@@ -997,7 +1014,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
         }
       }
       if (grp_id < nch) store_b(grp_id * 2);
-      if (grp_id + 2 < nch) store_b(grp_id * 2 + 1);
+      if (p.bpg == 2 && grp_id + 2 < nch) store_b(grp_id * 2 + 1);
       if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 2);
     } else {
     if (wt < 128) meta_s[wt] = (wt < nt) ? tokmeta[t0 + wt] : 0;
@@ -1014,7 +1031,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
     }
     grp.sync();
     if (grp_id < nch) store_b(grp_id * 2);
-    if (grp_id + 2 < nch) store_b(grp_id * 2 + 1);
+    if (p.bpg == 2 && grp_id + 2 < nch) store_b(grp_id * 2 + 1);
     if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 1);
     if (p.attn_in_kernel) {
       attention_tile<false, 32>(d, c, grp, t0, nt, meta_s, gs, gs, nullptr);
@@ -1050,14 +1067,15 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
     for (int j = grp_id; j < nch; j += 2) {
       const int n = j >> 1;                                      // this group's chunk counter
-      const int i = grp_id * 2 + (n & 1);                        // accumulator / B buffer
-      const uint32_t ph = (uint32_t)(n >> 1) & 1u;
+      const int i = grp_id * 2 + (n & (p.bpg - 1));              // accumulator / B buffer
+      const uint32_t ph = (uint32_t)(n / p.bpg) & 1u;
+      const int ahead = 2 * p.bpg;                               // chunks until this buffer is used again
       const int s = j % p.ystages;
       const uint32_t yph = (uint32_t)(j / p.ystages) & 1u;
       ptx::mbar_wait_or_trap(&t_full[i], ph, __LINE__);
       if (wl == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 8 + j * 4);
       // MMA j has consumed B buffer i: restage it right away (async copies fly during the epilogue)
-      if (j + 4 < nch) load_b(j + 4, i);
+      if (j + ahead < nch) load_b(j + ahead, i);
       ptx::mbar_wait_or_trap(&y_full[s], yph, __LINE__);
       if (wl == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 4);
       ptx::tc_fence_after_sync();
@@ -1067,7 +1085,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
       ptx::fence_proxy_async_smem();                            // generic writes -> visible to the TMA store
       ptx::mbar_arrive(&y_done[s]);
       if (wl == 0) ptx::prog_mark(3 + grp_id, j + 1);
-      if (j + 4 < nch) store_b(i);
+      if (j + ahead < nch) store_b(i);
       if (wl == 0) ptx::prog_mark(5 + grp_id, j + 1);
       if (wl == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 11 + j * 4);
     }
@@ -1098,7 +1116,9 @@ static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaSt
   const int attn_kcap = min(max(a.klen_hint, 1), 32 * kKeyBlocksMax);
   // (the fp32 row staging `gs` is only needed when the attention runs inside this kernel)
   const size_t gs_bytes = sep_attn ? 0 : (size_t)128 * d.r * 4;
-  const size_t fixed = (size_t)5 * kblocks * 16384 + gs_bytes + 1024 + 512;
+  // two B-tile buffers per worker group when they fit next to a 4-slot y ring, else one (r > 64)
+  p.bpg = ((size_t)5 * kblocks * 16384 + gs_bytes + 1024 + 512 + 2 * 32768 <= 224 * 1024) ? 2 : 1;
+  const size_t fixed = (size_t)(1 + 2 * p.bpg) * kblocks * 16384 + gs_bytes + 1024 + 512;
   const size_t limit = 224 * 1024;
   while (p.kcap > 1 && fixed + (size_t)p.kcap * (d.r + 1) * 4 + 2 * 32768 > limit) p.kcap /= 2;
   const size_t key_bytes = ((size_t)p.kcap * (d.r + 1) + 1) * 4;
@@ -1122,7 +1142,7 @@ static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaSt
   float* g_stash = a.h_stash + (size_t)d.T * d.r;
   if (sep_attn) {
     if (!(d.dbg_skip & 64)) {
-      if (attn_smem > 48 * 1024) {
+      if (attn_smem > 40 * 1024) {
         e = cudaFuncSetAttribute(k_attn_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem);
         if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
       }
@@ -1138,7 +1158,7 @@ static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaSt
       } else if (d.r <= 128) {
         const int C = d.r <= 64 ? 2 : 4;
         const size_t sm3 = ((size_t)((attn_kcap + 1) & ~1) * 32 * C + 32 * 32 * C) * 4;
-        if (sm3 > 48 * 1024) {
+        if (sm3 > 40 * 1024) {                   // (static shared memory counts towards the 48 KB default too)
           cudaFuncSetAttribute(k_attn_fwd_rank<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
           cudaFuncSetAttribute(k_attn_fwd_rank<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm3);
         }
@@ -1614,6 +1634,8 @@ k_bwd_prep(const __nv_bfloat16* __restrict__ Bw, __nv_bfloat16* __restrict__ Bt,
   if (threadIdx.x == 0) dbg_stamp_g(dbg, blockIdx.x, 107);
 }
 
+static int launch_attn_nopack(const DevDesc& d, const SimtArgs& a, cudaStream_t st);   // k_attn_pack without the packing
+
 // fused = the merged attention-backward + pack kernel follows (partial dG buffers, nothing zero-filled
 // but dK and the counters); otherwise the legacy kernels run on a complete dG in a.dh.
 static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, bool fused) {
@@ -1630,7 +1652,8 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   // staging of the forward's stash then overlaps this kernel
   static int dg_stages_env = -1;
   if (dg_stages_env < 0) { const char* e = getenv("MOKA_DGRAD_STAGES"); dg_stages_env = e ? atoi(e) : 0; }
-  const size_t limit = (fused && !dg_stages_env ? 168 : 200) * 1024;
+  size_t limit = (fused && !dg_stages_env ? 168 : 200) * 1024;
+  if ((limit - fixed) / p.stage_bytes < 2) limit = 200 * 1024;   // large ranks: the ring needs the room itself
   p.stages = (int)((limit - fixed) / p.stage_bytes);
   if (p.stages > 5) p.stages = 5;
   if (dg_stages_env > 0 && p.stages > dg_stages_env) p.stages = dg_stages_env;
@@ -1665,7 +1688,12 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
     if (int rc = check_launch_tc()) return rc;
   }
   if (fused) return MOKA_OK;
-  // legacy: attention backward on the small [T, r] tensors, in place in a.dh
+  // not fused (the wgrad stage cannot use the packed operands): attention backward on the small [T, r]
+  // tensors, in place in a.dh, dK left in a.dK for the consumer
+  if (d.r <= 128 && a.klen_hint <= 128 && d.r % 4 == 0) {
+    if (d.dbg_skip & 16) return MOKA_OK;
+    return launch_attn_nopack(d, a, st);
+  }
   if (d.r <= 32 && a.klen_hint <= 128 && (d.r <= 16 || a.klen_hint <= 64)) {
     const int kblocks = (max(a.klen_hint, 1) + 31) / 32;
     const int gps = (d.S + 31) / 32;
@@ -1675,7 +1703,7 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
     const size_t sm = ((size_t)2 * KBs * 32 * (R + 1) + 3 * 32 * R) * 4;
 #define MOKA_LAUNCH_ATTN_BWD(RR, KK)                                                                     \
     do {                                                                                                \
-      if (sm > 48 * 1024) cudaFuncSetAttribute(k_attn_bwd_tile<RR, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
+      if (sm > 40 * 1024) cudaFuncSetAttribute(k_attn_bwd_tile<RR, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm); \
       k_attn_bwd_tile<RR, KK><<<grid, 256, sm, st>>>(d, a.tokmeta, a.kidx, a.klen, a.h_stash, a.dh, a.dK, gps); \
     } while (0)
     if (R == 8) { if (KBs == 1) MOKA_LAUNCH_ATTN_BWD(8, 1); else if (KBs == 2) MOKA_LAUNCH_ATTN_BWD(8, 2); else MOKA_LAUNCH_ATTN_BWD(8, 4); }
@@ -1692,7 +1720,7 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   const size_t row_bytes = (size_t)2 * 32 * d.r * 4;
   while (kcap > 1 && row_bytes + kcap * per_key > 96 * 1024) kcap /= 2;
   const size_t smem2 = row_bytes + kcap * per_key + 64;
-  if (smem2 > 48 * 1024) {
+  if (smem2 > 40 * 1024) {
     e = cudaFuncSetAttribute(k_attn_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
     if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
   }
@@ -1827,8 +1855,10 @@ k_pack_dh(DevDesc d, int rp, int NPW, int KP, const uint8_t* __restrict__ tokmet
 //      parked tiles with dK folded onto the key rows (threadfence + counter: the classic last-block
 //      pattern, no second launch and no grid-wide barrier).
 struct AttnPackParams {
-  int rp, NPW, KP, bps;             // bps = 64-token blocks per sample
+  int rp, NPW, KP, bps;             // bps = 32-token blocks per sample
   float scale;
+  int pack;                         // 1: emit the packed wgrad operands (fused chain); 0: only write dh back to dG0 and
+                                    // reduce dK (the consumer - k_pack_dh or the warp-FMA wgrad - folds dK itself)
 };
 
 template <int R, int TT>
@@ -2121,6 +2151,14 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
     }
   }
   if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 117);
+  if (!p.pack) {
+    if (anyq)                                         // rows without queries are unchanged: dh == dG already
+      for (int i = tid; i < nt * R; i += NT) {
+        const int tt = i / R, j = i - tt * R;
+        if (j < r) dG0[(tbase + tt) * r + j] = dhs[i];
+      }
+    return;
+  }
   if (!anykey) {
     for (int i = tid; i < TT * R; i += NT) { const int tt = i / R, j = i - tt * R; vs[tt * RS + j] = dhs[i]; }
     __syncthreads();
@@ -2292,6 +2330,8 @@ struct WgradTcParams {
   int tsplit, ntiles;
   int xs, ds, nop;                 // ring depths: X pairs / dX pairs (32 KB slots), operand buffers
   int has_dx, dbg;
+  int prefetch_dx;                 // dx tiles may be loaded before the dependency wait (false for the later passes of a
+                                   // rank-chunked call: the pass in front is still writing dx)
   uint32_t w_box_bytes;            // one 64-column box of the weight slice: NPW x 128 B
   uint32_t op_bytes;               // operand buffer: dHc tile + dHcT hi/lo tiles
   uint32_t tmem_cols;
@@ -2385,7 +2425,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       const uint32_t op_tx = (uint32_t)kbx * 16384u + 4u * hct_blk;
       // x and dx are older than this call (the first kernel of the call waited for them): fill their
       // rings before the dependency wait; the packed dh operands come from the kernel just before
-      const int npre_x = min(ntt, p.xs), npre_d = p.has_dx ? min(ntt, p.ds) : 0;
+      const int npre_x = min(ntt, p.xs), npre_d = (p.has_dx && p.prefetch_dx) ? min(ntt, p.ds) : 0;
       for (int j = 0; j < npre_x; ++j) {
         uint8_t* xt = xring + (size_t)j * 32768;
         ptx::mbar_arrive_expect_tx(&x_full[j], 32768u);
@@ -2593,18 +2633,23 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
 
 // Tensor map over a row-major bf16 matrix with an explicit box (cols multiple of 8 elements).
 // Can the merged attention-backward + pack kernel (k_attn_pack) serve this call?
-static bool wgrad_plan(const DevDesc& d, bool has_dx, int num_sms, WgradTcParams& p, PackLayout& L, size_t& fixed);
+static bool wgrad_plan(const DevDesc& d, bool has_dx, int num_sms, WgradTcParams& p, PackLayout& L, size_t& fixed,
+                       int& nchunks);
 
 bool tc_backward_fused_ok(const DevDesc& d, int klen_hint, bool has_dx) {
   WgradTcParams p;
   PackLayout L;
   size_t fixed;
-  return d.r <= 128 && klen_hint <= 128 && d.S % 8 == 0 && d.S <= 32768 && wgrad_plan(d, has_dx, 148, p, L, fixed);
+  int nchunks;
+  return d.r <= 128 && klen_hint <= 128 && d.S % 8 == 0 && d.S <= 32768 &&
+         wgrad_plan(d, has_dx, 148, p, L, fixed, nchunks);
 }
 
 static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayout& L, int dg_partials,
-                            __nv_bfloat16* hc, __nv_bfloat16* hct_hi, __nv_bfloat16* hct_lo, cudaStream_t st) {
+                            __nv_bfloat16* hc, __nv_bfloat16* hct_hi, __nv_bfloat16* hct_lo, cudaStream_t st,
+                            int pack = 1) {
   AttnPackParams p;
+  p.pack = pack;
   p.rp = L.rp; p.NPW = L.NPW; p.KP = L.KP; p.bps = (d.S + 31) / 32;
   p.scale = d.pre * d.drop_scale;
   const int kblocks = (max(a.klen_hint, 1) + 31) / 32;
@@ -2616,7 +2661,7 @@ static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayou
   cudaError_t e = cudaSuccess;
 #define MOKA_LAUNCH_ATTN_PACK(RR, KK, NN)                                                                    \
   do {                                                                                                       \
-    if (sm > 48 * 1024)                                                                                      \
+    if (sm > 40 * 1024)                                                                                      \
       cudaFuncSetAttribute(k_attn_pack<RR, KK, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);    \
     e = launch_pdl(k_attn_pack<RR, KK, NN>, dim3(d.B * p.bps), dim3(NN), sm, st, d, p, a.tokmeta, a.kidx, a.klen, \
                    (const float*)a.h_stash, a.dh, dG1, a.dK, a.counters, hc, hct_hi, hct_lo);                  \
@@ -2632,11 +2677,38 @@ static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayou
   return check_launch_tc();
 }
 
+static int launch_attn_nopack(const DevDesc& d, const SimtArgs& a, cudaStream_t st) {
+  const PackLayout L0 = pack_layout(d.T, d.r, d.M);
+  return launch_attn_pack(d, a, L0, 0, nullptr, nullptr, nullptr, st, 0);
+}
+
 // Shape checks and ring sizing of k_wgrad_tc (false: the kernel cannot tile this shape).
-static bool wgrad_plan(const DevDesc& d, bool has_dx, int num_sms, WgradTcParams& p, PackLayout& L, size_t& fixed) {
+static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParams& p, PackLayout& L, size_t& fixed);
+
+// nchunks > 1: the packed rank axis (M r columns) does not fit the kernel's shared-memory tiles in one piece
+// (r = 64 with three modalities, r = 128): the kernel then runs once per MODALITY - a "one modality" problem on
+// sub-matrices of the packed operands and on A_m / dA_m.  dx is read-modify-written by every pass, but a token
+// belongs to one modality, so its row gets a non-zero update (and a bf16 rounding that changes it) in exactly
+// one of them: results are identical to a single pass.
+static bool wgrad_plan(const DevDesc& d, bool has_dx, int num_sms, WgradTcParams& p, PackLayout& L, size_t& fixed,
+                       int& nchunks) {
+  nchunks = 1;
+  if (wgrad_plan1(d, has_dx, num_sms, p, L, fixed)) return true;
+  if (d.r % 64 || d.T % 8 || d.M < 2) return false;
+  DevDesc d1 = d;
+  d1.M = 1;                                                   // one pass per modality (see launch_wgrad_tc)
+  PackLayout L1;
+  if (!wgrad_plan1(d1, has_dx, num_sms, p, L1, fixed)) return false;
+  L = pack_layout(d.T, d.r, d.M);                             // the pack step still produces the full operands
+  nchunks = d.M;
+  return true;
+}
+
+static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParams& p, PackLayout& L, size_t& fixed) {
   if (d.T % 8) return false;                                  // transposed operand rows must be 16-byte multiples
   L = pack_layout(d.T, d.r, d.M);
   if (L.NPW > 256) return false;
+  p.prefetch_dx = 1;
   p.T = d.T; p.d_in = d.d_in; p.r = d.r; p.rp = L.rp; p.M = d.M; p.NPW = L.NPW; p.KP = L.KP;
   p.ntiles = (d.T + 127) / 128;
   const int slices = d.d_in / 128;
@@ -2682,7 +2754,8 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   WgradTcParams p;
   PackLayout L;
   size_t fixed;
-  if (!wgrad_plan(d, a.dx != nullptr, num_sms, p, L, fixed)) return MOKA_EUNSUPPORTED;
+  int nchunks;
+  if (!wgrad_plan(d, a.dx != nullptr, num_sms, p, L, fixed, nchunks)) return MOKA_EUNSUPPORTED;
   const int slices = d.d_in / 128;
   char* pk = static_cast<char*>(a.pack);
   __nv_bfloat16* hc = reinterpret_cast<__nv_bfloat16*>(pk);
@@ -2704,12 +2777,39 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   CUtensorMap tx, tdx, ta[3], thc, thh, thl;
   if (!make_tmap(&tx, a.x, (uint64_t)d.T, (uint64_t)d.d_in, 128)) return MOKA_EUNSUPPORTED;
   if (!make_tmap(&tdx, p.has_dx ? a.dx : a.x, (uint64_t)d.T, (uint64_t)d.d_in, 128)) return MOKA_EUNSUPPORTED;
+  const size_t smem = (size_t)(p.xs + p.ds) * 32768 + fixed;
+  if (nchunks > 1) {
+    cudaError_t e = d.drop_thresh
+                        ? cudaFuncSetAttribute(k_wgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(k_wgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+    const __nv_bfloat16* const* Aw = reinterpret_cast<const __nv_bfloat16* const*>(a.A);
+    for (int c = 0; c < nchunks; ++c) {                        // c = modality; r % 64 == 0, so rp == r
+      const __nv_bfloat16* Ac = Aw[c];
+      float* dAc = a.dA[c];
+      const uint64_t w = (uint64_t)L.rp;                       // packed columns of one modality
+      CUtensorMap tac, thc_c, thh_c, thl_c;
+      if (!make_tmap(&tac, Ac, w, (uint64_t)d.d_in, (uint32_t)w)) return MOKA_EUNSUPPORTED;
+      if (!make_tmap_strided(&thc_c, hc + (size_t)c * w, (uint64_t)d.T, w, (uint64_t)L.KP, 128)) return MOKA_EUNSUPPORTED;
+      if (!make_tmap(&thh_c, hct_hi + (size_t)c * w * d.T, w, (uint64_t)d.T, (uint32_t)w)) return MOKA_EUNSUPPORTED;
+      if (!make_tmap(&thl_c, hct_lo + (size_t)c * w * d.T, w, (uint64_t)d.T, (uint32_t)w)) return MOKA_EUNSUPPORTED;
+      p.prefetch_dx = (c == 0);
+      if (d.drop_thresh)
+        e = launch_pdl(k_wgrad_tc<true>, dim3(slices * p.tsplit), dim3(kWgradDropThreads), smem, st, tx, tdx, tac, tac, tac,
+                       thc_c, thh_c, thl_c, p, d, dAc, dAc, dAc);
+      else
+        e = launch_pdl(k_wgrad_tc<false>, dim3(slices * p.tsplit), dim3(kWgradThreads), smem, st, tx, tdx, tac, tac, tac,
+                       thc_c, thh_c, thl_c, p, d, dAc, dAc, dAc);
+      if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+      if (int rc = check_launch_tc()) return rc;
+    }
+    return MOKA_OK;
+  }
   for (int m = 0; m < 3; ++m)
     if (!make_tmap(&ta[m], a.A[m < d.M ? m : 0], (uint64_t)d.r, (uint64_t)d.d_in, (uint32_t)d.r)) return MOKA_EUNSUPPORTED;
   if (!make_tmap(&thc, hc, (uint64_t)d.T, (uint64_t)L.KP, 128)) return MOKA_EUNSUPPORTED;
   if (!make_tmap(&thh, hct_hi, (uint64_t)L.NPW, (uint64_t)d.T, (uint32_t)L.NPW)) return MOKA_EUNSUPPORTED;
   if (!make_tmap(&thl, hct_lo, (uint64_t)L.NPW, (uint64_t)d.T, (uint32_t)L.NPW)) return MOKA_EUNSUPPORTED;
-  const size_t smem = (size_t)(p.xs + p.ds) * 32768 + fixed;
   cudaError_t e = d.drop_thresh
                       ? cudaFuncSetAttribute(k_wgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                       : cudaFuncSetAttribute(k_wgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
