@@ -32,7 +32,7 @@ WORKLOADS = {
     # BASELINE.json configs[1]
     'llama2-7b-vt-m2-r8-s2048': dict(variant='vt', model='7b', r=8, M=2, S=2048, B=4, layout='c2', w=0.05),
     # BASELINE.json configs[3] (13B, r=64, seq 4096)
-    'llama2-13b-vt-m2-r64-s4096': dict(variant='vt', model='13b', r=64, M=2, S=4096, B=1, layout='c4', w=0.05),
+    'llama2-13b-vt-m2-r64-s4096': dict(variant='vt', model='13b', r=64, M=2, S=4096, B=4, layout='c4', w=0.05),
     # smoke-sized
     'tiny-avt': dict(variant='avt', model='tiny', r=16, M=3, S=512, B=2, layout='c3', w=1.0),
 }
