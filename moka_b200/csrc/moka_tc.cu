@@ -742,6 +742,238 @@ k_attn_fwd_rank(DevDesc d, int kcap, int gps, const uint8_t* __restrict__ tokmet
   if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 103);
 }
 
+// ---------------------------------------------------------------------------- k_attn_fwd_mma
+// Forward attention on the (warp-level) tensor cores: mma.sync.m16n8k16 bf16 with fp32 accumulation, every
+// fp32 operand split into hi + lo bf16 halves and three products per tile (hi*hi + lo*hi + hi*lo), which keeps
+// the scores and the weighted sums at fp32-level accuracy.  A warp owns 16 tokens (one m-tile) and ALL keys of
+// their sample, so the softmax is warp-local (quad shuffles), as in flash attention:
+//   S[16, LP]  = H[16, R] K^T        (A = H rows, B = K rows, k = rank)
+//   O[16, R]   = P[16, LP] K         (A = P straight from the S accumulator registers, B = K^T rows, k = key)
+// K is staged once per CTA as bf16 hi/lo in both orientations; 64 tokens per CTA (4 warps).  This replaces the
+// SIMT forms above whenever r % 8 == 0: ~5x fewer instructions at r = 16, ~50x at r = 64.
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_bf16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 xh = __float2bfloat16_rn(x), yh = __float2bfloat16_rn(y);
+  hi = pack_bf16(__bfloat162float(xh), __bfloat162float(yh));
+  lo = pack_bf16(x - __bfloat162float(xh), y - __bfloat162float(yh));
+}
+
+template <int R, int LP>      // R: rank padded to 16; LP: keys padded to 16 (<= 128)
+__global__ void __launch_bounds__(256)
+k_attn_fwd_mma(DevDesc d, int gps, const uint8_t* __restrict__ tokmeta, const int32_t* __restrict__ kidx,
+               const int32_t* __restrict__ klen, const float* __restrict__ h0, const float* __restrict__ h1,
+               float* __restrict__ h_final, float* __restrict__ g_out, float* __restrict__ lse_out) {
+  constexpr int TT = 64, HS = R + 4;                 // fp32 row stride of the token rows
+  constexpr int KS = R + 8, TS = LP + 8;             // bf16 row strides: K [LP][KS], K^T [R][TS] (conflict-free fragment loads)
+  extern __shared__ __align__(16) uint8_t sm_mma[];
+  float* hs = reinterpret_cast<float*>(sm_mma);                         // [TT][HS]
+  __nv_bfloat16* Khi = reinterpret_cast<__nv_bfloat16*>(hs + TT * HS);  // [LP][KS]
+  __nv_bfloat16* Klo = Khi + LP * KS;
+  __nv_bfloat16* Thi = Klo + LP * KS;                                   // [R][TS]
+  __nv_bfloat16* Tlo = Thi + R * TS;
+  __shared__ int s_code[TT];
+  __shared__ int s_kpos[LP];                         // in-sample position of key k, -1 = zero row
+  constexpr int NTH = 256;                           // 4 compute warps (one m-tile each) + 4 that only help staging
+  const int r = d.r;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x / gps;
+  const int s0 = (blockIdx.x % gps) * TT;
+  const int nt = min(TT, d.S - s0);
+  const size_t tbase = (size_t)b * d.S + s0;
+  const int L = min(klen[b], LP);
+  if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 102);
+  int myq = 0;
+  if (tid < TT) {
+    const int code = (tid < nt) ? (tokmeta[tbase + tid] & MOKA_MOD_MASK) : 0;
+    s_code[tid] = code;
+    myq = code >= MOKA_MOD_VIS;
+  }
+  const int anyq = __syncthreads_or(myq) && L > 0;
+  ptx::pdl_trigger();                                // (see k_attn_fwd_split)
+  // key positions / validity are older than this call: resolve the two dependent lookups before the wait
+  if (anyq && tid < LP) {
+    int pos = -1;
+    if (tid < L) {
+      pos = kidx[(size_t)b * d.Lk + tid];
+      if (!(tokmeta[(size_t)b * d.S + pos] & MOKA_KEY_VALID)) pos = -1;
+    }
+    s_kpos[tid] = pos;
+  }
+  ptx::pdl_wait();                                   // h comes from k_down_tc
+  __syncthreads();
+  constexpr int R4 = R / 4;
+  const int r4 = r >> 2;
+  for (int i = tid; i < TT * R4; i += NTH) {
+    const int tt = i / R4, j4 = i - tt * R4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tt < nt && j4 < r4) {
+      const size_t off = (tbase + tt) * r + j4 * 4;
+      v = *reinterpret_cast<const float4*>(h0 + off);
+      if (h1) {
+        const float4 w = *reinterpret_cast<const float4*>(h1 + off);
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+      }
+      if (h_final) *reinterpret_cast<float4*>(h_final + off) = v;
+      if (!anyq) *reinterpret_cast<float4*>(g_out + off) = v;          // no query in this tile: g == h
+    }
+    *reinterpret_cast<float4*>(hs + tt * HS + j4 * 4) = v;
+  }
+  if (!anyq) { if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 103); return; }
+  // keys -> bf16 hi / lo, both orientations (rows beyond L and invalid keys are zero); four loads in flight
+  // per thread before the first use
+  for (int base = 0; base < LP * R4; base += 4 * NTH) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + tid + u * NTH;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < LP * R4) {
+        const int k = idx / R4, j = (idx - k * R4) * 4;
+        const int pos = s_kpos[k];
+        if (pos >= 0 && j < r) {
+          const size_t t = (size_t)b * d.S + pos;
+          v[u] = *reinterpret_cast<const float4*>(h0 + t * r + j);
+          if (h1) {
+            const float4 w = *reinterpret_cast<const float4*>(h1 + t * r + j);
+            v[u].x += w.x; v[u].y += w.y; v[u].z += w.z; v[u].w += w.w;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int idx = base + tid + u * NTH;
+      if (idx >= LP * R4) continue;
+      const int k = idx / R4, j = (idx - k * R4) * 4;
+      const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat16 hi = __float2bfloat16_rn(f[e]);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(f[e] - __bfloat162float(hi));
+        Khi[k * KS + j + e] = hi; Klo[k * KS + j + e] = lo;
+        Thi[(j + e) * TS + k] = hi; Tlo[(j + e) * TS + k] = lo;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- one m-tile (16 tokens) per compute warp
+  const int m0 = (warp & 3) * 16;
+  bool any = false;
+  if (warp < 4)
+    for (int i = 0; i < 16; ++i) any |= (s_code[m0 + i] >= MOKA_MOD_VIS);
+  const int g = lane >> 2, t = lane & 3;
+  if (any) {
+    constexpr int NT = LP / 8;
+    float S[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) { S[n][0] = S[n][1] = S[n][2] = S[n][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < R / 16; ++ks) {
+      uint32_t ahi[4], alo[4];
+      {
+        const float2 x0 = *reinterpret_cast<const float2*>(hs + (m0 + g) * HS + ks * 16 + 2 * t);
+        const float2 x1 = *reinterpret_cast<const float2*>(hs + (m0 + g + 8) * HS + ks * 16 + 2 * t);
+        const float2 x2 = *reinterpret_cast<const float2*>(hs + (m0 + g) * HS + ks * 16 + 2 * t + 8);
+        const float2 x3 = *reinterpret_cast<const float2*>(hs + (m0 + g + 8) * HS + ks * 16 + 2 * t + 8);
+        split_bf16x2(x0.x, x0.y, ahi[0], alo[0]); split_bf16x2(x1.x, x1.y, ahi[1], alo[1]);
+        split_bf16x2(x2.x, x2.y, ahi[2], alo[2]); split_bf16x2(x3.x, x3.y, ahi[3], alo[3]);
+      }
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const int krow = n * 8 + g;
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(Khi + krow * KS + ks * 16 + 2 * t);
+        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(Khi + krow * KS + ks * 16 + 2 * t + 8);
+        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(Klo + krow * KS + ks * 16 + 2 * t);
+        const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(Klo + krow * KS + ks * 16 + 2 * t + 8);
+        mma_bf16_16816(S[n], ahi, bh0, bh1);
+        mma_bf16_16816(S[n], alo, bh0, bh1);
+        mma_bf16_16816(S[n], ahi, bl0, bl1);
+      }
+    }
+    // softmax over the L keys of rows g (c0, c1) and g + 8 (c2, c3); key index of c0 / c2 = n*8 + 2t, c1 / c3 = +1
+    const float sl = d.sm_scale * kLog2e;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = n * 8 + 2 * t + e < L;
+        S[n][e] = ok ? S[n][e] * sl : -INFINITY;
+        S[n][2 + e] = ok ? S[n][2 + e] * sl : -INFINITY;
+        mx0 = fmaxf(mx0, S[n][e]); mx1 = fmaxf(mx1, S[n][2 + e]);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        S[n][e] = exp2f(S[n][e] - mx0); l0 += S[n][e];
+        S[n][2 + e] = exp2f(S[n][2 + e] - mx1); l1 += S[n][2 + e];
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    // O = P K : the S accumulators of two adjacent n-tiles are exactly one A fragment (16 keys) of P
+    constexpr int NO = R / 8;
+    float O[NO][4];
+#pragma unroll
+    for (int n = 0; n < NO; ++n) { O[n][0] = O[n][1] = O[n][2] = O[n][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < LP / 16; ++kk) {
+      if (kk * 16 >= L) break;                       // uniform
+      uint32_t phi[4], plo[4];
+      split_bf16x2(S[2 * kk][0], S[2 * kk][1], phi[0], plo[0]);
+      split_bf16x2(S[2 * kk][2], S[2 * kk][3], phi[1], plo[1]);
+      split_bf16x2(S[2 * kk + 1][0], S[2 * kk + 1][1], phi[2], plo[2]);
+      split_bf16x2(S[2 * kk + 1][2], S[2 * kk + 1][3], phi[3], plo[3]);
+#pragma unroll
+      for (int n = 0; n < NO; ++n) {
+        const int rrow = n * 8 + g;                  // rank index = n of the B operand
+        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(Thi + rrow * TS + kk * 16 + 2 * t);
+        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(Thi + rrow * TS + kk * 16 + 2 * t + 8);
+        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(Tlo + rrow * TS + kk * 16 + 2 * t);
+        const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(Tlo + rrow * TS + kk * 16 + 2 * t + 8);
+        mma_bf16_16816(O[n], phi, bh0, bh1);
+        mma_bf16_16816(O[n], plo, bh0, bh1);
+        mma_bf16_16816(O[n], phi, bl0, bl1);
+      }
+    }
+    // g = h + w / l * O for query rows (others keep h); O[n]: rows g / g+8, rank columns n*8 + 2t, +1
+    const int row0 = m0 + g, row1 = m0 + g + 8;
+    const bool q0 = s_code[row0] >= MOKA_MOD_VIS, q1 = s_code[row1] >= MOKA_MOD_VIS;
+    const float sc0 = q0 ? d.attn_w / l0 : 0.f, sc1 = q1 ? d.attn_w / l1 : 0.f;
+    if (t == 0) {
+      if (q0) lse_out[tbase + row0] = mx0 + log2f(l0);
+      if (q1) lse_out[tbase + row1] = mx1 + log2f(l1);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < NO; ++n) {
+      const int c = n * 8 + 2 * t;
+      float2* p0 = reinterpret_cast<float2*>(hs + row0 * HS + c);
+      float2* p1 = reinterpret_cast<float2*>(hs + row1 * HS + c);
+      float2 v0 = *p0, v1 = *p1;
+      v0.x = fmaf(sc0, O[n][0], v0.x); v0.y = fmaf(sc0, O[n][1], v0.y);
+      v1.x = fmaf(sc1, O[n][2], v1.x); v1.y = fmaf(sc1, O[n][3], v1.y);
+      *p0 = v0; *p1 = v1;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < TT * R4; i += NTH) {
+    const int tt = i / R4, j4 = i - tt * R4;
+    if (tt < nt && j4 < r4)
+      *reinterpret_cast<float4*>(g_out + (tbase + tt) * r + j4 * 4) = *reinterpret_cast<const float4*>(hs + tt * HS + j4 * 4);
+  }
+  if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 103);
+}
+
 // ---------------------------------------------------------------------------- k_up_tc
 //   Y[128 tok, 128 cols] = Y0 + (post_m g)[128 tok, r] . B[128 cols, r]^T   per column chunk
 // Warp 0 streams the y0 tiles in with TMA, the 128 worker threads (warps 2..5) run the rank-r
@@ -1149,7 +1381,26 @@ static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaSt
       const int gps = (d.S + 31) / 32;
       float* hfin = partials ? a.h_stash : (float*)nullptr;
       float* lse = g_stash + (size_t)d.T * d.r;
-      if (d.r <= 32) {
+      static int attn_simt = -1;
+      if (attn_simt < 0) { const char* ev = getenv("MOKA_ATTN_SIMT"); attn_simt = (ev && ev[0] == '1') ? 1 : 0; }
+      if (!attn_simt && attn_kcap <= 128 && d.r <= 128) {
+        // warp-level tensor cores (mma.sync, hi/lo split operands)
+        const int R = round_up(d.r, 16) <= 16 ? 16 : (d.r <= 32 ? 32 : (d.r <= 64 ? 64 : 128));
+        const int LP = attn_kcap <= 64 ? 64 : 128;
+        const size_t smm = (size_t)64 * (R + 4) * 4 + (size_t)2 * LP * (R + 8) * 2 + (size_t)2 * R * (LP + 8) * 2;
+        const int gps64 = (d.S + 63) / 64;
+#define MOKA_LAUNCH_ATTN_MMA(RR, LL)                                                                                   \
+        do {                                                                                                           \
+          if (smm > 40 * 1024) cudaFuncSetAttribute(k_attn_fwd_mma<RR, LL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smm); \
+          e = launch_pdl(k_attn_fwd_mma<RR, LL>, dim3(d.B * gps64), dim3(256), smm, st, d, gps64, a.tokmeta, a.kidx, a.klen, \
+                         h0, h1, hfin, g_stash, lse);                                                                  \
+        } while (0)
+        if (R == 16) { if (LP == 64) MOKA_LAUNCH_ATTN_MMA(16, 64); else MOKA_LAUNCH_ATTN_MMA(16, 128); }
+        else if (R == 32) { if (LP == 64) MOKA_LAUNCH_ATTN_MMA(32, 64); else MOKA_LAUNCH_ATTN_MMA(32, 128); }
+        else if (R == 64) { if (LP == 64) MOKA_LAUNCH_ATTN_MMA(64, 64); else MOKA_LAUNCH_ATTN_MMA(64, 128); }
+        else { if (LP == 64) MOKA_LAUNCH_ATTN_MMA(128, 64); else MOKA_LAUNCH_ATTN_MMA(128, 128); }
+#undef MOKA_LAUNCH_ATTN_MMA
+      } else if (d.r <= 32) {
         const int R = d.r <= 8 ? 8 : (d.r <= 16 ? 16 : 32);
         const size_t sm2 = ((size_t)attn_kcap * (R + 4) + 32 * R) * 4;
         if (R == 8) e = launch_pdl(k_attn_fwd_split<8>, dim3(d.B * gps), dim3(256), sm2, st, d, attn_kcap, gps, a.tokmeta, a.kidx, a.klen, h0, h1, hfin, g_stash, lse);
