@@ -1449,7 +1449,9 @@ struct DgradTcParams {
   uint32_t stage_bytes, bt_bytes;  // stage = [box0 16K][box1 16K][Bt kb0][Bt kb1]
   int dbg;
   int dg_mode;                     // 0 plain store (csplit == 1), 1 one partial buffer per split, 2 reduce into zeroed dG
-  int nbuf;                        // dB accumulators in TMEM (2, or 1 when rk = 128)
+  int nbuf;                        // dB accumulator sets in TMEM (2, or 1 when rk = 128)
+  int wide;                        // 128-column pairs per pipeline stage (2 when TMEM / smem allow: halves the
+                                   // per-stage hand-offs of the single MMA-issuing thread)
   uint32_t tmem_cols, d2_col;      // D2 buffers start at column d2_col
 };
 
@@ -1479,6 +1481,9 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
   const int p_beg = (int)((long long)split * p.pairs / p.csplit);
   const int p_end = (int)((long long)(split + 1) * p.pairs / p.csplit);
   const int np = p_end - p_beg;
+  const int W = p.wide;
+  const int ns = (np + W - 1) / W;                             // pipeline stages of this CTA
+  const uint32_t dy_bytes = 32768u * (uint32_t)W;             // dY part of a stage; the B^T blocks follow
   const int r = p.r;
   if (threadIdx.x == 0) { dbg_stamp_g(p.dbg, blockIdx.x, 108); dbg_stamp(p.dbg, blockIdx.x, 0); }
 
@@ -1505,33 +1510,35 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
     if (lane == 0) {
       // dy is older than this call's first kernel (k_bwd_prep waited for it): its tiles stream in
       // right away; the B^T blocks are written by k_bwd_prep, so they follow the dependency wait
-      const int npre = min(np, p.stages);
-      for (int j = 0; j < npre; ++j) {
-        uint8_t* st = ring + (size_t)j * p.stage_bytes;
-        ptx::mbar_arrive_expect_tx(&full[j], 32768u + p.bt_bytes);
-        const int col = (p_beg + j) * 128;
-        ptx::tma_load_2d(st, &tm_dy, &full[j], col, t0, ptx::kEvictFirst);
-        ptx::tma_load_2d(st + 16384, &tm_dy, &full[j], col + 64, t0, ptx::kEvictFirst);
-      }
+      // stage j holds the pairs j W .. j W + nq - 1 (nq < W only in an odd tail)
+      auto load_dy = [&](int j, uint64_t* bar, uint8_t* st) {
+        const int nq = min(W, np - j * W);
+        ptx::mbar_arrive_expect_tx(bar, (uint32_t)nq * (32768u + p.bt_bytes));
+        for (int q = 0; q < nq; ++q) {
+          const int col = (p_beg + j * W + q) * 128;
+          ptx::tma_load_2d(st + (size_t)q * 32768, &tm_dy, bar, col, t0, ptx::kEvictFirst);
+          ptx::tma_load_2d(st + (size_t)q * 32768 + 16384, &tm_dy, bar, col + 64, t0, ptx::kEvictFirst);
+        }
+      };
+      auto load_bt = [&](int j, uint64_t* bar, uint8_t* st) {   // B^T blocks [rk rows x 64 cols] (L2-resident)
+        const int nq = min(W, np - j * W);
+        for (int q = 0; q < nq; ++q) {
+          const int col = (p_beg + j * W + q) * 128;
+          ptx::tma_load_2d(st + dy_bytes + (size_t)(2 * q) * gt_block, &tm_bt, bar, col, 0, ptx::kEvictLast);
+          ptx::tma_load_2d(st + dy_bytes + (size_t)(2 * q + 1) * gt_block, &tm_bt, bar, col + 64, 0, ptx::kEvictLast);
+        }
+      };
+      const int npre = min(ns, p.stages);
+      for (int j = 0; j < npre; ++j) load_dy(j, &full[j], ring + (size_t)j * p.stage_bytes);
       ptx::pdl_wait();
-      for (int j = 0; j < npre; ++j) {
-        uint8_t* st = ring + (size_t)j * p.stage_bytes;
-        const int col = (p_beg + j) * 128;
-        ptx::tma_load_2d(st + 32768, &tm_bt, &full[j], col, 0, ptx::kEvictLast);
-        ptx::tma_load_2d(st + 32768 + gt_block, &tm_bt, &full[j], col + 64, 0, ptx::kEvictLast);
-      }
-      for (int j = npre; j < np; ++j) {
+      for (int j = 0; j < npre; ++j) load_bt(j, &full[j], ring + (size_t)j * p.stage_bytes);
+      for (int j = npre; j < ns; ++j) {
         const int s = j % p.stages;
         const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
         ptx::mbar_wait_or_trap(&empty[s], ph ^ 1u, __LINE__);
         uint8_t* st = ring + (size_t)s * p.stage_bytes;
-        ptx::mbar_arrive_expect_tx(&full[s], 32768u + p.bt_bytes);
-        const int col = (p_beg + j) * 128;
-        ptx::tma_load_2d(st, &tm_dy, &full[s], col, t0, ptx::kEvictFirst);
-        ptx::tma_load_2d(st + 16384, &tm_dy, &full[s], col + 64, t0, ptx::kEvictFirst);
-        // B^T blocks [rk rows x 64 cols] of the pre-transposed copy (L2-resident)
-        ptx::tma_load_2d(st + 32768, &tm_bt, &full[s], col, 0, ptx::kEvictLast);
-        ptx::tma_load_2d(st + 32768 + gt_block, &tm_bt, &full[s], col + 64, 0, ptx::kEvictLast);
+        load_dy(j, &full[s], st);
+        load_bt(j, &full[s], st);
       }
     }
   } else if (warp == 1) {
@@ -1550,33 +1557,35 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
         g_desc[k] = ptx::smem_desc_sw128(gta + (uint32_t)(k >> 2) * g2_block + (k & 3) * 32, 1024, 0);
       ptx::mbar_wait_or_trap(&wfull[0], 0, __LINE__);
       dbg_stamp(p.dbg, blockIdx.x, 2);
-      for (int j = 0; j < np; ++j) {
+      for (int j = 0; j < ns; ++j) {
         const int s = j % p.stages;
         const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
         const int i = p.nbuf == 2 ? (j & 1) : 0;
         const uint32_t ph2 = (uint32_t)(p.nbuf == 2 ? (j >> 1) : j) & 1u;
+        const int nq = min(W, np - j * W);
         ptx::mbar_wait_or_trap(&full[s], ph, __LINE__);
         if (j == 0) dbg_stamp(p.dbg, blockIdx.x, 3);
         if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 8 + j * 3);
         ptx::mbar_wait_or_trap(&d2_empty[i], ph2 ^ 1u, __LINE__);
         if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 3);
         ptx::tc_fence_after_sync();
-        const uint32_t sa = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
-        const uint32_t bta = sa + 32768u;
-        // MMA1: K = 128 columns of this pair (two boxes, four 16-wide steps each)
-        const uint64_t a1 = a1_base + (uint64_t)(sa >> 4);
-        const uint64_t b1 = a1_base + (uint64_t)(bta >> 4);
-        const uint64_t a2 = a2_base + (uint64_t)(sa >> 4);
-        // MMA2: M = 128 columns (two 64-wide atoms 16 KB apart), K = 128 tokens in 8 steps of 16.
-        // The two products accumulate into different TMEM regions: issued alternately, so that consecutive
-        // instructions never wait on the same accumulator.
-        const uint32_t d2 = tmem_base + p.d2_col + (uint32_t)i * 2u * (uint32_t)p.rk;
+        const uint32_t sa0 = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
+        for (int q = 0; q < nq; ++q) {
+          const uint32_t sa = sa0 + (uint32_t)q * 32768u;
+          const uint32_t bta = sa0 + dy_bytes + (uint32_t)(2 * q) * gt_block;
+          // MMA1: K = 128 columns of this pair (two boxes, four 16-wide steps each)
+          const uint64_t a1 = a1_base + (uint64_t)(sa >> 4);
+          const uint64_t b1 = a1_base + (uint64_t)(bta >> 4);
+          const uint64_t a2 = a2_base + (uint64_t)(sa >> 4);
+          // MMA2: M = 128 columns (two 64-wide atoms 16 KB apart), K = 128 tokens in 8 steps of 16
+          const uint32_t d2 = tmem_base + p.d2_col + (uint32_t)(i * W + q) * 2u * (uint32_t)p.rk;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int box = k >> 2, kk = k & 3;
-          ptx::umma_bf16(tmem_base, a1 + (uint64_t)((box * 16384 + kk * 32) >> 4),
-                         b1 + (uint64_t)((box * gt_block + kk * 32) >> 4), idesc1, (j > 0 || k > 0) ? 1u : 0u);
-          ptx::umma_bf16(d2, a2 + (uint64_t)((k * 2048) >> 4), g_desc[k], idesc2, k > 0 ? 1u : 0u);
+          for (int k = 0; k < 8; ++k) {
+            const int box = k >> 2, kk = k & 3;
+            ptx::umma_bf16(tmem_base, a1 + (uint64_t)((box * 16384 + kk * 32) >> 4),
+                           b1 + (uint64_t)((box * gt_block + kk * 32) >> 4), idesc1, (j > 0 || q > 0 || k > 0) ? 1u : 0u);
+            ptx::umma_bf16(d2, a2 + (uint64_t)((k * 2048) >> 4), g_desc[k], idesc2, k > 0 ? 1u : 0u);
+          }
         }
         ptx::umma_commit(&empty[s]);
         ptx::umma_commit(&d2_full[i]);
@@ -1623,22 +1632,26 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
     ptx::pdl_wait();
 
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int j = 0; j < np; ++j) {
+    for (int j = 0; j < ns; ++j) {
       const int i = p.nbuf == 2 ? (j & 1) : 0;
       const uint32_t ph2 = (uint32_t)(p.nbuf == 2 ? (j >> 1) : j) & 1u;
+      const int nq = min(W, np - j * W);
       ptx::mbar_wait_or_trap(&d2_full[i], ph2, __LINE__);
       if (wt == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 32 + j * 2);
       ptx::tc_fence_after_sync();
-      const int col = (p_beg + j) * 128 + row;               // TMEM lane <-> output column
-      float* dst = dB + (size_t)col * r;
-      for (int c8 = 0; c8 < r; c8 += 8) {                       // r % 8 == 0 on this path
-        float v[8], w[8];
-        ptx::tmem_ld8(lane_base + p.d2_col + (uint32_t)(i * 2 * p.rk + c8), v);          // hi product
-        ptx::tmem_ld8(lane_base + p.d2_col + (uint32_t)(i * 2 * p.rk + p.rk + c8), w);   // lo product
-        ptx::tmem_ld_wait();
-        if (p.dbg & 2) continue;                                // timing experiment: no dB reductions
-        red_add_v4_f32(dst + c8, v[0] + w[0], v[1] + w[1], v[2] + w[2], v[3] + w[3]);
-        red_add_v4_f32(dst + c8 + 4, v[4] + w[4], v[5] + w[5], v[6] + w[6], v[7] + w[7]);
+      for (int q = 0; q < nq; ++q) {
+        const int col = (p_beg + j * W + q) * 128 + row;       // TMEM lane <-> output column
+        float* dst = dB + (size_t)col * r;
+        const uint32_t acc = lane_base + p.d2_col + (uint32_t)((i * W + q) * 2 * p.rk);
+        for (int c8 = 0; c8 < r; c8 += 8) {                     // r % 8 == 0 on this path
+          float v[8], w[8];
+          ptx::tmem_ld8(acc + (uint32_t)c8, v);                 // hi product
+          ptx::tmem_ld8(acc + (uint32_t)(p.rk + c8), w);        // lo product
+          ptx::tmem_ld_wait();
+          if (p.dbg & 2) continue;                              // timing experiment: no dB reductions
+          red_add_v4_f32(dst + c8, v[0] + w[0], v[1] + w[1], v[2] + w[2], v[3] + w[3]);
+          red_add_v4_f32(dst + c8 + 4, v[4] + w[4], v[5] + w[5], v[6] + w[6], v[7] + w[7]);
+        }
       }
       ptx::tc_fence_before_sync();
       ptx::mbar_arrive(&d2_empty[i]);
@@ -1897,8 +1910,17 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   p.csplit = (ntiles < num_sms && ntiles * 2 <= num_sms + num_sms / 4 && p.pairs >= 8) ? 2 : 1;
   p.dg_mode = p.csplit == 1 ? 0 : (fused ? 1 : 2);
   p.bt_bytes = 2u * (uint32_t)p.rk * 128u;
-  p.stage_bytes = 32768u + p.bt_bytes;
   const size_t fixed = (size_t)4 * p.rk * 128 + 1024 + 512;
+  // two pairs (256 columns) per stage when two stages of that size and two sets of dB accumulators fit
+  static int dg_wide_env = -1;
+  if (dg_wide_env < 0) { const char* e = getenv("MOKA_DGRAD_WIDE"); dg_wide_env = e ? atoi(e) : 2; }
+  {
+    const uint32_t dgc0 = tmem_cols_for(p.rk);
+    const size_t st2 = 2 * (32768u + (size_t)p.bt_bytes);
+    p.wide = (dg_wide_env >= 2 && dgc0 + 8 * p.rk <= 512 && 2 * st2 + fixed <= 200 * 1024 &&
+              (d.d_out / 128) / p.csplit >= 4) ? 2 : 1;
+  }
+  p.stage_bytes = (uint32_t)p.wide * (32768u + p.bt_bytes);
   // fused chain: leave ~56 KB of the SM's shared memory to an early-launched k_attn_pack CTA, whose
   // staging of the forward's stash then overlaps this kernel
   static int dg_stages_env = -1;
@@ -1913,8 +1935,8 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   { static int nodb = -1; if (nodb < 0) { const char* e = getenv("MOKA_DBG_NO_DB"); nodb = (e && e[0] == '1') ? 2 : 0; } p.dbg |= nodb; }
   const uint32_t dgc = tmem_cols_for(p.rk);
   p.d2_col = dgc;
-  p.nbuf = (dgc + 4 * p.rk <= 512) ? 2 : 1;                  // [128 x 2 rk] dB accumulators next to dG in TMEM
-  p.tmem_cols = tmem_cols_for((int)dgc + p.nbuf * 2 * p.rk);
+  p.nbuf = (dgc + 4 * p.wide * p.rk <= 512) ? 2 : 1;         // sets of `wide` [128 x 2 rk] dB accumulators next to dG
+  p.tmem_cols = tmem_cols_for((int)dgc + p.nbuf * p.wide * 2 * p.rk);
   // pre-transposed B in the (otherwise unused until the pack step) packed-operand workspace
   __nv_bfloat16* Bt = static_cast<__nv_bfloat16*>(a.pack);
   CUtensorMap tdy, tbt;
