@@ -226,6 +226,9 @@ __device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lan
 __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" :: "l"(p), "f"(v) : "memory");
 }
+__device__ __forceinline__ void red_add_v2_f32(float* p, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" :: "l"(p), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ void red_add_v4_f32(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }

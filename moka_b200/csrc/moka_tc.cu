@@ -2182,7 +2182,12 @@ __device__ __forceinline__ void pack_rows(const DevDesc& d, const AttnPackParams
 //   phase B  thread <-> (key, 4 rank indices): dK[k] = sum_t (p w)[t,k] dg_t + (ds/sqrt r)[t,k] h_t as an
 //            outer-product accumulation over the CTA's tokens - every dK element has one owner, so there is
 //            no cross-warp reduction (shared-memory float atomics are CAS loops on this hardware).
-template <int R, int KB, int NT>
+// MMA = true: phases A and B on the warp-level tensor cores (mma.sync m16n8k16 bf16, hi/lo split operands, see
+// k_attn_fwd_mma).  Phase A: warp <-> 16 tokens x all keys, in chunks of 32 keys:  S = H K^T and dP = dG K^T,
+// P = exp2(S - lse), dS = P (w dP - D), dh += (dS/sqrt r) K with dS taken straight from the accumulator
+// registers; the factors p w and dS/sqrt(r) go to shared memory as bf16 hi/lo, key-major.  Phase B: every warp
+// owns [16 keys x 8 ranks] tiles of dK = (p w)^T dG + (dS/sqrt r)^T H over the CTA's 32 tokens.
+template <int R, int KB, int NT, bool MMA = false>
 __global__ void __launch_bounds__(NT)
 k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, const int32_t* __restrict__ kidx,
             const int32_t* __restrict__ klen, const float* __restrict__ h_stash, float* __restrict__ dG0,
@@ -2278,7 +2283,180 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
     reinterpret_cast<float4*>(dhs)[i] = v;
   }
   __syncthreads();
-  if (anyq && R > 32) {
+  if constexpr (MMA) {
+    if (anyq) {
+      constexpr int R16 = R < 16 ? 16 : R;
+      constexpr int LPp = KP32 + 8, HP = R16 + 8, TP = 40;
+      __nv_bfloat16* Thi = reinterpret_cast<__nv_bfloat16*>(vs + TT * RS);   // [R16][LPp]  K^T (rank-major)
+      __nv_bfloat16* Tlo = Thi + R16 * LPp;
+      __nv_bfloat16* Hh = Tlo + R16 * LPp;                                   // [TT][HP] token rows of h / dG
+      __nv_bfloat16* Hl = Hh + TT * HP;
+      __nv_bfloat16* Gh = Hl + TT * HP;
+      __nv_bfloat16* Gl = Gh + TT * HP;
+      __nv_bfloat16* HTh = Gl + TT * HP;                                     // [R16][TP] the same, rank-major
+      __nv_bfloat16* HTl = HTh + R16 * TP;
+      __nv_bfloat16* GTh = HTl + R16 * TP;
+      __nv_bfloat16* GTl = GTh + R16 * TP;
+      __nv_bfloat16* PWh = GTl + R16 * TP;                                   // [KP32][TP] p w, key-major
+      __nv_bfloat16* PWl = PWh + KP32 * TP;
+      __nv_bfloat16* DSh = PWl + KP32 * TP;                                  // [KP32][TP] ds / sqrt(r)
+      __nv_bfloat16* DSl = DSh + KP32 * TP;
+      // ---- operand tiles from the fp32 rows staged above
+      for (int i = tid; i < KP32 * R16; i += NT) {
+        const int k = i / R16, j = i - k * R16;
+        const float v = (j < R) ? Ks[k * KS + j] : 0.f;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        Thi[j * LPp + k] = hi;
+        Tlo[j * LPp + k] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      }
+      for (int i = tid; i < TT * R16; i += NT) {
+        const int tt = i / R16, j = i - tt * R16;
+        const float hv = (j < R) ? hs[tt * R + j] : 0.f, gv = (j < R) ? dgs[tt * R + j] : 0.f;
+        const __nv_bfloat16 hh = __float2bfloat16_rn(hv), gh = __float2bfloat16_rn(gv);
+        const __nv_bfloat16 hl = __float2bfloat16_rn(hv - __bfloat162float(hh));
+        const __nv_bfloat16 gl = __float2bfloat16_rn(gv - __bfloat162float(gh));
+        Hh[tt * HP + j] = hh; Hl[tt * HP + j] = hl; Gh[tt * HP + j] = gh; Gl[tt * HP + j] = gl;
+        HTh[j * TP + tt] = hh; HTl[j * TP + tt] = hl; GTh[j * TP + tt] = gh; GTl[j * TP + tt] = gl;
+      }
+      __syncthreads();
+      const int g = lane >> 2, t = lane & 3;
+      auto ld32 = [](const __nv_bfloat16* q) { return *reinterpret_cast<const uint32_t*>(q); };
+      auto pk16 = [](const __nv_bfloat16* a, const __nv_bfloat16* b2) {
+        return (uint32_t)__bfloat16_as_ushort(*a) | ((uint32_t)__bfloat16_as_ushort(*b2) << 16);
+      };
+      if (warp < 2) {
+        // ---- phase A: this warp's 16 tokens against all keys
+        const int m0 = warp * 16;
+        const int r0 = m0 + g, r1 = m0 + g + 8;
+        const bool q0 = s_code[r0] >= MOKA_MOD_VIS, q1 = s_code[r1] >= MOKA_MOD_VIS;
+        float Dl = 0.f;
+        if (lane < 16) {
+          const int row = m0 + lane;
+          for (int j = 0; j < R; ++j) Dl = fmaf(dgs[row * R + j], gs[row * R + j] - hs[row * R + j], Dl);
+        }
+        const float D0 = __shfl_sync(0xffffffffu, Dl, g), D1 = __shfl_sync(0xffffffffu, Dl, g + 8);
+        const float lse0 = s_lse[r0], lse1 = s_lse[r1];
+        const float sl = d.sm_scale * kLog2e;
+        constexpr int NO = R16 / 8;
+        float O[NO][4];
+#pragma unroll
+        for (int n = 0; n < NO; ++n) { O[n][0] = O[n][1] = O[n][2] = O[n][3] = 0.f; }
+#pragma unroll 1
+        for (int c = 0; c < KB; ++c) {
+          if (c * 32 >= L) break;
+          float S[4][4], dP[4][4];
+#pragma unroll
+          for (int n = 0; n < 4; ++n)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { S[n][e] = 0.f; dP[n][e] = 0.f; }
+#pragma unroll
+          for (int ks = 0; ks < R16 / 16; ++ks) {
+            uint32_t ah[4], al[4], gh4[4], gl4[4];
+            const int c0 = ks * 16 + 2 * t;
+            ah[0] = ld32(Hh + r0 * HP + c0); ah[1] = ld32(Hh + r1 * HP + c0);
+            ah[2] = ld32(Hh + r0 * HP + c0 + 8); ah[3] = ld32(Hh + r1 * HP + c0 + 8);
+            al[0] = ld32(Hl + r0 * HP + c0); al[1] = ld32(Hl + r1 * HP + c0);
+            al[2] = ld32(Hl + r0 * HP + c0 + 8); al[3] = ld32(Hl + r1 * HP + c0 + 8);
+            gh4[0] = ld32(Gh + r0 * HP + c0); gh4[1] = ld32(Gh + r1 * HP + c0);
+            gh4[2] = ld32(Gh + r0 * HP + c0 + 8); gh4[3] = ld32(Gh + r1 * HP + c0 + 8);
+            gl4[0] = ld32(Gl + r0 * HP + c0); gl4[1] = ld32(Gl + r1 * HP + c0);
+            gl4[2] = ld32(Gl + r0 * HP + c0 + 8); gl4[3] = ld32(Gl + r1 * HP + c0 + 8);
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+              const int key = c * 32 + n * 8 + g;
+              const uint32_t b0h = pk16(Thi + (c0) * LPp + key, Thi + (c0 + 1) * LPp + key);
+              const uint32_t b1h = pk16(Thi + (c0 + 8) * LPp + key, Thi + (c0 + 9) * LPp + key);
+              const uint32_t b0l = pk16(Tlo + (c0) * LPp + key, Tlo + (c0 + 1) * LPp + key);
+              const uint32_t b1l = pk16(Tlo + (c0 + 8) * LPp + key, Tlo + (c0 + 9) * LPp + key);
+              mma_bf16_16816(S[n], ah, b0h, b1h); mma_bf16_16816(S[n], al, b0h, b1h); mma_bf16_16816(S[n], ah, b0l, b1l);
+              mma_bf16_16816(dP[n], gh4, b0h, b1h); mma_bf16_16816(dP[n], gl4, b0h, b1h); mma_bf16_16816(dP[n], gh4, b0l, b1l);
+            }
+          }
+          // p, ds and the two factors; S is overwritten with ds / sqrt(r) (the A operand of the dh product)
+#pragma unroll
+          for (int n = 0; n < 4; ++n) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int key = c * 32 + n * 8 + 2 * t + e;
+              const bool ok = key < L;
+              const float p0 = (ok && q0) ? exp2f(S[n][e] * sl - lse0) : 0.f;
+              const float p1 = (ok && q1) ? exp2f(S[n][2 + e] * sl - lse1) : 0.f;
+              const float ds0 = p0 * (dP[n][e] * d.attn_w - D0) * d.sm_scale;
+              const float ds1 = p1 * (dP[n][2 + e] * d.attn_w - D1) * d.sm_scale;
+              const float pw0 = p0 * d.attn_w, pw1 = p1 * d.attn_w;
+              S[n][e] = ds0; S[n][2 + e] = ds1;
+              __nv_bfloat16 hi = __float2bfloat16_rn(pw0);
+              PWh[key * TP + r0] = hi; PWl[key * TP + r0] = __float2bfloat16_rn(pw0 - __bfloat162float(hi));
+              hi = __float2bfloat16_rn(pw1);
+              PWh[key * TP + r1] = hi; PWl[key * TP + r1] = __float2bfloat16_rn(pw1 - __bfloat162float(hi));
+              hi = __float2bfloat16_rn(ds0);
+              DSh[key * TP + r0] = hi; DSl[key * TP + r0] = __float2bfloat16_rn(ds0 - __bfloat162float(hi));
+              hi = __float2bfloat16_rn(ds1);
+              DSh[key * TP + r1] = hi; DSl[key * TP + r1] = __float2bfloat16_rn(ds1 - __bfloat162float(hi));
+            }
+          }
+          // dh += (ds / sqrt r) K : two k-steps of 16 keys, A fragments straight from the registers
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            uint32_t dh4[4], dl4[4];
+            split_bf16x2(S[2 * kk][0], S[2 * kk][1], dh4[0], dl4[0]);
+            split_bf16x2(S[2 * kk][2], S[2 * kk][3], dh4[1], dl4[1]);
+            split_bf16x2(S[2 * kk + 1][0], S[2 * kk + 1][1], dh4[2], dl4[2]);
+            split_bf16x2(S[2 * kk + 1][2], S[2 * kk + 1][3], dh4[3], dl4[3]);
+#pragma unroll
+            for (int n = 0; n < NO; ++n) {
+              const __nv_bfloat16* th = Thi + (n * 8 + g) * LPp + c * 32 + kk * 16 + 2 * t;
+              const __nv_bfloat16* tl = Tlo + (n * 8 + g) * LPp + c * 32 + kk * 16 + 2 * t;
+              const uint32_t b0h = ld32(th), b1h = ld32(th + 8), b0l = ld32(tl), b1l = ld32(tl + 8);
+              mma_bf16_16816(O[n], dh4, b0h, b1h); mma_bf16_16816(O[n], dl4, b0h, b1h); mma_bf16_16816(O[n], dh4, b0l, b1l);
+            }
+          }
+        }
+#pragma unroll
+        for (int n = 0; n < NO; ++n) {
+          const int col = n * 8 + 2 * t;
+          if (col < r) {
+            if (q0) { dhs[r0 * R + col] += O[n][0]; dhs[r0 * R + col + 1] += O[n][1]; }
+            if (q1) { dhs[r1 * R + col] += O[n][2]; dhs[r1 * R + col + 1] += O[n][3]; }
+          }
+        }
+      }
+      __syncthreads();
+      if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 116);
+      // ---- phase B: dK tiles [16 keys x 8 ranks], one owner each
+      {
+        constexpr int NRK = R16 / 8;
+        const int ntk = (min(L, KP32) + 15) / 16;
+        for (int tile = warp; tile < ntk * NRK; tile += NT / 32) {
+          const int mk = tile / NRK, nr = tile - mk * NRK;
+          float C[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            const int c0 = ks * 16 + 2 * t;
+            const int k0 = (mk * 16 + g) * TP, k1 = (mk * 16 + g + 8) * TP, nb = (nr * 8 + g) * TP;
+            uint32_t ah[4], al[4];
+            ah[0] = ld32(PWh + k0 + c0); ah[1] = ld32(PWh + k1 + c0); ah[2] = ld32(PWh + k0 + c0 + 8); ah[3] = ld32(PWh + k1 + c0 + 8);
+            al[0] = ld32(PWl + k0 + c0); al[1] = ld32(PWl + k1 + c0); al[2] = ld32(PWl + k0 + c0 + 8); al[3] = ld32(PWl + k1 + c0 + 8);
+            uint32_t b0h = ld32(GTh + nb + c0), b1h = ld32(GTh + nb + c0 + 8), b0l = ld32(GTl + nb + c0), b1l = ld32(GTl + nb + c0 + 8);
+            mma_bf16_16816(C, ah, b0h, b1h); mma_bf16_16816(C, al, b0h, b1h); mma_bf16_16816(C, ah, b0l, b1l);
+            ah[0] = ld32(DSh + k0 + c0); ah[1] = ld32(DSh + k1 + c0); ah[2] = ld32(DSh + k0 + c0 + 8); ah[3] = ld32(DSh + k1 + c0 + 8);
+            al[0] = ld32(DSl + k0 + c0); al[1] = ld32(DSl + k1 + c0); al[2] = ld32(DSl + k0 + c0 + 8); al[3] = ld32(DSl + k1 + c0 + 8);
+            b0h = ld32(HTh + nb + c0); b1h = ld32(HTh + nb + c0 + 8); b0l = ld32(HTl + nb + c0); b1l = ld32(HTl + nb + c0 + 8);
+            mma_bf16_16816(C, ah, b0h, b1h); mma_bf16_16816(C, al, b0h, b1h); mma_bf16_16816(C, ah, b0l, b1l);
+          }
+          const int key0 = mk * 16 + g, key1 = key0 + 8, col = nr * 8 + 2 * t;
+          if (col < r) {
+            if (key0 < L && (C[0] != 0.f || C[1] != 0.f))
+              red_add_v2_f32(&dK_glob[((size_t)b * d.Lk + key0) * r + col], C[0], C[1]);
+            if (key1 < L && (C[2] != 0.f || C[3] != 0.f))
+              red_add_v2_f32(&dK_glob[((size_t)b * d.Lk + key1) * r + col], C[2], C[3]);
+          }
+        }
+      }
+      __syncthreads();                                 // the operand tiles share nothing with `vs`, but keep the phases apart
+    }
+  }
+  if (!MMA && anyq && R > 32) {
     // ---- phase A, rank-parallel form (R = 64 / 128): lane <-> R/32 consecutive rank indices, the dot
     // products over the rank are warp reductions, one key at a time (two in flight)
     if constexpr (R > 32) {
@@ -2339,7 +2517,7 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
       }
     }
   }
-  if (anyq && R <= 32) {
+  if (!MMA && anyq && R <= 32) {
     // ---- phase A
     const float sl = d.sm_scale * kLog2e;
     const int comp = (R == 32) ? lane : (R == 16 ? (lane >> 1) : (lane >> 2));
@@ -2402,7 +2580,7 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
       if (writer && comp < r) dhs[tt * R + comp] += dh_tot;
     }
   }
-  if (anyq) {
+  if (!MMA && anyq) {
     __syncthreads();
     if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 116);
     // ---- phase B: dK[k, 4 jq..] = sum over the CTA's tokens, one owner per element
@@ -2932,6 +3110,28 @@ static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayou
   const size_t sm = ((size_t)4 * 32 * R + 2 * 32 * KBs * 32 + (size_t)KBs * 32 * KS + 32 * (R + 1)) * 4;
   const float* dG1 = dg_partials ? a.dh_att : nullptr;
   cudaError_t e = cudaSuccess;
+  static int attn_simt = -1;
+  if (attn_simt < 0) { const char* ev = getenv("MOKA_ATTN_SIMT"); attn_simt = (ev && ev[0] == '1') ? 1 : 0; }
+  if (!attn_simt && R <= 64) {
+    // phases A / B on the warp-level tensor cores: bf16 hi/lo operand tiles behind the fp32 staging arrays
+    const int R16 = R < 16 ? 16 : R, KP32 = KBs * 32;
+    const size_t extra = ((size_t)2 * R16 * (KP32 + 8) + (size_t)4 * 32 * (R16 + 8) + (size_t)4 * R16 * 40 +
+                          (size_t)4 * KP32 * 40) * 2;
+    const size_t smm = sm + extra;
+#define MOKA_LAUNCH_ATTN_PACK_MMA(RR, KK)                                                                    \
+    do {                                                                                                     \
+      cudaFuncSetAttribute(k_attn_pack<RR, KK, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smm); \
+      e = launch_pdl(k_attn_pack<RR, KK, 256, true>, dim3(d.B * p.bps), dim3(256), smm, st, d, p, a.tokmeta, a.kidx, \
+                     a.klen, (const float*)a.h_stash, a.dh, dG1, a.dK, a.counters, hc, hct_hi, hct_lo);       \
+    } while (0)
+    if (R == 8) { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK_MMA(8, 1); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK_MMA(8, 2); else MOKA_LAUNCH_ATTN_PACK_MMA(8, 4); }
+    else if (R == 16) { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK_MMA(16, 1); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK_MMA(16, 2); else MOKA_LAUNCH_ATTN_PACK_MMA(16, 4); }
+    else if (R == 32) { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK_MMA(32, 1); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK_MMA(32, 2); else MOKA_LAUNCH_ATTN_PACK_MMA(32, 4); }
+    else { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK_MMA(64, 1); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK_MMA(64, 2); else MOKA_LAUNCH_ATTN_PACK_MMA(64, 4); }
+#undef MOKA_LAUNCH_ATTN_PACK_MMA
+    if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+    return check_launch_tc();
+  }
 #define MOKA_LAUNCH_ATTN_PACK(RR, KK, NN)                                                                    \
   do {                                                                                                       \
     if (sm > 40 * 1024)                                                                                      \
