@@ -2662,8 +2662,9 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
     if (tid == 0) {
       int n = 0, w = word;
       uint32_t m = bits;
+      const int nwords = (p.bps + 31) >> 5;              // mask words that can have bits at all
       while (n < PB) {
-        if (m == 0u) { if (++w >= 32) break; m = s_blkmask[w]; continue; }
+        if (m == 0u) { if (++w >= nwords) { w = 32; break; } m = s_blkmask[w]; continue; }
         const int bit = __ffs(m) - 1;
         m &= m - 1u;
         s_list[n] = w * 32 + bit;
