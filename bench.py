@@ -316,8 +316,15 @@ def main():
 
     # roofline of the fused MokaLinear fwd+bwd (algorithmic bytes of SURVEY 8d / DESIGN.md)
     alg_bytes, dur_ms, per_kind = 0.0, 0.0, {'fwd': [0.0, 0.0], 'bwd': [0.0, 0.0]}
-    for kind, T, d_in, d_out, e, ev in events:
-        b = e * T * ((d_in + 2 * d_out) if kind == 'fwd' else (3 * d_in + d_out))
+    n_delta = 0
+    for kind, T, d_in, d_out, e, ev, delta in events:
+        if delta:
+            # MOKA_FLAG_DELTA_OUT: the residual read moved into the frozen GEMM's epilogue (beta = 1); the calls
+            # timed here only write y / dx, so only those bytes are credited to them
+            b = e * T * ((d_in + d_out) if kind == 'fwd' else (2 * d_in + d_out))
+            n_delta += 1
+        else:
+            b = e * T * ((d_in + 2 * d_out) if kind == 'fwd' else (3 * d_in + d_out))
         t = ev[0].elapsed_time(ev[1])
         alg_bytes += b; dur_ms += t
         per_kind[kind][0] += b; per_kind[kind][1] += t
@@ -341,6 +348,8 @@ def main():
                         modalities=wl['M'], lora_dropout=wl['dropout'], grad_checkpointing=args.grad_checkpointing,
                         parallelism=f'dp{world}-zero{args.zero_stage}', kernel_path=uses_tc,
                         adapted_linears=len(pm.moka_layers()), trainable_params=eng.trainable_numel(),
+                        gemm_fusion=('delta-out: adapter term written alone, frozen GEMM accumulates onto it (beta=1)'
+                                     if n_delta else 'off: adapter added in place after the frozen GEMM'),
                         l2='per-step activations (>1 GB) exceed the 126 MB L2; no explicit flush',
                         base='frozen random-init Llama-2 (cuBLAS GEMMs + SDPA via PyTorch)'),
             e2e=dict(value=e2e_value, unit='tokens/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
@@ -353,7 +362,9 @@ def main():
                           traffic=372.8e6, traffic_shape='one fwd+bwd call pair, T=8192 d=4096->4096 r=16 (ncu)',
                           peak_source=peak_kind,
                           kernel='fused MokaLinear fwd+bwd (libmoka.so calls, CUDA events per call)',
-                          calls=len(events),
+                          calls=len(events), delta_out_calls=n_delta,
+                          bytes_per_token=('e(3 d_in + 2 d_out): fwd d_in + d_out, bwd 2 d_in + d_out [delta-out calls]' if n_delta
+                                           else 'e(4 d_in + 3 d_out) [SURVEY 8d]'),
                           fwd_gbs=per_kind['fwd'][0] / max(per_kind['fwd'][1], 1e-9) / 1e6,
                           bwd_gbs=per_kind['bwd'][0] / max(per_kind['bwd'][1], 1e-9) / 1e6,
                           share_of_step=dur_ms / ms_dev),

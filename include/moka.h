@@ -52,6 +52,13 @@ enum {
 enum {
   MOKA_FLAG_FORCE_SIMT = 1,   /* use the warp-FMA kernels even when the tcgen05 path applies */
   MOKA_FLAG_FORCE_TC = 2,     /* fail with MOKA_EUNSUPPORTED instead of falling back to warp-FMA */
+  /* Frozen-GEMM epilogue fusion: the outputs are WRITE-ONLY.  moka_forward stores the adapter
+   * term alone into y (y0 is ignored and may be NULL; tokens in no mask get zeros), moka_backward stores the
+   * adapter's input gradient alone into dx (previous contents ignored).  The caller then runs the frozen GEMM
+   * with beta = 1 onto that buffer (y.addmm_(x, W0^T), dx.addmm_(dy, W0)), so the residual read happens in the
+   * GEMM's epilogue instead of in these kernels.  Only on the tcgen05 path: MOKA_EUNSUPPORTED otherwise
+   * (ask moka_supports_delta first). */
+  MOKA_FLAG_DELTA_OUT = 4,
   /* per-stage vetoes of the tcgen05 path (debugging / A-B measurements) */
   MOKA_FLAG_NO_TC_DOWN = 1 << 8, MOKA_FLAG_NO_TC_UP = 1 << 9,
   MOKA_FLAG_NO_TC_DGRAD = 1 << 10, MOKA_FLAG_NO_TC_WGRAD = 1 << 11,
@@ -169,6 +176,10 @@ int64_t moka_launch_count(void);
 
 /* 1 when the tcgen05/TMA path would be taken for this descriptor, else 0. */
 int moka_uses_tensor_cores(const MokaDesc* desc);
+
+/* 1 when moka_forward AND moka_backward (with a dx buffer iff has_dx) accept MOKA_FLAG_DELTA_OUT for this
+ * descriptor, else 0. */
+int moka_supports_delta(const MokaDesc* desc, int has_dx);
 
 const char* moka_strerror(int code);
 int moka_version(void);

@@ -15,12 +15,13 @@ MOKA_BF16, MOKA_F32 = 0, 1
 VARIANT_AVT, VARIANT_VT = 0, 1
 MOD_NONE, MOD_TEXT, MOD_VIS, MOD_AUD = 0, 1, 2, 3
 MOD_MASK, KEY_VALID = 0x7, 0x8
-FLAG_FORCE_SIMT, FLAG_FORCE_TC = 1, 2
+FLAG_FORCE_SIMT, FLAG_FORCE_TC, FLAG_DELTA_OUT = 1, 2, 4
+MOKA_EUNSUPPORTED = -4
 META_EMPTY_QUESTION, META_OVERLAP, META_KEY_OVERFLOW = 1, 2, 4
 
 EXPORTS = ['moka_workspace_bytes', 'moka_forward', 'moka_backward', 'moka_build_token_meta',
            'moka_dropout_keep_mask', 'moka_adamw_step', 'moka_launch_count',
-           'moka_uses_tensor_cores', 'moka_strerror', 'moka_version', 'moka_rope', 'moka_debug_read',
+           'moka_uses_tensor_cores', 'moka_supports_delta', 'moka_strerror', 'moka_version', 'moka_rope', 'moka_debug_read',
            'moka_debug_trap_buffer']
 
 
@@ -76,6 +77,8 @@ def load():
     lib.moka_launch_count.argtypes = []
     lib.moka_uses_tensor_cores.restype = c_int32
     lib.moka_uses_tensor_cores.argtypes = [D]
+    lib.moka_supports_delta.restype = c_int32
+    lib.moka_supports_delta.argtypes = [D, c_int32]
     lib.moka_strerror.restype = c_char_p
     lib.moka_strerror.argtypes = [c_int32]
     lib.moka_version.restype = c_int32

@@ -112,12 +112,22 @@ int moka_uses_tensor_cores(const MokaDesc* desc) {
   return tc_stages(desc, d) ? 1 : 0;
 }
 
+int moka_supports_delta(const MokaDesc* desc, int has_dx) {
+  if (validate(desc) != MOKA_OK) return 0;
+  DevDesc d = make_dev(desc, 0, 0);
+  const int tcs = tc_stages(desc, d);
+  if ((tcs & kStageAll) != kStageAll) return 0;
+  return tc_backward_fused_ok(d, desc->Lk, has_dx != 0) ? 1 : 0;
+}
+
 int moka_forward(const MokaDesc* desc, const void* x, const void* y0, void* y,
                  const void* const* A, const void* Bw,
                  const uint8_t* tokmeta, const int32_t* kidx, const int32_t* klen,
                  float* h_stash, uint64_t seed, uint64_t offset,
                  void* workspace, size_t workspace_bytes, moka_stream_t stream) {
   if (int e = validate(desc)) return e;
+  const bool delta = (desc->flags & MOKA_FLAG_DELTA_OUT) != 0;
+  if (delta) y0 = y;                                           // write-only output: y0 is not read
   if (!x || !y0 || !y || !A || !Bw || !tokmeta || !klen || !h_stash) return MOKA_EINVAL;
   if (desc->Lk > 0 && !kidx) return MOKA_EINVAL;
   for (int m = 0; m < desc->M; ++m) if (!A[m]) return MOKA_EINVAL;
@@ -139,10 +149,12 @@ int moka_forward(const MokaDesc* desc, const void* x, const void* y0, void* y,
   const int skip = (desc->flags >> MOKA_FLAG_DBG_SKIP_SHIFT) & 0xff;     // timing aid only
   d.dbg_skip = skip;
   d.dbg = tc_dbg_enabled();
+  d.delta = delta ? 1 : 0;
+  if (delta && tcs != (kStageDown | kStageUp)) return MOKA_EUNSUPPORTED;   // write-only outputs: tcgen05 kernels only
   if (tcs == (kStageDown | kStageUp)) {
     // both stages on the tensor-core path: one call so that they can agree on the split-reduction layout
     int e = tc_forward(d, a, num_sms(), st, tcs);
-    if (e != MOKA_EUNSUPPORTED || force) return e;
+    if (e != MOKA_EUNSUPPORTED || force || delta) return e;
     // a shape the tensor-core kernels cannot tile (shared-memory budget): redo stage by stage below
     // (the down-projection is idempotent)
   }
@@ -191,6 +203,9 @@ int moka_backward(const MokaDesc* desc, const void* dy, const void* x, const flo
   const bool force = (desc->flags & MOKA_FLAG_FORCE_TC) != 0;
   d.dbg_skip = (desc->flags >> MOKA_FLAG_DBG_SKIP_SHIFT) & 0xff;          // timing aid only
   d.dbg = tc_dbg_enabled();
+  d.delta = ((desc->flags & MOKA_FLAG_DELTA_OUT) && dx) ? 1 : 0;
+  if (d.delta && !(tcs == (kStageDgrad | kStageWgrad) && tc_backward_fused_ok(d, desc->Lk, true)))
+    return MOKA_EUNSUPPORTED;                                  // write-only dx: fused tcgen05 chain only
   if (tcs == (kStageDgrad | kStageWgrad) && tc_backward_fused_ok(d, desc->Lk, dx != nullptr)) {
     // whole backward on the tensor-core path: four kernels chained by programmatic dependent launch,
     // the first of which zero-fills what needs it (no memset node in the chain)

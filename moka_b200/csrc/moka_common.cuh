@@ -29,6 +29,7 @@ struct DevDesc {            // by-value kernel argument (POD)
   int num_tiles;
   int dbg_skip;             // MOKA_FLAG_DBG_SKIP bits (timing aid)
   int dbg;                  // in-kernel time stamps enabled (MOKA_DEBUG_TIMING=1)
+  int delta;                // MOKA_FLAG_DELTA_OUT: y / dx receive the adapter term only (write-only outputs)
 };
 
 // ---------------------------------------------------------------------------- vectors

@@ -132,10 +132,20 @@ int debug_read(unsigned long long* host, int n) {
 }
 
 // ---------------------------------------------------------------------------- k_down_tc
+// Column-order rotation of the streaming kernels: every CTA walks its column blocks starting at a different one
+// (wrapping around), so that the small weight tiles all CTAs need (A_m boxes in k_down_tc, B^T blocks in
+// k_dgrad_tc) are not requested by every SM from the same L2 lines at the same moment.  MOKA_NO_ROT=1: off.
+static int rot_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MOKA_NO_ROT"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v;
+}
+
 struct DownTcParams {
   int T, d_in, r, rp, M, NP;       // rp = r rounded to 8 (rows per modality block), NP = padded N
   int ksplit, kblocks;             // split of the d_in reduction across CTAs; kblocks = d_in / (64 kbox)
   int kbox;                        // 64-column TMA boxes per pipeline stage (1 or 2)
+  int rot;                         // rotate the column-block order per CTA (see rot_enabled)
   int stages;
   uint32_t stage_bytes, w_bytes, tmem_cols;
   float scale;                     // pre * dropout scale
@@ -167,6 +177,8 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   if (threadIdx.x == 0) { dbg_stamp_g(p.dbg, blockIdx.x, 100); dbg_stamp(p.dbg, blockIdx.x, 0); }
   const int kb0 = (int)((long long)split * p.kblocks / p.ksplit);
   const int kb1 = (int)((long long)(split + 1) * p.kblocks / p.ksplit);
+  const int nkb = kb1 - kb0;
+  const int krot = p.rot ? (int)(((unsigned)tile * 5u + (unsigned)split * 3u) % (unsigned)nkb) : 0;   // first block of this CTA
 
   // rows of the weight tiles that TMA never writes (padding between modality blocks) must be 0
   const uint32_t xbytes = 16384u * (uint32_t)p.kbox;
@@ -197,8 +209,8 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   if (warp == 0) {
     if (lane == 0) {
       const uint32_t tx = (16384u + (uint32_t)p.M * (uint32_t)p.r * 128u) * (uint32_t)p.kbox;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        const int it = kb - kb0, s = it % p.stages;
+      for (int it = 0; it < nkb; ++it) {
+        const int kb = kb0 + (it + krot) % nkb, s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         ptx::mbar_wait_or_trap(&empty[s], ph ^ 1u, __LINE__);
         uint8_t* xs = ring + (size_t)s * p.stage_bytes;
@@ -258,8 +270,8 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       const int mrow = mt & 127, part = mt >> 7;
       const unsigned long long rowbase = dropout_row_base(d, t0 + mrow);
       const int nsg = 2 * p.kbox;                              // super-groups per stage
-      for (int kb = kb0; kb < kb1; ++kb) {
-        const int it = kb - kb0, s = it % p.stages;
+      for (int it = 0; it < nkb; ++it) {
+        const int kb = kb0 + (it + krot) % nkb, s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         ptx::mbar_wait_or_trap(&full[s], ph, __LINE__);
         const uint32_t xs = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
@@ -339,6 +351,7 @@ static int launch_down_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cuda
   const size_t min_stages = (ntiles * p.ksplit <= num_sms) ? 4 : 2;
   p.kbox = (kbox_env == 2 && d.d_in % 128 == 0 && budget0 / ((16384u + p.w_bytes) * 2u) >= min_stages) ? 2 : 1;
   p.kblocks = d.d_in / (64 * p.kbox);
+  p.rot = rot_enabled();
   p.stage_bytes = (16384u + p.w_bytes) * (uint32_t)p.kbox;
   // one CTA per SM when the grid does not exceed the SM count: spend the whole shared memory on the
   // ring (tcgen05.commit frees a stage ~1.5k cycles after issue, so >= 6 stages keep HBM busy)
@@ -987,6 +1000,8 @@ struct UpTcParams {
   int write_g;
   int attn_in_kernel;              // 0: g rows come precomputed from k_attn_fwd (h_in0 = g)
   int bpg;                         // B-tile buffers / TMEM accumulators per worker group: 2, or 1 when r > 64
+  int delta;                       // MOKA_FLAG_DELTA_OUT: y receives the adapter term only (no y0 read)
+  int rot;                         // rotate the chunk order per CTA (see rot_enabled)
   int dbg;
 };
 
@@ -1002,7 +1017,9 @@ __device__ __forceinline__ void named_sync(int id, int n) {
 // DROP (k_wgrad_tc with lora_dropout > 0): the accumulator is the gradient with respect to the DROPPED input,
 // so it is masked with the row's keep bits (km16: 16 bytes, one per 8-column chunk of the 128-column tile,
 // produced when the x tile of the same rows was masked) before it is added.
-template <bool DROP = false>
+// DELTA (MOKA_FLAG_DELTA_OUT): the tile is write-only - the slot holds no data, the accumulator is rounded to
+// bf16 and stored; the frozen GEMM adds its product onto it afterwards (beta = 1).
+template <bool DROP = false, bool DELTA = false>
 __device__ __forceinline__ void add_acc_to_tile(uint32_t tmem_row_addr, uint32_t tile_smem, uint32_t row,
                                                 uint64_t* tmem_free = nullptr, const uint32_t* km16 = nullptr) {
 #pragma unroll
@@ -1010,7 +1027,8 @@ __device__ __forceinline__ void add_acc_to_tile(uint32_t tmem_row_addr, uint32_t
     const uint32_t box = tile_smem + (uint32_t)half * 16384u;
     uint4 yv[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) yv[c] = ptx::lds128(box + ptx::sw128_offset(row, (uint32_t)c));
+    for (int c = 0; c < 8; ++c)
+      yv[c] = DELTA ? make_uint4(0u, 0u, 0u, 0u) : ptx::lds128(box + ptx::sw128_offset(row, (uint32_t)c));
     float acc[2][32];
     ptx::tmem_ld32(tmem_row_addr + (uint32_t)(half * 64), acc[0]);
     ptx::tmem_ld32(tmem_row_addr + (uint32_t)(half * 64 + 32), acc[1]);
@@ -1074,6 +1092,8 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
   const int c_beg = (int)((long long)split * p.chunks / p.nsplit);
   const int c_end = (int)((long long)(split + 1) * p.chunks / p.nsplit);
   const int nch = c_end - c_beg;
+  const int crot = p.rot ? (int)(((unsigned)tile * 5u + (unsigned)split * 3u) % (unsigned)nch) : 0;
+  auto chunk_of = [&](int j) { return c_beg + (j + crot) % nch; };   // j-th column chunk this CTA processes
   if (threadIdx.x == 0) dbg_stamp_g(p.dbg, blockIdx.x, 104);
   // last kernel of the forward chain: whatever follows (the first kernel of the next libmoka call waits
   // before it touches memory; anything else is a normal stream-ordered launch) may start its prologue now
@@ -1105,8 +1125,13 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
         const uint32_t ph = (uint32_t)(j / p.ystages) & 1u;
         ptx::mbar_wait_or_trap(&y_empty[s], ph ^ 1u, __LINE__);
         uint8_t* yt = ytiles + (size_t)s * 32768;
+        if (p.delta) {                                           // write-only output: the free slot is all the workers need
+          ptx::mbar_arrive(&y_full[s]);
+          ptx::prog_mark(0, j + 1);
+          continue;
+        }
         ptx::mbar_arrive_expect_tx(&y_full[s], 32768u);
-        const int col = (c_beg + j) * 128;
+        const int col = chunk_of(j) * 128;
         ptx::tma_load_2d(yt, &tm_y0, &y_full[s], col, t0, ptx::kEvictFirst);
         ptx::tma_load_2d(yt + 16384, &tm_y0, &y_full[s], col + 64, t0, ptx::kEvictFirst);
         ptx::prog_mark(0, j + 1);
@@ -1150,7 +1175,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
         const uint32_t ph = (uint32_t)(j / p.ystages) & 1u;
         ptx::mbar_wait_or_trap(&y_done[s], ph, __LINE__);
         uint8_t* yt = ytiles + (size_t)s * 32768;
-        const int col = (c_beg + j) * 128;
+        const int col = chunk_of(j) * 128;
         ptx::tma_store_2d(&tm_y, yt, col, t0);
         ptx::tma_store_2d(&tm_y, yt + 16384, col + 64, t0);
         ptx::tma_store_commit();
@@ -1189,7 +1214,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
         const int kb = ch >> 3, chb = ch & 7;                   // 64-wide K block and chunk inside it
         const int slot = (i >> 1) * p.bpg + (i & 1);              // barrier index i = group * 2 + buffer -> smem slot
         uint8_t* dst = btiles + ((size_t)slot * kblocks + kb) * 16384 + ptx::sw128_offset((uint32_t)n, (uint32_t)chb);
-        const __nv_bfloat16* src = Bw + (size_t)((c_beg + j) * 128 + n) * r + (k < r ? k : 0);
+        const __nv_bfloat16* src = Bw + (size_t)(chunk_of(j) * 128 + n) * r + (k < r ? k : 0);
         ptx::cp_async16(ptx::smem_u32(dst), src, k < r);
       }
       ptx::cp_async_commit();
@@ -1312,7 +1337,10 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
       if (wl == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 4);
       ptx::tc_fence_after_sync();
       uint8_t* yt = ytiles + (size_t)s * 32768;
-      add_acc_to_tile(lane_base + (uint32_t)(i * 128), ptx::smem_u32(yt), (uint32_t)row, &t_empty[i]);
+      if (p.delta)
+        add_acc_to_tile<false, true>(lane_base + (uint32_t)(i * 128), ptx::smem_u32(yt), (uint32_t)row, &t_empty[i]);
+      else
+        add_acc_to_tile(lane_base + (uint32_t)(i * 128), ptx::smem_u32(yt), (uint32_t)row, &t_empty[i]);
       if (wl == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 10 + j * 4);
       ptx::fence_proxy_async_smem();                            // generic writes -> visible to the TMA store
       ptx::mbar_arrive(&y_done[s]);
@@ -1336,6 +1364,11 @@ static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaSt
   const int ntiles = (d.T + 127) / 128;
   p.nsplit = 1;
   while (ntiles * p.nsplit * 2 <= num_sms + num_sms / 4 && p.chunks / (p.nsplit * 2) >= 4) p.nsplit *= 2;
+  {
+    static int up_nsplit_env = -1;                 // tuning aid: force the column split of k_up_tc
+    if (up_nsplit_env < 0) { const char* e = getenv("MOKA_UP_NSPLIT"); up_nsplit_env = e ? atoi(e) : 0; }
+    if (up_nsplit_env > 0 && p.chunks / up_nsplit_env >= 2) p.nsplit = up_nsplit_env;
+  }
   const int kblocks = (p.rk + 63) / 64;
   p.kcap = min(max(a.klen_hint, 1), 32 * kKeyBlocksMax);
   // attention as its own kernel (k_attn_fwd) whenever the sample's keys fit its shared memory
@@ -1362,9 +1395,11 @@ static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaSt
   if (p.ystages == 3) p.ystages = 2;
   if (p.ystages < 2) return MOKA_EUNSUPPORTED;
   p.write_g = 1;
+  p.delta = d.delta;
+  p.rot = rot_enabled();
   p.dbg = dbg_enabled();
   CUtensorMap ty0, ty;
-  if (!make_tmap(&ty0, a.y0, (uint64_t)d.T, (uint64_t)d.d_out, 128)) return MOKA_EUNSUPPORTED;
+  if (!make_tmap(&ty0, d.delta ? a.y : a.y0, (uint64_t)d.T, (uint64_t)d.d_out, 128)) return MOKA_EUNSUPPORTED;
   if (!make_tmap(&ty, a.y, (uint64_t)d.T, (uint64_t)d.d_out, 128)) return MOKA_EUNSUPPORTED;
   const size_t smem = (size_t)p.ystages * 32768 + fixed + key_bytes;
   cudaError_t e = cudaFuncSetAttribute(k_up_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1450,6 +1485,7 @@ struct DgradTcParams {
   int dbg;
   int dg_mode;                     // 0 plain store (csplit == 1), 1 one partial buffer per split, 2 reduce into zeroed dG
   int nbuf;                        // dB accumulator sets in TMEM (2, or 1 when rk = 128)
+  int rot;                         // rotate the pair order per CTA (see rot_enabled)
   int wide;                        // 128-column pairs per pipeline stage (2 when TMEM / smem allow: halves the
                                    // per-stage hand-offs of the single MMA-issuing thread)
   uint32_t tmem_cols, d2_col;      // D2 buffers start at column d2_col
@@ -1481,6 +1517,8 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
   const int p_beg = (int)((long long)split * p.pairs / p.csplit);
   const int p_end = (int)((long long)(split + 1) * p.pairs / p.csplit);
   const int np = p_end - p_beg;
+  const int prot = p.rot ? (int)(((unsigned)tile * 5u + (unsigned)split * 3u) % (unsigned)np) : 0;
+  auto pair_of = [&](int i) { return p_beg + (i + prot) % np; };   // i-th pair this CTA processes
   const int W = p.wide;
   const int ns = (np + W - 1) / W;                             // pipeline stages of this CTA
   const uint32_t dy_bytes = 32768u * (uint32_t)W;             // dY part of a stage; the B^T blocks follow
@@ -1515,7 +1553,7 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
         const int nq = min(W, np - j * W);
         ptx::mbar_arrive_expect_tx(bar, (uint32_t)nq * (32768u + p.bt_bytes));
         for (int q = 0; q < nq; ++q) {
-          const int col = (p_beg + j * W + q) * 128;
+          const int col = pair_of(j * W + q) * 128;
           ptx::tma_load_2d(st + (size_t)q * 32768, &tm_dy, bar, col, t0, ptx::kEvictFirst);
           ptx::tma_load_2d(st + (size_t)q * 32768 + 16384, &tm_dy, bar, col + 64, t0, ptx::kEvictFirst);
         }
@@ -1523,7 +1561,7 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
       auto load_bt = [&](int j, uint64_t* bar, uint8_t* st) {   // B^T blocks [rk rows x 64 cols] (L2-resident)
         const int nq = min(W, np - j * W);
         for (int q = 0; q < nq; ++q) {
-          const int col = (p_beg + j * W + q) * 128;
+          const int col = pair_of(j * W + q) * 128;
           ptx::tma_load_2d(st + dy_bytes + (size_t)(2 * q) * gt_block, &tm_bt, bar, col, 0, ptx::kEvictLast);
           ptx::tma_load_2d(st + dy_bytes + (size_t)(2 * q + 1) * gt_block, &tm_bt, bar, col + 64, 0, ptx::kEvictLast);
         }
@@ -1582,8 +1620,10 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const int box = k >> 2, kk = k & 3;
+            if (!(p.dbg & 4))
             ptx::umma_bf16(tmem_base, a1 + (uint64_t)((box * 16384 + kk * 32) >> 4),
                            b1 + (uint64_t)((box * gt_block + kk * 32) >> 4), idesc1, (j > 0 || q > 0 || k > 0) ? 1u : 0u);
+            if (!(p.dbg & 8))
             ptx::umma_bf16(d2, a2 + (uint64_t)((k * 2048) >> 4), g_desc[k], idesc2, k > 0 ? 1u : 0u);
           }
         }
@@ -1640,7 +1680,7 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
       if (wt == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 32 + j * 2);
       ptx::tc_fence_after_sync();
       for (int q = 0; q < nq; ++q) {
-        const int col = (p_beg + j * W + q) * 128 + row;       // TMEM lane <-> output column
+        const int col = pair_of(j * W + q) * 128 + row;       // TMEM lane <-> output column
         float* dst = dB + (size_t)col * r;
         const uint32_t acc = lane_base + p.d2_col + (uint32_t)((i * W + q) * 2 * p.rk);
         for (int c8 = 0; c8 < r; c8 += 8) {                     // r % 8 == 0 on this path
@@ -1902,12 +1942,22 @@ static int launch_attn_nopack(const DevDesc& d, const SimtArgs& a, cudaStream_t 
 
 // fused = the merged attention-backward + pack kernel follows (partial dG buffers, nothing zero-filled
 // but dK and the counters); otherwise the legacy kernels run on a complete dG in a.dh.
+// Column split of k_dgrad_tc (one dG partial buffer per split); k_attn_pack must agree.
+static int dgrad_csplit(const DevDesc& d, int num_sms) {
+  const int ntiles = (d.T + 127) / 128, pairs = d.d_out / 128;
+  int cs = (ntiles < num_sms && ntiles * 2 <= num_sms + num_sms / 4 && pairs >= 8) ? 2 : 1;
+  static int dg_csplit_env = -1;                   // tuning aid: force the split
+  if (dg_csplit_env < 0) { const char* e = getenv("MOKA_DGRAD_CSPLIT"); dg_csplit_env = e ? atoi(e) : 0; }
+  if ((dg_csplit_env == 1 || dg_csplit_env == 2) && pairs >= 8) cs = dg_csplit_env;
+  return cs;
+}
+
 static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, bool fused) {
   DgradTcParams p;
   p.T = d.T; p.d_out = d.d_out; p.r = d.r; p.rk = round_up(d.r, 16);
   p.pairs = d.d_out / 128;
   const int ntiles = (d.T + 127) / 128;
-  p.csplit = (ntiles < num_sms && ntiles * 2 <= num_sms + num_sms / 4 && p.pairs >= 8) ? 2 : 1;
+  p.csplit = dgrad_csplit(d, num_sms);
   p.dg_mode = p.csplit == 1 ? 0 : (fused ? 1 : 2);
   p.bt_bytes = 2u * (uint32_t)p.rk * 128u;
   const size_t fixed = (size_t)4 * p.rk * 128 + 1024 + 512;
@@ -1920,6 +1970,7 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
     p.wide = (dg_wide_env >= 2 && dgc0 + 8 * p.rk <= 512 && 2 * st2 + fixed <= 200 * 1024 &&
               (d.d_out / 128) / p.csplit >= 4) ? 2 : 1;
   }
+  p.rot = rot_enabled();
   p.stage_bytes = (uint32_t)p.wide * (32768u + p.bt_bytes);
   // fused chain: leave ~56 KB of the SM's shared memory to an early-launched k_attn_pack CTA, whose
   // staging of the forward's stash then overlaps this kernel
@@ -1933,6 +1984,8 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   if (p.stages < 2) return MOKA_EUNSUPPORTED;
   p.dbg = dbg_enabled();
   { static int nodb = -1; if (nodb < 0) { const char* e = getenv("MOKA_DBG_NO_DB"); nodb = (e && e[0] == '1') ? 2 : 0; } p.dbg |= nodb; }
+  // timing experiments (results invalid): MOKA_DBG_DGRAD_SKIP=1 drops the dG product, =2 the dB product
+  { static int sk = -1; if (sk < 0) { const char* e = getenv("MOKA_DBG_DGRAD_SKIP"); sk = e ? (atoi(e) & 3) << 2 : 0; } p.dbg |= sk; }
   const uint32_t dgc = tmem_cols_for(p.rk);
   p.d2_col = dgc;
   p.nbuf = (dgc + 4 * p.wide * p.rk <= 512) ? 2 : 1;         // sets of `wide` [128 x 2 rk] dB accumulators next to dG
@@ -2782,6 +2835,8 @@ struct WgradTcParams {
   int tsplit, ntiles;
   int xs, ds, nop;                 // ring depths: X pairs / dX pairs (32 KB slots), operand buffers
   int has_dx, dbg;
+  int delta;                       // MOKA_FLAG_DELTA_OUT: dx tiles are write-only in this pass (no dx read)
+  int rot;                         // rotate the tile order per column slice (see rot_enabled)
   int prefetch_dx;                 // dx tiles may be loaded before the dependency wait (false for the later passes of a
                                    // rank-chunked call: the pass in front is still writing dx)
   uint32_t w_box_bytes;            // one 64-column box of the weight slice: NPW x 128 B
@@ -2833,6 +2888,10 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   const int tt_beg = (int)((long long)split * p.ntiles / p.tsplit);
   const int tt_end = (int)((long long)(split + 1) * p.ntiles / p.tsplit);
   const int ntt = tt_end - tt_beg;
+  // the column slices of one token range all read the same packed dh operand tiles: each slice starts at a
+  // different tile of the range so that they do not ask the same L2 lines for them at the same moment
+  const int trot = p.rot ? (int)(((unsigned)slice * 5u) % (unsigned)ntt) : 0;
+  auto tile_of = [&](int j) { return tt_beg + (j + trot) % ntt; };
   if (threadIdx.x == 0) { dbg_stamp_g(p.dbg, blockIdx.x, 112); dbg_stamp(p.dbg, blockIdx.x, 1); }
   if (threadIdx.x == 0) ptx::pdl_trigger();                   // last kernel of the backward chain (see k_up_tc)
 
@@ -2881,18 +2940,19 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       for (int j = 0; j < npre_x; ++j) {
         uint8_t* xt = xring + (size_t)j * 32768;
         ptx::mbar_arrive_expect_tx(&x_full[j], 32768u);
-        ptx::tma_load_2d(xt, &tm_x, &x_full[j], col0, (tt_beg + j) * 128, ptx::kEvictFirst);
-        ptx::tma_load_2d(xt + 16384, &tm_x, &x_full[j], col0 + 64, (tt_beg + j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d(xt, &tm_x, &x_full[j], col0, tile_of(j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d(xt + 16384, &tm_x, &x_full[j], col0 + 64, tile_of(j) * 128, ptx::kEvictFirst);
       }
       for (int j = 0; j < npre_d; ++j) {
         uint8_t* dt = dring + (size_t)j * 32768;
+        if (p.delta) { ptx::mbar_arrive(&d_full[j]); continue; }   // write-only dx: a free slot is enough
         ptx::mbar_arrive_expect_tx(&d_full[j], 32768u);
-        ptx::tma_load_2d(dt, &tm_dx, &d_full[j], col0, (tt_beg + j) * 128, ptx::kEvictFirst);
-        ptx::tma_load_2d(dt + 16384, &tm_dx, &d_full[j], col0 + 64, (tt_beg + j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d(dt, &tm_dx, &d_full[j], col0, tile_of(j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d(dt + 16384, &tm_dx, &d_full[j], col0 + 64, tile_of(j) * 128, ptx::kEvictFirst);
       }
       ptx::pdl_wait();
       for (int j = 0; j < ntt; ++j) {
-        const int t0 = (tt_beg + j) * 128;
+        const int t0 = tile_of(j) * 128;
         if (j >= npre_x) {   // the big streams first: they have their own ring slots and must never wait on the MMAs
           const int s = j % p.xs;
           const uint32_t ph = (uint32_t)(j / p.xs) & 1u;
@@ -2907,9 +2967,13 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
           const uint32_t ph = (uint32_t)(j / p.ds) & 1u;
           ptx::mbar_wait_or_trap(&d_empty[s], ph ^ 1u, __LINE__);
           uint8_t* dt = dring + (size_t)s * 32768;
-          ptx::mbar_arrive_expect_tx(&d_full[s], 32768u);
-          ptx::tma_load_2d(dt, &tm_dx, &d_full[s], col0, t0, ptx::kEvictFirst);
-          ptx::tma_load_2d(dt + 16384, &tm_dx, &d_full[s], col0 + 64, t0, ptx::kEvictFirst);
+          if (p.delta) {
+            ptx::mbar_arrive(&d_full[s]);
+          } else {
+            ptx::mbar_arrive_expect_tx(&d_full[s], 32768u);
+            ptx::tma_load_2d(dt, &tm_dx, &d_full[s], col0, t0, ptx::kEvictFirst);
+            ptx::tma_load_2d(dt + 16384, &tm_dx, &d_full[s], col0 + 64, t0, ptx::kEvictFirst);
+          }
         }
         {   // packed dh operands of tile j (L2-resident; nop buffers, recycled when their MMAs retire)
           const int ob = j % p.nop;
@@ -2983,7 +3047,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         const uint32_t k = (uint32_t)(j / p.xs);
         ptx::mbar_wait_or_trap(&x_full[s], k & 1u, __LINE__);
         if (p.has_dx && k > 0) ptx::mbar_wait_or_trap(&km_free[s], (k - 1u) & 1u, __LINE__);
-        const unsigned long long rowbase = dropout_row_base(d, (long long)(tt_beg + j) * 128 + mrow);
+        const unsigned long long rowbase = dropout_row_base(d, (long long)tile_of(j) * 128 + mrow);
         const uint32_t boxaddr = ptx::smem_u32(xring + (size_t)s * 32768) + (uint32_t)box * 16384u;
 #pragma unroll
         for (int hs = 0; hs < 2; ++hs) {                         // a box = two 32-column super-groups
@@ -3001,7 +3065,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       for (int j = 0; j < ntt; ++j) {
         const int s = j % p.ds;
         const uint32_t ph = (uint32_t)(j / p.ds) & 1u;
-        const int t0 = (tt_beg + j) * 128;
+        const int t0 = tile_of(j) * 128;
         ptx::mbar_wait_or_trap(&d_done[s], ph, __LINE__);
         uint8_t* dt = dring + (size_t)s * 32768;
         ptx::tma_store_2d(&tm_dx, dt, col0, t0);
@@ -3039,7 +3103,12 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         if (st) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 4);
         ptx::tc_fence_after_sync();
         uint8_t* dt = dring + (size_t)s * 32768;
-        if (DROP)
+        if (p.delta) {
+          if (DROP)
+            add_acc_to_tile<true, true>(lane_base + (uint32_t)(i * 128), ptx::smem_u32(dt), (uint32_t)row, &t_empty[i], km_cur);
+          else
+            add_acc_to_tile<false, true>(lane_base + (uint32_t)(i * 128), ptx::smem_u32(dt), (uint32_t)row, &t_empty[i]);
+        } else if (DROP)
           add_acc_to_tile<true>(lane_base + (uint32_t)(i * 128), ptx::smem_u32(dt), (uint32_t)row, &t_empty[i], km_cur);
         else
           add_acc_to_tile(lane_base + (uint32_t)(i * 128), ptx::smem_u32(dt), (uint32_t)row, &t_empty[i]);
@@ -3057,6 +3126,12 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
     // stage the accumulator as [NPW][128 cols] fp32 in the (now idle) X ring so that each thread can
     // reduce four consecutive columns of one (modality, rank) row with a single red.v4
     float* stage = reinterpret_cast<float*>(xring);
+    // NPW x 512 bytes can be more than the X ring (one 32 KB slot at r = 128) and then runs into the dx ring,
+    // whose last tiles the TMA store engine may still be reading: wait until those slots have been read out
+    // (d_empty is what the store warp signals after cp.async.bulk.wait_group.read)
+    if (p.has_dx && (size_t)p.NPW * 512 > (size_t)p.xs * 32768)
+      for (int j = max(0, ntt - p.ds); j < ntt; ++j)
+        ptx::mbar_wait_or_trap(&d_empty[j % p.ds], (uint32_t)(j / p.ds) & 1u, __LINE__);
     for (int n8 = 0; n8 < p.NPW; n8 += 8) {
       float v[8];
       ptx::tmem_ld8(lane_base + d1_col + (uint32_t)n8, v);
@@ -3200,6 +3275,8 @@ static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParam
     p.tsplit = best;
   }
   p.has_dx = has_dx;
+  p.delta = (has_dx && d.delta) ? 1 : 0;
+  p.rot = rot_enabled();
   p.dbg = dbg_enabled();
   p.w_box_bytes = (uint32_t)p.NPW * 128u;
   p.op_bytes = (uint32_t)(p.KP / 64) * 16384u + 4u * p.w_box_bytes;
@@ -3221,6 +3298,8 @@ static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParam
   } else {
     p.xs = min(4, slots); p.ds = 0;
   }
+  // the dA flush stages [NPW][128] fp32 over the X ring and, past its end, the dx ring
+  if ((size_t)p.NPW * 512 > (size_t)(p.xs + p.ds) * 32768) return false;
   return true;
 }
 
@@ -3238,7 +3317,7 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   if (fused) {
     if (!(d.dbg_skip & 16)) {
       const int ntiles128 = (d.T + 127) / 128;
-      const int csplit = (ntiles128 < num_sms && ntiles128 * 2 <= num_sms + num_sms / 4 && d.d_out / 128 >= 8) ? 2 : 1;
+      const int csplit = dgrad_csplit(d, num_sms);
       if (int rc = launch_attn_pack(d, a, L, csplit > 1, hc, hct_hi, hct_lo, st)) return rc;
     }
   } else {
@@ -3268,6 +3347,7 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
       if (!make_tmap(&thh_c, hct_hi + (size_t)c * w * d.T, w, (uint64_t)d.T, (uint32_t)w)) return MOKA_EUNSUPPORTED;
       if (!make_tmap(&thl_c, hct_lo + (size_t)c * w * d.T, w, (uint64_t)d.T, (uint32_t)w)) return MOKA_EUNSUPPORTED;
       p.prefetch_dx = (c == 0);
+      p.delta = (c == 0 && p.has_dx && d.delta) ? 1 : 0;       // later passes add onto what the first one wrote
       if (d.drop_thresh)
         e = launch_pdl(k_wgrad_tc<true>, dim3(slices * p.tsplit), dim3(kWgradDropThreads), smem, st, tx, tdx, tac, tac, tac,
                        thc_c, thh_c, thl_c, p, d, dAc, dAc, dAc);

@@ -14,6 +14,7 @@ math in this package: CPU tensors or a missing library raise.
 from __future__ import annotations
 
 import math
+import os
 from typing import Any, List, Optional, Sequence
 
 import torch
@@ -31,6 +32,14 @@ _WORKSPACE = {}
 
 # optional per-call CUDA-event timing of the C-ABI calls (bench.py turns it on)
 TIMING = {'enabled': False, 'events': []}
+
+# Frozen-GEMM epilogue fusion (MOKA_FLAG_DELTA_OUT): the adapter kernels write their term
+# alone (no read of W0 x / W0^T dy) and the cuBLAS GEMM accumulates onto it with beta = 1.  Opt-in
+# (MOKA_DELTA=1 in the environment or FUSION['enabled'] = True) wherever the tcgen05 chain serves the shape:
+# measured on B200 it moves 32 % of the adapter's bytes into the GEMM epilogue but gains only ~0.5 % of the 7B
+# step (profiles/r01_delta_out.md), so the default stays the read-modify-write order (GEMM first, adapter
+# added in place), whose numbers are the ones SURVEY 8(d)'s byte model describes.
+FUSION = {'enabled': os.environ.get('MOKA_DELTA', '0') == '1', 'unsupported': set()}
 
 
 def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
@@ -86,9 +95,20 @@ class _MokaFn(torch.autograd.Function):
         x2 = x.reshape(B * S, d_in)
         if not x2.is_contiguous():
             x2 = x2.contiguous()
-        # frozen base, cuBLAS; the adapter is added in place.  Computed in the caller's shape so the
-        # returned tensor is not a view made inside this Function (callers may modify it in place).
-        y = F.linear(x2.view(shp), weight, bias)
+        desc = _make_desc(x2.shape, B, S, d_out, r, len(A), x.dtype, meta.Lk, sc, flags)
+        shape_key = (B, S, d_in, d_out, r, len(A), x.dtype, meta.Lk, flags, sc.p > 0.0)
+        delta = (FUSION['enabled'] and x.dtype == torch.bfloat16 and shape_key not in FUSION['unsupported'])
+        if delta and not lib.moka_supports_delta(desc, 1):
+            FUSION['unsupported'].add(shape_key)
+            delta = False
+        if delta:
+            # adapter term first (write-only), frozen GEMM accumulated onto it below (beta = 1)
+            y = torch.empty(*shp[:-1], d_out, dtype=x.dtype, device=x.device)
+            desc.flags = flags | _cabi.FLAG_DELTA_OUT
+        else:
+            # frozen base, cuBLAS; the adapter is added in place.  Computed in the caller's shape so the
+            # returned tensor is not a view made inside this Function (callers may modify it in place).
+            y = F.linear(x2.view(shp), weight, bias)
         h = torch.empty(2 * B * S * r + B * S, dtype=torch.float32, device=x.device)   # h, g, lse
         seed = offset = 0
         if sc.p > 0.0:
@@ -98,7 +118,6 @@ class _MokaFn(torch.autograd.Function):
             offset = int(torch.randint(0, 2 ** 62, (1,)).item())
         Ac = [a if a.is_contiguous() else a.contiguous() for a in A]
         Bc = Bw if Bw.is_contiguous() else Bw.contiguous()
-        desc = _make_desc(x2.shape, B, S, d_out, r, len(A), x.dtype, meta.Lk, sc, flags)
         ws = _workspace(x.device, int(lib.moka_workspace_bytes(desc)))
         stream = torch.cuda.current_stream(x.device).cuda_stream
         ev = None
@@ -110,12 +129,28 @@ class _MokaFn(torch.autograd.Function):
                                     _cabi.ptr_array([a.data_ptr() for a in Ac]), Bc.data_ptr(),
                                     meta.tokmeta.data_ptr(), meta.kidx.data_ptr(), meta.klen.data_ptr(),
                                     h.data_ptr(), seed, offset, ws.data_ptr(), ws.numel(), stream)
+        if delta and code == _cabi.MOKA_EUNSUPPORTED:
+            # a shape the write-only kernels cannot tile after all: remember it, redo in the usual order
+            FUSION['unsupported'].add(shape_key)
+            delta = False
+            desc.flags = flags
+            y = F.linear(x2.view(shp), weight, bias)
+            with torch.cuda.device(x.device):
+                code = lib.moka_forward(desc, x2.data_ptr(), y.data_ptr(), y.data_ptr(),
+                                        _cabi.ptr_array([a.data_ptr() for a in Ac]), Bc.data_ptr(),
+                                        meta.tokmeta.data_ptr(), meta.kidx.data_ptr(), meta.klen.data_ptr(),
+                                        h.data_ptr(), seed, offset, ws.data_ptr(), ws.numel(), stream)
         _cabi.check(code, 'moka_forward')
         if ev is not None:
             ev[1].record()
-            TIMING['events'].append(('fwd', B * S, d_in, d_out, x.element_size(), ev))
+            TIMING['events'].append(('fwd', B * S, d_in, d_out, x.element_size(), ev, delta))
+        if delta:
+            y.view(B * S, d_out).addmm_(x2, weight.t())          # y = adapter term + W0 x, one rounding
+            if bias is not None:
+                y.add_(bias)
         ctx.save_for_backward(x2, h, weight, Bc, *Ac)
         ctx.meta, ctx.sc, ctx.flags, ctx.seed, ctx.offset = meta, sc, flags, seed, offset
+        ctx.delta = delta
         ctx.x_shape = shp
         ctx.param_refs = (Bw, A)
         return y
@@ -131,7 +166,11 @@ class _MokaFn(torch.autograd.Function):
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
         need_dx = ctx.needs_input_grad[0]
-        dx = torch.matmul(dy2, weight) if need_dx else None        # frozen dgrad, cuBLAS
+        delta = ctx.delta and need_dx
+        if delta:
+            dx = torch.empty(B * S, d_in, dtype=dy2.dtype, device=dy2.device)   # adapter term first, GEMM onto it
+        else:
+            dx = torch.matmul(dy2, weight) if need_dx else None    # frozen dgrad, cuBLAS
         Bw_param, A_params = ctx.param_refs
         dev = x2.device
 
@@ -143,7 +182,8 @@ class _MokaFn(torch.autograd.Function):
 
         dB, dB_main = grad_buf(Bw_param, (d_out, r))
         dAs = [grad_buf(p, (r, d_in)) for p in A_params]
-        desc = _make_desc(x2.shape, B, S, d_out, r, len(Ac), x2.dtype, meta.Lk, sc, ctx.flags)
+        desc = _make_desc(x2.shape, B, S, d_out, r, len(Ac), x2.dtype, meta.Lk, sc,
+                          ctx.flags | (_cabi.FLAG_DELTA_OUT if delta else 0))
         nbytes = int(lib.moka_workspace_bytes(desc))
         ws = _workspace(dev, nbytes)
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -161,7 +201,9 @@ class _MokaFn(torch.autograd.Function):
         _cabi.check(code, 'moka_backward')
         if ev is not None:
             ev[1].record()
-            TIMING['events'].append(('bwd', B * S, d_in, d_out, x2.element_size(), ev))
+            TIMING['events'].append(('bwd', B * S, d_in, d_out, x2.element_size(), ev, delta))
+        if delta:
+            dx.addmm_(dy2, weight)                                 # dx = adapter term + W0^T dy, one rounding
         # tell the data-parallel engine that these parameters' gradients are complete
         for prm in (Bw_param, *A_params):
             cb = getattr(prm, '_moka_dp_ready', None)

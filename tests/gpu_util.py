@@ -30,12 +30,13 @@ def abi_forward(meta: TokenMeta, x, y0, A, Bw, sc: FusedScalars, flags=0, seed=0
     d_out, r = Bw.shape
     x2 = x.reshape(B * S, d_in).contiguous()
     y0c = y0.reshape(B * S, d_out).contiguous()
-    y = y0c.clone() if inplace else torch.empty_like(y0c)
+    delta = bool(flags & _cabi.FLAG_DELTA_OUT)      # write-only output: y starts as NaN, y0 is not passed at all
+    y = torch.full_like(y0c, float('nan')) if delta else (y0c.clone() if inplace else torch.empty_like(y0c))
     src = y if inplace else y0c
     h = torch.full((2 * B * S * r + B * S,), float('nan'), dtype=torch.float32, device=x.device)
     desc = _make_desc(x2.shape, B, S, d_out, r, len(A), x.dtype, meta.Lk, sc, flags)
     ws = torch.empty(int(lib.moka_workspace_bytes(desc)), dtype=torch.uint8, device=x.device)
-    code = lib.moka_forward(desc, x2.data_ptr(), src.data_ptr(), y.data_ptr(),
+    code = lib.moka_forward(desc, x2.data_ptr(), None if delta else src.data_ptr(), y.data_ptr(),
                             _cabi.ptr_array([a.data_ptr() for a in A]), Bw.data_ptr(),
                             meta.tokmeta.data_ptr(), meta.kidx.data_ptr(), meta.klen.data_ptr(),
                             h.data_ptr(), seed, offset, ws.data_ptr(), ws.numel(),
@@ -53,6 +54,8 @@ def abi_backward(meta: TokenMeta, x, dy, h, A, Bw, sc: FusedScalars, dx0=None, f
     x2 = x.reshape(B * S, d_in).contiguous()
     dy2 = dy.reshape(B * S, d_out).contiguous()
     dx = None if dx0 is None else dx0.reshape(B * S, d_in).clone().contiguous()
+    if dx is not None and (flags & _cabi.FLAG_DELTA_OUT):
+        dx.fill_(float('nan'))                       # write-only output: previous contents must not matter
     dA = [torch.zeros(r, d_in, dtype=torch.float32, device=x.device) for _ in A]
     dB = torch.zeros(d_out, r, dtype=torch.float32, device=x.device)
     desc = _make_desc(x2.shape, B, S, d_out, r, len(A), x.dtype, meta.Lk, sc, flags)

@@ -106,10 +106,11 @@ def run_point(variant, B, S, d_in, d_out, r, dtype, flags, iters, warmup, p=0.0,
             e1.record()
             torch.cuda.synchronize()
             iso[nm] = round(e0.elapsed_time(e1) / iters * 1e3, 2)
-    bytes_f = e * (d_in + 2 * d_out) * T
-    bytes_b = e * (3 * d_in + d_out) * T
+    delta = bool(flags & _cabi.FLAG_DELTA_OUT)      # write-only outputs: the residual read is the frozen GEMM's
+    bytes_f = e * ((d_in + d_out) if delta else (d_in + 2 * d_out)) * T
+    bytes_b = e * ((2 * d_in + d_out) if delta else (3 * d_in + d_out)) * T
     out = dict(variant='avt' if variant == VARIANT_AVT else 'vt', T=T, d_in=d_in, d_out=d_out, r=r,
-               dtype=str(dtype).split('.')[-1], tc=bool(lib.moka_uses_tensor_cores(desc)), dropout=p,
+               delta_out=delta, dtype=str(dtype).split('.')[-1], tc=bool(lib.moka_uses_tensor_cores(desc)), dropout=p,
                fwd_us=round(res['fwd'], 2), bwd_us=round(res['bwd'], 2), both_us=round(res['fwd+bwd'], 2),
                fwd_gbs=round(bytes_f / res['fwd'] / 1e3, 1), bwd_gbs=round(bytes_b / res['bwd'] / 1e3, 1),
                both_gbs=round((bytes_f + bytes_b) / res['fwd+bwd'] / 1e3, 1))
