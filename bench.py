@@ -356,10 +356,10 @@ def main():
                      ms_per_step=ms_e2e / args.steps, last_loss=last_loss),
             gpu_launches=int(launches),
             # traffic: dram__bytes_read + dram__bytes_write of one forward + backward chain from the ncu --set
-            # full capture in profiles/r01_ncu_chain_r16.md (T = 8192, 4096 -> 4096, r = 16; algorithmic
+            # full capture in profiles/r01_ncu_chain_r16_s3.md (T = 8192, 4096 -> 4096, r = 16; algorithmic
             # 469.8 MB, of which the writes still resident in the 126 MB L2 at kernel end are not counted)
             roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
-                          traffic=372.8e6, traffic_shape='one fwd+bwd call pair, T=8192 d=4096->4096 r=16 (ncu)',
+                          traffic=370.0e6, traffic_shape='one fwd+bwd call pair, T=8192 d=4096->4096 r=16 (ncu)',
                           peak_source=peak_kind,
                           kernel='fused MokaLinear fwd+bwd (libmoka.so calls, CUDA events per call)',
                           calls=len(events), delta_out_calls=n_delta,

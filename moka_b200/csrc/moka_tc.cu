@@ -346,16 +346,19 @@ static int launch_down_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cuda
   p.w_bytes = (uint32_t)p.NP * 128u;
   // two 64-column boxes per stage (256 contiguous bytes per token row and request: measured faster
   // than one) as long as the ring still holds >= 4 stages
-  const size_t budget0 = (ntiles * p.ksplit <= num_sms) ? 200 * 1024 : 100 * 1024;
+  static int down_budget_env = -1;                 // tuning aid: ring budget in KB (200: one CTA per SM, 100: two)
+  if (down_budget_env < 0) { const char* e = getenv("MOKA_DOWN_BUDGET"); down_budget_env = e ? atoi(e) : 0; }
+  const bool one_per_sm = down_budget_env ? down_budget_env > 110 : (ntiles * p.ksplit <= num_sms);
+  const size_t budget0 = one_per_sm ? 200 * 1024 : 100 * 1024;
   // (two CTAs per SM share the SM's in-flight bytes: two stages each are enough there)
-  const size_t min_stages = (ntiles * p.ksplit <= num_sms) ? 4 : 2;
+  const size_t min_stages = one_per_sm ? 4 : 2;
   p.kbox = (kbox_env == 2 && d.d_in % 128 == 0 && budget0 / ((16384u + p.w_bytes) * 2u) >= min_stages) ? 2 : 1;
   p.kblocks = d.d_in / (64 * p.kbox);
   p.rot = rot_enabled();
   p.stage_bytes = (16384u + p.w_bytes) * (uint32_t)p.kbox;
   // one CTA per SM when the grid does not exceed the SM count: spend the whole shared memory on the
   // ring (tcgen05.commit frees a stage ~1.5k cycles after issue, so >= 6 stages keep HBM busy)
-  const size_t budget = (ntiles * p.ksplit <= num_sms) ? 200 * 1024 : 100 * 1024;
+  const size_t budget = budget0;
   p.stages = (int)(budget / p.stage_bytes);
   if (p.stages > 10) p.stages = 10;
   if (p.stages < 2) p.stages = 2;
@@ -2836,7 +2839,6 @@ struct WgradTcParams {
   int xs, ds, nop;                 // ring depths: X pairs / dX pairs (32 KB slots), operand buffers
   int has_dx, dbg;
   int delta;                       // MOKA_FLAG_DELTA_OUT: dx tiles are write-only in this pass (no dx read)
-  int rot;                         // rotate the tile order per column slice (see rot_enabled)
   int prefetch_dx;                 // dx tiles may be loaded before the dependency wait (false for the later passes of a
                                    // rank-chunked call: the pass in front is still writing dx)
   uint32_t w_box_bytes;            // one 64-column box of the weight slice: NPW x 128 B
@@ -2888,10 +2890,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   const int tt_beg = (int)((long long)split * p.ntiles / p.tsplit);
   const int tt_end = (int)((long long)(split + 1) * p.ntiles / p.tsplit);
   const int ntt = tt_end - tt_beg;
-  // the column slices of one token range all read the same packed dh operand tiles: each slice starts at a
-  // different tile of the range so that they do not ask the same L2 lines for them at the same moment
-  const int trot = p.rot ? (int)(((unsigned)slice * 5u) % (unsigned)ntt) : 0;
-  auto tile_of = [&](int j) { return tt_beg + (j + trot) % ntt; };
+  // (walking the token range in a per-slice rotated order was measured 4 % SLOWER: the column slices of a
+  // range share their packed dh operand tiles through L2 when they walk it together)
   if (threadIdx.x == 0) { dbg_stamp_g(p.dbg, blockIdx.x, 112); dbg_stamp(p.dbg, blockIdx.x, 1); }
   if (threadIdx.x == 0) ptx::pdl_trigger();                   // last kernel of the backward chain (see k_up_tc)
 
@@ -2940,19 +2940,19 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       for (int j = 0; j < npre_x; ++j) {
         uint8_t* xt = xring + (size_t)j * 32768;
         ptx::mbar_arrive_expect_tx(&x_full[j], 32768u);
-        ptx::tma_load_2d(xt, &tm_x, &x_full[j], col0, tile_of(j) * 128, ptx::kEvictFirst);
-        ptx::tma_load_2d(xt + 16384, &tm_x, &x_full[j], col0 + 64, tile_of(j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d(xt, &tm_x, &x_full[j], col0, (tt_beg + j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d(xt + 16384, &tm_x, &x_full[j], col0 + 64, (tt_beg + j) * 128, ptx::kEvictFirst);
       }
       for (int j = 0; j < npre_d; ++j) {
         uint8_t* dt = dring + (size_t)j * 32768;
         if (p.delta) { ptx::mbar_arrive(&d_full[j]); continue; }   // write-only dx: a free slot is enough
         ptx::mbar_arrive_expect_tx(&d_full[j], 32768u);
-        ptx::tma_load_2d(dt, &tm_dx, &d_full[j], col0, tile_of(j) * 128, ptx::kEvictFirst);
-        ptx::tma_load_2d(dt + 16384, &tm_dx, &d_full[j], col0 + 64, tile_of(j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d(dt, &tm_dx, &d_full[j], col0, (tt_beg + j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d(dt + 16384, &tm_dx, &d_full[j], col0 + 64, (tt_beg + j) * 128, ptx::kEvictFirst);
       }
       ptx::pdl_wait();
       for (int j = 0; j < ntt; ++j) {
-        const int t0 = tile_of(j) * 128;
+        const int t0 = (tt_beg + j) * 128;
         if (j >= npre_x) {   // the big streams first: they have their own ring slots and must never wait on the MMAs
           const int s = j % p.xs;
           const uint32_t ph = (uint32_t)(j / p.xs) & 1u;
@@ -3047,7 +3047,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         const uint32_t k = (uint32_t)(j / p.xs);
         ptx::mbar_wait_or_trap(&x_full[s], k & 1u, __LINE__);
         if (p.has_dx && k > 0) ptx::mbar_wait_or_trap(&km_free[s], (k - 1u) & 1u, __LINE__);
-        const unsigned long long rowbase = dropout_row_base(d, (long long)tile_of(j) * 128 + mrow);
+        const unsigned long long rowbase = dropout_row_base(d, (long long)(tt_beg + j) * 128 + mrow);
         const uint32_t boxaddr = ptx::smem_u32(xring + (size_t)s * 32768) + (uint32_t)box * 16384u;
 #pragma unroll
         for (int hs = 0; hs < 2; ++hs) {                         // a box = two 32-column super-groups
@@ -3065,7 +3065,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       for (int j = 0; j < ntt; ++j) {
         const int s = j % p.ds;
         const uint32_t ph = (uint32_t)(j / p.ds) & 1u;
-        const int t0 = tile_of(j) * 128;
+        const int t0 = (tt_beg + j) * 128;
         ptx::mbar_wait_or_trap(&d_done[s], ph, __LINE__);
         uint8_t* dt = dring + (size_t)s * 32768;
         ptx::tma_store_2d(&tm_dx, dt, col0, t0);
@@ -3276,7 +3276,6 @@ static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParam
   }
   p.has_dx = has_dx;
   p.delta = (has_dx && d.delta) ? 1 : 0;
-  p.rot = rot_enabled();
   p.dbg = dbg_enabled();
   p.w_box_bytes = (uint32_t)p.NPW * 128u;
   p.op_bytes = (uint32_t)(p.KP / 64) * 16384u + 4u * p.w_box_bytes;
