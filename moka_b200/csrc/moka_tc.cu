@@ -78,6 +78,16 @@ static inline uint32_t tmem_cols_for(int n) {
 
 constexpr int kTcThreads = 192;
 constexpr int kWorkers = 128;                                   // worker threads of a group (one per TMEM lane)
+constexpr int kWorkerWarps = kWorkers / 32;
+
+// One mbarrier arrival per WARP instead of one per thread (a stage barrier with 128-512 per-thread arrivals is
+// 128-512 serialised shared-memory atomics on one word): every lane first fences its own shared-memory writes /
+// TMEM reads, __syncwarp() orders them before lane 0's release-arrive.  Barriers signalled this way are
+// initialised with the number of WARPS.
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) ptx::mbar_arrive(bar);
+}
 
 // Launch with programmatic stream serialization (see moka_ptx.cuh: pdl_wait / pdl_trigger).
 // MOKA_NO_PDL=1 falls back to plain stream order (A/B measurements).
@@ -188,7 +198,7 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); ptx::mbar_init(&ready[s], 4 * kWorkers);
+      ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); ptx::mbar_init(&ready[s], 4 * kWorkerWarps);
     }
     ptx::mbar_init(tmem_full, 1);
     ptx::fence_mbar_init();
@@ -281,7 +291,7 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
                                (uint32_t)(sg & 1));
         }
         ptx::fence_proxy_async_smem();                           // generic writes -> visible to the tensor core
-        ptx::mbar_arrive(&ready[s]);
+        warp_arrive(&ready[s]);
       }
     }
     if (warp < 6) {                                              // (the extra masking warps have no epilogue role)
@@ -1038,7 +1048,7 @@ __device__ __forceinline__ void add_acc_to_tile(uint32_t tmem_row_addr, uint32_t
     ptx::tmem_ld_wait();
     if (half == 1 && tmem_free) {              // accumulator fully read: hand the TMEM buffer back early
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(tmem_free);
+      warp_arrive(tmem_free);
     }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -1104,10 +1114,10 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.ystages; ++s) {
-      ptx::mbar_init(&y_full[s], 1); ptx::mbar_init(&y_empty[s], 1); ptx::mbar_init(&y_done[s], kWorkers);
+      ptx::mbar_init(&y_full[s], 1); ptx::mbar_init(&y_empty[s], 1); ptx::mbar_init(&y_done[s], kWorkerWarps);
     }
     for (int i = 0; i < 4; ++i) {
-      ptx::mbar_init(&b_full[i], kWorkers); ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], kWorkers);
+      ptx::mbar_init(&b_full[i], kWorkerWarps); ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], kWorkerWarps);
     }
     ptx::mbar_init(g_full, 1);
     ptx::fence_mbar_init();
@@ -1225,7 +1235,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
     auto store_b = [&](int i) {
       ptx::cp_async_wait_all();
       ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(&b_full[i]);
+      warp_arrive(&b_full[i]);
     };
 
     if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 0);
@@ -1346,7 +1356,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
         add_acc_to_tile(lane_base + (uint32_t)(i * 128), ptx::smem_u32(yt), (uint32_t)row, &t_empty[i]);
       if (wl == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 10 + j * 4);
       ptx::fence_proxy_async_smem();                            // generic writes -> visible to the TMA store
-      ptx::mbar_arrive(&y_done[s]);
+      warp_arrive(&y_done[s]);
       if (wl == 0) ptx::prog_mark(3 + grp_id, j + 1);
       if (j + ahead < nch) store_b(i);
       if (wl == 0) ptx::prog_mark(5 + grp_id, j + 1);
@@ -1532,7 +1542,7 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
     for (int s = 0; s < p.stages; ++s) {
       ptx::mbar_init(&full[s], 1); ptx::mbar_init(&wfull[s], 1); ptx::mbar_init(&empty[s], 1);
     }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&d2_full[i], 1); ptx::mbar_init(&d2_empty[i], kWorkers); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&d2_full[i], 1); ptx::mbar_init(&d2_empty[i], kWorkerWarps); }
     ptx::mbar_init(dg_full, 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tm_dy); ptx::prefetch_tmap(&tm_bt);
@@ -1697,7 +1707,7 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
         }
       }
       ptx::tc_fence_before_sync();
-      ptx::mbar_arrive(&d2_empty[i]);
+      warp_arrive(&d2_empty[i]);
       if (wt == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 33 + j * 2);
     }
     // dG partial of this CTA
@@ -2901,14 +2911,14 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.xs; ++s) {
       ptx::mbar_init(&x_full[s], 1); ptx::mbar_init(&x_empty[s], 1);
-      ptx::mbar_init(&x_ready[s], 2 * kWorkers); ptx::mbar_init(&km_free[s], kWorkers);
+      ptx::mbar_init(&x_ready[s], 2 * kWorkerWarps); ptx::mbar_init(&km_free[s], kWorkerWarps);
     }
     for (int s = 0; s < p.ds; ++s) {
-      ptx::mbar_init(&d_full[s], 1); ptx::mbar_init(&d_empty[s], 1); ptx::mbar_init(&d_done[s], kWorkers);
+      ptx::mbar_init(&d_full[s], 1); ptx::mbar_init(&d_empty[s], 1); ptx::mbar_init(&d_done[s], kWorkerWarps);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&op_full[i], 1); ptx::mbar_init(&op_empty[i], 1);
-      ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], kWorkers);
+      ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], kWorkerWarps);
     }
     ptx::mbar_init(w_full, 1);
     ptx::mbar_init(a_full, 1);
@@ -3056,7 +3066,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
           dropout_zero_dropped(k32, boxaddr + (uint32_t)mrow * 128u, (uint32_t)mrow & 7u, (uint32_t)hs);
         }
         ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&x_ready[s]);
+        warp_arrive(&x_ready[s]);
       }
     }
   } else if (warp == 6) {
@@ -3096,7 +3106,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
           ptx::mbar_wait_or_trap(&x_ready[sx], (uint32_t)(j / p.xs) & 1u, __LINE__);
           const uint4 kv = ptx::lds128(ptx::smem_u32(km_s + ((size_t)sx * 128 + row) * 4));
           km_cur[0] = kv.x; km_cur[1] = kv.y; km_cur[2] = kv.z; km_cur[3] = kv.w;
-          ptx::mbar_arrive(&km_free[sx]);
+          warp_arrive(&km_free[sx]);
         }
         if (st) dbg_stamp(p.dbg, blockIdx.x, 8 + j * 4);
         ptx::mbar_wait_or_trap(&d_full[s], dph, __LINE__);
@@ -3114,7 +3124,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
           add_acc_to_tile(lane_base + (uint32_t)(i * 128), ptx::smem_u32(dt), (uint32_t)row, &t_empty[i]);
         if (st) dbg_stamp(p.dbg, blockIdx.x, 10 + j * 4);
         ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&d_done[s]);
+        warp_arrive(&d_done[s]);
         if (st) dbg_stamp(p.dbg, blockIdx.x, 11 + j * 4);
       }
     }
