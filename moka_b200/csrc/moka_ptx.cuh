@@ -45,6 +45,25 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
   }
   return false;
 }
+// Sleeping wait (mbarrier.try_wait: the warp is suspended by the hardware until the phase completes or a
+// system time limit passes) for warps whose hand-off latency does not matter but whose polling would take issue
+// slots from the warps that do the work (the dropout-masking warps).
+__device__ __forceinline__ bool mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
+  for (uint32_t it = 0; it < (1u << 22); ++it) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return true;
+  }
+  return false;
+}
 // Optional post-mortem: a host-mapped word (moka_debug_trap_buffer) receives (source line << 32 | block << 12 |
 // thread) of the wait that timed out before the trap kills the context.
 __device__ unsigned long long* g_trap_buf = nullptr;
@@ -64,6 +83,10 @@ __device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity
     }
     asm volatile("trap;");
   }
+}
+
+__device__ __forceinline__ void mbar_sleep_or_trap(uint64_t* bar, uint32_t parity, int line = 0) {
+  if (!mbar_wait_sleep(bar, parity)) mbar_wait_or_trap(bar, parity, line);   // (falls through to the trapping spin)
 }
 
 // ------------------------------------------------------------------ programmatic dependent launch

@@ -245,7 +245,9 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
         const int it = kb - kb0, s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         ptx::mbar_wait_or_trap(&full[s], ph, __LINE__);                    // weights + x landed
+        if (it < 8) dbg_stamp(p.dbg, blockIdx.x, 8 + it * 3);
         if (DROP) ptx::mbar_wait_or_trap(&ready[s], ph, __LINE__);           // ... and x masked
+        if (it < 8) dbg_stamp(p.dbg, blockIdx.x, 9 + it * 3);
         if (it == 0) dbg_stamp(p.dbg, blockIdx.x, 3);
         ptx::tc_fence_after_sync();
         const uint32_t xa0 = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
@@ -262,6 +264,7 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
           }
         }
         ptx::umma_commit(&empty[s]);
+        if (it < 8) dbg_stamp(p.dbg, blockIdx.x, 10 + it * 3);
       }
       ptx::umma_commit(tmem_full);
       dbg_stamp(p.dbg, blockIdx.x, 4);
@@ -283,15 +286,18 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       for (int it = 0; it < nkb; ++it) {
         const int kb = kb0 + (it + krot) % nkb, s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
-        ptx::mbar_wait_or_trap(&full[s], ph, __LINE__);
+        ptx::mbar_sleep_or_trap(&full[s], ph, __LINE__);
+        if (mt == 0 && it < 8) dbg_stamp(p.dbg, blockIdx.x, 32 + it * 3);
         const uint32_t xs = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
         for (int sg = part; sg < nsg; sg += 4) {
           const uint32_t k32 = dropout_keep32(d, rowbase + (unsigned long long)(kb * nsg + sg));
           dropout_zero_dropped(k32, xs + (uint32_t)(sg >> 1) * 16384u + (uint32_t)mrow * 128u, (uint32_t)mrow & 7u,
                                (uint32_t)(sg & 1));
         }
+        if (mt == 0 && it < 8) dbg_stamp(p.dbg, blockIdx.x, 33 + it * 3);
         ptx::fence_proxy_async_smem();                           // generic writes -> visible to the tensor core
         warp_arrive(&ready[s]);
+        if (mt == 0 && it < 8) dbg_stamp(p.dbg, blockIdx.x, 34 + it * 3);
       }
     }
     if (warp < 6) {                                              // (the extra masking warps have no epilogue role)
@@ -3055,8 +3061,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       for (int j = 0; j < ntt; ++j) {
         const int s = j % p.xs;
         const uint32_t k = (uint32_t)(j / p.xs);
-        ptx::mbar_wait_or_trap(&x_full[s], k & 1u, __LINE__);
-        if (p.has_dx && k > 0) ptx::mbar_wait_or_trap(&km_free[s], (k - 1u) & 1u, __LINE__);
+        ptx::mbar_sleep_or_trap(&x_full[s], k & 1u, __LINE__);
+        if (p.has_dx && k > 0) ptx::mbar_sleep_or_trap(&km_free[s], (k - 1u) & 1u, __LINE__);
         const unsigned long long rowbase = dropout_row_base(d, (long long)(tt_beg + j) * 128 + mrow);
         const uint32_t boxaddr = ptx::smem_u32(xring + (size_t)s * 32768) + (uint32_t)box * 16384u;
 #pragma unroll

@@ -27,7 +27,8 @@ M = 3 if variant == VARIANT_AVT else 2
 masks = [m.to(dev) for m in layout_masks(variant, B, S, 'c3' if variant == VARIANT_AVT else 'c2')]
 meta = build_token_meta_avt(masks) if variant == VARIANT_AVT else build_token_meta_vt(*masks)
 s = 16.0 / r
-sc = FusedScalars(s, (1, 1, 1), 1.0, 0.0) if variant == VARIANT_AVT else FusedScalars(1.0, (s, s, s), 0.05, 0.0)
+PDROP = float(os.environ.get('MOKA_DBG_P', '0'))
+sc = FusedScalars(s, (1, 1, 1), 1.0, PDROP) if variant == VARIANT_AVT else FusedScalars(1.0, (s, s, s), 0.05, PDROP)
 x = torch.randn(T, d, device=dev).bfloat16(); y = torch.randn(T, d, device=dev).bfloat16()
 dy = torch.randn(T, d, device=dev).bfloat16(); dx = torch.randn(T, d, device=dev).bfloat16()
 A = [(torch.randn(r, d, device=dev) * d ** -0.5).bfloat16() for _ in range(M)]
@@ -103,3 +104,8 @@ if kern == 'dgrad':
     for j in range(8):
         m = lambda i: rel[:, i].mean()
         print(f'stage {j}: mma full {m(8+j*3):8.0f} d2_empty {m(9+j*3):8.0f} issued {m(10+j*3):8.0f} | workers d2_full {m(32+j*2):8.0f} epilogue done {m(33+j*2):8.0f}')
+
+if kern == 'down':
+    for j in range(8):
+        m = lambda i: rel[:, i].mean()
+        print(f'stage {j}: mma full {m(8+j*3):8.0f} ready {m(9+j*3):8.0f} committed {m(10+j*3):8.0f} | mask full {m(32+j*3):8.0f} masked {m(33+j*3):8.0f} arrived {m(34+j*3):8.0f}')
