@@ -69,6 +69,50 @@ def test_facades_match_reference_autograd_fp32(path):
         assert unused.grad is None                       # lora_B.image never receives a gradient
 
 
+@pytest.mark.parametrize('variant', ['avt', 'vt'])
+def test_gemm_epilogue_fusion_under_autograd(variant):
+    """layer.FUSION (MOKA_FLAG_DELTA_OUT + beta = 1 GEMMs) through the facades and autograd, bf16:
+    same bars against the oracle as the default order, and the two orders agree with each other."""
+    from moka_b200 import layer as L
+    v = mo.VARIANT_AVT if variant == 'avt' else mo.VARIANT_VT
+    M, layout, w = (3, 'c3', 1.0) if variant == 'avt' else (2, 'c2', 0.05)
+    B, S, d_in, d_out, r = 2, 2048, 512, 768, 16
+    x, W0, A, Bw, dy, masks = mo.synth_layer_inputs(v, B, S, d_in, d_out, r, M, layout, seed=3)
+    g = dict(variant=v, d_in=d_in, d_out=d_out, r=r, alpha=16, w=w, M=M, W0=W0, A=A, Bw=Bw, masks=masks)
+    meta = mo.build_token_meta_avt(masks) if variant == 'avt' else mo.build_token_meta_vt(*masks)
+    sc = mo.FusedScalars.for_variant(v, lora_alpha=16, r=r, w=w)
+    bf = lambda t: t.to(torch.bfloat16).double()
+    xb, dyb = bf(x), bf(dy)
+    W0b, Ab, Bwb = bf(W0), [bf(a) for a in A], bf(Bw)
+    ty, th = mo.fused_forward(meta, xb, xb @ W0b.t(), Ab, Bwb, sc)
+    tdxa, tdA, tdB, _ = mo.fused_backward(meta, xb, dyb, th, Ab, Bwb, sc)
+    tdx = tdxa + dyb @ W0b
+    outs = {}
+    was = L.FUSION['enabled']
+    try:
+        for mode in (False, True):
+            L.FUSION['enabled'] = mode
+            layer, args, params, _ = _facade(g, torch.bfloat16)
+            xd = x.to(torch.bfloat16).to(DEV).requires_grad_(True)
+            y = layer(xd, *args)
+            y.backward(dy.to(torch.bfloat16).to(DEV))
+            torch.cuda.synchronize()
+            outs[mode] = (y.detach().cpu(), xd.grad.cpu(), [p.grad.float().cpu() for p in params])
+            # the frozen product is rounded once more in the default order; the bar on the totals covers both
+            assert mo.rel_l2(outs[mode][0], bf(ty)) <= 4e-3
+            assert mo.rel_l2(outs[mode][1], bf(tdx)) <= 4e-3
+            for m in range(M):
+                assert mo.rel_l2(outs[mode][2][m], tdA[m]) <= 1e-2            # bf16 parameter gradients
+            assert mo.rel_l2(outs[mode][2][-1], tdB) <= 1e-2
+    finally:
+        L.FUSION['enabled'] = was
+    assert not L.FUSION['unsupported']                                          # the fused order really ran
+    # one rounding of W0 x + term (fused) against two (default): the fused result is at least as close
+    assert mo.rel_l2(outs[True][0], ty) <= mo.rel_l2(outs[False][0], ty) * 1.02 + 1e-6
+    assert mo.rel_l2(outs[True][0], outs[False][0]) <= 5e-3
+    assert mo.rel_l2(outs[True][1], outs[False][1]) <= 5e-3
+
+
 def test_decode_branches_match_reference(golden_dir):
     from moka_b200.layer import MokaLinearAVT, MokaLinearVT
     g = torch.load(os.path.join(golden_dir, 'decode_plain_lora.pt'), weights_only=False)
