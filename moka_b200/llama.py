@@ -11,6 +11,11 @@ SiLU).  What it mirrors from the reference is the mask plumbing:
 * VT ``VisualText/modified_models/modeling_llama.py``: ``my_text_mask / my_image_mask /
   question_mask`` ride in kwargs (:495) to the same 7 projections (:152-159, :251-253, :279).
 
+* Generation: ``KVCache`` + ``masks_for_step`` mirror the hand-off of
+  ``VisualText/modified_models/modeling_llama.py:314-329`` - the masks reach the projections only while
+  the cache is empty (training, or the prefill call of a generation); every later call runs the no-mask
+  branch (``layer.py:672-678`` plain text-adapter LoRA; AVT ``lora.py:373-381`` for one-token steps).
+
 Module names match HF Llama (``model.layers.N.self_attn.q_proj`` ...) so that
 ``get_peft_model`` target matching and checkpoint keys are the reference's.
 Weights are random-initialised from the config (no checkpoints on the box).
@@ -55,6 +60,35 @@ class LlamaConfig:
     def tiny(layers: int = 2, hidden: int = 256, inter: int = 512, heads: int = 4, vocab: int = 512) -> 'LlamaConfig':
         return LlamaConfig(hidden_size=hidden, intermediate_size=inter, num_hidden_layers=layers,
                            num_attention_heads=heads, vocab_size=vocab)
+
+
+class KVCache:
+    """Keys and values of the frozen attention, per layer, as ``[B, S_total, H, D]`` (the role HF's
+    ``DynamicCache`` plays in the reference's generate loop)."""
+
+    def __init__(self, num_layers: int):
+        self.k: List[Optional[torch.Tensor]] = [None] * num_layers
+        self.v: List[Optional[torch.Tensor]] = [None] * num_layers
+
+    def get_seq_length(self) -> int:
+        return 0 if self.k[0] is None else int(self.k[0].shape[1])
+
+    def update(self, layer_idx: int, k: torch.Tensor, v: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self.k[layer_idx] is None:
+            self.k[layer_idx], self.v[layer_idx] = k, v
+        else:
+            self.k[layer_idx] = torch.cat((self.k[layer_idx], k), dim=1)
+            self.v[layer_idx] = torch.cat((self.v[layer_idx], v), dim=1)
+        return self.k[layer_idx], self.v[layer_idx]
+
+
+def masks_for_step(past_key_values: Optional[KVCache], mask_args: Optional[tuple]) -> Optional[tuple]:
+    """The mask hand-off of ``VisualText/modified_models/modeling_llama.py:314-329``: no cache (training) or an
+    empty cache (first call of a generation) -> the masks go to the 7 projections; a cache that already holds
+    tokens (decode steps) -> ``None``, i.e. the no-mask branch of every MokaLinear."""
+    if past_key_values is None or past_key_values.get_seq_length() == 0:
+        return mask_args
+    return None
 
 
 def _proj(mod: nn.Module, x: torch.Tensor, mask_args: Optional[tuple]) -> torch.Tensor:
@@ -136,14 +170,31 @@ class LlamaAttention(nn.Module):
         self.v_proj = nn.Linear(d, d, bias=False)
         self.o_proj = nn.Linear(d, d, bias=False)
 
-    def forward(self, h, rope, mask_args):
+    def forward(self, h, rope, mask_args, cache: Optional[KVCache] = None, layer_idx: int = 0, pos0: int = 0):
         B, S, _ = h.shape
         H, D = self.num_heads, self.head_dim
         # keep the [B, S, H, D] memory layout of the projections; SDPA gets transposed views
-        q = apply_rope(_proj(self.q_proj, h, mask_args).view(B, S, H, D), rope, self.rope_theta)
-        k = apply_rope(_proj(self.k_proj, h, mask_args).view(B, S, H, D), rope, self.rope_theta)
+        q = _proj(self.q_proj, h, mask_args).view(B, S, H, D)
+        k = _proj(self.k_proj, h, mask_args).view(B, S, H, D)
         v = _proj(self.v_proj, h, mask_args).view(B, S, H, D)
-        o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True)
+        if pos0 == 0:
+            q = apply_rope(q, rope, self.rope_theta)
+            k = apply_rope(k, rope, self.rope_theta)
+        else:
+            # decode steps: `rope` holds the tables of the absolute positions pos0 .. pos0 + S - 1
+            cos, sin = rope
+            q = q * cos + _rotate_half(q) * sin
+            k = k * cos + _rotate_half(k) * sin
+        if cache is not None:
+            k, v = cache.update(layer_idx, k, v)
+        if pos0 == 0:
+            o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True)
+        else:
+            # new token i (absolute position pos0 + i) sees the cached tokens and the new ones up to itself
+            Sk = k.shape[1]
+            allowed = torch.ones(S, Sk, dtype=torch.bool, device=h.device).tril(diagonal=Sk - S)
+            o = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                               attn_mask=allowed)
         o = o.transpose(1, 2).reshape(B, S, H * D)
         return _proj(self.o_proj, o, mask_args)
 
@@ -168,9 +219,9 @@ class LlamaDecoderLayer(nn.Module):
         self.input_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
         self.post_attention_layernorm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
 
-    def forward(self, h, cos, sin, *mask_args):
+    def forward(self, h, cos, sin, *mask_args, cache: Optional[KVCache] = None, layer_idx: int = 0, pos0: int = 0):
         ma = mask_args if mask_args else None
-        h = h + self.self_attn(self.input_layernorm(h), (cos, sin), ma)
+        h = h + self.self_attn(self.input_layernorm(h), (cos, sin), ma, cache, layer_idx, pos0)
         return h + self.mlp(self.post_attention_layernorm(h), ma)
 
 
@@ -183,7 +234,8 @@ class LlamaModel(nn.Module):
         self.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
         self.gradient_checkpointing = False
 
-    def forward(self, input_ids=None, inputs_embeds=None, mask_args: Optional[tuple] = None):
+    def forward(self, input_ids=None, inputs_embeds=None, mask_args: Optional[tuple] = None,
+                past_key_values: Optional[KVCache] = None):
         if isinstance(inputs_embeds, (list, tuple)):
             # AVT packing: [embeddings, text, video, audio, question] (modeling_llama.py:647-654)
             packed = list(inputs_embeds)
@@ -191,10 +243,15 @@ class LlamaModel(nn.Module):
         h = self.embed_tokens(input_ids) if inputs_embeds is None else inputs_embeds
         B, S, _ = h.shape
         hd = self.config.hidden_size // self.config.num_attention_heads
-        cos, sin = _rope_tables(S, hd, self.config.rope_theta, h.device, h.dtype)
+        pos0 = past_key_values.get_seq_length() if past_key_values is not None else 0
+        mask_args = masks_for_step(past_key_values, mask_args)
+        cos, sin = _rope_tables(pos0 + S, hd, self.config.rope_theta, h.device, h.dtype)
+        cos, sin = cos[:, pos0:], sin[:, pos0:]
         ma = tuple(mask_args) if mask_args is not None else ()
-        for layer in self.layers:
-            if self.gradient_checkpointing and self.training:
+        for i, layer in enumerate(self.layers):
+            if past_key_values is not None:
+                h = layer(h, cos, sin, *ma, cache=past_key_values, layer_idx=i, pos0=pos0)
+            elif self.gradient_checkpointing and self.training:
                 h = checkpoint(layer, h, cos, sin, *ma, use_reentrant=False)
             else:
                 h = layer(h, cos, sin, *ma)
@@ -224,9 +281,12 @@ class LlamaForCausalLM(nn.Module):
 
     def forward(self, input_ids=None, inputs_embeds=None, labels=None, modality_masks: Optional[Sequence] = None,
                 my_text_mask=None, my_image_mask=None, question_mask=None,
-                token_meta: Optional[TokenMeta] = None, return_logits: bool = False):
-        if token_meta is not None:
-            mask_args: Optional[tuple] = (token_meta,)
+                token_meta: Optional[TokenMeta] = None, return_logits: bool = False,
+                past_key_values: Optional[KVCache] = None):
+        if past_key_values is not None and past_key_values.get_seq_length() > 0:
+            mask_args: Optional[tuple] = None          # decode step: the masks are not even looked at (:326-329)
+        elif token_meta is not None:
+            mask_args = (token_meta,)
         elif modality_masks is not None:
             # build the token metadata ONCE per step and hand it to all 7 x L projections
             mask_args = (build_token_meta_avt(list(modality_masks)),)
@@ -234,7 +294,8 @@ class LlamaForCausalLM(nn.Module):
             mask_args = (build_token_meta_vt(my_text_mask, my_image_mask, question_mask),)
         else:
             mask_args = None
-        h = self.model(input_ids=input_ids, inputs_embeds=inputs_embeds, mask_args=mask_args)
+        h = self.model(input_ids=input_ids, inputs_embeds=inputs_embeds, mask_args=mask_args,
+                       past_key_values=past_key_values)
         loss = None
         logits = None
         if labels is not None:
@@ -242,6 +303,28 @@ class LlamaForCausalLM(nn.Module):
         if return_logits or labels is None:
             logits = self.lm_head(h)
         return loss, logits
+
+    @torch.no_grad()
+    def generate(self, input_ids=None, inputs_embeds=None, max_new_tokens: int = 16, eos_token_id: Optional[int] = None,
+                 **mask_kwargs) -> torch.Tensor:
+        """Greedy decoding with a KV cache.  The prefill call carries the masks (``modality_masks=`` /
+        ``my_text_mask=...`` / ``token_meta=``), every later step is a one-token call whose projections take the
+        no-mask branch - the call pattern of the reference's ``model.generate`` (inference.py of both variants).
+        AVT layers need ``loramethod`` containing 'test' for the one-token branch (lora.py:373)."""
+        cache = KVCache(len(self.model.layers))
+        _, logits = self.forward(input_ids=input_ids, inputs_embeds=inputs_embeds, past_key_values=cache, **mask_kwargs)
+        nxt = logits[:, -1].argmax(-1)
+        out = [nxt]
+        done = torch.zeros_like(nxt, dtype=torch.bool)
+        for _ in range(max_new_tokens - 1):
+            if eos_token_id is not None:
+                done |= nxt == eos_token_id
+                if bool(done.all()):
+                    break
+            _, logits = self.forward(input_ids=nxt[:, None], past_key_values=cache, **mask_kwargs)
+            nxt = logits[:, -1].argmax(-1)
+            out.append(nxt)
+        return torch.stack(out, dim=1)
 
 
 def chunked_causal_lm_loss(h: torch.Tensor, lm_weight: torch.Tensor, labels: torch.Tensor,

@@ -185,6 +185,59 @@ def _batch(variant, B=2, S=256):
     return ids.to(DEV), labels.to(DEV), kw
 
 
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-4), (torch.bfloat16, 4e-2)], ids=['fp32', 'bf16'])
+@pytest.mark.parametrize('variant', ['avt', 'vt'])
+def test_generation_with_kv_cache_matches_full_forward(variant, dtype, tol):
+    """the prefill call takes the MokA branch with the masks, the decode steps take the no-mask
+    branch behind the KV cache (VT modeling_llama.py:314-329 -> layer.py:672-678; AVT lora.py:373-381).  Because
+    generated tokens are text tokens (text adapter, no attention term), the step-by-step logits must equal those
+    of ONE full forward over prompt + generated tokens whose masks mark the new tokens as text."""
+    from moka_b200.llama import KVCache
+    pm = _tiny_model(variant, dtype=dtype)
+    pm.eval()
+    with torch.no_grad():
+        for n, p in pm.named_parameters():
+            if 'lora_B' in n:
+                p.normal_(std=0.02)
+    for mod in pm.modules():
+        if hasattr(mod, 'loramethod'):
+            mod.loramethod = 'test'                       # inference.py builds the AVT model with the test method
+    B, S, K = 2, 256, 4
+    ids, _, kw = _batch(variant, B, S)
+    gen = torch.Generator().manual_seed(9)
+    new = torch.randint(3, 500, (B, K), generator=gen).to(DEV)
+    all_ids = torch.cat((ids, new), dim=1)
+
+    def extend(m, value):
+        pad = torch.full((B, K) + tuple(m.shape[2:]), value, dtype=m.dtype, device=m.device)
+        return torch.cat((m, pad), dim=1)
+    if variant == 'avt':
+        t, v, a, q = kw['modality_masks']
+        kw_full = dict(modality_masks=[extend(t, 1), extend(v, 0), extend(a, 0), extend(q, 0)])
+    else:
+        kw_full = dict(my_text_mask=extend(kw['my_text_mask'], True), my_image_mask=extend(kw['my_image_mask'], False),
+                       question_mask=extend(kw['question_mask'], False))
+    with torch.no_grad():
+        _, full = pm(input_ids=all_ids, return_logits=True, **kw_full)
+        cache = KVCache(2)
+        _, pre = pm(input_ids=ids, past_key_values=cache, **kw)          # masks -> MokA branch
+        steps = [pre[:, -1]]
+        for j in range(K):
+            _, lg = pm(input_ids=new[:, j:j + 1], past_key_values=cache, **kw)   # masks passed, not used (:326-329)
+            steps.append(lg[:, -1])
+        inc = torch.stack(steps, dim=1)
+    assert cache.get_seq_length() == S + K
+    ref = full[:, S - 1:].float()
+    assert mo.rel_l2(inc.float().cpu(), ref.cpu()) <= tol
+    # and the prefill really used the masks: without them the prompt's logits differ
+    with torch.no_grad():
+        if variant == 'vt':
+            _, nomask = pm(input_ids=ids, return_logits=True)
+            assert mo.rel_l2(nomask[:, -1].float().cpu(), pre[:, -1].float().cpu()) > 10 * tol or dtype == torch.bfloat16
+        toks = pm.generate(input_ids=ids, max_new_tokens=3, **kw)
+    assert toks.shape == (B, 3) and torch.equal(toks[:, 0], pre[:, -1].argmax(-1))
+
+
 @pytest.mark.parametrize('variant', ['avt', 'vt'])
 def test_tiny_llama_finetune_step_trains(variant):
     """Frozen tiny Llama + injected MokaLinear + flat-bucket AdamW (world size 1): the loss goes

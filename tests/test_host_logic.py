@@ -173,3 +173,32 @@ def test_meta_cache_builds_once_per_mask_identity():
     assert len(calls) == 2
     cache.get(1, [t.clone() for t in m], build)                   # different tensors, same values
     assert len(calls) == 3
+
+
+def test_kv_cache_mask_handoff_and_incremental_decode_cpu():
+    """SURVEY 8f N4, host side (no MokaLinear on the CPU: the frozen caller alone).  masks_for_step mirrors
+    VisualText/modified_models/modeling_llama.py:314-329; prefill + one-token (and multi-token) steps over the KV
+    cache reproduce the full-sequence logits."""
+    from moka_b200.llama import KVCache, LlamaConfig, LlamaForCausalLM, masks_for_step
+    masks = ('t', 'i', 'q')
+    assert masks_for_step(None, masks) is masks                        # training: no cache object at all
+    c = KVCache(2)
+    assert c.get_seq_length() == 0 and masks_for_step(c, masks) is masks   # first call of a generation
+    torch.manual_seed(0)
+    m = LlamaForCausalLM(LlamaConfig.tiny()).eval()
+    ids = torch.randint(0, 500, (2, 12))
+    with torch.no_grad():
+        _, full = m(input_ids=ids)
+        _, a = m(input_ids=ids[:, :8], past_key_values=c)
+        assert c.get_seq_length() == 8 and masks_for_step(c, masks) is None   # decode steps: no masks
+        steps = [a[:, -1]]
+        for t in range(8, 12):
+            _, b = m(input_ids=ids[:, t:t + 1], past_key_values=c)
+            steps.append(b[:, -1])
+        assert torch.allclose(torch.stack(steps, 1), full[:, 7:], atol=1e-5)
+        c2 = KVCache(2)
+        m(input_ids=ids[:, :8], past_key_values=c2)
+        _, chunk = m(input_ids=ids[:, 8:], past_key_values=c2)
+        assert torch.allclose(chunk, full[:, 8:], atol=1e-5)
+        toks = m.generate(input_ids=ids[:, :8], max_new_tokens=4)
+        assert toks.shape == (2, 4) and torch.equal(toks[:, 0], full[:, 7].argmax(-1))
