@@ -180,7 +180,7 @@ def build_model(wl, device, ckpt):
 def host_batch(wl, cfg, rank):
     """Synthetic batch in PINNED host memory: token ids, labels and the reference-shaped masks."""
     import torch
-    from oracle.moka_oracle import VARIANT_AVT, VARIANT_VT, layout_masks   # span layouts only
+    from moka_b200.layouts import VARIANT_AVT, VARIANT_VT, layout_masks
     B, S = wl['B'], wl['S']
     gen = torch.Generator().manual_seed(1234 + rank)
     ids = torch.randint(3, cfg.vocab_size, (B, S), generator=gen)
@@ -369,6 +369,22 @@ def main():
                           bwd_gbs=per_kind['bwd'][0] / max(per_kind['bwd'][1], 1e-9) / 1e6,
                           share_of_step=dur_ms / ms_dev),
             clocks=clocks)
+        if world == 1:
+            # the same calls timed ALONE (back to back, rotating buffers, no GEMMs around them, SM clock not under
+            # the step's power cap) at the step's most frequent shape: explains the gap to the in-step figure above
+            try:
+                import tools.microbench as mb
+                from moka_b200.layouts import VARIANT_AVT, VARIANT_VT
+                d = cfg.hidden_size
+                torch.cuda.empty_cache()
+                iso = mb.run_point(VARIANT_AVT if wl['M'] == 3 else VARIANT_VT, wl['B'], wl['S'], d, d, wl['r'],
+                                   torch.bfloat16, args.flags, 10, 3, wl['dropout'], nbuf=2)
+                line['roofline']['isolated'] = dict(
+                    shape=f"T={wl['B'] * wl['S']} {d}->{d} r={wl['r']} lora_dropout={wl['dropout']}",
+                    fwd_us=iso['fwd_us'], bwd_us=iso['bwd_us'], achieved=iso['both_gbs'], frac=iso['both_gbs'] / peak,
+                    note='tools/microbench.py run_point: CUDA events over 10 back-to-back fwd+bwd pairs')
+            except Exception as exc:                       # never let the explanatory leg break the bench line
+                line['roofline']['isolated'] = dict(error=str(exc)[:200])
         if world == 1 and not args.skip_cpu_baseline:
             base, _ = cpu_reference_leg(wl, seconds_budget=25.0, steps=1, warmup=0)
             line['cpu_baseline'] = base

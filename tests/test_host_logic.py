@@ -202,3 +202,18 @@ def test_kv_cache_mask_handoff_and_incremental_decode_cpu():
         assert torch.allclose(chunk, full[:, 8:], atol=1e-5)
         toks = m.generate(input_ids=ids[:, :8], max_new_tokens=4)
         assert toks.shape == (2, 4) and torch.equal(toks[:, 0], full[:, 7].argmax(-1))
+
+
+def test_product_span_layouts_equal_the_oracles():
+    """bench.py and tools/ build their workloads from moka_b200.layouts (the GPU arm never imports oracle/);
+    the oracle keeps its own generator for the tests.  They must describe the same spans."""
+    from moka_b200 import layouts
+    from oracle import moka_oracle as mo
+    assert (layouts.VARIANT_AVT, layouts.VARIANT_VT) == (mo.VARIANT_AVT, mo.VARIANT_VT)
+    for variant, layout, S in ((mo.VARIANT_VT, 'c1', 128), (mo.VARIANT_VT, 'c2', 2048), (mo.VARIANT_VT, 'c2', 256),
+                               (mo.VARIANT_AVT, 'c3', 2048), (mo.VARIANT_AVT, 'c3', 1024), (mo.VARIANT_VT, 'c4', 4096)):
+        a = layouts.layout_masks(variant, 3, S, layout)
+        b = mo.layout_masks(variant, 3, S, layout)
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert x.dtype == y.dtype and torch.equal(x, y)

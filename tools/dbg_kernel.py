@@ -12,7 +12,7 @@ import torch
 from moka_b200 import _cabi
 from moka_b200.layer import FusedScalars, _make_desc
 from moka_b200.metadata import build_token_meta_avt, build_token_meta_vt
-from oracle.moka_oracle import VARIANT_AVT, VARIANT_VT, layout_masks
+from moka_b200.layouts import VARIANT_AVT, VARIANT_VT, layout_masks
 
 kern = sys.argv[1] if len(sys.argv) > 1 else 'up'
 variant = VARIANT_VT if (len(sys.argv) > 2 and sys.argv[2] == 'vt') else VARIANT_AVT

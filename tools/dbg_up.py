@@ -7,7 +7,7 @@ import numpy as np
 import torch
 from moka_b200 import _cabi
 from tools.microbench import run_point
-from oracle.moka_oracle import VARIANT_AVT, VARIANT_VT
+from moka_b200.layouts import VARIANT_AVT, VARIANT_VT
 
 variant = VARIANT_AVT if (len(sys.argv) < 2 or sys.argv[1] == 'avt') else VARIANT_VT
 row = run_point(variant, 4, 2048, 4096, 4096, 16, torch.bfloat16, 0, 2, 1)

@@ -8,7 +8,7 @@ import numpy as np
 import torch
 from moka_b200 import _cabi
 from tools.microbench import run_point
-from oracle.moka_oracle import VARIANT_AVT
+from moka_b200.layouts import VARIANT_AVT
 
 row = run_point(VARIANT_AVT, 4, 2048, 4096, 4096, 16, torch.bfloat16, 0, 2, 1)   # last timed pass is fwd+bwd: wgrad stamps win
 print(row)

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import tools.microbench as mb  # noqa: E402
 from moka_b200 import _cabi  # noqa: E402
-from oracle.moka_oracle import VARIANT_AVT  # noqa: E402
+from moka_b200.layouts import VARIANT_AVT
 
 
 def main():
@@ -28,7 +28,7 @@ def main():
     dev = 'cuda:0'
     from moka_b200.layer import FusedScalars, _make_desc
     from moka_b200.metadata import build_token_meta_avt
-    from oracle.moka_oracle import layout_masks
+    from moka_b200.layouts import layout_masks
     B, S, d, M = 4, 2048, 4096, 3
     T = B * S
     masks = [m.to(dev) for m in layout_masks(VARIANT_AVT, B, S, 'c3')]

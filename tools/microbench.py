@@ -12,7 +12,7 @@ sys.path.insert(0, ROOT)
 from moka_b200 import _cabi  # noqa: E402
 from moka_b200.layer import FusedScalars, _make_desc  # noqa: E402
 from moka_b200.metadata import build_token_meta_avt, build_token_meta_vt  # noqa: E402
-from oracle.moka_oracle import VARIANT_AVT, VARIANT_VT, layout_masks  # noqa: E402  (mask layouts only)
+from moka_b200.layouts import VARIANT_AVT, VARIANT_VT, layout_masks
 
 PEAK = 6550.4
 try:

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import tools.microbench as mb
-from oracle.moka_oracle import VARIANT_AVT
+from moka_b200.layouts import VARIANT_AVT
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 p = float(sys.argv[2]) if len(sys.argv) > 2 else 0.05
 flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0          # 4 = MOKA_FLAG_DELTA_OUT
