@@ -188,7 +188,7 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   const int kb0 = (int)((long long)split * p.kblocks / p.ksplit);
   const int kb1 = (int)((long long)(split + 1) * p.kblocks / p.ksplit);
   const int nkb = kb1 - kb0;
-  const int krot = p.rot ? (int)(((unsigned)tile * 5u + (unsigned)split * 3u) % (unsigned)nkb) : 0;   // first block of this CTA
+  const int krot = p.rot ? (int)(((unsigned)tile * 7u + (unsigned)split * 3u) % (unsigned)nkb) : 0;   // first block of this CTA
 
   // rows of the weight tiles that TMA never writes (padding between modality blocks) must be 0
   const uint32_t xbytes = 16384u * (uint32_t)p.kbox;
@@ -1111,7 +1111,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
   const int c_beg = (int)((long long)split * p.chunks / p.nsplit);
   const int c_end = (int)((long long)(split + 1) * p.chunks / p.nsplit);
   const int nch = c_end - c_beg;
-  const int crot = p.rot ? (int)(((unsigned)tile * 5u + (unsigned)split * 3u) % (unsigned)nch) : 0;
+  const int crot = p.rot ? (int)(((unsigned)tile * 7u + (unsigned)split * 3u) % (unsigned)nch) : 0;
   auto chunk_of = [&](int j) { return c_beg + (j + crot) % nch; };   // j-th column chunk this CTA processes
   if (threadIdx.x == 0) dbg_stamp_g(p.dbg, blockIdx.x, 104);
   // last kernel of the forward chain: whatever follows (the first kernel of the next libmoka call waits
@@ -1536,7 +1536,7 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
   const int p_beg = (int)((long long)split * p.pairs / p.csplit);
   const int p_end = (int)((long long)(split + 1) * p.pairs / p.csplit);
   const int np = p_end - p_beg;
-  const int prot = p.rot ? (int)(((unsigned)tile * 5u + (unsigned)split * 3u) % (unsigned)np) : 0;
+  const int prot = p.rot ? (int)(((unsigned)tile * 7u + (unsigned)split * 3u) % (unsigned)np) : 0;
   auto pair_of = [&](int i) { return p_beg + (i + prot) % np; };   // i-th pair this CTA processes
   const int W = p.wide;
   const int ns = (np + W - 1) / W;                             // pipeline stages of this CTA
