@@ -90,6 +90,16 @@ class ClockSampler:
                     samples=len(sm))
 
 
+def kernel_path_name(wl, d, flags):
+    """Which kernels serve the step's square projections, as the library itself reports it."""
+    import torch
+    from moka_b200 import _cabi
+    from moka_b200.layer import FusedScalars, _make_desc
+    sc = FusedScalars(1.0, (1.0, 1.0, 1.0), 1.0, wl['dropout'])
+    desc = _make_desc((wl['B'] * wl['S'], d), wl['B'], wl['S'], d, wl['r'], wl['M'], torch.bfloat16, 128, sc, flags)
+    return 'tcgen05+TMA' if _cabi.load().moka_uses_tensor_cores(desc) else 'warp-FMA'
+
+
 # --------------------------------------------------------------------------- CPU baseline (oracle port)
 def cpu_reference_leg(wl: dict, seconds_budget: float = 25.0, steps: int = 1, warmup: int = 0):
     """Times the reference's algorithm (oracle/moka_oracle.py *_reference_form: the same op sequence as
@@ -256,9 +266,6 @@ def main():
     device = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=device)
-    if args.flags:
-        for cls in (moka_layer.MokaLinearAVT, moka_layer.MokaLinearVT):
-            pass
     pm, cfg = build_model(wl, device, args.grad_checkpointing)
     if args.flags:
         for m in pm.moka_layers():
@@ -334,12 +341,7 @@ def main():
     if rank == 0:
         value = tokens_per_step * args.steps / (ms_dev * 1e-3)
         e2e_value = tokens_per_step * args.steps / (ms_e2e * 1e-3)
-        uses_tc = None
-        try:
-            lay = pm.moka_layers()[0]
-            uses_tc = 'tcgen05+TMA' if not (args.flags & 1) else 'warp-FMA'
-        except Exception:
-            pass
+        uses_tc = kernel_path_name(wl, cfg.hidden_size, args.flags)
         line = dict(
             metric='tokens/sec Llama-2-7B MokA fine-tune step', value=value, unit='tokens/s', n_gpus=world,
             steps=args.steps, warmup=warmup, ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='weak',

@@ -217,3 +217,17 @@ def test_product_span_layouts_equal_the_oracles():
         assert len(a) == len(b)
         for x, y in zip(a, b):
             assert x.dtype == y.dtype and torch.equal(x, y)
+
+
+def test_flag_constants_match_the_header_and_fusion_is_opt_in():
+    """_cabi's flag values are the header's; the GEMM-epilogue fusion (MOKA_FLAG_DELTA_OUT) is off unless asked
+    for, so every default number is the read-modify-write order that SURVEY 8(d)'s byte model describes."""
+    hdr = open(os.path.join(ROOT, 'include', 'moka.h')).read()
+    vals = {k: int(v) for k, v in re.findall(r'(MOKA_FLAG_[A-Z_]+)\s*=\s*(\d+)\s*,', hdr)}
+    assert vals['MOKA_FLAG_FORCE_SIMT'] == _cabi.FLAG_FORCE_SIMT
+    assert vals['MOKA_FLAG_FORCE_TC'] == _cabi.FLAG_FORCE_TC
+    assert vals['MOKA_FLAG_DELTA_OUT'] == _cabi.FLAG_DELTA_OUT
+    assert int(re.search(r'MOKA_EUNSUPPORTED\s*=\s*(-?\d+)', hdr).group(1)) == _cabi.MOKA_EUNSUPPORTED
+    from moka_b200 import layer
+    if os.environ.get('MOKA_DELTA', '0') != '1':
+        assert layer.FUSION['enabled'] is False

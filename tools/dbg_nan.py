@@ -6,8 +6,6 @@ import torch
 from moka_b200 import _cabi
 if os.environ.get('MOKA_LIB'):                       # A/B against another build of the library
     _cabi.LIB_PATH = os.environ['MOKA_LIB']
-    import ctypes
-    _orig = ctypes.CDLL.__getattr__
 from oracle import moka_oracle as mo
 from tests import test_gpu_parity as tp
 
