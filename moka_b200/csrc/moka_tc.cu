@@ -151,6 +151,12 @@ static int rot_enabled() {
   return v;
 }
 
+// (i + rot) mod n for 0 <= i, rot < n without the integer division a `%` by a run-time n costs in every stage
+__device__ __forceinline__ int rot_index(int i, int rot, int n) {
+  const int k = i + rot;
+  return k >= n ? k - n : k;
+}
+
 struct DownTcParams {
   int T, d_in, r, rp, M, NP;       // rp = r rounded to 8 (rows per modality block), NP = padded N
   int ksplit, kblocks;             // split of the d_in reduction across CTAs; kblocks = d_in / (64 kbox)
@@ -220,7 +226,7 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
     if (lane == 0) {
       const uint32_t tx = (16384u + (uint32_t)p.M * (uint32_t)p.r * 128u) * (uint32_t)p.kbox;
       for (int it = 0; it < nkb; ++it) {
-        const int kb = kb0 + (it + krot) % nkb, s = it % p.stages;
+        const int kb = kb0 + rot_index(it, krot, nkb), s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         ptx::mbar_wait_or_trap(&empty[s], ph ^ 1u, __LINE__);
         uint8_t* xs = ring + (size_t)s * p.stage_bytes;
@@ -284,7 +290,7 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       const unsigned long long rowbase = dropout_row_base(d, t0 + mrow);
       const int nsg = 2 * p.kbox;                              // super-groups per stage
       for (int it = 0; it < nkb; ++it) {
-        const int kb = kb0 + (it + krot) % nkb, s = it % p.stages;
+        const int kb = kb0 + rot_index(it, krot, nkb), s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         ptx::mbar_sleep_or_trap(&full[s], ph, __LINE__);
         if (mt == 0 && it < 8) dbg_stamp(p.dbg, blockIdx.x, 32 + it * 3);
@@ -1112,7 +1118,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
   const int c_end = (int)((long long)(split + 1) * p.chunks / p.nsplit);
   const int nch = c_end - c_beg;
   const int crot = p.rot ? (int)(((unsigned)tile * 7u + (unsigned)split * 3u) % (unsigned)nch) : 0;
-  auto chunk_of = [&](int j) { return c_beg + (j + crot) % nch; };   // j-th column chunk this CTA processes
+  auto chunk_of = [&](int j) { return c_beg + rot_index(j, crot, nch); };   // j-th column chunk this CTA processes
   if (threadIdx.x == 0) dbg_stamp_g(p.dbg, blockIdx.x, 104);
   // last kernel of the forward chain: whatever follows (the first kernel of the next libmoka call waits
   // before it touches memory; anything else is a normal stream-ordered launch) may start its prologue now
@@ -1537,7 +1543,7 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
   const int p_end = (int)((long long)(split + 1) * p.pairs / p.csplit);
   const int np = p_end - p_beg;
   const int prot = p.rot ? (int)(((unsigned)tile * 7u + (unsigned)split * 3u) % (unsigned)np) : 0;
-  auto pair_of = [&](int i) { return p_beg + (i + prot) % np; };   // i-th pair this CTA processes
+  auto pair_of = [&](int i) { return p_beg + rot_index(i, prot, np); };   // i-th pair this CTA processes
   const int W = p.wide;
   const int ns = (np + W - 1) / W;                             // pipeline stages of this CTA
   const uint32_t dy_bytes = 32768u * (uint32_t)W;             // dY part of a stage; the B^T blocks follow
