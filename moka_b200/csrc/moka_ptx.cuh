@@ -51,7 +51,7 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ bool mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
 #pragma unroll 1
-  for (uint32_t it = 0; it < (1u << 22); ++it) {
+  for (uint32_t it = 0; it < (1u << 14); ++it) {   // bounded: a wait that never completes must reach the trap below
     uint32_t done;
     asm volatile(
         "{\n\t"
