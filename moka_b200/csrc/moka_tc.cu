@@ -145,6 +145,15 @@ int debug_read(unsigned long long* host, int n) {
 // Column-order rotation of the streaming kernels: every CTA walks its column blocks starting at a different one
 // (wrapping around), so that the small weight tiles all CTAs need (A_m boxes in k_down_tc, B^T blocks in
 // k_dgrad_tc) are not requested by every SM from the same L2 lines at the same moment.  MOKA_NO_ROT=1: off.
+// MOKA_DROP_EARLY=1: the masking warps generate the keep bits of a stage BEFORE they wait for its data (the bits
+// depend on (row, column group) only), leaving just the sparse zero stores and the fence after the TMA arrival.
+// Same bits, same result; written at the end of round 1 without a GPU to time it on, hence off by default.
+static int drop_early_bits() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MOKA_DROP_EARLY"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v;
+}
+
 static int rot_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("MOKA_NO_ROT"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -162,6 +171,7 @@ struct DownTcParams {
   int ksplit, kblocks;             // split of the d_in reduction across CTAs; kblocks = d_in / (64 kbox)
   int kbox;                        // 64-column TMA boxes per pipeline stage (1 or 2)
   int rot;                         // rotate the column-block order per CTA (see rot_enabled)
+  int early_bits;                  // DROP: generate a stage's keep bits before waiting for its data (see drop_early_bits)
   int stages;
   uint32_t stage_bytes, w_bytes, tmem_cols;
   float scale;                     // pre * dropout scale
@@ -288,18 +298,22 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
       const int mt = threadIdx.x - 64;                         // 0 .. 511
       const int mrow = mt & 127, part = mt >> 7;
       const unsigned long long rowbase = dropout_row_base(d, t0 + mrow);
-      const int nsg = 2 * p.kbox;                              // super-groups per stage
+      const int nsg = 2 * p.kbox;                              // super-groups per stage (<= 4: at most one per thread)
+      const bool has_item = part < nsg;
       for (int it = 0; it < nkb; ++it) {
         const int kb = kb0 + rot_index(it, krot, nkb), s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
+        // the keep bits depend on (row, column group) only, not on the data: with early_bits they are generated
+        // BEFORE the wait for the stage, so that what follows the TMA arrival is just the zero stores and the fence
+        uint32_t k32 = 0xffffffffu;
+        if (has_item && p.early_bits) k32 = dropout_keep32(d, rowbase + (unsigned long long)(kb * nsg + part));
         ptx::mbar_sleep_or_trap(&full[s], ph, __LINE__);
         if (mt == 0 && it < 8) dbg_stamp(p.dbg, blockIdx.x, 32 + it * 3);
+        if (has_item && !p.early_bits) k32 = dropout_keep32(d, rowbase + (unsigned long long)(kb * nsg + part));
         const uint32_t xs = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
-        for (int sg = part; sg < nsg; sg += 4) {
-          const uint32_t k32 = dropout_keep32(d, rowbase + (unsigned long long)(kb * nsg + sg));
-          dropout_zero_dropped(k32, xs + (uint32_t)(sg >> 1) * 16384u + (uint32_t)mrow * 128u, (uint32_t)mrow & 7u,
-                               (uint32_t)(sg & 1));
-        }
+        if (has_item)
+          dropout_zero_dropped(k32, xs + (uint32_t)(part >> 1) * 16384u + (uint32_t)mrow * 128u, (uint32_t)mrow & 7u,
+                               (uint32_t)(part & 1));
         if (mt == 0 && it < 8) dbg_stamp(p.dbg, blockIdx.x, 33 + it * 3);
         ptx::fence_proxy_async_smem();                           // generic writes -> visible to the tensor core
         warp_arrive(&ready[s]);
@@ -377,6 +391,7 @@ static int launch_down_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cuda
   p.kbox = (kbox_env == 2 && d.d_in % 128 == 0 && budget0 / ((16384u + p.w_bytes) * 2u) >= min_stages) ? 2 : 1;
   p.kblocks = d.d_in / (64 * p.kbox);
   p.rot = rot_enabled();
+  p.early_bits = drop_early_bits();
   p.stage_bytes = (16384u + p.w_bytes) * (uint32_t)p.kbox;
   // one CTA per SM when the grid does not exceed the SM count: spend the whole shared memory on the
   // ring (tcgen05.commit frees a stage ~1.5k cycles after issue, so >= 6 stages keep HBM busy)
@@ -2861,6 +2876,7 @@ struct WgradTcParams {
   int xs, ds, nop;                 // ring depths: X pairs / dX pairs (32 KB slots), operand buffers
   int has_dx, dbg;
   int delta;                       // MOKA_FLAG_DELTA_OUT: dx tiles are write-only in this pass (no dx read)
+  int early_bits;                  // DROP: keep bits generated before the tile's waits (see drop_early_bits)
   int prefetch_dx;                 // dx tiles may be loaded before the dependency wait (false for the later passes of a
                                    // rank-chunked call: the pass in front is still writing dx)
   uint32_t w_box_bytes;            // one 64-column box of the weight slice: NPW x 128 B
@@ -3067,15 +3083,26 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       for (int j = 0; j < ntt; ++j) {
         const int s = j % p.xs;
         const uint32_t k = (uint32_t)(j / p.xs);
+        // keep bits of this thread's two 32-column super-groups: data-independent (early_bits: generated before the waits)
+        const unsigned long long rowbase = dropout_row_base(d, (long long)(tt_beg + j) * 128 + mrow);
+        uint32_t k32v[2] = {0xffffffffu, 0xffffffffu};
+        if (p.early_bits) {
+#pragma unroll
+          for (int hs = 0; hs < 2; ++hs)
+            k32v[hs] = dropout_keep32(d, rowbase + (unsigned long long)((col0 >> 5) + box * 2 + hs));
+        }
         ptx::mbar_sleep_or_trap(&x_full[s], k & 1u, __LINE__);
         if (p.has_dx && k > 0) ptx::mbar_sleep_or_trap(&km_free[s], (k - 1u) & 1u, __LINE__);
-        const unsigned long long rowbase = dropout_row_base(d, (long long)(tt_beg + j) * 128 + mrow);
+        if (!p.early_bits) {
+#pragma unroll
+          for (int hs = 0; hs < 2; ++hs)
+            k32v[hs] = dropout_keep32(d, rowbase + (unsigned long long)((col0 >> 5) + box * 2 + hs));
+        }
         const uint32_t boxaddr = ptx::smem_u32(xring + (size_t)s * 32768) + (uint32_t)box * 16384u;
 #pragma unroll
         for (int hs = 0; hs < 2; ++hs) {                         // a box = two 32-column super-groups
-          const uint32_t k32 = dropout_keep32(d, rowbase + (unsigned long long)((col0 >> 5) + box * 2 + hs));
-          km_s[((size_t)s * 128 + mrow) * 4 + box * 2 + hs] = k32;
-          dropout_zero_dropped(k32, boxaddr + (uint32_t)mrow * 128u, (uint32_t)mrow & 7u, (uint32_t)hs);
+          km_s[((size_t)s * 128 + mrow) * 4 + box * 2 + hs] = k32v[hs];
+          dropout_zero_dropped(k32v[hs], boxaddr + (uint32_t)mrow * 128u, (uint32_t)mrow & 7u, (uint32_t)hs);
         }
         ptx::fence_proxy_async_smem();
         warp_arrive(&x_ready[s]);
@@ -3298,6 +3325,7 @@ static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParam
   }
   p.has_dx = has_dx;
   p.delta = (has_dx && d.delta) ? 1 : 0;
+  p.early_bits = drop_early_bits();
   p.dbg = dbg_enabled();
   p.w_box_bytes = (uint32_t)p.NPW * 128u;
   p.op_bytes = (uint32_t)(p.KP / 64) * 16384u + 4u * p.w_box_bytes;
