@@ -2,7 +2,7 @@
 """bench.py -- Llama-2-7B MokA fine-tune step throughput on B200 (tokens/s, whole job).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's arm (N=1 plain, N>1 under torchrun)
-    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's own layers on the host cores (oracle/_ref)
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for what every key means.
 A "step" = forward + backward + adapter-gradient sync + sharded AdamW of one micro-batch of
@@ -100,58 +100,178 @@ def kernel_path_name(wl, d, flags):
     return 'tcgen05+TMA' if _cabi.load().moka_uses_tensor_cores(desc) else 'warp-FMA'
 
 
-# --------------------------------------------------------------------------- CPU baseline (oracle port)
-def cpu_reference_leg(wl: dict, seconds_budget: float = 25.0, steps: int = 1, warmup: int = 0):
-    """Times the reference's algorithm (oracle/moka_oracle.py *_reference_form: the same op sequence as
-    the reference layers, frozen GEMM included, autograd backward) on the host cores.
-    Sample: the 7 MokaLinear projections of ONE decoder layer on ONE sequence; tokens/s is
-    S / (num_layers * t_layer), i.e. an upper bound on what a whole CPU step could reach
-    (attention, norms, lm_head and the optimizer are left out)."""
+# --------------------------------------------------------------------------- CPU baseline (the reference itself)
+_MODEL_DIMS = {'7b': (4096, 11008, 32), '13b': (5120, 13824, 40), 'tiny': (256, 512, 2)}
+
+
+def _reference_layers(wl, shapes, dt, device='cpu'):
+    """One reference MokA layer per projection shape.  kind 'reference': the UNMODIFIED reference modules from
+    oracle/_ref (vendored copy of AudioVisualText/peft_hyper and VisualText/modified_peft, see
+    oracle/vendor_ref.py) -- lora.py:277-532 / layer.py:389-685, lora_dropout as configured, train mode.
+    kind 'port': the oracle's op-by-op restatement (only when oracle/_ref is absent)."""
     import torch
     from oracle import moka_oracle as mo
+    from oracle import ref_loader as rl
+    r, M = wl['r'], wl['M']
+    avt = wl['variant'] == 'avt'
+    if rl.available():
+        Lin = rl.import_avt_linear() if avt else rl.import_vt_linear()
+        layers = []
+        for d_in, d_out in shapes:
+            if avt:
+                l = rl.make_avt(Lin, d_in, d_out, r, M, 16, wl['w'], dtype=dt, dropout=wl['dropout'], device=device)
+                torch.nn.init.normal_(l.lora_B0.weight, std=0.02)
+            else:
+                l = rl.make_vt(Lin, d_in, d_out, r, 16, wl['w'], dtype=dt, dropout=wl['dropout'], device=device)
+                torch.nn.init.normal_(l.lora_B['text'].weight, std=0.02)
+            l.train()
+            layers.append(l)
+        return 'reference', layers
+    gen = torch.Generator().manual_seed(0)
+    layers = []
+    for d_in, d_out in shapes:
+        W0 = (torch.randn(d_out, d_in, generator=gen) * 0.02).to(dt).to(device)
+        A = [(torch.rand(r, d_in, generator=gen) - 0.5).to(dt).to(device).requires_grad_(True) for _ in range(M)]
+        Bw = (torch.randn(d_out, r, generator=gen) * 0.02).to(dt).to(device).requires_grad_(True)
+        if avt:
+            layers.append(lambda x, masks, W0=W0, A=A, Bw=Bw: mo.avt_reference_form(
+                x, W0, A, Bw, masks, lora_alpha=16, blc_weight=wl['w']))
+        else:
+            layers.append(lambda x, masks, W0=W0, A=A, Bw=Bw: mo.vt_reference_form(
+                x, W0, A[0], A[1], Bw, masks[0], masks[1], masks[2], lora_alpha=16, attn_weight=wl['w']))
+    return 'port', layers
+
+
+def _call_reference(layer, x, masks, avt, kind):
+    if kind == 'port':
+        return layer(x, masks)
+    return layer(x, masks) if avt else layer(x, masks[0], masks[1], masks[2])
+
+
+def cpu_reference_leg(wl: dict, seconds_budget: float = 25.0, steps: int = 5, warmup: int = 2,
+                      dtypes=('f32', 'bf16')):
+    """Times the reference's own CPU implementation of the path on the host cores (all of them).
+    Sample: the 7 MokaLinear projections (frozen GEMM included, autograd backward) of ONE decoder layer on ONE
+    sequence of S tokens, `warmup` untimed repetitions then the median of `steps` (>= 5 unless the time budget
+    runs out), in fp32 and in bf16 (the dtype the reference trains in).  tokens/s = S / (num_layers * t_layer):
+    an UPPER BOUND on what a whole CPU step could reach (attention, norms, lm_head, optimizer left out)."""
+    import torch
+    from moka_b200.layouts import VARIANT_AVT, VARIANT_VT, layout_masks
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    S, r, M = wl['S'], wl['r'], wl['M']
-    variant = mo.VARIANT_AVT if wl['variant'] == 'avt' else mo.VARIANT_VT
-    hidden, inter, layers = {'7b': (4096, 11008, 32), '13b': (5120, 13824, 40), 'tiny': (256, 512, 2)}[wl['model']]
+    S = wl['S']
+    avt = wl['variant'] == 'avt'
+    hidden, inter, layers = _MODEL_DIMS[wl['model']]
     shapes = [(hidden, hidden)] * 4 + [(hidden, inter)] * 2 + [(inter, hidden)]
-    masks = mo.layout_masks(variant, 1, S, wl['layout'])
-    gen = torch.Generator().manual_seed(0)
-    dt = torch.float32
+    masks = layout_masks(VARIANT_AVT if avt else VARIANT_VT, 1, S, wl['layout'])
+    per = {}
+    kind = 'port'
+    for tag in dtypes:
+        dt = torch.float32 if tag == 'f32' else torch.bfloat16
+        kind, mods = _reference_layers(wl, shapes, dt)
+        gen = torch.Generator().manual_seed(0)
+        xs = [torch.randn(1, S, d_in, generator=gen).to(dt) for d_in, _ in shapes]
 
-    def one_layer():
-        t0 = time.perf_counter()
-        for d_in, d_out in shapes:
-            x = torch.randn(1, S, d_in, generator=gen, dtype=dt).requires_grad_(True)
-            W0 = torch.randn(d_out, d_in, generator=gen, dtype=dt) * 0.02
-            A = [(torch.rand(r, d_in, generator=gen, dtype=dt) - 0.5).requires_grad_(True) for _ in range(M)]
-            Bw = (torch.randn(d_out, r, generator=gen, dtype=dt) * 0.02).requires_grad_(True)
-            t1 = time.perf_counter()
-            if variant == mo.VARIANT_AVT:
-                y = mo.avt_reference_form(x, W0, A, Bw, masks, lora_alpha=16, blc_weight=wl['w'])
-            else:
-                y = mo.vt_reference_form(x, W0, A[0], A[1], Bw, masks[0], masks[1], masks[2], lora_alpha=16,
-                                         attn_weight=wl['w'])
-            y.backward(torch.ones_like(y))
-            one_layer.compute += time.perf_counter() - t1
-        return time.perf_counter() - t0
+        def one_layer():
+            t0 = time.perf_counter()
+            for l, x0 in zip(mods, xs):
+                x = x0.clone().requires_grad_(True)
+                y = _call_reference(l, x, masks, avt, kind)
+                y.backward(torch.ones_like(y))
+            return time.perf_counter() - t0
 
-    one_layer.compute = 0.0
-    for _ in range(warmup):
-        one_layer()
-    times = []
-    for _ in range(max(1, steps)):
-        one_layer.compute = 0.0
-        one_layer()
-        times.append(one_layer.compute)
-        if sum(times) > seconds_budget:
-            break
-    t_layer = statistics.median(times)
+        t_start = time.perf_counter()
+        for _ in range(warmup):
+            one_layer()
+        times = []
+        for i in range(max(1, steps)):
+            times.append(one_layer())
+            if i >= 4 and time.perf_counter() - t_start > seconds_budget / len(dtypes):
+                break
+        per[tag] = dict(t_layer_s=statistics.median(times), reps=len(times), warmup=warmup)
+        del mods, xs
+    best = min(per, key=lambda k: per[k]['t_layer_s'])
+    t_layer = per[best]['t_layer_s']
     value = S / (layers * t_layer)
-    sample = (f'7 MokaLinear fwd+bwd (frozen GEMM included) of one decoder layer, 1 sequence of {S} tokens, fp32, '
-              f'{len(times)} repetition(s), median {t_layer:.3f} s/layer; tokens/s = S / ({layers} layers x t_layer) '
-              f'(attention, norms, lm_head, optimizer excluded)')
-    return dict(value=value, unit='tokens/s', cores=threads, kind='port', sample=sample), t_layer
+    what = ('the UNMODIFIED reference layers (oracle/_ref: ' +
+            ('peft_hyper.tuners.lora.Linear' if avt else 'peft.tuners.lora.layer.Linear') + ')'
+            if kind == 'reference' else "the oracle's op-by-op port (oracle/_ref absent)")
+    sample = (f'{what}: 7 MokaLinear fwd+bwd (frozen GEMM included) of one decoder layer, 1 sequence of {S} tokens, '
+              f"lora_dropout {wl['dropout']}, " +
+              ', '.join(f"{k}: median {v['t_layer_s']:.3f} s/layer over {v['reps']} reps after {v['warmup']} warm-ups"
+                        for k, v in per.items()) +
+              f'; value = the faster dtype ({best}); tokens/s = S / ({layers} layers x t_layer), an upper bound on a '
+              f'CPU step (attention, norms, lm_head, optimizer excluded)')
+    return dict(value=value, unit='tokens/s', cores=threads, kind=kind, dtype=best, sample=sample,
+                per_dtype={k: dict(tokens_per_s=S / (layers * v['t_layer_s']), **v) for k, v in per.items()}), t_layer
+
+
+def gpu_comparators(wl, d, device, iters=5, warmup=2):
+    """BASELINE.md section 4 comparators on the SAME GPU at the step's most frequent projection shape: the
+    unmodified reference layer run eagerly on CUDA (its own Python loops and host syncs), the plain-PyTorch
+    split-GEMM formulation (cuBLAS, gather-free) and this repo's MokaLinear module -- layer fwd+bwd, microseconds."""
+    import torch
+    import tools.microbench as mb
+    from moka_b200.layouts import VARIANT_AVT, VARIANT_VT, layout_masks
+    from moka_b200.layer import MokaLinearAVT, MokaLinearVT
+    avt = wl['variant'] == 'avt'
+    variant = VARIANT_AVT if avt else VARIANT_VT
+    B, S, r, M = wl['B'], wl['S'], wl['r'], wl['M']
+    bf = torch.bfloat16
+    out = dict(shape=f'T={B * S} {d}->{d} r={r} bf16, layer fwd+bwd incl. the frozen GEMM')
+    masks = [m.to(device) for m in layout_masks(variant, B, S, wl['layout'])]
+    x0 = torch.randn(B, S, d, device=device).to(bf)
+    dy = torch.randn(B, S, d, device=device).to(bf)
+
+    def time_it(fn):
+        for _ in range(warmup):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return round(e0.elapsed_time(e1) / iters * 1e3, 1)
+
+    try:
+        kind, (ref,) = _reference_layers(wl, [(d, d)], bf, device=device)
+
+        def run_ref():
+            x = x0.clone().requires_grad_(True)
+            _call_reference(ref, x, masks, avt, kind).backward(dy)
+        out['eager_reference_cuda_us'] = time_it(run_ref)
+        out['eager_reference_kind'] = kind
+        del ref
+    except Exception as exc:
+        out['eager_reference_cuda_us'] = None
+        out['eager_reference_error'] = str(exc)[:160]
+    if avt:
+        ours = MokaLinearAVT(d, d, rank=r, lora_alpha=16, lora_nums=M, blc_weight=wl['w'], lora_dropout=wl['dropout'],
+                             loramethod='train', bias=False).to(device, bf)
+        torch.nn.init.normal_(ours.lora_B0.weight, std=0.02)
+        args = ([masks],)
+    else:
+        base = torch.nn.Linear(d, d, bias=False)
+        ours = MokaLinearVT(base, 'image', r=r, lora_alpha=16, lora_dropout=wl['dropout'], attn_weight=wl['w'])
+        ours.update_layer('text', r, lora_alpha=16, lora_dropout=wl['dropout'])
+        ours.set_adapter(['image', 'text'])
+        ours = ours.to(device, bf)
+        torch.nn.init.normal_(ours.lora_B['text'].weight, std=0.02)
+        args = (masks,)
+    ours.train()
+
+    def run_ours():
+        x = x0.clone().requires_grad_(True)
+        ours(x, *args[0]).backward(dy)
+    out['moka_b200_us'] = time_it(run_ours)
+    try:
+        out['torch_split_gemm_adapter_only_us'] = round(mb.torch_split_gemm_us(variant, B, S, d, d, r, bf, iters, warmup), 1)
+    except Exception as exc:
+        out['torch_split_gemm_adapter_only_us'] = None
+        out['torch_split_gemm_error'] = str(exc)[:160]
+    return out
 
 
 # --------------------------------------------------------------------------- main arm
@@ -242,11 +362,11 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return 0
-        base, t_layer = cpu_reference_leg(wl, seconds_budget=120.0, steps=args.steps, warmup=args.warmup)
+        base, t_layer = cpu_reference_leg(wl, seconds_budget=150.0, steps=max(args.steps, 5), warmup=max(args.warmup, 2))
         line = dict(metric='tokens/sec Llama-2-7B MokA fine-tune step', value=base['value'], unit='tokens/s',
                     impl='reference', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                     ms_per_step=t_layer * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
-                    dtype='f32', data='synthetic',
+                    dtype=base['dtype'], data='synthetic',
                     config=dict(workload=args.workload, lora_dropout=args.dropout, sample=base['sample']),
                     cpu_baseline=base,
                     e2e=dict(value=base['value'], unit='tokens/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
@@ -388,8 +508,13 @@ def main():
             except Exception as exc:                       # never let the explanatory leg break the bench line
                 line['roofline']['isolated'] = dict(error=str(exc)[:200])
         if world == 1 and not args.skip_cpu_baseline:
-            base, _ = cpu_reference_leg(wl, seconds_budget=25.0, steps=1, warmup=0)
+            base, _ = cpu_reference_leg(wl, seconds_budget=30.0, steps=5, warmup=2)
             line['cpu_baseline'] = base
+            try:
+                torch.cuda.empty_cache()
+                line['gpu_comparators'] = gpu_comparators(wl, cfg.hidden_size, device)
+            except Exception as exc:                       # explanatory leg only
+                line['gpu_comparators'] = dict(error=str(exc)[:200])
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -29,71 +29,30 @@ sys.path.insert(0, ROOT)
 from oracle import moka_oracle as mo  # noqa: E402
 
 REF = '/root/reference'
-OUT = os.path.join(ROOT, 'tests', 'golden')
+OUT = os.environ.get('MOKA_GOLDEN_OUT', os.path.join(ROOT, 'tests', 'golden'))
+
+
+from oracle import ref_loader  # noqa: E402
 
 
 def _stub_accelerate():
-    import transformers  # noqa: F401  (must be imported before the stub)
-    import transformers.pytorch_utils  # noqa: F401
-    from transformers import PreTrainedModel  # noqa: F401
-    from transformers.modeling_outputs import SequenceClassifierOutput  # noqa: F401
-    acc = mock.MagicMock()
-    acc.__version__ = '0.30.0'
-    sys.modules['accelerate'] = acc
-    for n in ('accelerate.hooks', 'accelerate.utils', 'accelerate.utils.imports'):
-        sys.modules[n] = mock.MagicMock()
+    ref_loader.stub_accelerate()
 
 
 def import_avt_linear():
-    sys.path.insert(0, os.path.join(REF, 'AudioVisualText'))
-    from peft_hyper.tuners.lora import Linear
-    return Linear
+    return ref_loader.import_avt_linear(prefer_tree=True)      # the reference tree itself, not the vendored copy
 
 
 def import_vt_linear():
-    tmp = tempfile.mkdtemp(prefix='oracle_vt_')
-    os.symlink(os.path.join(REF, 'VisualText', 'modified_peft'), os.path.join(tmp, 'peft'))
-    sys.path.insert(0, tmp)
-    from peft.tuners.lora.layer import Linear
-    return Linear
+    return ref_loader.import_vt_linear(prefer_tree=True)
 
 
 def make_avt(Linear, d_in, d_out, r, M, alpha, w, W0, A, Bw, dtype):
-    digits = int(str(min(r, 9)) * M)
-    l = Linear(d_in, d_out, r=digits, lora_alpha=alpha, lora_nums=M, blc_alpha=1, blc_weight=w,
-               lora_dropout=0.0, reserved_modality=None, loramethod='train',
-               merge_weights=False, bias=False)
-    # ranks >= 10 are not expressible through the digit encoding: patch after construction
-    for i in range(M):
-        setattr(l, f'lora_A{i}', torch.nn.Linear(d_in, r, bias=False))
-    l.lora_B0 = torch.nn.Linear(r, d_out, bias=False)
-    l.r = [r] * M
-    l.d_k = r
-    l.scaling = [alpha / r]
-    l = l.to(dtype)
-    with torch.no_grad():
-        l.weight.copy_(W0.to(dtype))
-        for i in range(M):
-            getattr(l, f'lora_A{i}').weight.copy_(A[i].to(dtype))
-        l.lora_B0.weight.copy_(Bw.to(dtype))
-    l.weight.requires_grad_(False)
-    return l
+    return ref_loader.make_avt(Linear, d_in, d_out, r, M, alpha, w, W0, A, Bw, dtype)
 
 
 def make_vt(Linear, d_in, d_out, r, alpha, w, W0, A, Bw, dtype):
-    base = torch.nn.Linear(d_in, d_out, bias=False).to(dtype)
-    l = Linear(base, 'image', r=r, lora_alpha=alpha, lora_dropout=0.0, attn_weight=w)
-    l.update_layer('text', r, lora_alpha=alpha, lora_dropout=0.0, init_lora_weights=True,
-                   use_rslora=False, use_dora=False)
-    l.set_adapter(['image', 'text'])
-    l = l.to(dtype)
-    with torch.no_grad():
-        l.base_layer.weight.copy_(W0.to(dtype))
-        l.lora_A['text'].weight.copy_(A[0].to(dtype))
-        l.lora_A['image'].weight.copy_(A[1].to(dtype))
-        l.lora_B['text'].weight.copy_(Bw.to(dtype))
-    l.base_layer.weight.requires_grad_(False)
-    return l
+    return ref_loader.make_vt(Linear, d_in, d_out, r, alpha, w, W0, A, Bw, dtype)
 
 
 def run_avt(l, x, masks, dy, M):

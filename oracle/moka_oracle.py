@@ -271,12 +271,14 @@ def fused_forward(meta: TokenMeta, x: torch.Tensor, y0: torch.Tensor, A: Sequenc
 
     Returns (y, h) where ``h [B,S,r]`` is the pre-attention projection (the stash the
     backward re-uses).  Equivalent to avt_reference_form / vt_reference_form under the
-    metadata built by build_token_meta_*; verified in tests/test_oracle_forms.py."""
+    metadata built by build_token_meta_*; verified in tests/test_oracle_golden.py (both forms against
+    the reference-generated fixtures).  Device-agnostic: tensors and ``meta`` may live on a GPU (the
+    bench-geometry parity tests run this fp64 truth there)."""
     Bsz, S, d_in = x.shape
     r = A[0].shape[0]
     code = (meta.tokmeta.to(torch.int32) & MOD_MASK)
     u = _drop(x, keep, p)
-    h = torch.zeros(Bsz, S, r, dtype=x.dtype)
+    h = torch.zeros(Bsz, S, r, dtype=x.dtype, device=x.device)
     for m in range(len(A)):
         sel = code == (m + 1)
         if bool(sel.any()):
@@ -293,7 +295,7 @@ def fused_forward(meta: TokenMeta, x: torch.Tensor, y0: torch.Tensor, A: Sequenc
         q = h[b, qsel, :]
         P = torch.softmax(q @ K.t() / math.sqrt(r), dim=-1)
         g[b, qsel, :] = q + sc.w * (P @ K)
-    post = torch.zeros(Bsz, S, dtype=x.dtype)
+    post = torch.zeros(Bsz, S, dtype=x.dtype, device=x.device)
     for m in range(len(A)):
         post[code == (m + 1)] = sc.post[m]
     y = y0 + (g @ Bw.t()) * post[..., None]
@@ -312,7 +314,7 @@ def fused_backward(meta: TokenMeta, x: torch.Tensor, dy: torch.Tensor, h: torch.
     rs = 1.0 / math.sqrt(r)
     code = (meta.tokmeta.to(torch.int32) & MOD_MASK)
     u = _drop(x, keep, p)
-    post = torch.zeros(Bsz, S, dtype=x.dtype)
+    post = torch.zeros(Bsz, S, dtype=x.dtype, device=x.device)
     for m in range(len(A)):
         post[code == (m + 1)] = sc.post[m]
     # recompute g (cheap) exactly like the forward

@@ -126,7 +126,9 @@ def _assert_case(o, dtype, M):
         tol = 1e-5
     else:
         bf = lambda t: t.to(torch.bfloat16).double()
-        assert mo.rel_l2(o['h'], o['th']) <= 1e-5
+        # h is an fp32 accumulation over d_in products: the round-off grows like sqrt(d_in) (1.2e-5 at 11008)
+        d_in = o['dx'].shape[-1]
+        assert mo.rel_l2(o['h'], o['th']) <= 1e-5 * max(1.0, (d_in / 4096.0) ** 0.5)
         assert mo.rel_l2(o['y'], bf(o['ty'])) <= 1e-3
         assert mo.rel_l2(o['dx'], bf(o['tdx'])) <= 1e-3
         # element-wise too (a handful of corrupted rows hides under an l2 bar): within 2 bf16 ulps of the largest value
@@ -604,3 +606,70 @@ def test_dropout_on_tensor_core_path(variant, M, layout, r, d_in, d_out, S, p):
     for m in range(M):
         if float(o_fma['dA'][m].norm()) > 0:
             assert mo.rel_l2(o_tc['dA'][m], o_fma['dA'][m]) <= 1e-4
+
+
+# ----------------------------------------------------------------------------- bench geometry
+def _oracle_case_gpu(variant, B, S, d_in, d_out, r, M, layout, alpha, w, p=0.0, rng=(0, 0), seed=21, flags=0):
+    """Like _oracle_case, but at the sizes bench.py runs (T = B S >= 148 x 128 tokens: multi-wave / unsplit launch
+    plans): the inputs are generated on the GPU and the oracle's fp64 kernel form (fused_forward / fused_backward,
+    device-agnostic) runs there too.  Everything stays on the device; same dict layout as _oracle_case."""
+    from tests import gpu_util as gu
+    dev = gu.DEV
+    bf = torch.bfloat16
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    rnd = lambda *s: torch.randn(*s, generator=gen, device=dev, dtype=torch.float32)
+    x = rnd(B, S, d_in).to(bf)
+    A = [((torch.rand(r, d_in, generator=gen, device=dev) * 2 - 1) * d_in ** -0.5).to(bf) for _ in range(M)]
+    Bw = (rnd(d_out, r) * 0.02).to(bf)
+    dy = rnd(B, S, d_out).to(bf)
+    y0 = rnd(B, S, d_out).to(bf)
+    dx0 = rnd(B, S, d_in).to(bf)
+    masks = mo.layout_masks(variant, B, S, layout)
+    meta = gu.gpu_meta(variant, masks)
+    om = gu.oracle_meta(variant, masks)
+    ometa = mo.TokenMeta(om.tokmeta.to(dev), om.kidx.to(dev), om.klen.to(dev))
+    sc, osc = gu.scalars_for(variant, alpha, r, w, p)
+    keep = gu.keep_mask(B, S, d_in, d_out, r, M, bf, p, rng[0], rng[1]) if p > 0 else None
+    y, h = gu.abi_forward(meta, x, y0, A, Bw, sc, flags, rng[0], rng[1])
+    dx, dA, dB = gu.abi_backward(meta, x, dy, h, A, Bw, sc, dx0=dx0, flags=flags, seed=rng[0], offset=rng[1])
+    f = lambda t: t.double()
+    ty, th = mo.fused_forward(ometa, f(x), f(y0), [f(a) for a in A], f(Bw), osc, keep, p)
+    tdxa, tdA, tdB, _ = mo.fused_backward(ometa, f(x), f(dy), th, [f(a) for a in A], f(Bw), osc, keep, p)
+    T = B * S
+    return dict(y=y, dx=dx, dA=dA, dB=dB, h=h[:T * r].view(B, S, r), g=h[T * r:2 * T * r].view(B, S, r),
+                ty=ty, tdx=f(dx0) + tdxa, tdA=tdA, tdB=tdB, th=th, y0=f(y0), dx0=f(dx0), keep=keep, ometa=ometa)
+
+
+@pytest.mark.parametrize('d_in,d_out,p', [
+    (512, 768, 0.0), (512, 768, 0.05),
+    (4096, 4096, 0.0), (4096, 4096, 0.05),
+    (4096, 11008, 0.05), (11008, 4096, 0.05),
+], ids=['512x768_p0', '512x768_p05', '4096x4096_p0', '4096x4096_p05', '4096x11008_p05', '11008x4096_p05'])
+def test_bench_geometry_avt_r16(d_in, d_out, p):
+    """The launch geometry the headline number runs on (bench.py default workload): AVT, 3 modalities, r = 16,
+    layout c3, 16 sequences of 2048 tokens = 256 token tiles > 148 SMs, lora_dropout 0 and 0.05, at the three
+    Llama-2-7B projection shapes -- element-wise against the oracle (lora.py:460-532 semantics)."""
+    from moka_b200 import _cabi
+    from moka_b200.layer import _make_desc
+    from tests import gpu_util as gu
+    B, S, r, M = 16, 2048, 16, 3
+    assert B * S >= 148 * 128 + 1
+    sc, _ = gu.scalars_for(mo.VARIANT_AVT, 16, r, 1.0, p)
+    desc = _make_desc((B * S, d_in), B, S, d_out, r, M, torch.bfloat16, 96, sc, 0)
+    assert _cabi.load().moka_uses_tensor_cores(desc) == 1
+    o = _oracle_case_gpu(mo.VARIANT_AVT, B, S, d_in, d_out, r, M, 'c3', 16, 1.0, p=p, rng=(4321, 9))
+    if p > 0:
+        assert abs(1.0 - float(o['keep'].float().mean()) - p) < 2e-3
+    _assert_case(o, torch.bfloat16, M)
+
+
+@pytest.mark.parametrize('variant,M,layout,B,S,d,r,p', [
+    (mo.VARIANT_VT, 2, 'c2', 16, 2048, 4096, 8, 0.05),        # BASELINE configs[1] at the bench's token count
+    (mo.VARIANT_VT, 2, 'c4', 5, 4096, 5120, 64, 0.05),        # BASELINE configs[3]: 13B width, r = 64, S = 4096
+    (mo.VARIANT_AVT, 3, 'c3', 10, 2048, 4096, 4, 0.05),       # the reference's shipped rank (lora_r = 444)
+], ids=['c2_vt_r8_7b', 'c4_vt_r64_13b', 'avt_r4_7b'])
+def test_bench_geometry_other_configs(variant, M, layout, B, S, d, r, p):
+    assert B * S >= 148 * 128 + 1
+    w = 1.0 if variant == mo.VARIANT_AVT else 0.05
+    o = _oracle_case_gpu(variant, B, S, d, d, r, M, layout, 16, w, p=p, rng=(77, 3))
+    _assert_case(o, torch.bfloat16, M)
