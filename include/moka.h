@@ -145,6 +145,11 @@ int moka_build_token_meta(int32_t variant, int32_t B, int32_t S, int32_t Lk,
 int moka_dropout_keep_mask(const MokaDesc* desc, uint64_t seed, uint64_t offset,
                            uint8_t* keep, moka_stream_t stream);
 
+/* The drop probability the kernels realise for lora_dropout = p: round(4096 p) / 4096 (clamped to
+ * [1, 4095] / 4096), e.g. 0.05 -> 205/4096 = 0.050049.  Kept elements are scaled by 1 / (1 - that value), so the
+ * expectation of the dropped input is exact (nn.Dropout semantics, lora.py:267-270, at a 12-bit quantised rate). */
+float moka_effective_dropout_p(float p);
+
 /*
  * Sharded AdamW on the flat adapter parameter vector (ZeRO-1/2 optimizer shard; the
  * reference delegates this to DeepSpeed: VisualText/zero_stage2_config.json:23-34).

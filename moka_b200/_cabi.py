@@ -20,7 +20,7 @@ MOKA_EUNSUPPORTED = -4
 META_EMPTY_QUESTION, META_OVERLAP, META_KEY_OVERFLOW = 1, 2, 4
 
 EXPORTS = ['moka_workspace_bytes', 'moka_forward', 'moka_backward', 'moka_build_token_meta',
-           'moka_dropout_keep_mask', 'moka_adamw_step', 'moka_launch_count',
+           'moka_dropout_keep_mask', 'moka_effective_dropout_p', 'moka_adamw_step', 'moka_launch_count',
            'moka_uses_tensor_cores', 'moka_supports_delta', 'moka_strerror', 'moka_version', 'moka_rope', 'moka_debug_read',
            'moka_debug_trap_buffer']
 
@@ -64,6 +64,8 @@ def load():
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.moka_dropout_keep_mask.restype = c_int32
     lib.moka_dropout_keep_mask.argtypes = [D, c_uint64, c_uint64, c_void_p, c_void_p]
+    lib.moka_effective_dropout_p.restype = c_float
+    lib.moka_effective_dropout_p.argtypes = [c_float]
     lib.moka_adamw_step.restype = c_int32
     lib.moka_adamw_step.argtypes = [c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                     c_float, c_float, c_float, c_float, c_float, c_int32, c_float, c_void_p]

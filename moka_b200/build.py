@@ -16,8 +16,11 @@ STAMP = os.path.join(HERE, '.libmoka.stamp')
 
 SOURCES = ['moka_abi.cu', 'moka_simt.cu', 'moka_meta.cu', 'moka_optim.cu', 'moka_tc.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-              '-Xcompiler', '-fPIC', '--use_fast_math', '-Xptxas', '-v']
-# --use_fast_math only affects exp2f/div in the softmax (errors ~1e-7 rel, inside the fp32 bar)
+              '-Xcompiler', '-fPIC', '-Xptxas', '-v']
+# --use_fast_math only for the translation units that hold the attention softmax (exp2f / division: errors
+# ~1e-7 rel, inside the fp32 bar).  NOT for moka_optim.cu: AdamW keeps IEEE division / sqrt and denormals on the
+# fp32 master weights and moments, RoPE keeps the full-range sincosf.
+FAST_MATH = {'moka_simt.cu', 'moka_tc.cu'}
 
 
 def _nvcc() -> str:
@@ -33,7 +36,7 @@ def _digest() -> str:
     for f in files:
         with open(f, 'rb') as fh:
             h.update(f.encode()); h.update(fh.read())
-    h.update(' '.join(NVCC_FLAGS).encode())
+    h.update(' '.join(NVCC_FLAGS + sorted(FAST_MATH)).encode())
     return h.hexdigest()
 
 
@@ -48,7 +51,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     procs = []
     for src in SOURCES:
         obj = os.path.join(bdir, src.replace('.cu', '.o'))
-        cmd = [_nvcc(), *NVCC_FLAGS, '-I', os.path.join(ROOT, 'include'), '-I', CSRC, '-c',
+        cmd = [_nvcc(), *NVCC_FLAGS, *(['--use_fast_math'] if src in FAST_MATH else []),
+               '-I', os.path.join(ROOT, 'include'), '-I', CSRC, '-c',
                os.path.join(CSRC, src), '-o', obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)

@@ -54,11 +54,13 @@ static DevDesc make_dev(const MokaDesc* m, uint64_t seed, uint64_t offset) {
   d.attn_w = m->attn_w;
   d.sm_scale = 1.0f / sqrtf((float)m->r);
   if (m->dropout_p > 0.f) {
-    d.drop_scale = 1.0f / (1.0f - m->dropout_p);
     long t = lrintf(m->dropout_p * 4096.0f);
     if (t < 1) t = 1;
     if (t > 4095) t = 4095;
     d.drop_thresh = (uint32_t)t;
+    // the generator drops with probability t / 4096: scale by the probability actually realised, so that
+    // E[u] = x exactly (moka_effective_dropout_p reports it)
+    d.drop_scale = 1.0f / (1.0f - (float)t / 4096.0f);
     for (int i = 0; i < 12; ++i) d.drop_sel[i] = ((t >> i) & 1) ? 0xffffffffu : 0u;
   } else {
     d.drop_scale = 1.0f; d.drop_thresh = 0;
@@ -243,6 +245,14 @@ int moka_dropout_keep_mask(const MokaDesc* desc, uint64_t seed, uint64_t offset,
   if (!keep) return MOKA_EINVAL;
   DevDesc d = make_dev(desc, seed, offset);
   return launch_keep_mask(d, keep, static_cast<cudaStream_t>(stream));
+}
+
+float moka_effective_dropout_p(float p) {
+  if (!(p > 0.f)) return 0.f;
+  long t = lrintf(p * 4096.0f);
+  if (t < 1) t = 1;
+  if (t > 4095) t = 4095;
+  return (float)t / 4096.0f;
 }
 
 int moka_adamw_step(int64_t n, float* master, float* exp_avg, float* exp_avg_sq, const float* grad,

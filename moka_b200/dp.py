@@ -35,6 +35,9 @@ class AdamWConfig:
     betas: Tuple[float, float] = (0.9, 0.999)
     eps: float = 1e-8
     weight_decay: float = 0.0        # VisualText/zero_stage2_config.json:23-34 ("auto" -> trainer 0.0)
+    # "gradient_clipping": "auto" in both DeepSpeed configs (zero_stage2_config.json:14) = HF Trainer's
+    # max_grad_norm (1.0 by default); 0 disables.  The global norm is taken over the rank-averaged gradient.
+    max_grad_norm: float = 0.0
 
 
 def _cuda_adamw(n, master, m, v, grad, out, lr, b1, b2, eps, wd, step, gscale):
@@ -127,6 +130,9 @@ class AdapterDataParallel:
         self.comm_stream = torch.cuda.Stream(device=dev) if self.overlap else None
         self._handles: List = []
         self._launched = [False] * len(self.buckets)
+        self._sync = True                # False inside no_sync(): micro-batches accumulate locally, nothing is reduced
+        self._micro_batches = 0          # backward passes since the last step()
+        self.last_grad_norm: Optional[torch.Tensor] = None
         self.reset_pending()
 
     # ------------------------------------------------------------------ bookkeeping
@@ -137,11 +143,40 @@ class AdapterDataParallel:
 
     def _make_ready_cb(self, bi: int):
         def cb():
+            if not self._sync:
+                return                   # accumulating micro-batch: the gradient stays local until the last one
+            if self._launched[bi]:
+                # a second backward arrived after this bucket's collective was launched: its contribution would be
+                # dropped (stage 1/2) or added un-reduced (stage 0).  Accumulate under no_sync() instead.
+                raise RuntimeError('gradient accumulation without no_sync(): run every micro-batch but the last '
+                                   'inside `with engine.no_sync():` (or use engine.accumulate(i, n))')
             b = self.buckets[bi]
             b['pending'] -= 1
             if b['pending'] == 0 and self.overlap:
                 self._launch_bucket(bi)
         return cb
+
+    def no_sync(self):
+        """Context manager for gradient accumulation (``--gradient_accumulation_steps 2``,
+        VisualText/shell/train.sh:72): backward passes inside it only accumulate into the flat fp32 gradient;
+        the bucket collectives are armed by the first backward outside it and ``step()`` reduces whatever is
+        left.  Pass ``grad_scale = 1 / accumulation_steps`` to ``step()`` for the mean over micro-batches."""
+        eng = self
+
+        class _NoSync:
+            def __enter__(self_inner):
+                self_inner.prev = eng._sync
+                eng._sync = False
+
+            def __exit__(self_inner, *exc):
+                eng._sync = self_inner.prev
+                return False
+        return _NoSync()
+
+    def accumulate(self, micro_step: int, accumulation_steps: int):
+        """``with engine.accumulate(i, n):`` = no_sync() for every micro-batch but the last of the n."""
+        import contextlib
+        return self.no_sync() if (micro_step + 1) % accumulation_steps else contextlib.nullcontext()
 
     def trainable_numel(self) -> int:
         return sum(b['numel'] for b in self.buckets)
@@ -162,8 +197,8 @@ class AdapterDataParallel:
             dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.AVG, group=self.pg)
         else:
             # stage 0/1 (and gloo, which has no reduce-scatter): all-reduce then keep the owned slice
+            # SUM here; the 1 / world of the mean rides in the optimizer's grad_scale (no extra pass over the bucket)
             dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.pg)
-            g.mul_(1.0 / self.world)
             if self.stage != 0:
                 out.copy_(g[self.rank * b['shard']:(self.rank + 1) * b['shard']])
 
@@ -179,27 +214,57 @@ class AdapterDataParallel:
             self._reduce_bucket(bi)
 
     # ------------------------------------------------------------------ the step
+    def _grads_are_sums(self) -> bool:
+        """True when the reduced gradient still has to be divided by the world size (all-reduce SUM paths)."""
+        if self.world == 1:
+            return False
+        return not (self.stage == 2 and dist.get_backend(self.pg) != 'gloo')
+
     @torch.no_grad()
     def step(self, grad_scale: float = 1.0):
-        """Gradient sync (whatever was not already overlapped) + sharded AdamW + parameter all-gather."""
+        """Gradient sync (whatever was not already overlapped) + global-norm clipping + sharded AdamW +
+        parameter all-gather (per bucket, overlapped with the update of the next bucket)."""
+        if not self._sync:
+            raise RuntimeError('step() inside no_sync(): leave the context before the optimizer step')
         for bi in reversed(range(len(self.buckets))):
             self._launch_bucket(bi)
         if self.comm_stream is not None:
             torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
         self.step_count += 1
         c = self.cfg
-        if self.world == 1 or self.stage == 0:
-            grad = self.flat_grad                       # full vector, already averaged
-            out = self.flat_param
+        sharded = self.world > 1 and self.stage != 0
+        grad, out = (self.shard_grad, self.shard_out) if sharded else (self.flat_grad, self.flat_param)
+        scale = grad_scale * (1.0 / self.world if self._grads_are_sums() else 1.0)
+        if c.max_grad_norm and c.max_grad_norm > 0:
+            # global l2 norm of the (scaled, rank-averaged) gradient: shards partition the vector, so the squared
+            # norms add across ranks.  Stays on the device: the clip coefficient is applied as a tensor multiply.
+            sq = grad.float().pow(2).sum()
+            if sharded:
+                dist.all_reduce(sq, op=dist.ReduceOp.SUM, group=self.pg)
+            norm = sq.sqrt() * abs(scale)
+            self.last_grad_norm = norm
+            coef = torch.clamp(c.max_grad_norm / (norm + 1e-6), max=1.0)
+            grad.mul_(coef)
+        if not sharded:
+            self.update_fn(self.shard_numel, self.master, self.exp_avg, self.exp_avg_sq, grad, out,
+                           c.lr, c.betas[0], c.betas[1], c.eps, c.weight_decay, self.step_count, scale)
         else:
-            grad, out = self.shard_grad, self.shard_out
-        self.update_fn(self.shard_numel, self.master, self.exp_avg, self.exp_avg_sq, grad, out,
-                       c.lr, c.betas[0], c.betas[1], c.eps, c.weight_decay, self.step_count, grad_scale)
-        if self.world > 1 and self.stage != 0:
+            # bucket by bucket: the all-gather of bucket i (side stream) overlaps the update of bucket i + 1
             for b in self.buckets:
+                so, n = b['shard_off'], b['shard_len']
+                self.update_fn(n, self.master[so:so + n], self.exp_avg[so:so + n], self.exp_avg_sq[so:so + n],
+                               grad[so:so + n], out[so:so + n], c.lr, c.betas[0], c.betas[1], c.eps,
+                               c.weight_decay, self.step_count, scale)
                 full = self.flat_param[b['offset']:b['offset'] + b['padded']]
-                mine = self.shard_out[b['shard_off']:b['shard_off'] + b['shard_len']]
-                dist.all_gather_into_tensor(full, mine, group=self.pg)
+                mine = out[so:so + n]
+                if self.comm_stream is not None:
+                    self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+                    with torch.cuda.stream(self.comm_stream):
+                        dist.all_gather_into_tensor(full, mine, group=self.pg)
+                else:
+                    dist.all_gather_into_tensor(full, mine, group=self.pg)
+            if self.comm_stream is not None:
+                torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
         self.zero_grad()
 
     # ------------------------------------------------------------------ state (adapter-only checkpoints)

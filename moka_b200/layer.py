@@ -212,7 +212,14 @@ class _MokaFn(torch.autograd.Function):
         gB = None if dB_main else dB.to(Bw_param.dtype)
         gA = [None if main else g.to(p.dtype) for (g, main), p in zip(dAs, A_params)]
         gx = None if dx is None else dx.view(ctx.x_shape)
-        return (gx, None, None, gB, None, None, None, None, *gA)
+        # bias='all' / 'lora_only' (lora.py:234-245) makes the frozen layer's bias trainable: its gradient is the
+        # column sum of dy; a trainable BASE WEIGHT is not something MokA ever asks for - refuse instead of
+        # silently returning no gradient
+        if ctx.needs_input_grad[1]:
+            raise _cabi.MokaError('the wrapped base weight requires grad: MokaLinear keeps W0 frozen '
+                                  '(lora.py:333, layer.py:124-132)')
+        gbias = dy2.float().sum(0).to(dy2.dtype) if ctx.needs_input_grad[2] else None
+        return (gx, None, gbias, gB, None, None, None, None, *gA)
 
 
 def moka_linear_function(x, weight, bias, A: Sequence[torch.Tensor], Bw, meta: TokenMeta,
@@ -432,7 +439,13 @@ class MokaLinearVT(nn.Module):
             masks = [my_text_mask, my_image_mask, question_mask]
             meta = META_CACHE.get(_cabi.VARIANT_VT, masks,
                                   lambda: build_token_meta_vt(my_text_mask, my_image_mask, question_mask))
-        sc = FusedScalars(1.0, (s_text, self.scaling['image'], 0.0), self.attn_weight, self._dropout_p('text'))
+        p_drop = self._dropout_p('text')
+        if self._dropout_p('image') != p_drop:
+            # layer.py:607 / :617 apply lora_dropout['text'] to text rows and lora_dropout['image'] to image rows;
+            # the kernels take one p (both reference recipes configure the two adapters identically)
+            raise NotImplementedError(f"lora_dropout differs between the adapters (text {p_drop}, image "
+                                      f"{self._dropout_p('image')}): the fused kernels take one dropout rate")
+        sc = FusedScalars(1.0, (s_text, self.scaling['image'], 0.0), self.attn_weight, p_drop)
         A = [self.lora_A['text'].weight, self.lora_A['image'].weight]
         return moka_linear_function(x, bw.weight, bw.bias, A, self.lora_B['text'].weight, meta, sc,
                                     self.kernel_flags)

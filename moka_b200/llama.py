@@ -233,6 +233,13 @@ class LlamaModel(nn.Module):
         self.layers = nn.ModuleList([LlamaDecoderLayer(cfg) for _ in range(cfg.num_hidden_layers)])
         self.norm = RMSNorm(cfg.hidden_size, cfg.rms_norm_eps)
         self.gradient_checkpointing = False
+        # The reference's VT hand-off runs inside EACH decoder layer and asks ``past_key_value.get_seq_length()``,
+        # which reads layer 0's cache (VisualText/modified_models/modeling_llama.py:314-329): during a generation
+        # prefill layer 0 has already stored its keys when layer 1 asks, so layers 1..L-1 take the no-mask
+        # (plain text-adapter LoRA) branch on the prompt.  Default here: every layer sees the masks on the prompt,
+        # i.e. the prefill computes what training computed (a deliberate fix of that quirk).  Set this flag to get
+        # the reference's behaviour bit for bit (masks to layer 0 only whenever a cache is passed).
+        self.reference_compat_prefill = False
 
     def forward(self, input_ids=None, inputs_embeds=None, mask_args: Optional[tuple] = None,
                 past_key_values: Optional[KVCache] = None):
@@ -250,7 +257,8 @@ class LlamaModel(nn.Module):
         ma = tuple(mask_args) if mask_args is not None else ()
         for i, layer in enumerate(self.layers):
             if past_key_values is not None:
-                h = layer(h, cos, sin, *ma, cache=past_key_values, layer_idx=i, pos0=pos0)
+                ma_i = ma if (i == 0 or not self.reference_compat_prefill) else ()
+                h = layer(h, cos, sin, *ma_i, cache=past_key_values, layer_idx=i, pos0=pos0)
             elif self.gradient_checkpointing and self.training:
                 h = checkpoint(layer, h, cos, sin, *ma, use_reentrant=False)
             else:

@@ -85,3 +85,8 @@ def keep_mask(B, S, d_in, d_out, r, M, dtype, p, seed, offset):
 
 def oracle_meta(variant, masks):
     return mo.build_token_meta_avt(masks) if variant == mo.VARIANT_AVT else mo.build_token_meta_vt(*masks)
+
+
+def effective_p(p):
+    """The drop probability the kernels realise (round(4096 p) / 4096): what the oracle's 1/(1-p) scale must use."""
+    return float(_cabi.load().moka_effective_dropout_p(float(p))) if p > 0 else 0.0

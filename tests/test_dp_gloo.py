@@ -111,3 +111,67 @@ def test_single_process_engine_layout():
     assert not hasattr(model.frozen, 'main_grad')
     with pytest.raises(ValueError):
         AdapterDataParallel(model, zero_stage=3)
+
+
+def _worker_accum(rank, world, port, stage, ret):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        model = _Toy()
+        eng = AdapterDataParallel(model, AdamWConfig(lr=1e-2, weight_decay=0.01, max_grad_norm=1.0), zero_stage=stage,
+                                  num_buckets=2, update_fn=_ref_adamw, overlap=False)
+        params = [p for p in model.parameters() if p.requires_grad]
+        shapes = [p.shape for p in params]
+        accum = 2
+        for step in range(3):
+            for mb in range(accum):
+                with eng.accumulate(mb, accum):
+                    for p, g in zip(params, _grads_for(rank, shapes, 10 * step + mb)):
+                        p.main_grad.add_(g)
+                        p._moka_dp_ready()
+            eng.step(grad_scale=1.0 / accum)
+        # a second un-guarded backward after the collectives were armed must be refused, not silently dropped
+        eng2 = AdapterDataParallel(_Toy(), AdamWConfig(), zero_stage=stage, num_buckets=2, update_fn=_ref_adamw,
+                                   overlap=False)
+        eng2.overlap = True                               # arm the launch-on-ready path (gloo, same stream)
+        ps = [p for p in eng2.model.parameters() if p.requires_grad]
+        for p in ps:
+            p._moka_dp_ready()
+        refused = False
+        try:
+            ps[0]._moka_dp_ready()
+        except RuntimeError:
+            refused = True
+        flat = torch.cat([p.detach().reshape(-1) for p in params])
+        if rank == 0:
+            ret['flat'] = flat.clone()
+            ret['refused'] = refused
+            ret['norm'] = float(eng.last_grad_norm)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('stage', [0, 1, 2])
+def test_two_rank_gradient_accumulation_and_clipping(stage):
+    """two micro-batches per step (VisualText/shell/train.sh:72) under no_sync(), mean over micro-batches
+    and ranks, global-norm clipping at 1.0 -- against single-process torch.optim.AdamW + clip_grad_norm_."""
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_accum, args=(world, port, stage, ret), nprocs=world, join=True)
+    assert ret['refused']
+    model = _Toy()
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.AdamW(params, lr=1e-2, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    shapes = [p.shape for p in params]
+    norm = None
+    for step in range(3):
+        for i, p in enumerate(params):
+            p.grad = sum(_grads_for(r, shapes, 10 * step + mb)[i] for r in range(world) for mb in range(2)) / (world * 2)
+        norm = torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+    ref = torch.cat([p.detach().reshape(-1) for p in params])
+    assert torch.allclose(ret['flat'], ref, rtol=1e-5, atol=1e-6)
+    assert abs(ret['norm'] - float(norm)) <= 1e-4 * float(norm)

@@ -112,8 +112,9 @@ def _oracle_case(variant, B, S, d_in, d_out, r, M, layout, alpha, w, dtype, seed
     y, h = gu.abi_forward(meta, to(x), to(y0), [to(a) for a in A], to(Bw), sc, flags, rng[0], rng[1])
     dx, dA, dB = gu.abi_backward(meta, to(x), to(dy), h, [to(a) for a in A], to(Bw), sc, dx0=to(dx0),
                                  flags=flags, seed=rng[0], offset=rng[1])
-    ty, th = mo.fused_forward(ometa, x, y0, A, Bw, osc, keep, p)
-    tdxa, tdA, tdB, _ = mo.fused_backward(ometa, x, dy, th, A, Bw, osc, keep, p)
+    pe = gu.effective_p(p)
+    ty, th = mo.fused_forward(ometa, x, y0, A, Bw, osc, keep, pe)
+    tdxa, tdA, tdB, _ = mo.fused_backward(ometa, x, dy, th, A, Bw, osc, keep, pe)
     return dict(y=y.cpu(), dx=dx.cpu(), dA=[a.cpu() for a in dA], dB=dB.cpu(), h=h[:B * S * r].view(B, S, r).cpu(), g=h[B * S * r:2 * B * S * r].view(B, S, r).cpu(),
                 ty=ty, tdx=dx0 + tdxa, tdA=tdA, tdB=tdB, th=th, y0=y0, dx0=dx0, keep=keep, ometa=ometa)
 
@@ -633,8 +634,9 @@ def _oracle_case_gpu(variant, B, S, d_in, d_out, r, M, layout, alpha, w, p=0.0, 
     y, h = gu.abi_forward(meta, x, y0, A, Bw, sc, flags, rng[0], rng[1])
     dx, dA, dB = gu.abi_backward(meta, x, dy, h, A, Bw, sc, dx0=dx0, flags=flags, seed=rng[0], offset=rng[1])
     f = lambda t: t.double()
-    ty, th = mo.fused_forward(ometa, f(x), f(y0), [f(a) for a in A], f(Bw), osc, keep, p)
-    tdxa, tdA, tdB, _ = mo.fused_backward(ometa, f(x), f(dy), th, [f(a) for a in A], f(Bw), osc, keep, p)
+    pe = gu.effective_p(p)
+    ty, th = mo.fused_forward(ometa, f(x), f(y0), [f(a) for a in A], f(Bw), osc, keep, pe)
+    tdxa, tdA, tdB, _ = mo.fused_backward(ometa, f(x), f(dy), th, [f(a) for a in A], f(Bw), osc, keep, pe)
     T = B * S
     return dict(y=y, dx=dx, dA=dA, dB=dB, h=h[:T * r].view(B, S, r), g=h[T * r:2 * T * r].view(B, S, r),
                 ty=ty, tdx=f(dx0) + tdxa, tdA=tdA, tdB=tdB, th=th, y0=f(y0), dx0=f(dx0), keep=keep, ometa=ometa)
