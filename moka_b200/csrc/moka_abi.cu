@@ -85,6 +85,11 @@ static size_t ws_dh_bytes(const MokaDesc* m) { return align_up((size_t)m->B * m-
 static size_t ws_dk_bytes(const MokaDesc* m) { return align_up((size_t)m->B * (m->Lk > 0 ? m->Lk : 1) * m->r * 4, 256); }
 
 static size_t ws_cnt_bytes(const MokaDesc* m) { return align_up((size_t)m->B * 4, 256); }
+// number of [T, r] fp32 buffers at the head of the workspace: the partial dG buffers of the persistent k_dgrad_tc
+// (one per CTA that shares a token tile; at least the two the other paths use)
+static size_t ws_parts(const MokaDesc* m) {
+  return (size_t)tc_dgrad_parts_max(m->B * m->S, m->d_out, num_sms());
+}
 
 // stages the tcgen05 path takes for this call (flags bits 8..11 veto individual stages)
 static int tc_stages(const MokaDesc* m, const DevDesc& d) {
@@ -104,8 +109,8 @@ size_t moka_workspace_bytes(const MokaDesc* desc) {
   size_t pack = tc_pack_bytes(desc->B * desc->S, desc->r, desc->M);
   const size_t bt = (size_t)((desc->r + 15) / 16 * 16) * desc->d_out * 2;
   if (bt > pack) pack = bt;
-  // [dh | dh_att | dK | counters | pack]; the forward uses the first 2 T r floats for the partial h
-  return 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc) + ws_cnt_bytes(desc) + align_up(pack, 256) + 256;
+  // [dG partials (>= 2: dh | dh_att) | dK | counters | pack]; the forward uses the first 2 T r floats for the partial h
+  return ws_parts(desc) * ws_dh_bytes(desc) + ws_dk_bytes(desc) + ws_cnt_bytes(desc) + align_up(pack, 256) + 256;
 }
 
 int moka_uses_tensor_cores(const MokaDesc* desc) {
@@ -196,9 +201,10 @@ int moka_backward(const MokaDesc* desc, const void* dy, const void* x, const flo
   char* ws = static_cast<char*>(workspace);
   a.dh = reinterpret_cast<float*>(ws);
   a.dh_att = reinterpret_cast<float*>(ws + ws_dh_bytes(desc));
-  a.dK = reinterpret_cast<float*>(ws + 2 * ws_dh_bytes(desc));
-  a.counters = reinterpret_cast<int*>(ws + 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc));
-  a.pack = ws + 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc) + ws_cnt_bytes(desc);
+  const size_t parts_bytes = ws_parts(desc) * ws_dh_bytes(desc);
+  a.dK = reinterpret_cast<float*>(ws + parts_bytes);
+  a.counters = reinterpret_cast<int*>(ws + parts_bytes + ws_dk_bytes(desc));
+  a.pack = ws + parts_bytes + ws_dk_bytes(desc) + ws_cnt_bytes(desc);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int tcs = tc_stages(desc, d) & (kStageDgrad | kStageWgrad);
   if ((desc->flags & MOKA_FLAG_FORCE_TC) && tcs != (kStageDgrad | kStageWgrad)) return MOKA_EUNSUPPORTED;
@@ -216,7 +222,7 @@ int moka_backward(const MokaDesc* desc, const void* dy, const void* x, const flo
   }
   (void)force;
   // one memset covers dh (the tensor-core dgrad reduces into it), dh_att and dK
-  cudaError_t ce = cudaMemsetAsync(a.dh, 0, 2 * ws_dh_bytes(desc) + ws_dk_bytes(desc) + ws_cnt_bytes(desc), st);
+  cudaError_t ce = cudaMemsetAsync(a.dh, 0, parts_bytes + ws_dk_bytes(desc) + ws_cnt_bytes(desc), st);
   if (ce != cudaSuccess) { set_cuda_error(ce); return MOKA_ECUDA; }
   for (int stage : {kStageDgrad, kStageWgrad}) {
     int e = MOKA_EUNSUPPORTED;

@@ -22,6 +22,9 @@ struct SimtArgs {
   int klen_hint;    // upper bound on klen (kidx row stride)
 };
 
+// number of partial dG buffers the persistent k_dgrad_tc may write for this shape (>= 2)
+int tc_dgrad_parts_max(int T, int d_out, int num_sms);
+
 // bytes of the packed-operand workspace the tensor-core wgrad kernel needs
 size_t tc_pack_bytes(int T, int r, int M);
 

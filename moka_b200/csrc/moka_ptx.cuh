@@ -232,6 +232,88 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                :: "r"(smem_u32(bar)) : "memory");
 }
 
+// ------------------------------------------------------------------ warp-uniform issue (round 2)
+// tcgen05.mma / tcgen05.commit / TMA take their operands in UNIFORM registers.  Issued from divergent code
+// (`if (lane == 0) { ... }`) every operand goes through an ELECT / R2UR.BROADCAST waterfall loop: ~15 SASS
+// instructions and 70-100 cycles PER MMA on a single thread - measured: k_dgrad_tc's issue loop took 2.3k cycles per
+// stage with both of its products compiled out.  The fix is CUTLASS's: the whole warp runs the loop on warp-uniform
+// values (warp index made provably uniform with a shuffle) and only the instruction itself is predicated on one
+// elected lane, so the descriptors live in uniform registers.
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+// whole-warp forms: call from CONVERGENT code with warp-uniform arguments.  The election and the predicated
+// instruction sit in ONE asm block (no branch at the C++ level), so ptxas sees straight-line convergent code.
+__device__ __forceinline__ void umma_bf16_w(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}"
+      :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}"
+      :: "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_w(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.shared::cta.b64 _, [%0];\n\t"
+      "}"
+      :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_w(uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t"
+      "}"
+      :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_w(uint32_t smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                              uint64_t hint) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;\n\t"
+      "}"
+      :: "r"(smem_dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(hint)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d_w(const CUtensorMap* m, uint32_t smem_src, int c0, int c1) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];\n\t"
+      "}"
+      :: "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_src), "r"(c0), "r"(c1) : "memory");
+}
+
 // Byte offset of element (row, 16-byte chunk) inside a [rows x 128 B] tile stored with the
 // 128-byte swizzle (what TMA SWIZZLE_128B writes and what the UMMA SW128 descriptors read).
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t row, uint32_t chunk16) {

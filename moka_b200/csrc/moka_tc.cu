@@ -197,7 +197,7 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   uint64_t* ready = bars + 2 * p.stages + 1;                  // [stages] tile masked (DROP only)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * p.stages + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = ptx::uniform_warp_idx(), lane = threadIdx.x & 31;
   const int tile = blockIdx.x / p.ksplit, split = blockIdx.x % p.ksplit;
   const int t0 = tile * 128;
   if (threadIdx.x == 0) { dbg_stamp_g(p.dbg, blockIdx.x, 100); dbg_stamp(p.dbg, blockIdx.x, 0); }
@@ -233,57 +233,62 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   if (threadIdx.x == 0) dbg_stamp(p.dbg, blockIdx.x, 2);
 
   if (warp == 0) {
-    if (lane == 0) {
+    // ---- TMA producer: whole warp, warp-uniform values, one elected lane issues (see moka_ptx.cuh)
+    {
       const uint32_t tx = (16384u + (uint32_t)p.M * (uint32_t)p.r * 128u) * (uint32_t)p.kbox;
+      const uint32_t ring_a = ptx::uniform_u32(ptx::smem_u32(ring));
       for (int it = 0; it < nkb; ++it) {
         const int kb = kb0 + rot_index(it, krot, nkb), s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         ptx::mbar_wait_or_trap(&empty[s], ph ^ 1u, __LINE__);
-        uint8_t* xs = ring + (size_t)s * p.stage_bytes;
-        ptx::mbar_arrive_expect_tx(&full[s], tx);
+        const uint32_t xs = ring_a + (uint32_t)s * p.stage_bytes;
+        ptx::mbar_arrive_expect_tx_w(&full[s], tx);
         for (int bx = 0; bx < p.kbox; ++bx) {
           const int col = (kb * p.kbox + bx) * 64;
-          uint8_t* ws = xs + xbytes + (size_t)bx * p.w_bytes;
-          ptx::tma_load_2d(xs + (size_t)bx * 16384, &tm_x, &full[s], col, t0, ptx::kEvictFirst);
-          ptx::tma_load_2d(ws, &tm_a0, &full[s], col, 0, ptx::kEvictLast);
-          if (p.M > 1) ptx::tma_load_2d(ws + (size_t)p.rp * 128, &tm_a1, &full[s], col, 0, ptx::kEvictLast);
-          if (p.M > 2) ptx::tma_load_2d(ws + (size_t)2 * p.rp * 128, &tm_a2, &full[s], col, 0, ptx::kEvictLast);
+          const uint32_t ws = xs + xbytes + (uint32_t)bx * p.w_bytes;
+          ptx::tma_load_2d_w(xs + (uint32_t)bx * 16384u, &tm_x, &full[s], col, t0, ptx::kEvictFirst);
+          ptx::tma_load_2d_w(ws, &tm_a0, &full[s], col, 0, ptx::kEvictLast);
+          if (p.M > 1) ptx::tma_load_2d_w(ws + (uint32_t)p.rp * 128u, &tm_a1, &full[s], col, 0, ptx::kEvictLast);
+          if (p.M > 2) ptx::tma_load_2d_w(ws + 2u * (uint32_t)p.rp * 128u, &tm_a2, &full[s], col, 0, ptx::kEvictLast);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // ---- MMA issuer: whole warp, one elected lane issues
+    {
+      const uint32_t tb = ptx::uniform_u32(tmem_base);
+      const uint32_t ring_a = ptx::uniform_u32(ptx::smem_u32(ring));
       // N > 256 does not fit one instruction: two halves (each a multiple of 16)
       const int nparts = p.NP > 256 ? 2 : 1;
       const int npart = p.NP / nparts;
       const uint32_t idesc = ptx::idesc_bf16(128, (uint32_t)npart, 0, 0);
+      const uint64_t dbase = ptx::smem_desc_sw128(0, 1024, 0);
       for (int kb = kb0; kb < kb1; ++kb) {
         const int it = kb - kb0, s = it % p.stages;
         const uint32_t ph = (uint32_t)(it / p.stages) & 1u;
         ptx::mbar_wait_or_trap(&full[s], ph, __LINE__);                    // weights + x landed
-        if (it < 8) dbg_stamp(p.dbg, blockIdx.x, 8 + it * 3);
+        if (lane == 0 && it < 8) dbg_stamp(p.dbg, blockIdx.x, 8 + it * 3);
         if (DROP) ptx::mbar_wait_or_trap(&ready[s], ph, __LINE__);           // ... and x masked
-        if (it < 8) dbg_stamp(p.dbg, blockIdx.x, 9 + it * 3);
-        if (it == 0) dbg_stamp(p.dbg, blockIdx.x, 3);
+        if (lane == 0) { if (it < 8) dbg_stamp(p.dbg, blockIdx.x, 9 + it * 3); if (it == 0) dbg_stamp(p.dbg, blockIdx.x, 3); }
         ptx::tc_fence_after_sync();
-        const uint32_t xa0 = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
+        const uint32_t xa0 = ring_a + (uint32_t)s * p.stage_bytes;
         for (int bx = 0; bx < p.kbox; ++bx) {
           const uint32_t xa = xa0 + (uint32_t)bx * 16384u;
           const uint32_t wa = xa0 + xbytes + (uint32_t)bx * p.w_bytes;
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const uint64_t adesc = ptx::smem_desc_sw128(xa + k * 32, 1024, 0);
+            const uint64_t adesc = dbase + (uint64_t)((xa + k * 32) >> 4);
             for (int part = 0; part < nparts; ++part) {
-              const uint64_t bdesc = ptx::smem_desc_sw128(wa + (uint32_t)part * npart * 128u + k * 32, 1024, 0);
-              ptx::umma_bf16(tmem_base + (uint32_t)part * npart, adesc, bdesc, idesc, (it > 0 || bx > 0 || k > 0) ? 1u : 0u);
+              const uint64_t bdesc = dbase + (uint64_t)((wa + (uint32_t)part * npart * 128u + k * 32) >> 4);
+              ptx::umma_bf16_w(tb + (uint32_t)part * npart, adesc, bdesc, idesc, (it > 0 || bx > 0 || k > 0) ? 1u : 0u);
             }
           }
         }
-        ptx::umma_commit(&empty[s]);
-        if (it < 8) dbg_stamp(p.dbg, blockIdx.x, 10 + it * 3);
+        ptx::umma_commit_w(&empty[s]);
+        if (lane == 0 && it < 8) dbg_stamp(p.dbg, blockIdx.x, 10 + it * 3);
       }
-      ptx::umma_commit(tmem_full);
-      dbg_stamp(p.dbg, blockIdx.x, 4);
+      ptx::umma_commit_w(tmem_full);
+      if (lane == 0) dbg_stamp(p.dbg, blockIdx.x, 4);
     }
   } else {
     // ---- epilogue: thread <-> token row (TMEM lane); pick the columns of the token's modality
@@ -1125,7 +1130,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
   int* or_slot = reinterpret_cast<int*>(tmem_slot + 1);
   uint8_t* meta_s = reinterpret_cast<uint8_t*>(or_slot + 1);  // [128]
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = ptx::uniform_warp_idx(), lane = threadIdx.x & 31;
   const int tile = blockIdx.x / p.nsplit, split = blockIdx.x % p.nsplit;
   const int t0 = tile * 128;
   const int nt = min(128, p.T - t0);
@@ -1158,57 +1163,61 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer: y0 tiles, as far ahead as the ring allows
-    if (lane == 0) {
+    // ================= TMA producer: y0 tiles, as far ahead as the ring allows (whole warp, one elected lane issues)
+    {
+      const uint32_t yt_a = ptx::uniform_u32(ptx::smem_u32(ytiles));
       for (int j = 0; j < nch; ++j) {
         const int s = j % p.ystages;
         const uint32_t ph = (uint32_t)(j / p.ystages) & 1u;
         ptx::mbar_wait_or_trap(&y_empty[s], ph ^ 1u, __LINE__);
-        uint8_t* yt = ytiles + (size_t)s * 32768;
+        const uint32_t yt = yt_a + (uint32_t)s * 32768u;
         if (p.delta) {                                           // write-only output: the free slot is all the workers need
-          ptx::mbar_arrive(&y_full[s]);
-          ptx::prog_mark(0, j + 1);
+          ptx::mbar_arrive_w(&y_full[s]);
+          if (lane == 0) ptx::prog_mark(0, j + 1);
           continue;
         }
-        ptx::mbar_arrive_expect_tx(&y_full[s], 32768u);
+        ptx::mbar_arrive_expect_tx_w(&y_full[s], 32768u);
         const int col = chunk_of(j) * 128;
-        ptx::tma_load_2d(yt, &tm_y0, &y_full[s], col, t0, ptx::kEvictFirst);
-        ptx::tma_load_2d(yt + 16384, &tm_y0, &y_full[s], col + 64, t0, ptx::kEvictFirst);
-        ptx::prog_mark(0, j + 1);
+        ptx::tma_load_2d_w(yt, &tm_y0, &y_full[s], col, t0, ptx::kEvictFirst);
+        ptx::tma_load_2d_w(yt + 16384u, &tm_y0, &y_full[s], col + 64, t0, ptx::kEvictFirst);
+        if (lane == 0) ptx::prog_mark(0, j + 1);
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer
-    if (lane == 0) {
+    // ================= MMA issuer (whole warp, one elected lane issues)
+    {
+      const uint32_t tb = ptx::uniform_u32(tmem_base);
       const uint32_t idesc = ptx::idesc_bf16(128, 128, 0, 0);
-      const uint32_t ga = ptx::smem_u32(gtile);
+      const uint32_t ga = ptx::uniform_u32(ptx::smem_u32(gtile));
+      const uint32_t bt_a = ptx::uniform_u32(ptx::smem_u32(btiles));
+      const uint64_t dbase = ptx::smem_desc_sw128(0, 1024, 0);
       ptx::mbar_wait_or_trap(g_full, 0, __LINE__);
       for (int j = 0; j < nch; ++j) {
         // chunk j belongs to worker group (j & 1); each group rotates over two accumulator / B buffers
         const int i = (j & 1) * 2 + ((j >> 1) & (p.bpg - 1));
         const uint32_t ph = (uint32_t)((j >> 1) / p.bpg) & 1u;
         ptx::mbar_wait_or_trap(&b_full[i], ph, __LINE__);
-        if (j < 6) dbg_stamp(p.dbg, blockIdx.x, 32 + j * 3);
+        if (lane == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 32 + j * 3);
         ptx::mbar_wait_or_trap(&t_empty[i], ph ^ 1u, __LINE__);
-        if (j < 6) dbg_stamp(p.dbg, blockIdx.x, 33 + j * 3);
+        if (lane == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 33 + j * 3);
         ptx::tc_fence_after_sync();
-        const uint32_t ba = ptx::smem_u32(btiles + (size_t)((j & 1) * p.bpg + ((j >> 1) & (p.bpg - 1))) * kblocks * 16384);
+        const uint32_t ba = bt_a + (uint32_t)((j & 1) * p.bpg + ((j >> 1) & (p.bpg - 1))) * (uint32_t)kblocks * 16384u;
         int kdone = 0;
         for (int kb = 0; kb < kblocks; ++kb) {
           const int ksteps = min(4, (p.rk - kb * 64) / 16);
           for (int k = 0; k < ksteps; ++k, ++kdone) {
-            const uint64_t adesc = ptx::smem_desc_sw128(ga + kb * 16384 + k * 32, 1024, 0);
-            const uint64_t bdesc = ptx::smem_desc_sw128(ba + kb * 16384 + k * 32, 1024, 0);
-            ptx::umma_bf16(tmem_base + (uint32_t)i * 128u, adesc, bdesc, idesc, kdone > 0 ? 1u : 0u);
+            const uint64_t adesc = dbase + (uint64_t)((ga + kb * 16384 + k * 32) >> 4);
+            const uint64_t bdesc = dbase + (uint64_t)((ba + kb * 16384 + k * 32) >> 4);
+            ptx::umma_bf16_w(tb + (uint32_t)i * 128u, adesc, bdesc, idesc, kdone > 0 ? 1u : 0u);
           }
         }
-        ptx::umma_commit(&t_full[i]);
-        ptx::prog_mark(1, j + 1);
-        if (j < 6) dbg_stamp(p.dbg, blockIdx.x, 34 + j * 3);
+        ptx::umma_commit_w(&t_full[i]);
+        if (lane == 0) { ptx::prog_mark(1, j + 1); if (j < 6) dbg_stamp(p.dbg, blockIdx.x, 34 + j * 3); }
       }
     }
   } else if (warp == 10) {
-    // ================= TMA store issuer: tile j leaves as soon as the workers have updated it
+    // ================= TMA store issuer: tile j leaves as soon as the workers have updated it.  One lane: the bulk
+    // async-group (commit / wait_group) is per THREAD state
     if (lane == 0) {
       for (int j = 0; j < nch; ++j) {
         const int s = j % p.ystages;
@@ -1515,27 +1524,87 @@ static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaSt
 //   MMA1  dG[128 tok, rk]   += dY[128 tok, 128 cols] . B[128 cols, rk]          (dY K-major)
 //   MMA2  dB[128 cols, rk]   = dY^T[128 cols, 128 tok] . (post g)[128 tok, rk]  (dY MN-major, the
 //         same shared-memory tile read through a transposing descriptor; g split hi+lo bf16)
-// dB leaves through fp32 vector reductions, dG through a (2-way, hence order-independent)
-// reduction into the zeroed dG buffer; the attention backward runs afterwards in k_attn_bwd.
+// dB leaves through fp32 vector reductions; dG as plain stores into per-CTA PARTIAL buffers that the consumer
+// (k_attn_pack) sums.
+//
+// Persistent, stream-K style (round 2): the work is the list of U = ntiles x P (tile, 128-column pair) units in
+// tile-major order; CTA c of a one-CTA-per-SM grid of G owns the contiguous unit range
+// [floor(c U / G), floor((c+1) U / G)), so every SM gets the same number of bytes whatever the shape (256 tiles on
+// 148 SMs used to be two waves of one CTA per SM, the second 27 % empty) and the TMA ring never drains at a tile
+// boundary: the producer simply walks on into the next tile.  A range covers the tail of one tile, whole tiles and
+// the head of another; each (tile, CTA) SEGMENT has its own dG accumulator (two in TMEM, so the next segment's MMA1
+// starts while the workers drain the last one) and writes partial number (c - first CTA of the tile).  The G^T
+// operand of the next segment is fetched into registers while the current one streams and is written to shared
+// memory once the current segment's MMAs have retired.
 struct DgradTcParams {
   int T, d_out, r, rk;
-  int csplit, pairs;               // pairs = d_out / 128 column pairs, split across csplit CTAs
+  int pairs;                       // P = d_out / 128 column pairs per token tile
+  int grid;                        // G persistent CTAs
+  long long units;                 // U = ntiles * P
   int stages;
-  uint32_t stage_bytes, bt_bytes;  // stage = [box0 16K][box1 16K][Bt kb0][Bt kb1]
+  uint32_t stage_bytes, bt_bytes;  // stage = [pair 0: box0 16K, box1 16K]..[pair W-1][Bt blocks: 2 per pair]
   int dbg;
-  int dg_mode;                     // 0 plain store (csplit == 1), 1 one partial buffer per split, 2 reduce into zeroed dG
+  int dg_mode;                     // 0: plain stores into partial buffer (c - first CTA of the tile); 2: reduce into zeroed dG0
   int nbuf;                        // dB accumulator sets in TMEM (2, or 1 when rk = 128)
-  int rot;                         // rotate the pair order per CTA (see rot_enabled)
+  int ndg;                         // dG accumulators in TMEM (2, or 1 when TMEM is short)
   int wide;                        // 128-column pairs per pipeline stage (2 when TMEM / smem allow: halves the
                                    // per-stage hand-offs of the single MMA-issuing thread)
-  uint32_t tmem_cols, d2_col;      // D2 buffers start at column d2_col
+  uint32_t tmem_cols, dg_cols, d2_col;   // dG buffers at [0, ndg*dg_cols), D2 sets from d2_col
+  long long part_stride;           // floats between two dG partial buffers
+};
+
+// Which CTAs of the persistent k_dgrad_tc grid touch token tile `tile` (see the kernel): shared with the consumer
+// of the partial dG buffers.  start(c) = floor(c U / G); the CTA of unit u is floor(((u + 1) G - 1) / U).
+struct DgParts {
+  long long U;
+  long long stride;                // floats between partial buffers
+  int P, G;                        // G == 0: one complete buffer (no partials)
+};
+__host__ __device__ __forceinline__ int dg_cta_of_unit(long long U, int G, long long u) {
+  return (int)(((u + 1) * (long long)G - 1) / U);
+}
+__host__ __device__ __forceinline__ int dg_nparts(const DgParts& q, int tile) {
+  if (q.G == 0) return 1;
+  const long long u0 = (long long)tile * q.P;
+  return dg_cta_of_unit(q.U, q.G, u0 + q.P - 1) - dg_cta_of_unit(q.U, q.G, u0) + 1;
+}
+
+static int dgrad_grid(int T, int d_out, int num_sms) {
+  const long long U = (long long)((T + 127) / 128) * (d_out / 128);
+  return (int)std::min<long long>(num_sms, std::max<long long>(U, 1));
+}
+// upper bound on dg_nparts over all tiles (workspace sizing)
+int tc_dgrad_parts_max(int T, int d_out, int num_sms) {
+  const int P = d_out / 128, ntiles = (T + 127) / 128;
+  if (P <= 0) return 2;
+  DgParts q{(long long)ntiles * P, 0, P, dgrad_grid(T, d_out, num_sms)};
+  int mx = 2;
+  for (int t = 0; t < ntiles; ++t) mx = std::max(mx, dg_nparts(q, t));
+  return mx;
+}
+
+// the (tile, pair range) segments of a CTA's unit range, in order
+struct DgSegIter {
+  long long u, u_end;
+  int P;
+  int tile, pb, pe;                // current segment: pairs [pb, pe) of `tile`
+  __device__ __forceinline__ bool next() {
+    if (u >= u_end) return false;
+    tile = (int)(u / P);
+    const long long t0u = (long long)tile * P;
+    pb = (int)(u - t0u);
+    const long long e = (t0u + P < u_end) ? t0u + P : u_end;
+    pe = (int)(e - t0u);
+    u = e;
+    return true;
+  }
 };
 
 __global__ void __launch_bounds__(kTcThreads)
 k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_bt, DevDesc d,
            DgradTcParams p, const uint8_t* __restrict__ tokmeta,
-           const float* __restrict__ g_stash, float* __restrict__ dG0, float* __restrict__ dG1,
-           float* __restrict__ dB) {
+           const float* __restrict__ g_stash, float* __restrict__ dG0, float* __restrict__ dB,
+           uint32_t* __restrict__ zero_ptr, int zero_words) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t gt_block = (uint32_t)p.rk * 128u;            // one 64-column K block of B^T (rk rows)
@@ -1543,34 +1612,30 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
   uint8_t* gt = ring + (size_t)p.stages * p.stage_bytes;      // [2 kblocks][2 rk x 128 B]: rows 0..rk-1 hi, rk..2rk-1 lo
   uint64_t* bars = reinterpret_cast<uint64_t*>(gt + 2 * g2_block);
   uint64_t* full = bars;                       // TMA landed            [stages]
-  uint64_t* wfull = full + p.stages;           // B^T block staged      [stages]
-  uint64_t* empty = wfull + p.stages;          // MMAs done with stage  [stages]
+  uint64_t* empty = full + p.stages;           // MMAs done with stage  [stages]
   uint64_t* d2_full = empty + p.stages;        // [2]
   uint64_t* d2_empty = d2_full + 2;            // [2]
-  uint64_t* dg_full = d2_empty + 2;            // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dg_full + 1);
+  uint64_t* dg_full = d2_empty + 2;            // [2] dG accumulator of a segment final
+  uint64_t* dg_empty = dg_full + 2;            // [2] ... read out by the workers
+  uint64_t* gt_full = dg_empty + 2;            // [1] G^T operand of the next segment staged
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gt_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x / p.csplit, split = blockIdx.x % p.csplit;
-  const int t0 = tile * 128;
-  const int nt = min(128, p.T - t0);
-  const int p_beg = (int)((long long)split * p.pairs / p.csplit);
-  const int p_end = (int)((long long)(split + 1) * p.pairs / p.csplit);
-  const int np = p_end - p_beg;
-  const int prot = p.rot ? (int)(((unsigned)tile * 7u + (unsigned)split * 3u) % (unsigned)np) : 0;
-  auto pair_of = [&](int i) { return p_beg + rot_index(i, prot, np); };   // i-th pair this CTA processes
+  const int warp = ptx::uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int cta = blockIdx.x;
+  const long long u_beg = (long long)cta * p.units / p.grid;
+  const long long u_end = (long long)(cta + 1) * p.units / p.grid;
   const int W = p.wide;
-  const int ns = (np + W - 1) / W;                             // pipeline stages of this CTA
   const uint32_t dy_bytes = 32768u * (uint32_t)W;             // dY part of a stage; the B^T blocks follow
   const int r = p.r;
   if (threadIdx.x == 0) { dbg_stamp_g(p.dbg, blockIdx.x, 108); dbg_stamp(p.dbg, blockIdx.x, 0); }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) {
-      ptx::mbar_init(&full[s], 1); ptx::mbar_init(&wfull[s], 1); ptx::mbar_init(&empty[s], 1);
+    for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&d2_full[i], 1); ptx::mbar_init(&d2_empty[i], kWorkerWarps);
+      ptx::mbar_init(&dg_full[i], 1); ptx::mbar_init(&dg_empty[i], kWorkerWarps);
     }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&d2_full[i], 1); ptx::mbar_init(&d2_empty[i], kWorkerWarps); }
-    ptx::mbar_init(dg_full, 1);
+    ptx::mbar_init(gt_full, 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tm_dy); ptx::prefetch_tmap(&tm_bt);
   }
@@ -1585,186 +1650,283 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
   if (threadIdx.x == 0) ptx::pdl_trigger();
 
   if (warp == 0) {
-    if (lane == 0) {
+    // ---- TMA producer (whole warp, one elected lane issues)
+    {
       // dy is older than this call's first kernel (k_bwd_prep waited for it): its tiles stream in
       // right away; the B^T blocks are written by k_bwd_prep, so they follow the dependency wait
-      // stage j holds the pairs j W .. j W + nq - 1 (nq < W only in an odd tail)
-      auto load_dy = [&](int j, uint64_t* bar, uint8_t* st) {
-        const int nq = min(W, np - j * W);
-        ptx::mbar_arrive_expect_tx(bar, (uint32_t)nq * (32768u + p.bt_bytes));
+      const uint32_t ring_a = ptx::uniform_u32(ptx::smem_u32(ring));
+      auto load_dy = [&](int tile, int q0, int nq, uint64_t* bar, uint32_t st) {
+        ptx::mbar_arrive_expect_tx_w(bar, (uint32_t)nq * (32768u + p.bt_bytes));
         for (int q = 0; q < nq; ++q) {
-          const int col = pair_of(j * W + q) * 128;
-          ptx::tma_load_2d(st + (size_t)q * 32768, &tm_dy, bar, col, t0, ptx::kEvictFirst);
-          ptx::tma_load_2d(st + (size_t)q * 32768 + 16384, &tm_dy, bar, col + 64, t0, ptx::kEvictFirst);
+          const int col = (q0 + q) * 128;
+          ptx::tma_load_2d_w(st + (uint32_t)q * 32768u, &tm_dy, bar, col, tile * 128, ptx::kEvictFirst);
+          ptx::tma_load_2d_w(st + (uint32_t)q * 32768u + 16384u, &tm_dy, bar, col + 64, tile * 128, ptx::kEvictFirst);
         }
       };
-      auto load_bt = [&](int j, uint64_t* bar, uint8_t* st) {   // B^T blocks [rk rows x 64 cols] (L2-resident)
-        const int nq = min(W, np - j * W);
+      auto load_bt = [&](int q0, int nq, uint64_t* bar, uint32_t st) {   // B^T blocks [rk rows x 64 cols] (L2-resident)
         for (int q = 0; q < nq; ++q) {
-          const int col = pair_of(j * W + q) * 128;
-          ptx::tma_load_2d(st + dy_bytes + (size_t)(2 * q) * gt_block, &tm_bt, bar, col, 0, ptx::kEvictLast);
-          ptx::tma_load_2d(st + dy_bytes + (size_t)(2 * q + 1) * gt_block, &tm_bt, bar, col + 64, 0, ptx::kEvictLast);
+          const int col = (q0 + q) * 128;
+          ptx::tma_load_2d_w(st + dy_bytes + (uint32_t)(2 * q) * gt_block, &tm_bt, bar, col, 0, ptx::kEvictLast);
+          ptx::tma_load_2d_w(st + dy_bytes + (uint32_t)(2 * q + 1) * gt_block, &tm_bt, bar, col + 64, 0, ptx::kEvictLast);
         }
       };
-      const int npre = min(ns, p.stages);
-      for (int j = 0; j < npre; ++j) load_dy(j, &full[j], ring + (size_t)j * p.stage_bytes);
+      // first fill of the ring: dY before the dependency wait, the B^T blocks of the same stages after it
+      {
+        DgSegIter it{u_beg, u_end, p.pairs, 0, 0, 0};
+        int j = 0;
+        while (j < p.stages && it.next())
+          for (int q0 = it.pb; q0 < it.pe && j < p.stages; q0 += W, ++j)
+            load_dy(it.tile, q0, min(W, it.pe - q0), &full[j], ring_a + (uint32_t)j * p.stage_bytes);
+      }
       ptx::pdl_wait();
-      for (int j = 0; j < npre; ++j) load_bt(j, &full[j], ring + (size_t)j * p.stage_bytes);
-      for (int j = npre; j < ns; ++j) {
-        const int s = j % p.stages;
-        const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
-        ptx::mbar_wait_or_trap(&empty[s], ph ^ 1u, __LINE__);
-        uint8_t* st = ring + (size_t)s * p.stage_bytes;
-        load_dy(j, &full[s], st);
-        load_bt(j, &full[s], st);
+      DgSegIter it{u_beg, u_end, p.pairs, 0, 0, 0};
+      int j = 0;
+      while (it.next()) {
+        for (int q0 = it.pb; q0 < it.pe; q0 += W, ++j) {
+          const int nq = min(W, it.pe - q0);
+          const int s = j % p.stages;
+          const uint32_t st = ring_a + (uint32_t)s * p.stage_bytes;
+          if (j >= p.stages) {
+            ptx::mbar_wait_or_trap(&empty[s], (((uint32_t)(j / p.stages)) & 1u) ^ 1u, __LINE__);
+            load_dy(it.tile, q0, nq, &full[s], st);
+          }
+          load_bt(q0, nq, &full[s], st);
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // ---- MMA issuer: the WHOLE warp runs this loop on warp-uniform values, one elected lane issues (see moka_ptx.cuh)
+    {
+      const uint32_t tb = ptx::uniform_u32(tmem_base);
       const uint32_t idesc1 = ptx::idesc_bf16(128, (uint32_t)p.rk, 0, 0);     // dG: A K-major, B K-major
       // dB: A MN-major (transposed view of the dY tile); hi and lo halves of g stacked along N, so one
       // pass over the tile yields both products (the epilogue adds them)
       const uint32_t idesc2 = ptx::idesc_bf16(128, 2u * (uint32_t)p.rk, 1, 0);
-      const uint32_t gta = ptx::smem_u32(gt);
+      const uint32_t gta = ptx::uniform_u32(ptx::smem_u32(gt));
+      const uint32_t ring_a = ptx::uniform_u32(ptx::smem_u32(ring));
       // descriptors differ only in their 14-bit start-address field: build once, add offsets (>> 4)
       const uint64_t a1_base = ptx::smem_desc_sw128(0, 1024, 0);
       const uint64_t a2_base = ptx::smem_desc_sw128(0, 1024, 16384);
-      uint64_t g_desc[8];
+      const uint64_t g_base = a1_base + (uint64_t)(gta >> 4);
+      const uint32_t g2b = g2_block >> 4, gtb = gt_block >> 4;
+      DgSegIter it{u_beg, u_end, p.pairs, 0, 0, 0};
+      int j = 0, seg = 0;
+      while (it.next()) {
+        const int dgb = seg % p.ndg;
+        const uint32_t dgk = (uint32_t)(seg / p.ndg);
+        const uint32_t dg_acc = tb + (uint32_t)dgb * p.dg_cols;
+        ptx::mbar_wait_or_trap(&dg_empty[dgb], (dgk & 1u) ^ 1u, __LINE__);     // accumulator read out (two segments ago)
+        bool gt_ready = false;
+        for (int q0 = it.pb; q0 < it.pe; q0 += W, ++j) {
+          const int nq = min(W, it.pe - q0);
+          const int s = j % p.stages;
+          const int i = j % p.nbuf;
+          const uint32_t k2 = (uint32_t)(j / p.nbuf);
+          ptx::mbar_wait_or_trap(&full[s], ((uint32_t)(j / p.stages)) & 1u, __LINE__);
+          if (lane == 0) { if (j == 0) dbg_stamp(p.dbg, blockIdx.x, 3); if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 8 + j * 3); }
+          ptx::mbar_wait_or_trap(&d2_empty[i], (k2 & 1u) ^ 1u, __LINE__);
+          if (lane == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 3);
+          ptx::tc_fence_after_sync();
+          if (lane == 0 && j == 2) dbg_stamp(p.dbg, blockIdx.x, 48);
+          const uint32_t sa0 = ring_a + (uint32_t)s * p.stage_bytes;
+          if (!gt_ready) {
+            // first stage of a segment: the dG products do not need the G^T operand - issue them while the workers
+            // are still writing it, then wait for it
+            for (int q = 0; q < nq; ++q) {
+              const uint32_t sa = sa0 + (uint32_t)q * 32768u;
+              const uint32_t bta = sa0 + dy_bytes + (uint32_t)(2 * q) * gt_block;
+              const uint64_t a1 = a1_base + (uint64_t)(sa >> 4);
+              const uint64_t b1 = a1_base + (uint64_t)(bta >> 4);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        g_desc[k] = ptx::smem_desc_sw128(gta + (uint32_t)(k >> 2) * g2_block + (k & 3) * 32, 1024, 0);
-      ptx::mbar_wait_or_trap(&wfull[0], 0, __LINE__);
-      dbg_stamp(p.dbg, blockIdx.x, 2);
-      for (int j = 0; j < ns; ++j) {
-        const int s = j % p.stages;
-        const uint32_t ph = (uint32_t)(j / p.stages) & 1u;
-        const int i = p.nbuf == 2 ? (j & 1) : 0;
-        const uint32_t ph2 = (uint32_t)(p.nbuf == 2 ? (j >> 1) : j) & 1u;
-        const int nq = min(W, np - j * W);
-        ptx::mbar_wait_or_trap(&full[s], ph, __LINE__);
-        if (j == 0) dbg_stamp(p.dbg, blockIdx.x, 3);
-        if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 8 + j * 3);
-        ptx::mbar_wait_or_trap(&d2_empty[i], ph2 ^ 1u, __LINE__);
-        if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 3);
-        ptx::tc_fence_after_sync();
-        const uint32_t sa0 = ptx::smem_u32(ring + (size_t)s * p.stage_bytes);
-        for (int q = 0; q < nq; ++q) {
-          const uint32_t sa = sa0 + (uint32_t)q * 32768u;
-          const uint32_t bta = sa0 + dy_bytes + (uint32_t)(2 * q) * gt_block;
-          // MMA1: K = 128 columns of this pair (two boxes, four 16-wide steps each)
-          const uint64_t a1 = a1_base + (uint64_t)(sa >> 4);
-          const uint64_t b1 = a1_base + (uint64_t)(bta >> 4);
-          const uint64_t a2 = a2_base + (uint64_t)(sa >> 4);
-          // MMA2: M = 128 columns (two 64-wide atoms 16 KB apart), K = 128 tokens in 8 steps of 16
-          const uint32_t d2 = tmem_base + p.d2_col + (uint32_t)(i * W + q) * 2u * (uint32_t)p.rk;
+              for (int k = 0; k < 8; ++k) {
+                const int box = k >> 2, kk = k & 3;
+                if (!(p.dbg & 4))
+                ptx::umma_bf16_w(dg_acc, a1 + (uint64_t)((box * 16384 + kk * 32) >> 4),
+                                 b1 + (uint64_t)(box * gtb + ((kk * 32) >> 4)), idesc1, (q > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            ptx::mbar_wait_or_trap(gt_full, (uint32_t)seg & 1u, __LINE__);
+            if (lane == 0 && seg == 0) dbg_stamp(p.dbg, blockIdx.x, 2);
+            ptx::tc_fence_after_sync();
+            gt_ready = true;
+            for (int q = 0; q < nq; ++q) {
+              const uint32_t sa = sa0 + (uint32_t)q * 32768u;
+              const uint64_t a2 = a2_base + (uint64_t)(sa >> 4);
+              const uint32_t d2 = tb + p.d2_col + (uint32_t)(i * W + q) * 2u * (uint32_t)p.rk;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int box = k >> 2, kk = k & 3;
-            if (!(p.dbg & 4))
-            ptx::umma_bf16(tmem_base, a1 + (uint64_t)((box * 16384 + kk * 32) >> 4),
-                           b1 + (uint64_t)((box * gt_block + kk * 32) >> 4), idesc1, (j > 0 || q > 0 || k > 0) ? 1u : 0u);
-            if (!(p.dbg & 8))
-            ptx::umma_bf16(d2, a2 + (uint64_t)((k * 2048) >> 4), g_desc[k], idesc2, k > 0 ? 1u : 0u);
+              for (int k = 0; k < 8; ++k)
+                if (!(p.dbg & 8))
+                ptx::umma_bf16_w(d2, a2 + (uint64_t)((k * 2048) >> 4), g_base + (uint64_t)((k >> 2) * g2b + (((k & 3) * 32) >> 4)),
+                                 idesc2, k > 0 ? 1u : 0u);
+            }
+          } else {
+            for (int q = 0; q < nq; ++q) {
+              const uint32_t sa = sa0 + (uint32_t)q * 32768u;
+              const uint32_t bta = sa0 + dy_bytes + (uint32_t)(2 * q) * gt_block;
+              // MMA1: K = 128 columns of this pair (two boxes, four 16-wide steps each)
+              const uint64_t a1 = a1_base + (uint64_t)(sa >> 4);
+              const uint64_t b1 = a1_base + (uint64_t)(bta >> 4);
+              const uint64_t a2 = a2_base + (uint64_t)(sa >> 4);
+              // MMA2: M = 128 columns (two 64-wide atoms 16 KB apart), K = 128 tokens in 8 steps of 16
+              const uint32_t d2 = tb + p.d2_col + (uint32_t)(i * W + q) * 2u * (uint32_t)p.rk;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int box = k >> 2, kk = k & 3;
+                if (!(p.dbg & 4))
+                ptx::umma_bf16_w(dg_acc, a1 + (uint64_t)((box * 16384 + kk * 32) >> 4),
+                                 b1 + (uint64_t)(box * gtb + ((kk * 32) >> 4)), idesc1, 1u);
+                if (!(p.dbg & 8))
+                ptx::umma_bf16_w(d2, a2 + (uint64_t)((k * 2048) >> 4), g_base + (uint64_t)((k >> 2) * g2b + (((k & 3) * 32) >> 4)),
+                                 idesc2, k > 0 ? 1u : 0u);
+              }
+            }
           }
+          if (lane == 0 && j == 2) dbg_stamp(p.dbg, blockIdx.x, 49);
+          ptx::umma_commit_w(&empty[s]);
+          ptx::umma_commit_w(&d2_full[i]);
+          if (lane == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 10 + j * 3);
         }
-        ptx::umma_commit(&empty[s]);
-        ptx::umma_commit(&d2_full[i]);
-        if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 10 + j * 3);
+        ptx::umma_commit_w(&dg_full[dgb]);
+        ++seg;
       }
-      ptx::umma_commit(dg_full);
-      dbg_stamp(p.dbg, blockIdx.x, 4);
+      if (lane == 0) dbg_stamp(p.dbg, blockIdx.x, 4);
     }
   } else {
     const int wt = threadIdx.x - 64;
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    // G^T operand (post_m * g as hi + lo bf16): rows = rank index, K = tokens
-    {
-      const int t = t0 + row;
-      const uint8_t mb = (row < nt) ? tokmeta[t] : (uint8_t)0;  // issued together with the first g loads below
-      const uint32_t kblk = (uint32_t)(row >> 6) * g2_block, ch = (uint32_t)((row & 63) >> 3), in = (row & 7) * 2;
+    const int q4 = warp & 3;
+    const int row = q4 * 32 + lane;
+    // G^T operand (post_m * g as hi + lo bf16): rows = rank index, K = tokens.  `gq` = 16 rank values of this
+    // thread's token row starting at j0 (fp32, already scaled by post).
+    const uint32_t kblk = (uint32_t)(row >> 6) * g2_block, ch = (uint32_t)((row & 63) >> 3), in = (row & 7) * 2;
+    auto load_g16 = [&](int tile, int j0, float4 (&gq)[4], uint8_t& mb) {
+      const int t = tile * 128 + row;
+      const bool live = t < p.T;
+      mb = live ? tokmeta[t] : (uint8_t)0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        gq[u] = (live && j0 + 4 * u < r) ? *reinterpret_cast<const float4*>(g_stash + (size_t)t * r + j0 + 4 * u)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    auto store_g16 = [&](int j0, const float4 (&gq)[4], uint8_t mb) {
+      const int code = mb & MOKA_MOD_MASK;
+      const float ps = code ? d.post[code] : 0.f;
+      const float gvals[16] = {gq[0].x, gq[0].y, gq[0].z, gq[0].w, gq[1].x, gq[1].y, gq[1].z, gq[1].w,
+                               gq[2].x, gq[2].y, gq[2].z, gq[2].w, gq[3].x, gq[3].y, gq[3].z, gq[3].w};
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int jj = j0 + u;
+        const float gv = gvals[u] * ps;
+        const __nv_bfloat16 hi = __float2bfloat16_rn(gv);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(gv - __bfloat162float(hi));
+        *reinterpret_cast<__nv_bfloat16*>(gt + kblk + ptx::sw128_offset((uint32_t)jj, ch) + in) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(gt + kblk + ptx::sw128_offset((uint32_t)(p.rk + jj), ch) + in) = lo;
+      }
+    };
+    auto stage_gt_direct = [&](int tile) {
       for (int j0 = 0; j0 < p.rk; j0 += 16) {
         float4 gq[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          gq[u] = (row < nt && j0 + 4 * u < r) ? *reinterpret_cast<const float4*>(g_stash + (size_t)t * r + j0 + 4 * u)
-                                               : make_float4(0.f, 0.f, 0.f, 0.f);
-        const int code = mb & MOKA_MOD_MASK;
-        const float ps = code ? d.post[code] : 0.f;
-        const float gvals[16] = {gq[0].x, gq[0].y, gq[0].z, gq[0].w, gq[1].x, gq[1].y, gq[1].z, gq[1].w,
-                                 gq[2].x, gq[2].y, gq[2].z, gq[2].w, gq[3].x, gq[3].y, gq[3].z, gq[3].w};
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int jj = j0 + u;
-          const float gv = gvals[u] * ps;
-          const __nv_bfloat16 hi = __float2bfloat16_rn(gv);
-          const __nv_bfloat16 lo = __float2bfloat16_rn(gv - __bfloat162float(hi));
-          *reinterpret_cast<__nv_bfloat16*>(gt + kblk + ptx::sw128_offset((uint32_t)jj, ch) + in) = hi;
-          *reinterpret_cast<__nv_bfloat16*>(gt + kblk + ptx::sw128_offset((uint32_t)(p.rk + jj), ch) + in) = lo;
-        }
+        uint8_t mb;
+        load_g16(tile, j0, gq, mb);
+        store_g16(j0, gq, mb);
       }
-    }
-    ptx::fence_proxy_async_smem();
-    named_sync(2, kWorkers);
-    if (wt == 0) ptx::mbar_arrive(&wfull[0]);                  // G^T staged: the MMA thread may start
-    // dB / dG are written below: everything older than k_bwd_prep (zero-fills, earlier calls that
-    // shared the workspace) must be complete
+    };
+    auto publish_gt = [&]() {
+      ptx::fence_proxy_async_smem();
+      named_sync(2, kWorkers);
+      if (wt == 0) ptx::mbar_arrive(gt_full);
+    };
+    DgSegIter it{u_beg, u_end, p.pairs, 0, 0, 0};
+    bool have = it.next();
+    if (have) { stage_gt_direct(it.tile); publish_gt(); }
+    // dB / dG are written below: everything older than k_bwd_prep (earlier calls that shared the workspace)
+    // must be complete
     ptx::pdl_wait();
+    // zero-fill of the small reduction targets of the NEXT kernel (per-sample dK, arrival counters of
+    // k_attn_pack): that kernel's dependency wait covers this whole grid
+    for (int i2 = cta * kWorkers + wt; i2 < zero_words; i2 += p.grid * kWorkers) zero_ptr[i2] = 0u;
 
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int j = 0; j < ns; ++j) {
-      const int i = p.nbuf == 2 ? (j & 1) : 0;
-      const uint32_t ph2 = (uint32_t)(p.nbuf == 2 ? (j >> 1) : j) & 1u;
-      const int nq = min(W, np - j * W);
-      ptx::mbar_wait_or_trap(&d2_full[i], ph2, __LINE__);
-      if (wt == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 32 + j * 2);
-      ptx::tc_fence_after_sync();
-      for (int q = 0; q < nq; ++q) {
-        const int col = pair_of(j * W + q) * 128 + row;       // TMEM lane <-> output column
-        float* dst = dB + (size_t)col * r;
-        const uint32_t acc = lane_base + p.d2_col + (uint32_t)((i * W + q) * 2 * p.rk);
-        for (int c8 = 0; c8 < r; c8 += 8) {                     // r % 8 == 0 on this path
-          float v[8], w[8];
-          ptx::tmem_ld8(acc + (uint32_t)c8, v);                 // hi product
-          ptx::tmem_ld8(acc + (uint32_t)(p.rk + c8), w);        // lo product
-          ptx::tmem_ld_wait();
-          if (p.dbg & 2) continue;                              // timing experiment: no dB reductions
-          red_add_v4_f32(dst + c8, v[0] + w[0], v[1] + w[1], v[2] + w[2], v[3] + w[3]);
-          red_add_v4_f32(dst + c8 + 4, v[4] + w[4], v[5] + w[5], v[6] + w[6], v[7] + w[7]);
-        }
-      }
-      ptx::tc_fence_before_sync();
-      warp_arrive(&d2_empty[i]);
-      if (wt == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 33 + j * 2);
-    }
-    // dG partial of this CTA
-    ptx::mbar_wait_or_trap(dg_full, 0, __LINE__);
-    if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 5);
-    ptx::tc_fence_after_sync();
-    {
-      // tcgen05.ld is warp-collective: every lane issues it, only live token rows store
-      const int t = t0 + row;
-      const int code = (row < nt) ? (tokmeta[t] & MOKA_MOD_MASK) : 0;
-      const float ps = code ? d.post[code] : 0.f;
-      for (int c8 = 0; c8 < p.rk; c8 += 8) {
-        float v[8];
-        ptx::tmem_ld8(lane_base + (uint32_t)c8, v);
-        ptx::tmem_ld_wait();
-        if (c8 < r && row < nt) {
-          if (p.dg_mode == 2) {
-            if (code) {
-              float* dst = dG0 + (size_t)t * r + c8;
-              red_add_v4_f32(dst, v[0] * ps, v[1] * ps, v[2] * ps, v[3] * ps);
-              red_add_v4_f32(dst + 4, v[4] * ps, v[5] * ps, v[6] * ps, v[7] * ps);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
+    const bool preload = (p.rk == 16);                           // next segment's g rows parked in registers
+    int j = 0, seg = 0;
+    while (have) {
+      const int tile = it.tile, pb = it.pb, pe = it.pe;
+      DgSegIter nx = it;
+      const bool has_next = nx.next();
+      float4 gqn[4];
+      uint8_t mbn = 0;
+      if (has_next && preload) load_g16(nx.tile, 0, gqn, mbn);
+      for (int q0 = pb; q0 < pe; q0 += W, ++j) {
+        const int nq = min(W, pe - q0);
+        const int i = j % p.nbuf;
+        const uint32_t k2 = (uint32_t)(j / p.nbuf);
+        ptx::mbar_wait_or_trap(&d2_full[i], k2 & 1u, __LINE__);
+        if (wt == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 32 + j * 2);
+        ptx::tc_fence_after_sync();
+        for (int q = 0; q < nq; ++q) {
+          const int col = (q0 + q) * 128 + row;                  // TMEM lane <-> output column
+          float* dst = dB + (size_t)col * r;
+          const uint32_t acc = lane_base + p.d2_col + (uint32_t)((i * W + q) * 2 * p.rk);
+          for (int c8 = 0; c8 < r; c8 += 8) {
+            float v[8], w[8];
+            ptx::tmem_ld8(acc + (uint32_t)c8, v);                 // hi product
+            ptx::tmem_ld8(acc + (uint32_t)(p.rk + c8), w);        // lo product
+            ptx::tmem_ld_wait();
+            if (p.dbg & 2) continue;                              // timing experiment: no dB reductions
+            if (c8 + 8 <= r) {
+              red_add_v4_f32(dst + c8, v[0] + w[0], v[1] + w[1], v[2] + w[2], v[3] + w[3]);
+              red_add_v4_f32(dst + c8 + 4, v[4] + w[4], v[5] + w[5], v[6] + w[6], v[7] + w[7]);
+            } else {                                              // r % 8 == 4: the last half group
+              red_add_v4_f32(dst + c8, v[0] + w[0], v[1] + w[1], v[2] + w[2], v[3] + w[3]);
             }
-          } else {
-            // plain stores (zeros for tokens in no mask): nothing has to be zero-filled beforehand
-            float* dst = (split == 0 ? dG0 : dG1) + (size_t)t * r + c8;
-            *reinterpret_cast<float4*>(dst) = make_float4(v[0] * ps, v[1] * ps, v[2] * ps, v[3] * ps);
-            *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4] * ps, v[5] * ps, v[6] * ps, v[7] * ps);
           }
         }
+        ptx::tc_fence_before_sync();
+        warp_arrive(&d2_empty[i]);
+        if (wt == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 33 + j * 2);
       }
+      // ---- end of the segment: its MMAs must retire before the G^T buffer is rewritten
+      const int dgb = seg % p.ndg;
+      ptx::mbar_wait_or_trap(&dg_full[dgb], ((uint32_t)(seg / p.ndg)) & 1u, __LINE__);
+      if (wt == 0 && seg == 0) dbg_stamp(p.dbg, blockIdx.x, 5);
+      ptx::tc_fence_after_sync();
+      if (has_next) {
+        if (preload) store_g16(0, gqn, mbn); else stage_gt_direct(nx.tile);
+        publish_gt();
+      }
+      {
+        // dG partial of this segment.  tcgen05.ld is warp-collective: every lane issues it, only live rows store
+        const int t = tile * 128 + row;
+        const bool live = t < p.T;
+        const int code = live ? (tokmeta[t] & MOKA_MOD_MASK) : 0;
+        const float ps = code ? d.post[code] : 0.f;
+        const int part = cta - dg_cta_of_unit(p.units, p.grid, (long long)tile * p.pairs);
+        float* dGp = dG0 + (p.dg_mode == 2 ? 0 : (size_t)part * (size_t)p.part_stride);
+        const uint32_t acc = lane_base + (uint32_t)dgb * p.dg_cols;
+        for (int c8 = 0; c8 < p.rk; c8 += 8) {
+          float v[8];
+          ptx::tmem_ld8(acc + (uint32_t)c8, v);
+          ptx::tmem_ld_wait();
+          if (c8 < r && live) {
+            float* dst = dGp + (size_t)t * r + c8;
+            const bool full8 = c8 + 8 <= r;
+            if (p.dg_mode == 2) {
+              if (code) {
+                red_add_v4_f32(dst, v[0] * ps, v[1] * ps, v[2] * ps, v[3] * ps);
+                if (full8) red_add_v4_f32(dst + 4, v[4] * ps, v[5] * ps, v[6] * ps, v[7] * ps);
+              }
+            } else {
+              // plain stores (zeros for tokens in no mask): nothing has to be zero-filled beforehand
+              *reinterpret_cast<float4*>(dst) = make_float4(v[0] * ps, v[1] * ps, v[2] * ps, v[3] * ps);
+              if (full8) *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4] * ps, v[5] * ps, v[6] * ps, v[7] * ps);
+            }
+          }
+        }
+        ptx::tc_fence_before_sync();
+        warp_arrive(&dg_empty[dgb]);
+      }
+      it = nx;
+      have = has_next;
+      ++seg;
     }
   }
   ptx::tc_fence_before_sync();
@@ -1981,15 +2143,14 @@ k_bwd_prep(const __nv_bfloat16* __restrict__ Bw, __nv_bfloat16* __restrict__ Bt,
 static int launch_attn_nopack(const DevDesc& d, const SimtArgs& a, cudaStream_t st);   // k_attn_pack without the packing
 
 // fused = the merged attention-backward + pack kernel follows (partial dG buffers, nothing zero-filled
-// but dK and the counters); otherwise the legacy kernels run on a complete dG in a.dh.
-// Column split of k_dgrad_tc (one dG partial buffer per split); k_attn_pack must agree.
-static int dgrad_csplit(const DevDesc& d, int num_sms) {
-  const int ntiles = (d.T + 127) / 128, pairs = d.d_out / 128;
-  int cs = (ntiles < num_sms && ntiles * 2 <= num_sms + num_sms / 4 && pairs >= 8) ? 2 : 1;
-  static int dg_csplit_env = -1;                   // tuning aid: force the split
-  if (dg_csplit_env < 0) { const char* e = getenv("MOKA_DGRAD_CSPLIT"); dg_csplit_env = e ? atoi(e) : 0; }
-  if ((dg_csplit_env == 1 || dg_csplit_env == 2) && pairs >= 8) cs = dg_csplit_env;
-  return cs;
+// but dK and the counters); otherwise the legacy kernels run on a complete dG in a.dh (reduced into the zeroed buffer).
+static DgParts dgrad_parts(const DevDesc& d, int num_sms, bool fused, long long stride) {
+  DgParts q;
+  q.P = d.d_out / 128;
+  q.U = (long long)((d.T + 127) / 128) * q.P;
+  q.G = fused ? dgrad_grid(d.T, d.d_out, num_sms) : 0;
+  q.stride = stride;
+  return q;
 }
 
 static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaStream_t st, bool fused) {
@@ -1997,39 +2158,38 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   p.T = d.T; p.d_out = d.d_out; p.r = d.r; p.rk = round_up(d.r, 16);
   p.pairs = d.d_out / 128;
   const int ntiles = (d.T + 127) / 128;
-  p.csplit = dgrad_csplit(d, num_sms);
-  p.dg_mode = p.csplit == 1 ? 0 : (fused ? 1 : 2);
+  p.units = (long long)ntiles * p.pairs;
+  p.grid = dgrad_grid(d.T, d.d_out, num_sms);
+  p.dg_mode = fused ? 0 : 2;
+  p.part_stride = (long long)(a.dh_att - a.dh);
   p.bt_bytes = 2u * (uint32_t)p.rk * 128u;
   const size_t fixed = (size_t)4 * p.rk * 128 + 1024 + 512;
-  // two pairs (256 columns) per stage when two stages of that size and two sets of dB accumulators fit
+  // TMEM: [dG x ndg][dB sets: nbuf x wide x 2 rk]
+  p.dg_cols = tmem_cols_for(p.rk);
   static int dg_wide_env = -1;
   if (dg_wide_env < 0) { const char* e = getenv("MOKA_DGRAD_WIDE"); dg_wide_env = e ? atoi(e) : 2; }
+  const size_t limit = 226 * 1024;
   {
-    const uint32_t dgc0 = tmem_cols_for(p.rk);
+    // two pairs (256 columns) per stage when two sets of that many dB accumulators fit next to two dG accumulators
+    // and the ring still gets three stages
     const size_t st2 = 2 * (32768u + (size_t)p.bt_bytes);
-    p.wide = (dg_wide_env >= 2 && dgc0 + 8 * p.rk <= 512 && 2 * st2 + fixed <= 200 * 1024 &&
-              (d.d_out / 128) / p.csplit >= 4) ? 2 : 1;
+    p.wide = (dg_wide_env >= 2 && 2 * p.dg_cols + 8 * p.rk <= 512 && 3 * st2 + fixed <= limit) ? 2 : 1;
   }
-  p.rot = rot_enabled();
+  p.nbuf = (p.dg_cols + 4 * p.wide * p.rk <= 512) ? 2 : 1;
+  p.ndg = (2 * p.dg_cols + p.nbuf * p.wide * 2 * p.rk <= 512) ? 2 : 1;
+  p.d2_col = (uint32_t)p.ndg * p.dg_cols;
+  p.tmem_cols = tmem_cols_for((int)p.d2_col + p.nbuf * p.wide * 2 * p.rk);
   p.stage_bytes = (uint32_t)p.wide * (32768u + p.bt_bytes);
-  // fused chain: leave ~56 KB of the SM's shared memory to an early-launched k_attn_pack CTA, whose
-  // staging of the forward's stash then overlaps this kernel
   static int dg_stages_env = -1;
   if (dg_stages_env < 0) { const char* e = getenv("MOKA_DGRAD_STAGES"); dg_stages_env = e ? atoi(e) : 0; }
-  size_t limit = (fused && !dg_stages_env ? 168 : 200) * 1024;
-  if ((limit - fixed) / p.stage_bytes < 2) limit = 200 * 1024;   // large ranks: the ring needs the room itself
   p.stages = (int)((limit - fixed) / p.stage_bytes);
-  if (p.stages > 5) p.stages = 5;
+  if (p.stages > 6) p.stages = 6;
   if (dg_stages_env > 0 && p.stages > dg_stages_env) p.stages = dg_stages_env;
   if (p.stages < 2) return MOKA_EUNSUPPORTED;
   p.dbg = dbg_enabled();
   { static int nodb = -1; if (nodb < 0) { const char* e = getenv("MOKA_DBG_NO_DB"); nodb = (e && e[0] == '1') ? 2 : 0; } p.dbg |= nodb; }
   // timing experiments (results invalid): MOKA_DBG_DGRAD_SKIP=1 drops the dG product, =2 the dB product
   { static int sk = -1; if (sk < 0) { const char* e = getenv("MOKA_DBG_DGRAD_SKIP"); sk = e ? (atoi(e) & 3) << 2 : 0; } p.dbg |= sk; }
-  const uint32_t dgc = tmem_cols_for(p.rk);
-  p.d2_col = dgc;
-  p.nbuf = (dgc + 4 * p.wide * p.rk <= 512) ? 2 : 1;         // sets of `wide` [128 x 2 rk] dB accumulators next to dG
-  p.tmem_cols = tmem_cols_for((int)dgc + p.nbuf * p.wide * 2 * p.rk);
   // pre-transposed B in the (otherwise unused until the pack step) packed-operand workspace
   __nv_bfloat16* Bt = static_cast<__nv_bfloat16*>(a.pack);
   CUtensorMap tdy, tbt;
@@ -2048,8 +2208,8 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
     if (int rc = check_launch_tc()) return rc;
   }
   if (!(d.dbg_skip & 8)) {
-    e = launch_pdl(k_dgrad_tc, dim3(ntiles * p.csplit), dim3(kTcThreads), smem, st, tdy, tbt, d, p, a.tokmeta,
-                   a.h_stash + (size_t)d.T * d.r, a.dh, a.dh_att, a.dB);
+    e = launch_pdl(k_dgrad_tc, dim3(p.grid), dim3(kTcThreads), smem, st, tdy, tbt, d, p, a.tokmeta,
+                   (const float*)(a.h_stash + (size_t)d.T * d.r), a.dh, a.dB, (uint32_t*)nullptr, 0);
     if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
     if (int rc = check_launch_tc()) return rc;
   }
@@ -2284,7 +2444,7 @@ template <int R, int KB, int NT, bool MMA = false>
 __global__ void __launch_bounds__(NT)
 k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, const int32_t* __restrict__ kidx,
             const int32_t* __restrict__ klen, const float* __restrict__ h_stash, float* __restrict__ dG0,
-            const float* __restrict__ dG1, float* __restrict__ dK_glob, int* __restrict__ counters,
+            DgParts parts, float* __restrict__ dK_glob, int* __restrict__ counters,
             __nv_bfloat16* __restrict__ hc, __nv_bfloat16* __restrict__ hct_hi, __nv_bfloat16* __restrict__ hct_lo) {
   constexpr int TT = 32;
   constexpr int TPW = TT / (NT / 32);               // tokens per warp
@@ -2308,6 +2468,7 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
   __shared__ uint32_t s_blkmask[32];
   __shared__ int s_kidx[KP32];                      // the sample's key positions (finisher)
   __shared__ int s_last;
+  __shared__ int s_np[TT];                          // partial dG buffers holding a share of this token's row
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x / p.bps;
   const int s0 = (blockIdx.x % p.bps) * TT;
@@ -2326,6 +2487,7 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
     s_code[tid] = code;
     s_base[tid] = code ? (code - 1) * p.rp : -1;
     s_lse[tid] = (code >= MOKA_MOD_VIS) ? lse[tbase + tid] : 0.f;
+    s_np[tid] = dg_nparts(parts, (int)((tbase + tid) >> 7));
     myq = code >= MOKA_MOD_VIS;
     mykey = (mb & MOKA_KEY_VALID) && code;
   }
@@ -2366,9 +2528,11 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
     const int tt = i / R4, j = (i - tt * R4) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tt < nt && j < r) {
-      v = *reinterpret_cast<const float4*>(dG0 + (tbase + tt) * r + j);
-      if (dG1) {
-        const float4 w = *reinterpret_cast<const float4*>(dG1 + (tbase + tt) * r + j);
+      const float* src = dG0 + (tbase + tt) * r + j;
+      v = *reinterpret_cast<const float4*>(src);
+      const int np = s_np[tt];                          // partials of the persistent k_dgrad_tc (fixed order: bit-reproducible)
+      for (int q = 1; q < np; ++q) {
+        const float4 w = *reinterpret_cast<const float4*>(src + (size_t)q * (size_t)parts.stride);
         v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
       }
     }
@@ -2922,7 +3086,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(km_free + p.xs);
   uint32_t* km_s = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [xs][128 rows][4 words] (DROP)
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = ptx::uniform_warp_idx(), lane = threadIdx.x & 31;
   const int slice = blockIdx.x / p.tsplit, split = blockIdx.x % p.tsplit;
   const int col0 = slice * 128;
   const int tt_beg = (int)((long long)split * p.ntiles / p.tsplit);
@@ -2962,31 +3126,36 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   const uint32_t d1_col = 256;                                // dx accumulators at [0,256), dA at [256, 256+NPW)
 
   if (warp == 0) {
-    if (lane == 0) {
+    // ---- TMA producer (whole warp on warp-uniform values, one elected lane issues: see moka_ptx.cuh)
+    {
+      const uint32_t w_a = ptx::uniform_u32(ptx::smem_u32(wtile));
+      const uint32_t x_a = ptx::uniform_u32(ptx::smem_u32(xring));
+      const uint32_t d_a = ptx::uniform_u32(ptx::smem_u32(dring));
+      const uint32_t op_a = ptx::uniform_u32(ptx::smem_u32(op));
       // weights of this column slice, once
-      ptx::mbar_arrive_expect_tx(w_full, 2u * (uint32_t)p.M * (uint32_t)p.r * 128u);
+      ptx::mbar_arrive_expect_tx_w(w_full, 2u * (uint32_t)p.M * (uint32_t)p.r * 128u);
       for (int box = 0; box < 2; ++box) {
-        uint8_t* wb = wtile + (size_t)box * p.w_box_bytes;
-        ptx::tma_load_2d(wb, &tm_a0, w_full, col0 + box * 64, 0, ptx::kEvictLast);
-        if (p.M > 1) ptx::tma_load_2d(wb + (size_t)p.rp * 128, &tm_a1, w_full, col0 + box * 64, 0, ptx::kEvictLast);
-        if (p.M > 2) ptx::tma_load_2d(wb + (size_t)2 * p.rp * 128, &tm_a2, w_full, col0 + box * 64, 0, ptx::kEvictLast);
+        const uint32_t wb = w_a + (uint32_t)box * p.w_box_bytes;
+        ptx::tma_load_2d_w(wb, &tm_a0, w_full, col0 + box * 64, 0, ptx::kEvictLast);
+        if (p.M > 1) ptx::tma_load_2d_w(wb + (uint32_t)p.rp * 128u, &tm_a1, w_full, col0 + box * 64, 0, ptx::kEvictLast);
+        if (p.M > 2) ptx::tma_load_2d_w(wb + 2u * (uint32_t)p.rp * 128u, &tm_a2, w_full, col0 + box * 64, 0, ptx::kEvictLast);
       }
       const uint32_t op_tx = (uint32_t)kbx * 16384u + 4u * hct_blk;
       // x and dx are older than this call (the first kernel of the call waited for them): fill their
       // rings before the dependency wait; the packed dh operands come from the kernel just before
       const int npre_x = min(ntt, p.xs), npre_d = (p.has_dx && p.prefetch_dx) ? min(ntt, p.ds) : 0;
       for (int j = 0; j < npre_x; ++j) {
-        uint8_t* xt = xring + (size_t)j * 32768;
-        ptx::mbar_arrive_expect_tx(&x_full[j], 32768u);
-        ptx::tma_load_2d(xt, &tm_x, &x_full[j], col0, (tt_beg + j) * 128, ptx::kEvictFirst);
-        ptx::tma_load_2d(xt + 16384, &tm_x, &x_full[j], col0 + 64, (tt_beg + j) * 128, ptx::kEvictFirst);
+        const uint32_t xt = x_a + (uint32_t)j * 32768u;
+        ptx::mbar_arrive_expect_tx_w(&x_full[j], 32768u);
+        ptx::tma_load_2d_w(xt, &tm_x, &x_full[j], col0, (tt_beg + j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d_w(xt + 16384u, &tm_x, &x_full[j], col0 + 64, (tt_beg + j) * 128, ptx::kEvictFirst);
       }
       for (int j = 0; j < npre_d; ++j) {
-        uint8_t* dt = dring + (size_t)j * 32768;
-        if (p.delta) { ptx::mbar_arrive(&d_full[j]); continue; }   // write-only dx: a free slot is enough
-        ptx::mbar_arrive_expect_tx(&d_full[j], 32768u);
-        ptx::tma_load_2d(dt, &tm_dx, &d_full[j], col0, (tt_beg + j) * 128, ptx::kEvictFirst);
-        ptx::tma_load_2d(dt + 16384, &tm_dx, &d_full[j], col0 + 64, (tt_beg + j) * 128, ptx::kEvictFirst);
+        const uint32_t dt = d_a + (uint32_t)j * 32768u;
+        if (p.delta) { ptx::mbar_arrive_w(&d_full[j]); continue; }   // write-only dx: a free slot is enough
+        ptx::mbar_arrive_expect_tx_w(&d_full[j], 32768u);
+        ptx::tma_load_2d_w(dt, &tm_dx, &d_full[j], col0, (tt_beg + j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d_w(dt + 16384u, &tm_dx, &d_full[j], col0 + 64, (tt_beg + j) * 128, ptx::kEvictFirst);
       }
       ptx::pdl_wait();
       for (int j = 0; j < ntt; ++j) {
@@ -2995,43 +3164,50 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
           const int s = j % p.xs;
           const uint32_t ph = (uint32_t)(j / p.xs) & 1u;
           ptx::mbar_wait_or_trap(&x_empty[s], ph ^ 1u, __LINE__);
-          uint8_t* xt = xring + (size_t)s * 32768;
-          ptx::mbar_arrive_expect_tx(&x_full[s], 32768u);
-          ptx::tma_load_2d(xt, &tm_x, &x_full[s], col0, t0, ptx::kEvictFirst);
-          ptx::tma_load_2d(xt + 16384, &tm_x, &x_full[s], col0 + 64, t0, ptx::kEvictFirst);
+          const uint32_t xt = x_a + (uint32_t)s * 32768u;
+          ptx::mbar_arrive_expect_tx_w(&x_full[s], 32768u);
+          ptx::tma_load_2d_w(xt, &tm_x, &x_full[s], col0, t0, ptx::kEvictFirst);
+          ptx::tma_load_2d_w(xt + 16384u, &tm_x, &x_full[s], col0 + 64, t0, ptx::kEvictFirst);
         }
         if (p.has_dx && j >= npre_d) {
           const int s = j % p.ds;
           const uint32_t ph = (uint32_t)(j / p.ds) & 1u;
           ptx::mbar_wait_or_trap(&d_empty[s], ph ^ 1u, __LINE__);
-          uint8_t* dt = dring + (size_t)s * 32768;
+          const uint32_t dt = d_a + (uint32_t)s * 32768u;
           if (p.delta) {
-            ptx::mbar_arrive(&d_full[s]);
+            ptx::mbar_arrive_w(&d_full[s]);
           } else {
-            ptx::mbar_arrive_expect_tx(&d_full[s], 32768u);
-            ptx::tma_load_2d(dt, &tm_dx, &d_full[s], col0, t0, ptx::kEvictFirst);
-            ptx::tma_load_2d(dt + 16384, &tm_dx, &d_full[s], col0 + 64, t0, ptx::kEvictFirst);
+            ptx::mbar_arrive_expect_tx_w(&d_full[s], 32768u);
+            ptx::tma_load_2d_w(dt, &tm_dx, &d_full[s], col0, t0, ptx::kEvictFirst);
+            ptx::tma_load_2d_w(dt + 16384u, &tm_dx, &d_full[s], col0 + 64, t0, ptx::kEvictFirst);
           }
         }
         {   // packed dh operands of tile j (L2-resident; nop buffers, recycled when their MMAs retire)
           const int ob = j % p.nop;
-          uint8_t* hc_t = op + (size_t)ob * p.op_bytes;
-          uint8_t* hct_t = hc_t + (size_t)kbx * 16384;
+          const uint32_t hc_t = op_a + (uint32_t)ob * p.op_bytes;
+          const uint32_t hct_t = hc_t + (uint32_t)kbx * 16384u;
           ptx::mbar_wait_or_trap(&op_empty[ob], ((uint32_t)(j / p.nop) & 1u) ^ 1u, __LINE__);
-          ptx::mbar_arrive_expect_tx(&op_full[ob], op_tx);
-          for (int kb = 0; kb < kbx; ++kb) ptx::tma_load_2d(hc_t + (size_t)kb * 16384, &tm_hc, &op_full[ob], kb * 64, t0, ptx::kEvictLast);
+          ptx::mbar_arrive_expect_tx_w(&op_full[ob], op_tx);
+          for (int kb = 0; kb < kbx; ++kb) ptx::tma_load_2d_w(hc_t + (uint32_t)kb * 16384u, &tm_hc, &op_full[ob], kb * 64, t0, ptx::kEvictLast);
           for (int kb = 0; kb < 2; ++kb) {
-            ptx::tma_load_2d(hct_t + (size_t)kb * hct_blk, &tm_hct_hi, &op_full[ob], t0 + kb * 64, 0, ptx::kEvictLast);
-            ptx::tma_load_2d(hct_t + (size_t)(2 + kb) * hct_blk, &tm_hct_lo, &op_full[ob], t0 + kb * 64, 0, ptx::kEvictLast);
+            ptx::tma_load_2d_w(hct_t + (uint32_t)kb * hct_blk, &tm_hct_hi, &op_full[ob], t0 + kb * 64, 0, ptx::kEvictLast);
+            ptx::tma_load_2d_w(hct_t + (uint32_t)(2 + kb) * hct_blk, &tm_hct_lo, &op_full[ob], t0 + kb * 64, 0, ptx::kEvictLast);
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    // ---- MMA issuer (whole warp, one elected lane issues)
+    {
+      const uint32_t tb = ptx::uniform_u32(tmem_base);
       const uint32_t idesc_a = ptx::idesc_bf16(128, (uint32_t)p.NPW, 1, 0);   // X^T (MN-major) . dHcT (K-major)
       const uint32_t idesc_x = ptx::idesc_bf16(128, 128, 0, 1);               // dHc (K-major) . Acat (MN-major)
-      const uint32_t wa = ptx::smem_u32(wtile);
+      const uint32_t wa = ptx::uniform_u32(ptx::smem_u32(wtile));
+      const uint32_t x_a = ptx::uniform_u32(ptx::smem_u32(xring));
+      const uint32_t op_a = ptx::uniform_u32(ptx::smem_u32(op));
+      const uint64_t d_k = ptx::smem_desc_sw128(0, 1024, 0);                  // K-major operands
+      const uint64_t d_w = ptx::smem_desc_sw128(0, 1024, p.w_box_bytes);      // weights, MN-major (two boxes)
+      const uint64_t d_x = ptx::smem_desc_sw128(0, 1024, 16384);              // X tile, MN-major (two boxes)
       ptx::mbar_wait_or_trap(w_full, 0, __LINE__);
       for (int j = 0; j < ntt; ++j) {
         const int s = j % p.xs;
@@ -3039,40 +3215,40 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         const int i = j & 1;
         const uint32_t ph2 = (uint32_t)(j >> 1) & 1u;
         const int ob = j % p.nop;
-        const uint32_t hca = ptx::smem_u32(op + (size_t)ob * p.op_bytes);
+        const uint32_t hca = op_a + (uint32_t)ob * p.op_bytes;
         const uint32_t hcta = hca + (uint32_t)kbx * 16384u;
         ptx::mbar_wait_or_trap(&op_full[ob], (uint32_t)(j / p.nop) & 1u, __LINE__);
-        if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 40 + j * 3);
+        if (lane == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 40 + j * 3);
         ptx::mbar_wait_or_trap(&x_full[s], ph, __LINE__);
         if (DROP) ptx::mbar_wait_or_trap(&x_ready[s], ph, __LINE__);
-        if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 41 + j * 3);
+        if (lane == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 41 + j * 3);
         if (p.has_dx) ptx::mbar_wait_or_trap(&t_empty[i], ph2 ^ 1u, __LINE__);
-        if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 42 + j * 3);
+        if (lane == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 42 + j * 3);
         ptx::tc_fence_after_sync();
-        const uint32_t xa = ptx::smem_u32(xring + (size_t)s * 32768);
+        const uint32_t xa = x_a + (uint32_t)s * 32768u;
         if (p.has_dx) {
           // MMA-X first (the epilogue is waiting for it): K = NPW rank rows in steps of 16
           const int ksteps = p.NPW / 16;
           for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc = ptx::smem_desc_sw128(hca + (uint32_t)(k >> 2) * 16384u + (k & 3) * 32, 1024, 0);
-            const uint64_t bdesc = ptx::smem_desc_sw128(wa + (uint32_t)k * 2048u, 1024, p.w_box_bytes);
-            ptx::umma_bf16(tmem_base + (uint32_t)i * 128u, adesc, bdesc, idesc_x, k > 0 ? 1u : 0u);
+            const uint64_t adesc = d_k + (uint64_t)((hca + (uint32_t)(k >> 2) * 16384u + (k & 3) * 32) >> 4);
+            const uint64_t bdesc = d_w + (uint64_t)((wa + (uint32_t)k * 2048u) >> 4);
+            ptx::umma_bf16_w(tb + (uint32_t)i * 128u, adesc, bdesc, idesc_x, k > 0 ? 1u : 0u);
           }
-          ptx::umma_commit(&t_full[i]);
+          ptx::umma_commit_w(&t_full[i]);
         }
         // MMA-A: K = 128 tokens (8 steps), hi then lo
 #pragma unroll
         for (int part = 0; part < 2; ++part)
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const uint64_t adesc = ptx::smem_desc_sw128(xa + k * 2048, 1024, 16384);
-            const uint64_t bdesc = ptx::smem_desc_sw128(hcta + (uint32_t)(2 * part + (k >> 2)) * hct_blk + (k & 3) * 32, 1024, 0);
-            ptx::umma_bf16(tmem_base + d1_col, adesc, bdesc, idesc_a, (j > 0 || part > 0 || k > 0) ? 1u : 0u);
+            const uint64_t adesc = d_x + (uint64_t)((xa + k * 2048) >> 4);
+            const uint64_t bdesc = d_k + (uint64_t)((hcta + (uint32_t)(2 * part + (k >> 2)) * hct_blk + (k & 3) * 32) >> 4);
+            ptx::umma_bf16_w(tb + d1_col, adesc, bdesc, idesc_a, (j > 0 || part > 0 || k > 0) ? 1u : 0u);
           }
-        ptx::umma_commit(&x_empty[s]);
-        ptx::umma_commit(&op_empty[ob]);
+        ptx::umma_commit_w(&x_empty[s]);
+        ptx::umma_commit_w(&op_empty[ob]);
       }
-      ptx::umma_commit(a_full);
+      ptx::umma_commit_w(a_full);
     }
   } else if (warp >= 7) {
     // ================= dropout masking warps (DROP only): thread <-> (token row, 64-column box of the x tile).
@@ -3221,7 +3397,7 @@ bool tc_backward_fused_ok(const DevDesc& d, int klen_hint, bool has_dx) {
          wgrad_plan(d, has_dx, 148, p, L, fixed, nchunks);
 }
 
-static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayout& L, int dg_partials,
+static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayout& L, const DgParts& parts,
                             __nv_bfloat16* hc, __nv_bfloat16* hct_hi, __nv_bfloat16* hct_lo, cudaStream_t st,
                             int pack = 1) {
   AttnPackParams p;
@@ -3233,7 +3409,6 @@ static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayou
   const int KBs = kblocks <= 1 ? 1 : (kblocks <= 2 ? 2 : 4);
   const int KS = R <= 32 ? R + 1 : R;
   const size_t sm = ((size_t)4 * 32 * R + 2 * 32 * KBs * 32 + (size_t)KBs * 32 * KS + 32 * (R + 1)) * 4;
-  const float* dG1 = dg_partials ? a.dh_att : nullptr;
   cudaError_t e = cudaSuccess;
   static int attn_simt = -1;
   if (attn_simt < 0) { const char* ev = getenv("MOKA_ATTN_SIMT"); attn_simt = (ev && ev[0] == '1') ? 1 : 0; }
@@ -3247,7 +3422,7 @@ static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayou
     do {                                                                                                     \
       cudaFuncSetAttribute(k_attn_pack<RR, KK, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smm); \
       e = launch_pdl(k_attn_pack<RR, KK, 256, true>, dim3(d.B * p.bps), dim3(256), smm, st, d, p, a.tokmeta, a.kidx, \
-                     a.klen, (const float*)a.h_stash, a.dh, dG1, a.dK, a.counters, hc, hct_hi, hct_lo);       \
+                     a.klen, (const float*)a.h_stash, a.dh, parts, a.dK, a.counters, hc, hct_hi, hct_lo);     \
     } while (0)
     if (R == 8) { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK_MMA(8, 1); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK_MMA(8, 2); else MOKA_LAUNCH_ATTN_PACK_MMA(8, 4); }
     else if (R == 16) { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK_MMA(16, 1); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK_MMA(16, 2); else MOKA_LAUNCH_ATTN_PACK_MMA(16, 4); }
@@ -3262,7 +3437,7 @@ static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayou
     if (sm > 40 * 1024)                                                                                      \
       cudaFuncSetAttribute(k_attn_pack<RR, KK, NN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);    \
     e = launch_pdl(k_attn_pack<RR, KK, NN>, dim3(d.B * p.bps), dim3(NN), sm, st, d, p, a.tokmeta, a.kidx, a.klen, \
-                   (const float*)a.h_stash, a.dh, dG1, a.dK, a.counters, hc, hct_hi, hct_lo);                  \
+                   (const float*)a.h_stash, a.dh, parts, a.dK, a.counters, hc, hct_hi, hct_lo);                \
   } while (0)
   if (R == 8) { if (KBs == 1) MOKA_LAUNCH_ATTN_PACK(8, 1, 512); else if (KBs == 2) MOKA_LAUNCH_ATTN_PACK(8, 2, 512); else MOKA_LAUNCH_ATTN_PACK(8, 4, 512); }
   // (R = 16 at 512 threads needs 128 registers: one CTA per SM and a second wave; 256 threads fit two)
@@ -3277,7 +3452,7 @@ static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayou
 
 static int launch_attn_nopack(const DevDesc& d, const SimtArgs& a, cudaStream_t st) {
   const PackLayout L0 = pack_layout(d.T, d.r, d.M);
-  return launch_attn_pack(d, a, L0, 0, nullptr, nullptr, nullptr, st, 0);
+  return launch_attn_pack(d, a, L0, dgrad_parts(d, 0, false, 0), nullptr, nullptr, nullptr, st, 0);
 }
 
 // Shape checks and ring sizing of k_wgrad_tc (false: the kernel cannot tile this shape).
@@ -3366,8 +3541,8 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   if (fused) {
     if (!(d.dbg_skip & 16)) {
       const int ntiles128 = (d.T + 127) / 128;
-      const int csplit = dgrad_csplit(d, num_sms);
-      if (int rc = launch_attn_pack(d, a, L, csplit > 1, hc, hct_hi, hct_lo, st)) return rc;
+      if (int rc = launch_attn_pack(d, a, L, dgrad_parts(d, num_sms, true, (long long)(a.dh_att - a.dh)), hc, hct_hi,
+                                    hct_lo, st)) return rc;
     }
   } else {
     k_pack_dh<<<(d.T + 63) / 64, 256, (size_t)64 * (d.r + 1) * 4, st>>>(d, L.rp, L.NPW, L.KP, a.tokmeta, a.kidx, a.klen, a.dh,

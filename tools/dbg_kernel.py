@@ -105,6 +105,10 @@ if kern == 'dgrad':
         m = lambda i: rel[:, i].mean()
         print(f'stage {j}: mma full {m(8+j*3):8.0f} d2_empty {m(9+j*3):8.0f} issued {m(10+j*3):8.0f} | workers d2_full {m(32+j*2):8.0f} epilogue done {m(33+j*2):8.0f}')
 
+if kern == 'dgrad':
+    m = lambda i: rel[:, i].mean()
+    print(f'stage 2 detail: d2_empty {m(15):8.0f} fence {m(48):8.0f} mmas issued {m(49):8.0f} commit1 {m(50):8.0f} commit2 {m(16):8.0f}')
+
 if kern == 'down':
     for j in range(8):
         m = lambda i: rel[:, i].mean()
