@@ -115,13 +115,14 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // Optional in-kernel timestamps (cycle counter of the SM) for tuning: slot layout is per kernel.
 // Written only when MOKA_DEBUG_TIMING=1; read back through moka_debug_read().
 constexpr int kDbgSlots = 128;                                  // per CTA: 0..63 cycle stamps, 100.. wall-clock timeline
-__device__ unsigned long long g_dbg[148 * 2 * kDbgSlots];
+constexpr int kDbgCtas = 148 * 4;
+__device__ unsigned long long g_dbg[kDbgCtas * kDbgSlots];
 __device__ __forceinline__ void dbg_stamp(int enabled, int cta, int slot) {
-  if ((enabled & 1) && cta < 148 * 2 && slot < 64) g_dbg[cta * kDbgSlots + slot] = clock64();
+  if ((enabled & 1) && cta < kDbgCtas && slot < 64) g_dbg[cta * kDbgSlots + slot] = clock64();
 }
 // wall-clock (globaltimer, ns) stamps: comparable across CTAs; slots 60 (entry) / 61 (exit) by convention
 __device__ __forceinline__ void dbg_stamp_g(int enabled, int cta, int slot) {
-  if ((enabled & 1) && cta < 148 * 2 && slot < kDbgSlots) {
+  if ((enabled & 1) && cta < kDbgCtas && slot < kDbgSlots) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_dbg[cta * kDbgSlots + slot] = t;
@@ -137,7 +138,7 @@ int debug_set_trap_buffer(unsigned long long* mapped) {
   return cudaMemcpyToSymbol(ptx::g_trap_buf, &mapped, sizeof(mapped)) == cudaSuccess ? MOKA_OK : MOKA_ECUDA;
 }
 int debug_read(unsigned long long* host, int n) {
-  if (n > 148 * 2 * kDbgSlots) n = 148 * 2 * kDbgSlots;
+  if (n > kDbgCtas * kDbgSlots) n = kDbgCtas * kDbgSlots;
   return cudaMemcpyFromSymbol(host, g_dbg, (size_t)n * 8) == cudaSuccess ? MOKA_OK : MOKA_ECUDA;
 }
 
@@ -3397,6 +3398,10 @@ bool tc_backward_fused_ok(const DevDesc& d, int klen_hint, bool has_dx) {
          wgrad_plan(d, has_dx, 148, p, L, fixed, nchunks);
 }
 
+}  // namespace moka
+#include "moka_attn_bwd2.cuh"
+namespace moka {
+
 static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayout& L, const DgParts& parts,
                             __nv_bfloat16* hc, __nv_bfloat16* hct_hi, __nv_bfloat16* hct_lo, cudaStream_t st,
                             int pack = 1) {
@@ -3412,6 +3417,40 @@ static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayou
   cudaError_t e = cudaSuccess;
   static int attn_simt = -1;
   if (attn_simt < 0) { const char* ev = getenv("MOKA_ATTN_SIMT"); attn_simt = (ev && ev[0] == '1') ? 1 : 0; }
+  static int attn_v1 = -1;                         // MOKA_ATTN_BWD_V1=1: the first-generation k_attn_pack (A/B measurements)
+  if (attn_v1 < 0) { const char* ev = getenv("MOKA_ATTN_BWD_V1"); attn_v1 = (ev && ev[0] == '1') ? 1 : 0; }
+  if (!attn_simt && !attn_v1 && pack && R <= 64) {
+    // second generation (moka_attn_bwd2.cuh): 64 / 128 tokens per CTA, every warp on the tensor cores, dK straight
+    // from transposed accumulators, key tiles finished by dedicated CTAs
+    const int R16 = R < 16 ? 16 : R;
+    int num_sms = 148;
+    { int dev = 0; if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+    int TT = 128;
+    if (R16 == 64 || d.B * ((d.S + 127) / 128) < num_sms - num_sms / 8) TT = 64;
+    const size_t smm = attn_bwd2_smem(R16, KBs, TT);
+    if (smm <= 220 * 1024) {
+      p.bps = (d.S + TT - 1) / TT;
+      const int nq = d.B * p.bps;
+#define MOKA_LAUNCH_ATTN_BWD2(RR, KK, TTT)                                                                   \
+      do {                                                                                                   \
+        cudaFuncSetAttribute(k_attn_bwd2<RR, KK, TTT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smm); \
+        e = launch_pdl(k_attn_bwd2<RR, KK, TTT>, dim3(2 * nq), dim3(256), smm, st, d, p, nq, a.tokmeta, a.kidx, \
+                       a.klen, (const float*)a.h_stash, a.dh, parts, a.dK, a.counters, hc, hct_hi, hct_lo);   \
+      } while (0)
+#define MOKA_LAUNCH_ATTN_BWD2_K(RR, TTT)                                                                     \
+      do {                                                                                                   \
+        if (KBs == 1) MOKA_LAUNCH_ATTN_BWD2(RR, 1, TTT); else if (KBs == 2) MOKA_LAUNCH_ATTN_BWD2(RR, 2, TTT); \
+        else MOKA_LAUNCH_ATTN_BWD2(RR, 4, TTT);                                                              \
+      } while (0)
+      if (R16 == 16) { if (TT == 128) MOKA_LAUNCH_ATTN_BWD2_K(16, 128); else MOKA_LAUNCH_ATTN_BWD2_K(16, 64); }
+      else if (R16 == 32) { if (TT == 128) MOKA_LAUNCH_ATTN_BWD2_K(32, 128); else MOKA_LAUNCH_ATTN_BWD2_K(32, 64); }
+      else MOKA_LAUNCH_ATTN_BWD2_K(64, 64);
+#undef MOKA_LAUNCH_ATTN_BWD2_K
+#undef MOKA_LAUNCH_ATTN_BWD2
+      if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+      return check_launch_tc();
+    }
+  }
   if (!attn_simt && R <= 64) {
     // phases A / B on the warp-level tensor cores: bf16 hi/lo operand tiles behind the fp32 staging arrays
     const int R16 = R < 16 ? 16 : R, KP32 = KBs * 32;

@@ -66,7 +66,7 @@ for _ in range(2):
     torch.cuda.synchronize()
     run(only)
     torch.cuda.synchronize()
-n = 148 * 2 * 128
+n = 148 * 4 * 128
 buf = (ctypes.c_ulonglong * n)()
 _cabi.check(lib.moka_debug_read(buf, n), 'debug_read')
 a = np.frombuffer(buf, dtype=np.uint64).reshape(-1, 128).astype(np.int64)

@@ -51,7 +51,7 @@ for i in range(4):
 torch.cuda.synchronize()
 run(4)
 torch.cuda.synchronize()
-n = 148 * 2 * 128
+n = 148 * 4 * 128
 buf = (ctypes.c_ulonglong * n)()
 _cabi.check(lib.moka_debug_read(buf, n), 'debug_read')
 a = np.frombuffer(buf, dtype=np.uint64).reshape(-1, 128).astype(np.int64)
@@ -76,11 +76,11 @@ for rrow in rows:
     print('%-10s %5d | %8.2f %8.2f %8.2f | %8.2f %8.2f %8.2f' % rrow)
 
 # attn_pack phases (per CTA, relative to t_ref)
-names = [(110, 'entry'), (114, 'staged (pre-wait)'), (115, 'wait passed'), (116, 'phase A done'), (117, 'phase B done'),
+names = [(110, 'entry'), (114, 'staged (pre-wait)'), (115, 'wait passed'), (116, 'phase A done'), (117, 'phase B done / compute done'),
          (118, 'packed/parked'), (119, 'arrived'), (111, 'exit')]
 ent = a[:, 110]
 sel = ent > ent.max() - 1_000_000
-q = sel & (a[:, 116] > a[:, 110])          # CTAs that ran the attention
+q = sel & (a[:, 117] > a[:, 110])          # CTAs that ran the attention (query phase)
 print('attn_pack CTAs: %d recorded, %d with queries' % (sel.sum(), q.sum()))
 for slot, nm in names:
     for lab, m in (('all', sel), ('query', q)):
