@@ -444,6 +444,7 @@ def main():
     # roofline of the fused MokaLinear fwd+bwd (algorithmic bytes of SURVEY 8d / DESIGN.md)
     alg_bytes, dur_ms, per_kind = 0.0, 0.0, {'fwd': [0.0, 0.0], 'bwd': [0.0, 0.0]}
     n_delta = 0
+    by_shape = {}
     for kind, T, d_in, d_out, e, ev, delta in events:
         if delta:
             # MOKA_FLAG_DELTA_OUT: the residual read moved into the frozen GEMM's epilogue (beta = 1); the calls
@@ -455,6 +456,8 @@ def main():
         t = ev[0].elapsed_time(ev[1])
         alg_bytes += b; dur_ms += t
         per_kind[kind][0] += b; per_kind[kind][1] += t
+        bs = by_shape.setdefault(f'{d_in}x{d_out}', dict(fwd_ms=0.0, bwd_ms=0.0, fwd_bytes=0.0, bwd_bytes=0.0, calls=0))
+        bs[kind + '_ms'] += t; bs[kind + '_bytes'] += b; bs['calls'] += 1
     peak, peak_kind = peak_hbm()
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9 if dur_ms > 0 else 0.0
 
@@ -489,7 +492,13 @@ def main():
                                            else 'e(4 d_in + 3 d_out) [SURVEY 8d]'),
                           fwd_gbs=per_kind['fwd'][0] / max(per_kind['fwd'][1], 1e-9) / 1e6,
                           bwd_gbs=per_kind['bwd'][0] / max(per_kind['bwd'][1], 1e-9) / 1e6,
-                          share_of_step=dur_ms / ms_dev),
+                          share_of_step=dur_ms / ms_dev,
+                          by_shape={k: dict(calls=v['calls'],
+                                            fwd_us=round(v['fwd_ms'] * 2e3 / max(v['calls'], 1), 1),
+                                            bwd_us=round(v['bwd_ms'] * 2e3 / max(v['calls'], 1), 1),
+                                            frac=round((v['fwd_bytes'] + v['bwd_bytes']) / max(v['fwd_ms'] + v['bwd_ms'], 1e-9)
+                                                       / 1e6 / peak, 4))
+                                    for k, v in by_shape.items()}),
             clocks=clocks)
         if world == 1:
             # the same calls timed ALONE (back to back, rotating buffers, no GEMMs around them, SM clock not under

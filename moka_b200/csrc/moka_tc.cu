@@ -146,13 +146,13 @@ int debug_read(unsigned long long* host, int n) {
 // Column-order rotation of the streaming kernels: every CTA walks its column blocks starting at a different one
 // (wrapping around), so that the small weight tiles all CTAs need (A_m boxes in k_down_tc, B^T blocks in
 // k_dgrad_tc) are not requested by every SM from the same L2 lines at the same moment.  MOKA_NO_ROT=1: off.
-// MOKA_DROP_EARLY=1: the masking warps generate the keep bits of a stage BEFORE they wait for its data (the bits
+// Early keep bits: the masking warps generate the keep bits of a stage BEFORE they wait for its data (the bits
 // depend on (row, column group) only), leaving just the sparse zero stores and the fence after the TMA arrival.
-// Same bits, same result; written at the end of round 1 without a GPU to time it on, hence off by default.
-static int drop_early_bits() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("MOKA_DROP_EARLY"); v = (e && e[0] == '1') ? 1 : 0; }
-  return v;
+// Same bits, same result.  Timed in round 2: on by default in k_down_tc, off in k_wgrad_tc; MOKA_DROP_EARLY=0/1 forces both.
+static int drop_early_bits(int dflt) {
+  static int v = -2;                               // -1: not set in the environment -> per-kernel default
+  if (v == -2) { const char* e = getenv("MOKA_DROP_EARLY"); v = e ? ((e[0] == '1') ? 1 : 0) : -1; }
+  return v < 0 ? dflt : v;
 }
 
 static int rot_enabled() {
@@ -397,7 +397,7 @@ static int launch_down_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cuda
   p.kbox = (kbox_env == 2 && d.d_in % 128 == 0 && budget0 / ((16384u + p.w_bytes) * 2u) >= min_stages) ? 2 : 1;
   p.kblocks = d.d_in / (64 * p.kbox);
   p.rot = rot_enabled();
-  p.early_bits = drop_early_bits();
+  p.early_bits = drop_early_bits(1);               // measured round 2: k_down_tc 64.9 -> 60.8 us (T = 32768, d = 4096)
   p.stage_bytes = (16384u + p.w_bytes) * (uint32_t)p.kbox;
   // one CTA per SM when the grid does not exceed the SM count: spend the whole shared memory on the
   // ring (tcgen05.commit frees a stage ~1.5k cycles after issue, so >= 6 stages keep HBM busy)
@@ -1711,84 +1711,66 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
       const uint64_t g_base = a1_base + (uint64_t)(gta >> 4);
       const uint32_t g2b = g2_block >> 4, gtb = gt_block >> 4;
       DgSegIter it{u_beg, u_end, p.pairs, 0, 0, 0};
+      // ring slot / accumulator indices and barrier parities are carried along (no division per stage)
       int j = 0, seg = 0;
+      int s = 0; uint32_t s_ph = 0;                   // ring slot of stage j, parity of its `full` phase
+      int i2 = 0; uint32_t i2_ph = 0;                 // dB accumulator set of stage j, parity of its k-th use
+      int dgb = 0; uint32_t dg_ph = 0;                // dG accumulator of the segment
       while (it.next()) {
-        const int dgb = seg % p.ndg;
-        const uint32_t dgk = (uint32_t)(seg / p.ndg);
         const uint32_t dg_acc = tb + (uint32_t)dgb * p.dg_cols;
-        ptx::mbar_wait_or_trap(&dg_empty[dgb], (dgk & 1u) ^ 1u, __LINE__);     // accumulator read out (two segments ago)
+        ptx::mbar_wait_or_trap(&dg_empty[dgb], dg_ph ^ 1u, __LINE__);          // accumulator read out (two segments ago)
+        ptx::tc_fence_after_sync();
         bool gt_ready = false;
         for (int q0 = it.pb; q0 < it.pe; q0 += W, ++j) {
           const int nq = min(W, it.pe - q0);
-          const int s = j % p.stages;
-          const int i = j % p.nbuf;
-          const uint32_t k2 = (uint32_t)(j / p.nbuf);
-          ptx::mbar_wait_or_trap(&full[s], ((uint32_t)(j / p.stages)) & 1u, __LINE__);
+          ptx::mbar_wait_or_trap(&full[s], s_ph, __LINE__);
           if (lane == 0) { if (j == 0) dbg_stamp(p.dbg, blockIdx.x, 3); if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 8 + j * 3); }
-          ptx::mbar_wait_or_trap(&d2_empty[i], (k2 & 1u) ^ 1u, __LINE__);
-          if (lane == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 3);
-          ptx::tc_fence_after_sync();
-          if (lane == 0 && j == 2) dbg_stamp(p.dbg, blockIdx.x, 48);
           const uint32_t sa0 = ring_a + (uint32_t)s * p.stage_bytes;
-          if (!gt_ready) {
-            // first stage of a segment: the dG products do not need the G^T operand - issue them while the workers
-            // are still writing it, then wait for it
-            for (int q = 0; q < nq; ++q) {
-              const uint32_t sa = sa0 + (uint32_t)q * 32768u;
-              const uint32_t bta = sa0 + dy_bytes + (uint32_t)(2 * q) * gt_block;
-              const uint64_t a1 = a1_base + (uint64_t)(sa >> 4);
-              const uint64_t b1 = a1_base + (uint64_t)(bta >> 4);
+          // MMA1 (dG += dY B) touches neither the dB accumulators nor the G^T operand: issue it first, so that the
+          // waits below (and their tcgen05 fence, ~190 cycles) run while the tensor pipe works on these
+          for (int q = 0; q < nq; ++q) {
+            const uint32_t sa = sa0 + (uint32_t)q * 32768u;
+            const uint32_t bta = sa0 + dy_bytes + (uint32_t)(2 * q) * gt_block;
+            const uint64_t a1 = a1_base + (uint64_t)(sa >> 4);
+            const uint64_t b1 = a1_base + (uint64_t)(bta >> 4);
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int box = k >> 2, kk = k & 3;
-                if (!(p.dbg & 4))
-                ptx::umma_bf16_w(dg_acc, a1 + (uint64_t)((box * 16384 + kk * 32) >> 4),
-                                 b1 + (uint64_t)(box * gtb + ((kk * 32) >> 4)), idesc1, (q > 0 || k > 0) ? 1u : 0u);
-              }
+            for (int k = 0; k < 8; ++k) {
+              const int box = k >> 2, kk = k & 3;
+              if (!(p.dbg & 4))
+              ptx::umma_bf16_w(dg_acc, a1 + (uint64_t)((box * 16384 + kk * 32) >> 4),
+                               b1 + (uint64_t)(box * gtb + ((kk * 32) >> 4)), idesc1, (q0 > it.pb || q > 0 || k > 0) ? 1u : 0u);
             }
+          }
+          ptx::mbar_wait_or_trap(&d2_empty[i2], i2_ph ^ 1u, __LINE__);
+          if (lane == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 3);
+          if (!gt_ready) {
             ptx::mbar_wait_or_trap(gt_full, (uint32_t)seg & 1u, __LINE__);
             if (lane == 0 && seg == 0) dbg_stamp(p.dbg, blockIdx.x, 2);
-            ptx::tc_fence_after_sync();
             gt_ready = true;
-            for (int q = 0; q < nq; ++q) {
-              const uint32_t sa = sa0 + (uint32_t)q * 32768u;
-              const uint64_t a2 = a2_base + (uint64_t)(sa >> 4);
-              const uint32_t d2 = tb + p.d2_col + (uint32_t)(i * W + q) * 2u * (uint32_t)p.rk;
+          }
+          ptx::tc_fence_after_sync();
+          if (lane == 0 && j == 2) dbg_stamp(p.dbg, blockIdx.x, 48);
+          // MMA2: M = 128 columns (two 64-wide atoms 16 KB apart), K = 128 tokens in 8 steps of 16
+          for (int q = 0; q < nq; ++q) {
+            const uint32_t sa = sa0 + (uint32_t)q * 32768u;
+            const uint64_t a2 = a2_base + (uint64_t)(sa >> 4);
+            const uint32_t d2 = tb + p.d2_col + (uint32_t)(i2 * W + q) * 2u * (uint32_t)p.rk;
 #pragma unroll
-              for (int k = 0; k < 8; ++k)
-                if (!(p.dbg & 8))
-                ptx::umma_bf16_w(d2, a2 + (uint64_t)((k * 2048) >> 4), g_base + (uint64_t)((k >> 2) * g2b + (((k & 3) * 32) >> 4)),
-                                 idesc2, k > 0 ? 1u : 0u);
-            }
-          } else {
-            for (int q = 0; q < nq; ++q) {
-              const uint32_t sa = sa0 + (uint32_t)q * 32768u;
-              const uint32_t bta = sa0 + dy_bytes + (uint32_t)(2 * q) * gt_block;
-              // MMA1: K = 128 columns of this pair (two boxes, four 16-wide steps each)
-              const uint64_t a1 = a1_base + (uint64_t)(sa >> 4);
-              const uint64_t b1 = a1_base + (uint64_t)(bta >> 4);
-              const uint64_t a2 = a2_base + (uint64_t)(sa >> 4);
-              // MMA2: M = 128 columns (two 64-wide atoms 16 KB apart), K = 128 tokens in 8 steps of 16
-              const uint32_t d2 = tb + p.d2_col + (uint32_t)(i * W + q) * 2u * (uint32_t)p.rk;
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int box = k >> 2, kk = k & 3;
-                if (!(p.dbg & 4))
-                ptx::umma_bf16_w(dg_acc, a1 + (uint64_t)((box * 16384 + kk * 32) >> 4),
-                                 b1 + (uint64_t)(box * gtb + ((kk * 32) >> 4)), idesc1, 1u);
-                if (!(p.dbg & 8))
-                ptx::umma_bf16_w(d2, a2 + (uint64_t)((k * 2048) >> 4), g_base + (uint64_t)((k >> 2) * g2b + (((k & 3) * 32) >> 4)),
-                                 idesc2, k > 0 ? 1u : 0u);
-              }
-            }
+            for (int k = 0; k < 8; ++k)
+              if (!(p.dbg & 8))
+              ptx::umma_bf16_w(d2, a2 + (uint64_t)((k * 2048) >> 4), g_base + (uint64_t)((k >> 2) * g2b + (((k & 3) * 32) >> 4)),
+                               idesc2, k > 0 ? 1u : 0u);
           }
           if (lane == 0 && j == 2) dbg_stamp(p.dbg, blockIdx.x, 49);
           ptx::umma_commit_w(&empty[s]);
-          ptx::umma_commit_w(&d2_full[i]);
+          ptx::umma_commit_w(&d2_full[i2]);
           if (lane == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 10 + j * 3);
+          if (++s == p.stages) { s = 0; s_ph ^= 1u; }
+          if (++i2 == p.nbuf) { i2 = 0; i2_ph ^= 1u; }
         }
         ptx::umma_commit_w(&dg_full[dgb]);
         ++seg;
+        if (++dgb == p.ndg) { dgb = 0; dg_ph ^= 1u; }
       }
       if (lane == 0) dbg_stamp(p.dbg, blockIdx.x, 4);
     }
@@ -3539,7 +3521,7 @@ static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParam
   }
   p.has_dx = has_dx;
   p.delta = (has_dx && d.delta) ? 1 : 0;
-  p.early_bits = drop_early_bits();
+  p.early_bits = drop_early_bits(0);               // (k_wgrad_tc: 160.3 -> 161.3 us with early bits: off)
   p.dbg = dbg_enabled();
   p.w_box_bytes = (uint32_t)p.NPW * 128u;
   p.op_bytes = (uint32_t)(p.KP / 64) * 16384u + 4u * p.w_box_bytes;
