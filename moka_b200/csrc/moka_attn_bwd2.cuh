@@ -36,15 +36,9 @@ __device__ __forceinline__ void pack_rows2(const DevDesc& d, const AttnPackParam
   for (int i = tid; i < nt * cpr; i += nthr) {
     const int tt = i / cpr, n0 = (i - tt * cpr) * 8;
     const int base = s_base[tt];
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int j = n0 + e - base;
-      v[e] = (base >= 0 && j >= 0 && j < r) ? rows[tt * stride + j] * p.scale : 0.f;
-    }
-    uint4 o;
-    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-    *reinterpret_cast<uint4*>(hc + (tbase + tt) * p.KP + n0) = o;
+    const float* rowp = rows + tt * stride;
+    *reinterpret_cast<uint4*>(hc + (tbase + tt) * p.KP + n0) =
+        hc_chunk([&](int j) { return rowp[j]; }, base, r, n0, p.lo_off, p.scale);
   }
   const int tch = (nt + 7) / 8;                     // S % 8 == 0: 8-token chunks never straddle a sample
   for (int i = tid; i < p.NPW * tch; i += nthr) {

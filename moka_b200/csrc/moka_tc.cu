@@ -1264,8 +1264,16 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
         const int kb = ch >> 3, chb = ch & 7;                   // 64-wide K block and chunk inside it
         const int slot = (i >> 1) * p.bpg + (i & 1);              // barrier index i = group * 2 + buffer -> smem slot
         uint8_t* dst = btiles + ((size_t)slot * kblocks + kb) * 16384 + ptx::sw128_offset((uint32_t)n, (uint32_t)chb);
-        const __nv_bfloat16* src = Bw + (size_t)(chunk_of(j) * 128 + n) * r + (k < r ? k : 0);
-        ptx::cp_async16(ptx::smem_u32(dst), src, k < r);
+        const __nv_bfloat16* row_src = Bw + (size_t)(chunk_of(j) * 128 + n) * r;
+        if (k + 8 <= r) {
+          ptx::cp_async16(ptx::smem_u32(dst), row_src + k, true);
+        } else if (k < r) {
+          // r % 8 == 4: the last four rank values of the row (8 bytes, 8-byte aligned), the rest of the chunk is zero
+          ptx::cp_async8(ptx::smem_u32(dst), row_src + k);
+          *reinterpret_cast<uint2*>(dst + 8) = make_uint2(0u, 0u);
+        } else {
+          ptx::cp_async16(ptx::smem_u32(dst), Bw, false);          // beyond the rank: zero-fill (no bytes are read)
+        }
       }
       ptx::cp_async_commit();
     };
@@ -2245,13 +2253,36 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
 //                  of  dx = dHc . [A_0;A_1;A_2]),
 //   dHcT [2, NPW, T]  its transpose, split into hi + lo bf16 so that the weight gradient
 //                  dA = dHcT . X keeps fp32-level accuracy.
-struct PackLayout { int rp, NPW, KP; size_t hc_bytes, hct_bytes; };
+struct PackLayout { int rp, NPW, KP, lo_off; size_t hc_bytes, hct_bytes; };
+
+// One 16-byte chunk (columns n0 .. n0 + 7) of a packed dHc row.  Columns [0, NPW) hold bf16(dh); when the padded K
+// axis has room (2 NPW <= KP: every r <= 8, and r = 16 with two modalities) columns [lo_off, 2 lo_off) hold the bf16
+// RESIDUAL of the same values and k_wgrad_tc runs its dx product over both halves against a duplicated weight tile:
+// dx = dh A then sees dh at fp32-level accuracy.  It matters exactly where the adapter term is large next to
+// W0^T dy - small ranks, whose alpha / r scale is big (r = 4: 4x the r = 16 term; its dx missed the 1e-3 bar by 20 %).
+template <typename F>
+__device__ __forceinline__ uint4 hc_chunk(F val, int base, int r, int n0, int lo_off, float scale) {
+  float o[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int col = n0 + e;
+    const bool islo = lo_off > 0 && col >= lo_off;
+    const int j = (islo ? col - lo_off : col) - base;
+    const float x = (base >= 0 && j >= 0 && j < r) ? val(j) * scale : 0.f;
+    const float hi = __bfloat162float(__float2bfloat16_rn(x));
+    o[e] = islo ? x - hi : hi;
+  }
+  uint4 q;
+  q.x = pack_bf16(o[0], o[1]); q.y = pack_bf16(o[2], o[3]); q.z = pack_bf16(o[4], o[5]); q.w = pack_bf16(o[6], o[7]);
+  return q;
+}
 
 static PackLayout pack_layout(int T, int r, int M) {
   PackLayout L;
   L.rp = round_up(r, 8);
   L.NPW = round_up(M * L.rp, 16);
   L.KP = round_up(L.NPW, 64);
+  L.lo_off = (2 * L.NPW <= L.KP) ? L.NPW : 0;
   L.hc_bytes = ((size_t)T * L.KP * 2 + 255) & ~size_t(255);
   L.hct_bytes = ((size_t)L.NPW * T * 2 + 255) & ~size_t(255);
   return L;
@@ -2275,7 +2306,7 @@ __device__ __forceinline__ int find_key_slot(const int32_t* __restrict__ row, in
 // One CTA per 64 tokens: rows are gathered into shared memory once (coalesced), then written as
 // dHc rows and as dHcT columns (64 consecutive tokens = 128 contiguous bytes per packed row).
 __global__ void __launch_bounds__(256)
-k_pack_dh(DevDesc d, int rp, int NPW, int KP, const uint8_t* __restrict__ tokmeta,
+k_pack_dh(DevDesc d, int rp, int NPW, int KP, int lo_off, const uint8_t* __restrict__ tokmeta,
           const int32_t* __restrict__ kidx, const int32_t* __restrict__ klen, const float* __restrict__ dh,
           const float* __restrict__ dh_att, const float* __restrict__ dK, __nv_bfloat16* __restrict__ hc,
           __nv_bfloat16* __restrict__ hct_hi, __nv_bfloat16* __restrict__ hct_lo, float scale) {
@@ -2319,15 +2350,9 @@ k_pack_dh(DevDesc d, int rp, int NPW, int KP, const uint8_t* __restrict__ tokmet
   for (int i = tid; i < nt * cpr; i += 256) {
     const int tt = i / cpr, n0 = (i - tt * cpr) * 8;
     const int base = s_base[tt];
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int j = n0 + e - base;
-      v[e] = (base >= 0 && j >= 0 && j < r) ? vs[tt * (r + 1) + j] * scale : 0.f;
-    }
-    uint4 o;
-    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-    *reinterpret_cast<uint4*>(hc + ((size_t)t0 + tt) * KP + n0) = o;
+    const float* rowp = vs + tt * (r + 1);
+    *reinterpret_cast<uint4*>(hc + ((size_t)t0 + tt) * KP + n0) =
+        hc_chunk([&](int j) { return rowp[j]; }, base, r, n0, lo_off, scale);
   }
   // dHcT columns (hi + lo); T % 8 == 0 so 8-token chunks never straddle the end
   const int tch = (nt + 7) / 8;
@@ -2365,6 +2390,7 @@ k_pack_dh(DevDesc d, int rp, int NPW, int KP, const uint8_t* __restrict__ tokmet
 //      pattern, no second launch and no grid-wide barrier).
 struct AttnPackParams {
   int rp, NPW, KP, bps;             // bps = 32-token blocks per sample
+  int lo_off;                       // residual half of the dHc rows (see hc_chunk), 0 = none
   float scale;
   int pack;                         // 1: emit the packed wgrad operands (fused chain); 0: only write dh back to dG0 and
                                     // reduce dK (the consumer - k_pack_dh or the warp-FMA wgrad - folds dK itself)
@@ -2381,15 +2407,9 @@ __device__ __forceinline__ void pack_rows(const DevDesc& d, const AttnPackParams
   for (int i = tid; i < nt * cpr; i += nthr) {
     const int tt = i / cpr, n0 = (i - tt * cpr) * 8;
     const int base = s_base[tt];
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int j = n0 + e - base;
-      v[e] = (base >= 0 && j >= 0 && j < r) ? vs[tt * VS + j] * p.scale : 0.f;
-    }
-    uint4 o;
-    o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-    *reinterpret_cast<uint4*>(hc + (tbase + tt) * p.KP + n0) = o;
+    const float* rowp = vs + tt * VS;
+    *reinterpret_cast<uint4*>(hc + (tbase + tt) * p.KP + n0) =
+        hc_chunk([&](int j) { return rowp[j]; }, base, r, n0, p.lo_off, p.scale);
   }
   const int tch = (nt + 7) / 8;                     // S % 8 == 0: 8-token chunks never straddle a sample
   for (int i = tid; i < p.NPW * tch; i += nthr) {
@@ -2975,15 +2995,8 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
       if (!s_parked[q] || pos >= d.S) continue;
       const int base = s_base_all[q * TT + tt];
       const float* row = vs_all + (q * TT + tt) * RS;
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int j = n0 + e - base;
-        v[e] = (base >= 0 && j >= 0 && j < r) ? row[j] * p.scale : 0.f;
-      }
-      uint4 o;
-      o.x = pack_bf16(v[0], v[1]); o.y = pack_bf16(v[2], v[3]); o.z = pack_bf16(v[4], v[5]); o.w = pack_bf16(v[6], v[7]);
-      *reinterpret_cast<uint4*>(hc + ((size_t)b * d.S + pos) * p.KP + n0) = o;
+      *reinterpret_cast<uint4*>(hc + ((size_t)b * d.S + pos) * p.KP + n0) =
+          hc_chunk([&](int j) { return row[j]; }, base, r, n0, p.lo_off, p.scale);
     }
     constexpr int TCH = TT / 8;
     for (int i = tid; i < nl * p.NPW * TCH; i += NT) {
@@ -3019,6 +3032,7 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
 // and adds dXadd onto the dx tile in shared memory before the TMA store (read-modify-write of dx).
 struct WgradTcParams {
   int T, d_in, r, rp, M, NPW, KP;
+  int lo_off;                      // dHc rows carry a residual half at this column (0: none): the dx product runs over both
   int tsplit, ntiles;
   int xs, ds, nop;                 // ring depths: X pairs / dX pairs (32 KB slots), operand buffers
   int has_dx, dbg;
@@ -3026,7 +3040,8 @@ struct WgradTcParams {
   int early_bits;                  // DROP: keep bits generated before the tile's waits (see drop_early_bits)
   int prefetch_dx;                 // dx tiles may be loaded before the dependency wait (false for the later passes of a
                                    // rank-chunked call: the pass in front is still writing dx)
-  uint32_t w_box_bytes;            // one 64-column box of the weight slice: NPW x 128 B
+  uint32_t w_box_bytes;            // one 64-column box of the weight slice: (NPW, or 2 NPW with the residual half) x 128 B
+  uint32_t hct_blk;                // one [NPW rows x 64 tokens] block of the transposed operand
   uint32_t op_bytes;               // operand buffer: dHc tile + dHcT hi/lo tiles
   uint32_t tmem_cols;
 };
@@ -3046,7 +3061,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
            WgradTcParams p, DevDesc d, float* __restrict__ dA0, float* __restrict__ dA1, float* __restrict__ dA2) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t hct_blk = (uint32_t)p.NPW * 128u;            // [NPW rows x 64 tokens] block
+  const uint32_t hct_blk = p.hct_blk;                         // [NPW rows x 64 tokens] block
   const int kbx = p.KP / 64;                                  // K blocks of the dHc tile
   uint8_t* xring = base;                                      // [xs][2 boxes][128 x 128 B]
   uint8_t* dring = xring + (size_t)p.xs * 32768;              // [ds][2 boxes][128 x 128 B]
@@ -3116,13 +3131,15 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       const uint32_t d_a = ptx::uniform_u32(ptx::smem_u32(dring));
       const uint32_t op_a = ptx::uniform_u32(ptx::smem_u32(op));
       // weights of this column slice, once
-      ptx::mbar_arrive_expect_tx_w(w_full, 2u * (uint32_t)p.M * (uint32_t)p.r * 128u);
-      for (int box = 0; box < 2; ++box) {
-        const uint32_t wb = w_a + (uint32_t)box * p.w_box_bytes;
-        ptx::tma_load_2d_w(wb, &tm_a0, w_full, col0 + box * 64, 0, ptx::kEvictLast);
-        if (p.M > 1) ptx::tma_load_2d_w(wb + (uint32_t)p.rp * 128u, &tm_a1, w_full, col0 + box * 64, 0, ptx::kEvictLast);
-        if (p.M > 2) ptx::tma_load_2d_w(wb + 2u * (uint32_t)p.rp * 128u, &tm_a2, w_full, col0 + box * 64, 0, ptx::kEvictLast);
-      }
+      const int wcopies = p.lo_off ? 2 : 1;                    // second copy: rows lo_off.. (the residual half of dHc)
+      ptx::mbar_arrive_expect_tx_w(w_full, (uint32_t)wcopies * 2u * (uint32_t)p.M * (uint32_t)p.r * 128u);
+      for (int cp = 0; cp < wcopies; ++cp)
+        for (int box = 0; box < 2; ++box) {
+          const uint32_t wb = w_a + (uint32_t)box * p.w_box_bytes + (uint32_t)cp * (uint32_t)p.lo_off * 128u;
+          ptx::tma_load_2d_w(wb, &tm_a0, w_full, col0 + box * 64, 0, ptx::kEvictLast);
+          if (p.M > 1) ptx::tma_load_2d_w(wb + (uint32_t)p.rp * 128u, &tm_a1, w_full, col0 + box * 64, 0, ptx::kEvictLast);
+          if (p.M > 2) ptx::tma_load_2d_w(wb + 2u * (uint32_t)p.rp * 128u, &tm_a2, w_full, col0 + box * 64, 0, ptx::kEvictLast);
+        }
       const uint32_t op_tx = (uint32_t)kbx * 16384u + 4u * hct_blk;
       // x and dx are older than this call (the first kernel of the call waited for them): fill their
       // rings before the dependency wait; the packed dh operands come from the kernel just before
@@ -3211,7 +3228,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         const uint32_t xa = x_a + (uint32_t)s * 32768u;
         if (p.has_dx) {
           // MMA-X first (the epilogue is waiting for it): K = NPW rank rows in steps of 16
-          const int ksteps = p.NPW / 16;
+          const int ksteps = (p.lo_off ? 2 * p.NPW : p.NPW) / 16;   // (+ the residual half of the dHc rows)
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t adesc = d_k + (uint64_t)((hca + (uint32_t)(k >> 2) * 16384u + (k & 3) * 32) >> 4);
             const uint64_t bdesc = d_w + (uint64_t)((wa + (uint32_t)k * 2048u) >> 4);
@@ -3389,7 +3406,7 @@ static int launch_attn_pack(const DevDesc& d, const SimtArgs& a, const PackLayou
                             int pack = 1) {
   AttnPackParams p;
   p.pack = pack;
-  p.rp = L.rp; p.NPW = L.NPW; p.KP = L.KP; p.bps = (d.S + 31) / 32;
+  p.rp = L.rp; p.NPW = L.NPW; p.KP = L.KP; p.lo_off = L.lo_off; p.bps = (d.S + 31) / 32;
   p.scale = d.pre * d.drop_scale;
   const int kblocks = (max(a.klen_hint, 1) + 31) / 32;
   const int R = d.r <= 8 ? 8 : (d.r <= 16 ? 16 : (d.r <= 32 ? 32 : (d.r <= 64 ? 64 : 128)));
@@ -3523,8 +3540,10 @@ static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParam
   p.delta = (has_dx && d.delta) ? 1 : 0;
   p.early_bits = drop_early_bits(0);               // (k_wgrad_tc: 160.3 -> 161.3 us with early bits: off)
   p.dbg = dbg_enabled();
-  p.w_box_bytes = (uint32_t)p.NPW * 128u;
-  p.op_bytes = (uint32_t)(p.KP / 64) * 16384u + 4u * p.w_box_bytes;
+  p.lo_off = L.lo_off;
+  p.hct_blk = (uint32_t)p.NPW * 128u;
+  p.w_box_bytes = (uint32_t)(p.lo_off ? 2 * p.NPW : p.NPW) * 128u;
+  p.op_bytes = (uint32_t)(p.KP / 64) * 16384u + 4u * p.hct_blk;
   p.tmem_cols = 512;
   const size_t limit = 226 * 1024;
   // prefer two operand buffers (breaks the MMA -> reload -> MMA chain); the dx ring then gets 2 slots
@@ -3566,7 +3585,7 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
                                     hct_lo, st)) return rc;
     }
   } else {
-    k_pack_dh<<<(d.T + 63) / 64, 256, (size_t)64 * (d.r + 1) * 4, st>>>(d, L.rp, L.NPW, L.KP, a.tokmeta, a.kidx, a.klen, a.dh,
+    k_pack_dh<<<(d.T + 63) / 64, 256, (size_t)64 * (d.r + 1) * 4, st>>>(d, L.rp, L.NPW, L.KP, L.lo_off, a.tokmeta, a.kidx, a.klen, a.dh,
                                                                        a.dh_att, a.dK, hc, hct_hi, hct_lo,
                                                                        d.pre * d.drop_scale);
     if (int rc = check_launch_tc()) return rc;
@@ -3627,7 +3646,7 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
 int tc_stage_mask(const DevDesc& d, int dtype) {
   if (dtype != MOKA_BF16) return 0;                 // fp32 storage keeps exact fp32 FMA (1e-5 bar)
   if (d.d_in % 64 || d.d_out % 64) return 0;
-  if (d.r % 8 || d.r > 128) return 0;
+  if (d.r % 4 || d.r > 128) return 0;         // (r = 4, the reference's shipped rank, pads to 8 / 16 inside the tiles)
   if (!get_encode_fn()) return 0;
   int mask = kStageDown;
   if (d.d_out % 128 == 0) mask |= kStageUp | kStageDgrad;

@@ -416,14 +416,14 @@ def test_delta_out_unsupported_on_warp_fma_path():
     from moka_b200 import _cabi
     from moka_b200.layer import _make_desc
     from tests import gpu_util as gu
-    sc, _ = gu.scalars_for(mo.VARIANT_VT, 16, 4, 0.05)
+    sc, _ = gu.scalars_for(mo.VARIANT_VT, 16, 2, 0.05)
     lib = _cabi.load()
-    d = _make_desc((256, 256), 2, 128, 256, 4, 2, torch.bfloat16, 8, sc, 0)           # r = 4: warp-FMA kernels
+    d = _make_desc((256, 256), 2, 128, 256, 2, 2, torch.bfloat16, 8, sc, 0)           # r = 2 (not a multiple of 4): warp-FMA kernels
     assert lib.moka_supports_delta(d, 1) == 0
     d32 = _make_desc((256, 256), 2, 128, 256, 8, 2, torch.float32, 8, sc, 0)         # fp32 storage: warp-FMA kernels
     assert lib.moka_supports_delta(d32, 1) == 0
     with pytest.raises(_cabi.MokaError):
-        _oracle_case(mo.VARIANT_VT, 2, 128, 256, 256, 4, 2, 'c1', 16, 0.05, torch.bfloat16, flags=_cabi.FLAG_DELTA_OUT)
+        _oracle_case(mo.VARIANT_VT, 2, 128, 256, 256, 2, 2, 'c1', 16, 0.05, torch.bfloat16, flags=_cabi.FLAG_DELTA_OUT)
 
 
 def test_rank_chunked_wgrad_dx_is_clean_every_time():
@@ -675,3 +675,27 @@ def test_bench_geometry_other_configs(variant, M, layout, B, S, d, r, p):
     w = 1.0 if variant == mo.VARIANT_AVT else 0.05
     o = _oracle_case_gpu(variant, B, S, d, d, r, M, layout, 16, w, p=p, rng=(77, 3))
     _assert_case(o, torch.bfloat16, M)
+
+
+@pytest.mark.parametrize('variant,M,layout', [(mo.VARIANT_AVT, 3, 'c3'), (mo.VARIANT_VT, 2, 'c2')], ids=['avt', 'vt'])
+@pytest.mark.parametrize('p', [0.0, 0.05], ids=['p0', 'p05'])
+def test_rank4_runs_on_the_tensor_core_chain(variant, M, layout, p):
+    """r = 4 is what both reference recipes ship (AudioVisualText/configs/unified_config.py:91 lora_r=444,
+    VisualText/train/train.py:545): bf16 r = 4 takes the tcgen05 chain (rank padded to 8 / 16 inside the tiles),
+    matches the oracle and the warp-FMA kernels."""
+    from moka_b200 import _cabi
+    from moka_b200.layer import _make_desc
+    from tests import gpu_util as gu
+    r, B, S, d_in, d_out = 4, 2, 2048, 1024, 768
+    w = 1.0 if variant == mo.VARIANT_AVT else 0.05
+    sc, _ = gu.scalars_for(variant, 16, r, w, p)
+    desc = _make_desc((B * S, d_in), B, S, d_out, r, M, torch.bfloat16, 96, sc, 0)
+    assert _cabi.load().moka_uses_tensor_cores(desc) == 1
+    o_tc = _oracle_case(variant, B, S, d_in, d_out, r, M, layout, 16, w, torch.bfloat16, p=p, rng=(5, 6))
+    _assert_case(o_tc, torch.bfloat16, M)
+    o_fma = _oracle_case(variant, B, S, d_in, d_out, r, M, layout, 16, w, torch.bfloat16, p=p, rng=(5, 6), flags=FORCE_SIMT)
+    assert mo.rel_l2(o_tc['h'], o_fma['h']) <= 2e-6
+    assert mo.rel_l2(o_tc['dB'], o_fma['dB']) <= 1e-4
+    for m in range(M):
+        if float(o_fma['dA'][m].norm()) > 0:
+            assert mo.rel_l2(o_tc['dA'][m], o_fma['dA'][m]) <= 1e-4
