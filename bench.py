@@ -307,31 +307,47 @@ def build_model(wl, device, ckpt):
     return pm, cfg
 
 
+IMAGE_TOKEN_ID = 31999            # stand-in for the tokenizer's <image> id (VisualText/train/train.py:204)
+
+
 def host_batch(wl, cfg, rank):
-    """Synthetic batch in PINNED host memory: token ids, labels and the reference-shaped masks."""
+    """Synthetic batch in PINNED host memory, as the data pipeline holds it BEFORE any mask tensor exists
+    (SURVEY 8f N1): token ids, labels and - AVT - the per-sample segment table (unified_arch.py:139-240); VT needs
+    nothing else (its masks are a function of ids and labels, train.py:206-231)."""
     import torch
-    from moka_b200.layouts import VARIANT_AVT, VARIANT_VT, layout_masks
+    from moka_b200.layouts import layout_ids_labels, layout_segments
     B, S = wl['B'], wl['S']
     gen = torch.Generator().manual_seed(1234 + rank)
-    ids = torch.randint(3, cfg.vocab_size, (B, S), generator=gen)
-    labels = ids.clone()
-    variant = VARIANT_AVT if wl['variant'] == 'avt' else VARIANT_VT
-    masks = layout_masks(variant, B, S, wl['layout'])
-    ans = int(S * (1680 if wl['layout'] == 'c3' else 675) / 2048)
-    labels[:, :ans] = -100                          # loss on the answer span only
-    out = dict(input_ids=ids.pin_memory(), labels=labels.pin_memory(), masks=[m.contiguous().pin_memory() for m in masks])
+    if wl['variant'] == 'avt':
+        ids = torch.randint(3, cfg.vocab_size, (B, S), generator=gen)
+        labels = ids.clone()
+        labels[:, :int(S * 1680 / 2048)] = -100             # loss on the answer span only
+        out = dict(input_ids=ids.pin_memory(), labels=labels.pin_memory(),
+                   segments=layout_segments(B, S, wl['layout']).pin_memory())
+    else:
+        ids, labels = layout_ids_labels(B, S, wl['layout'], IMAGE_TOKEN_ID, cfg.vocab_size, seed=1234 + rank)
+        out = dict(input_ids=ids.pin_memory(), labels=labels.pin_memory())
     return out
 
 
 def to_device(hb, wl, device):
+    """Host -> device copies of one step's inputs and the device-side token metadata (no host synchronisation:
+    the status word is read once, after the timed region)."""
+    from moka_b200.metadata import build_token_meta_avt_from_segments, build_token_meta_vt_from_ids
     ids = hb['input_ids'].to(device, non_blocking=True)
     labels = hb['labels'].to(device, non_blocking=True)
-    masks = [m.to(device, non_blocking=True) for m in hb['masks']]
     if wl['variant'] == 'avt':
-        kw = dict(modality_masks=masks)
+        seg = hb['segments'].to(device, non_blocking=True)
+        meta = build_token_meta_avt_from_segments(seg, wl['S'], max_keys=128)
     else:
-        kw = dict(my_text_mask=masks[0], my_image_mask=masks[1], question_mask=masks[2])
-    return ids, labels, kw
+        meta = build_token_meta_vt_from_ids(ids, labels, IMAGE_TOKEN_ID, max_keys=128)
+        ids = torch_where_image(ids)
+    return ids, labels, dict(token_meta=meta)
+
+
+def torch_where_image(ids):
+    import torch
+    return torch.where(ids == IMAGE_TOKEN_ID, torch.zeros_like(ids), ids)     # train.py:213
 
 
 def main():
@@ -393,7 +409,7 @@ def main():
     eng = AdapterDataParallel(pm, AdamWConfig(lr=1e-4), zero_stage=args.zero_stage, num_buckets=4)
     hb = host_batch(wl, cfg, rank)
     tokens_per_step = wl['B'] * wl['S'] * world
-    h2d = sum(t.numel() * t.element_size() for t in [hb['input_ids'], hb['labels'], *hb['masks']])
+    h2d = sum(t.numel() * t.element_size() for t in hb.values())
 
     def step(dev_batch=None):
         ids, labels, kw = dev_batch if dev_batch is not None else to_device(hb, wl, device)
@@ -440,6 +456,7 @@ def main():
     events = list(moka_layer.TIMING['events'])
     ms_e2e, _, last_loss = timed(args.steps, resident=False, collect_events=False)
     clocks = sampler.stop() if rank == 0 else None
+    to_device(hb, wl, device)[2]['token_meta'].raise_if_error()      # the deferred metadata check, outside the timed region
 
     # roofline of the fused MokaLinear fwd+bwd (algorithmic bytes of SURVEY 8d / DESIGN.md)
     alg_bytes, dur_ms, per_kind = 0.0, 0.0, {'fwd': [0.0, 0.0], 'bwd': [0.0, 0.0]}

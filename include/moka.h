@@ -72,7 +72,17 @@ enum {
 enum {
   MOKA_META_EMPTY_QUESTION = 1,   /* AVT: a sample has no question token (reference: IndexError, lora.py:490) */
   MOKA_META_OVERLAP = 2,          /* a token is in more than one modality mask */
-  MOKA_META_KEY_OVERFLOW = 4      /* a sample has more key rows than Lk */
+  MOKA_META_KEY_OVERFLOW = 4,     /* a sample has more key rows than Lk */
+  MOKA_META_BAD_SEGMENT = 8       /* moka_build_token_meta_from_segments: unknown kind / negative length / sum > S */
+};
+
+/* segment kinds of moka_build_token_meta_from_segments */
+enum {
+  MOKA_SEG_END = 0,               /* terminates a sample's segment list */
+  MOKA_SEG_TEXT = 1,              /* text tokens (unified_arch.py:168-180) */
+  MOKA_SEG_VIDEO = 2,             /* <video> / <image> features -> video mask (:197-225) */
+  MOKA_SEG_AUDIO = 3,             /* <audio> features (:186-195) */
+  MOKA_SEG_QUESTION = 4           /* the text segment in front of <question_end>: text AND question (:153-166) */
 };
 
 typedef struct MokaDesc {
@@ -139,6 +149,29 @@ int moka_build_token_meta(int32_t variant, int32_t B, int32_t S, int32_t Lk,
                           const void* const* masks, int32_t mask_elem_bytes,
                           uint8_t* tokmeta, int32_t* kidx, int32_t* klen, int32_t* status,
                           moka_stream_t stream);
+
+/*
+ * SURVEY.md 8(f) N1 -- the metadata straight from what the data pipeline holds, with no mask tensors at all.
+ *
+ * VT (VisualText/train/train.py:206-231 + the collator :259-318): ``input_ids`` / ``labels`` int64 [B, S] as the
+ * collator pads them (image positions still carry ``image_token_id``; the dataset zeroes them only after it has
+ * derived its masks, :213), ``lengths`` int32 [B] = unpadded sample lengths (NULL: every sample is S long):
+ *   image = ids == image_token_id;  text = the other tokens inside the length;
+ *   question = !image && label == ignore_index && pos > last image position   (none when a sample has no image).
+ */
+int moka_build_token_meta_from_ids(int32_t B, int32_t S, int32_t Lk, const int64_t* input_ids, const int64_t* labels,
+                                   int64_t image_token_id, int64_t ignore_index, const int32_t* lengths,
+                                   uint8_t* tokmeta, int32_t* kidx, int32_t* klen, int32_t* status,
+                                   moka_stream_t stream);
+
+/*
+ * AVT (AudioVisualText/models/unified_arch.py:139-240, 304-312): ``segments`` int32 [B, max_segments, 2] =
+ * (MOKA_SEG_* kind, length) in sequence order, MOKA_SEG_END-terminated; samples are LEFT-padded to S like the
+ * reference pads them.  Same outputs and status word as moka_build_token_meta.
+ */
+int moka_build_token_meta_from_segments(int32_t B, int32_t S, int32_t Lk, int32_t max_segments, const int32_t* segments,
+                                        uint8_t* tokmeta, int32_t* kidx, int32_t* klen, int32_t* status,
+                                        moka_stream_t stream);
 
 /* Test hook: the dropout keep mask (1 = kept) moka_forward/backward use for (seed, offset),
  * uint8 [B*S, d_in].  Lets the oracle be run on the very same mask. */

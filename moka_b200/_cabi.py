@@ -17,9 +17,11 @@ MOD_NONE, MOD_TEXT, MOD_VIS, MOD_AUD = 0, 1, 2, 3
 MOD_MASK, KEY_VALID = 0x7, 0x8
 FLAG_FORCE_SIMT, FLAG_FORCE_TC, FLAG_DELTA_OUT = 1, 2, 4
 MOKA_EUNSUPPORTED = -4
-META_EMPTY_QUESTION, META_OVERLAP, META_KEY_OVERFLOW = 1, 2, 4
+META_EMPTY_QUESTION, META_OVERLAP, META_KEY_OVERFLOW, META_BAD_SEGMENT = 1, 2, 4, 8
+SEG_END, SEG_TEXT, SEG_VIDEO, SEG_AUDIO, SEG_QUESTION = 0, 1, 2, 3, 4
 
 EXPORTS = ['moka_workspace_bytes', 'moka_forward', 'moka_backward', 'moka_build_token_meta',
+           'moka_build_token_meta_from_ids', 'moka_build_token_meta_from_segments',
            'moka_dropout_keep_mask', 'moka_effective_dropout_p', 'moka_adamw_step', 'moka_launch_count',
            'moka_uses_tensor_cores', 'moka_supports_delta', 'moka_strerror', 'moka_version', 'moka_rope', 'moka_debug_read',
            'moka_debug_trap_buffer']
@@ -62,6 +64,12 @@ def load():
     lib.moka_build_token_meta.restype = c_int32
     lib.moka_build_token_meta.argtypes = [c_int32, c_int32, c_int32, c_int32, POINTER(c_void_p), c_int32,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.moka_build_token_meta_from_ids.restype = c_int32
+    lib.moka_build_token_meta_from_ids.argtypes = [c_int32, c_int32, c_int32, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
+                                                   c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.moka_build_token_meta_from_segments.restype = c_int32
+    lib.moka_build_token_meta_from_segments.argtypes = [c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.moka_dropout_keep_mask.restype = c_int32
     lib.moka_dropout_keep_mask.argtypes = [D, c_uint64, c_uint64, c_void_p, c_void_p]
     lib.moka_effective_dropout_p.restype = c_float

@@ -245,6 +245,27 @@ int moka_build_token_meta(int32_t variant, int32_t B, int32_t S, int32_t Lk,
                            static_cast<cudaStream_t>(stream));
 }
 
+int moka_build_token_meta_from_ids(int32_t B, int32_t S, int32_t Lk, const int64_t* input_ids, const int64_t* labels,
+                                   int64_t image_token_id, int64_t ignore_index, const int32_t* lengths,
+                                   uint8_t* tokmeta, int32_t* kidx, int32_t* klen, int32_t* status,
+                                   moka_stream_t stream) {
+  if (B <= 0 || S <= 0 || Lk <= 0 || !input_ids || !labels || !tokmeta || !kidx || !klen || !status) return MOKA_EINVAL;
+  return launch_build_meta_ids(B, S, Lk, reinterpret_cast<const long long*>(input_ids),
+                               reinterpret_cast<const long long*>(labels), (long long)image_token_id,
+                               (long long)ignore_index, lengths, tokmeta, kidx, klen, status,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int moka_build_token_meta_from_segments(int32_t B, int32_t S, int32_t Lk, int32_t max_segments, const int32_t* segments,
+                                        uint8_t* tokmeta, int32_t* kidx, int32_t* klen, int32_t* status,
+                                        moka_stream_t stream) {
+  if (B <= 0 || S <= 0 || Lk <= 0 || max_segments <= 0 || max_segments > 64 || !segments || !tokmeta || !kidx || !klen ||
+      !status)
+    return MOKA_EINVAL;
+  return launch_build_meta_segments(B, S, Lk, max_segments, segments, tokmeta, kidx, klen, status,
+                                    static_cast<cudaStream_t>(stream));
+}
+
 int moka_dropout_keep_mask(const MokaDesc* desc, uint64_t seed, uint64_t offset, uint8_t* keep,
                            moka_stream_t stream) {
   if (int e = validate(desc)) return e;

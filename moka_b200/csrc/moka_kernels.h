@@ -38,6 +38,12 @@ int launch_keep_mask(const DevDesc& d, uint8_t* keep, cudaStream_t st);
 int launch_build_meta(int variant, int B, int S, int Lk, const void* const* masks, int elem_bytes,
                       uint8_t* tokmeta, int32_t* kidx, int32_t* klen, int32_t* status, cudaStream_t st);
 
+int launch_build_meta_ids(int B, int S, int Lk, const long long* ids, const long long* labels, long long image_id,
+                          long long ignore_index, const int32_t* lengths, uint8_t* tokmeta, int32_t* kidx,
+                          int32_t* klen, int32_t* status, cudaStream_t st);
+int launch_build_meta_segments(int B, int S, int Lk, int max_seg, const int32_t* segs, uint8_t* tokmeta, int32_t* kidx,
+                               int32_t* klen, int32_t* status, cudaStream_t st);
+
 int launch_adamw(int64_t n, float* master, float* m, float* v, const float* grad, void* param_out, int dtype,
                  float lr, float b1, float b2, float eps, float wd, int step, float grad_scale, cudaStream_t st);
 

@@ -202,6 +202,55 @@ def set_peft_model_state_dict(model: nn.Module, peft_model_state_dict: Dict[str,
     return model.load_state_dict(peft_model_state_dict, strict=False)
 
 
+def get_non_lora_trainables_state_dict(model: nn.Module) -> Dict[str, torch.Tensor]:
+    """``non_lora_trainables.bin`` (AudioVisualText/scripts/finetune/finetune.py:196, 201;
+    ``get_peft_state_non_lora_maybe_zero_3`` trainer.py:84-89): every TRAINABLE parameter without ``lora_`` in its
+    name, keyed by ``named_parameters()`` of the wrapped model, on the CPU."""
+    return {k: t.detach().cpu() for k, t in model.named_parameters() if 'lora_' not in k and t.requires_grad}
+
+
+def save_reference_checkpoint(model: nn.Module, output_dir: str) -> None:
+    """What finetune.py:195-201 leaves in ``output_dir``: ``adapter_model.bin`` + ``non_lora_trainables.bin``."""
+    os.makedirs(output_dir, exist_ok=True)
+    lora = {k: t.detach().cpu() for k, t in model.named_parameters() if 'lora_' in k}
+    torch.save(get_peft_model_state_dict(model, lora), os.path.join(output_dir, 'adapter_model.bin'))
+    torch.save(get_non_lora_trainables_state_dict(model), os.path.join(output_dir, 'non_lora_trainables.bin'))
+
+
+def load_reference_checkpoint(model: nn.Module, ckpt_dir: str) -> Dict[str, List[str]]:
+    """The loader of AudioVisualText/scripts/finetune/inference_cut.py:174-184: ``non_lora_trainables.bin`` then
+    ``adapter_model.bin``, both ``strict=False``.  Returns the keys of each file that found NO parameter
+    (a reference checkpoint must leave both lists empty)."""
+    report = {}
+    for name in ('non_lora_trainables.bin', 'adapter_model.bin'):
+        path = os.path.join(ckpt_dir, name)
+        if not os.path.exists(path):
+            continue
+        sd = torch.load(path, map_location='cpu')
+        res = model.load_state_dict(sd, strict=False)
+        report[name] = list(res.unexpected_keys)
+    return report
+
+
+def load_safetensors_checkpoint(model: nn.Module, path: str, strict: bool = True):
+    """VT evaluation loader (VisualText/eval_benchmarks/mmbench/mmbench.py:576-577): the WHOLE wrapped model from
+    ``model.safetensors`` with ``strict=True`` - every key of the reference's PeftMixedModel state dict must exist
+    here under the same name (tests/golden/ckpt_keys.json pins them)."""
+    from safetensors.torch import load_file
+    if os.path.isdir(path):
+        path = os.path.join(path, 'model.safetensors')
+    return model.load_state_dict(load_file(path), strict=strict)
+
+
+def save_safetensors_checkpoint(model: nn.Module, path: str) -> None:
+    """``model.safetensors`` as HF Trainer writes it for the VT recipe (the whole state dict; shared tensors cloned)."""
+    from safetensors.torch import save_file
+    if os.path.isdir(path) or not path.endswith('.safetensors'):
+        os.makedirs(path, exist_ok=True)
+        path = os.path.join(path, 'model.safetensors')
+    save_file({k: v.detach().cpu().contiguous().clone() for k, v in model.state_dict().items()}, path)
+
+
 def get_mm_adapter_state(named_params: Iterable, keys_to_match: List[str]) -> Dict[str, torch.Tensor]:
     """``finetune_weights.bin`` of AudioVisualText/trainer.py:33-36, 183-218: parameters whose name
     contains any of ``save_modules`` (e.g. 'vl_projector,al_projector,lora')."""

@@ -129,6 +129,61 @@ def build_token_meta_vt(text_mask: torch.Tensor, image_mask: torch.Tensor,
 
 
 # ----------------------------------------------------------------------------------------
+# mask producers: what the reference's data pipeline does BEFORE the layer
+# ----------------------------------------------------------------------------------------
+def vt_masks_from_ids(input_ids: torch.Tensor, labels: torch.Tensor, image_token_id: int,
+                      lengths: Optional[Sequence[int]] = None, ignore_index: int = -100):
+    """VisualText/train/train.py:206-231 per sample, then the collator's right-padding with False
+    (:259-297).  ``input_ids`` / ``labels`` are the PADDED [B,S] tensors, ``lengths`` the unpadded lengths.
+    Returns (my_text_mask, my_image_mask, question_mask), each [B,S] bool."""
+    B, S = input_ids.shape
+    text = torch.zeros(B, S, dtype=torch.bool)
+    image = torch.zeros(B, S, dtype=torch.bool)
+    question = torch.zeros(B, S, dtype=torch.bool)
+    for b in range(B):
+        n = S if lengths is None else int(lengths[b])
+        ids = input_ids[b:b + 1, :n]
+        tgt = labels[b:b + 1, :n]
+        my_image_mask = ids == image_token_id                                  # :210
+        my_text_mask = ids != image_token_id                                   # :211
+        image_positions = torch.where(my_image_mask)[1]                        # :220
+        if len(image_positions) > 0:
+            last = image_positions[-1]
+            position_mask = (torch.arange(n) > last).unsqueeze(0)              # :224-225
+        else:
+            position_mask = torch.zeros_like(my_image_mask, dtype=torch.bool)  # :227
+        q = ~my_image_mask & (tgt == ignore_index) & position_mask             # :231
+        text[b, :n], image[b, :n], question[b, :n] = my_text_mask[0], my_image_mask[0], q[0]
+    return text, image, question
+
+
+SEG_END, SEG_TEXT, SEG_VIDEO, SEG_AUDIO, SEG_QUESTION = 0, 1, 2, 3, 4
+
+
+def avt_masks_from_segments(segments: Sequence[Sequence[Tuple[int, int]]], S: int):
+    """AudioVisualText/models/unified_arch.py:139-240 (per-segment mask pieces, concatenated :262-275) and the
+    LEFT padding of :304-312.  ``segments[b]`` = [(kind, length), ...].  Returns [text, video, audio, question],
+    each [B,S,1] int32."""
+    B = len(segments)
+    out = [torch.zeros(B, S, 1, dtype=torch.int32) for _ in range(4)]
+    for b, segs in enumerate(segments):
+        pieces = [[], [], [], []]
+        for kind, n in segs:
+            if kind == SEG_END:
+                break
+            one, zero = torch.ones(n, 1, dtype=torch.int32), torch.zeros(n, 1, dtype=torch.int32)
+            pieces[0].append(one if kind in (SEG_TEXT, SEG_QUESTION) else zero)   # :159, :171, :189 ...
+            pieces[1].append(one if kind == SEG_VIDEO else zero)
+            pieces[2].append(one if kind == SEG_AUDIO else zero)
+            pieces[3].append(one if kind == SEG_QUESTION else zero)               # :163 vs :175
+        cat = [torch.cat(p, 0) if p else torch.zeros(0, 1, dtype=torch.int32) for p in pieces]
+        n = cat[0].shape[0]
+        for k in range(4):
+            out[k][b, S - n:] = cat[k]                                            # left padding (:304-312)
+    return out
+
+
+# ----------------------------------------------------------------------------------------
 # reference-form restatements (op by op; dtype follows the inputs like the reference does)
 # ----------------------------------------------------------------------------------------
 def _drop(x: torch.Tensor, keep: Optional[torch.Tensor], p: float) -> torch.Tensor:
