@@ -213,13 +213,11 @@ class _MokaFn(torch.autograd.Function):
         gA = [None if main else g.to(p.dtype) for (g, main), p in zip(dAs, A_params)]
         gx = None if dx is None else dx.view(ctx.x_shape)
         # bias='all' / 'lora_only' (lora.py:234-245) makes the frozen layer's bias trainable: its gradient is the
-        # column sum of dy; a trainable BASE WEIGHT is not something MokA ever asks for - refuse instead of
-        # silently returning no gradient
-        if ctx.needs_input_grad[1]:
-            raise _cabi.MokaError('the wrapped base weight requires grad: MokaLinear keeps W0 frozen '
-                                  '(lora.py:333, layer.py:124-132)')
+        # column sum of dy.  A base weight that still requires grad (a layer used outside get_peft_model, which
+        # freezes it: lora.py:333, layer.py:124-132) gets what autograd would give it: dW0 = dy^T x (cuBLAS).
+        gW = torch.matmul(dy2.t(), x2) if ctx.needs_input_grad[1] else None
         gbias = dy2.float().sum(0).to(dy2.dtype) if ctx.needs_input_grad[2] else None
-        return (gx, None, gbias, gB, None, None, None, None, *gA)
+        return (gx, gW, gbias, gB, None, None, None, None, *gA)
 
 
 def moka_linear_function(x, weight, bias, A: Sequence[torch.Tensor], Bw, meta: TokenMeta,

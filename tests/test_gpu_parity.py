@@ -699,3 +699,33 @@ def test_rank4_runs_on_the_tensor_core_chain(variant, M, layout, p):
     for m in range(M):
         if float(o_fma['dA'][m].norm()) > 0:
             assert mo.rel_l2(o_tc['dA'][m], o_fma['dA'][m]) <= 1e-4
+
+
+def test_dropout_mask_statistics():
+    """The keep mask of the bit-sliced generator behaves like independent Bernoulli(p_eff) draws: the rate per
+    column, per row and per position inside the 32-column generator groups is uniform, neighbouring columns / rows
+    and the two halves of (seed, offset) space are uncorrelated (only the mean rate was checked)."""
+    from tests import gpu_util as gu
+    B, S, d = 2, 2048, 4096
+    p = 0.05
+    pe = gu.effective_p(p)
+    keep = gu.keep_mask(B, S, d, d, 16, 3, torch.bfloat16, p, 1234, 77).view(B * S, d).float()
+    drop = 1.0 - keep
+    n_rows, n_cols = drop.shape
+    assert abs(float(drop.mean()) - pe) < 5 * (pe * (1 - pe) / drop.numel()) ** 0.5
+    sig_col = (pe * (1 - pe) / n_rows) ** 0.5
+    sig_row = (pe * (1 - pe) / n_cols) ** 0.5
+    assert float((drop.mean(0) - pe).abs().max()) < 5.5 * sig_col          # every column
+    assert float((drop.mean(1) - pe).abs().max()) < 5.5 * sig_row          # every row
+    by_pos = drop.view(n_rows, n_cols // 32, 32).mean((0, 1))              # position inside the 32-column group
+    assert float((by_pos - pe).abs().max()) < 5 * (pe * (1 - pe) / (drop.numel() / 32)) ** 0.5
+    # chi-square of the per-column counts against Binomial(n_rows, pe): mean 1 per degree of freedom
+    chi = float((((drop.sum(0) - n_rows * pe) ** 2) / (n_rows * pe * (1 - pe))).mean())
+    assert 0.9 < chi < 1.1
+    c = drop - pe
+    var = pe * (1 - pe)
+    for a, b_ in ((c[:, :-1], c[:, 1:]), (c[:-1], c[1:]), (c[:, :-32], c[:, 32:]), (c[:-128], c[128:])):
+        corr = float((a * b_).mean()) / var
+        assert abs(corr) < 5.0 / a.numel() ** 0.5
+    other = 1.0 - gu.keep_mask(B, S, d, d, 16, 3, torch.bfloat16, p, 1234, 78).view(B * S, d).float()
+    assert abs(float(((other - pe) * c).mean()) / var) < 5.0 / c.numel() ** 0.5
