@@ -1048,6 +1048,10 @@ struct UpTcParams {
   int bpg;                         // B-tile buffers / TMEM accumulators per worker group: 2, or 1 when r > 64
   int delta;                       // MOKA_FLAG_DELTA_OUT: y receives the adapter term only (no y0 read)
   int rot;                         // rotate the chunk order per CTA (see rot_enabled)
+  int streamk;                     // 1: persistent grid, CTA c owns the units [c U / G, (c+1) U / G) of the (token tile,
+                                   //    128-column chunk) list (see the stream-K note); 0: one CTA per (tile, column split)
+  int grid;                        // G
+  long long units;                 // U = ntiles * chunks
   int dbg;
 };
 
@@ -1132,14 +1136,33 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
   uint8_t* meta_s = reinterpret_cast<uint8_t*>(or_slot + 1);  // [128]
 
   const int warp = ptx::uniform_warp_idx(), lane = threadIdx.x & 31;
-  const int tile = blockIdx.x / p.nsplit, split = blockIdx.x % p.nsplit;
-  const int t0 = tile * 128;
+  // work of this CTA: `nch` (tile, chunk) units.  Stream-K: a contiguous range of the tile-major unit list, possibly
+  // spanning several token tiles (segments); otherwise the column split `split` of one tile, in a rotated order.
+  long long u_beg = 0;
+  int tile, split, c_beg, nch, crot;
+  if (p.streamk) {
+    u_beg = (long long)blockIdx.x * p.units / p.grid;
+    nch = (int)((long long)(blockIdx.x + 1) * p.units / p.grid - u_beg);
+    tile = (int)(u_beg / p.chunks); split = 0; c_beg = 0; crot = 0;
+  } else {
+    tile = blockIdx.x / p.nsplit; split = blockIdx.x % p.nsplit;
+    c_beg = (int)((long long)split * p.chunks / p.nsplit);
+    nch = (int)((long long)(split + 1) * p.chunks / p.nsplit) - c_beg;
+    crot = p.rot ? (int)(((unsigned)tile * 7u + (unsigned)split * 3u) % (unsigned)nch) : 0;
+  }
+  const int t0 = tile * 128;                                  // first token tile of this CTA
   const int nt = min(128, p.T - t0);
-  const int c_beg = (int)((long long)split * p.chunks / p.nsplit);
-  const int c_end = (int)((long long)(split + 1) * p.chunks / p.nsplit);
-  const int nch = c_end - c_beg;
-  const int crot = p.rot ? (int)(((unsigned)tile * 7u + (unsigned)split * 3u) % (unsigned)nch) : 0;
-  auto chunk_of = [&](int j) { return c_beg + rot_index(j, crot, nch); };   // j-th column chunk this CTA processes
+  auto unit_of = [&](int j, int& tl, int& ch) {               // j-th unit this CTA processes -> (token tile, column chunk)
+    if (p.streamk) {
+      const long long u = u_beg + j;
+      tl = (int)(u / p.chunks);
+      ch = (int)(u - (long long)tl * p.chunks);
+    } else {
+      tl = tile;
+      ch = c_beg + rot_index(j, crot, nch);
+    }
+  };
+  auto chunk_of = [&](int j) { int tl, ch; unit_of(j, tl, ch); return ch; };
   if (threadIdx.x == 0) dbg_stamp_g(p.dbg, blockIdx.x, 104);
   // last kernel of the forward chain: whatever follows (the first kernel of the next libmoka call waits
   // before it touches memory; anything else is a normal stream-ordered launch) may start its prologue now
@@ -1178,9 +1201,11 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
           continue;
         }
         ptx::mbar_arrive_expect_tx_w(&y_full[s], 32768u);
-        const int col = chunk_of(j) * 128;
-        ptx::tma_load_2d_w(yt, &tm_y0, &y_full[s], col, t0, ptx::kEvictFirst);
-        ptx::tma_load_2d_w(yt + 16384u, &tm_y0, &y_full[s], col + 64, t0, ptx::kEvictFirst);
+        int tl, ch;
+        unit_of(j, tl, ch);
+        const int col = ch * 128;
+        ptx::tma_load_2d_w(yt, &tm_y0, &y_full[s], col, tl * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d_w(yt + 16384u, &tm_y0, &y_full[s], col + 64, tl * 128, ptx::kEvictFirst);
         if (lane == 0) ptx::prog_mark(0, j + 1);
       }
     }
@@ -1193,7 +1218,17 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
       const uint32_t bt_a = ptx::uniform_u32(ptx::smem_u32(btiles));
       const uint64_t dbase = ptx::smem_desc_sw128(0, 1024, 0);
       ptx::mbar_wait_or_trap(g_full, 0, __LINE__);
+      int cur_tile = tile;
+      uint32_t g_ph = 0;
       for (int j = 0; j < nch; ++j) {
+        if (p.streamk) {
+          int tl, ch;
+          unit_of(j, tl, ch);
+          if (tl != cur_tile) {                                  // next segment: its A operand (post * g of that tile)
+            cur_tile = tl; g_ph ^= 1u;
+            ptx::mbar_wait_or_trap(g_full, g_ph, __LINE__);
+          }
+        }
         // chunk j belongs to worker group (j & 1); each group rotates over two accumulator / B buffers
         const int i = (j & 1) * 2 + ((j >> 1) & (p.bpg - 1));
         const uint32_t ph = (uint32_t)((j >> 1) / p.bpg) & 1u;
@@ -1225,9 +1260,11 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
         const uint32_t ph = (uint32_t)(j / p.ystages) & 1u;
         ptx::mbar_wait_or_trap(&y_done[s], ph, __LINE__);
         uint8_t* yt = ytiles + (size_t)s * 32768;
-        const int col = chunk_of(j) * 128;
-        ptx::tma_store_2d(&tm_y, yt, col, t0);
-        ptx::tma_store_2d(&tm_y, yt + 16384, col + 64, t0);
+        int tl, ch;
+        unit_of(j, tl, ch);
+        const int col = ch * 128;
+        ptx::tma_store_2d(&tm_y, yt, col, tl * 128);
+        ptx::tma_store_2d(&tm_y, yt + 16384, col + 64, tl * 128);
         ptx::tma_store_commit();
         ptx::tma_store_wait_read<0>();                         // smem read out: the slot can take the next load now
         ptx::mbar_arrive(&y_empty[s]);
@@ -1286,12 +1323,42 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
     if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 0);
     if (grp_id < nch) load_b(grp_id, grp_id * 2);               // first two B tiles of each group, in flight early
     if (p.bpg == 2 && grp_id + 2 < nch) load_b(grp_id + 2, grp_id * 2 + 1);
+    // g rows come finished from k_attn_fwd: build the A operand (post_m * g, bf16) of token tile [t0s, t0s + nts)
+    // straight from global memory - every load of a thread is issued before its first use, so it costs one memory
+    // round trip instead of a chain of them
+    const int cpr_t = p.rk / 8;                                  // 16-byte chunks per token row
+    constexpr int kMaxItems = 4;                                 // 128 * cpr_t / 256 items per thread (rk <= 64)
+    auto stage_a = [&](int t0s, int nts, const int* pre_codes) {
+      for (int base = 0; base < 128 * cpr_t; base += kMaxItems * 2 * kWorkers) {
+        float4 ga[kMaxItems], gb[kMaxItems];
+#pragma unroll
+        for (int u = 0; u < kMaxItems; ++u) {
+          const int idx = base + wt + u * 2 * kWorkers;
+          const int n = idx / cpr_t, k = (idx - n * cpr_t) * 8;
+          ga[u] = gb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (idx < 128 * cpr_t && n < nts) {
+            if (k < r) ga[u] = *reinterpret_cast<const float4*>(h_in0 + (size_t)(t0s + n) * r + k);
+            if (k + 4 < r) gb[u] = *reinterpret_cast<const float4*>(h_in0 + (size_t)(t0s + n) * r + k + 4);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kMaxItems; ++u) {
+          const int idx = base + wt + u * 2 * kWorkers;
+          if (idx >= 128 * cpr_t) continue;
+          const int n = idx / cpr_t, chf = idx - n * cpr_t;      // chunk over the full rank
+          const int kb = chf >> 3, ch = chf & 7;
+          int code;
+          if (pre_codes && base == 0) code = pre_codes[u];
+          else code = (n < nts) ? (tokmeta[t0s + n] & MOKA_MOD_MASK) : 0;
+          const float ps = code ? d.post[code] : 0.f;
+          uint4 v;
+          v.x = pack_bf16(ga[u].x * ps, ga[u].y * ps); v.y = pack_bf16(ga[u].z * ps, ga[u].w * ps);
+          v.z = pack_bf16(gb[u].x * ps, gb[u].y * ps); v.w = pack_bf16(gb[u].z * ps, gb[u].w * ps);
+          *reinterpret_cast<uint4*>(gtile + (size_t)kb * 16384 + ptx::sw128_offset((uint32_t)n, (uint32_t)ch)) = v;
+        }
+      }
+    };
     if (!p.attn_in_kernel) {
-      // g rows come finished from k_attn_fwd: build the A operand (post_m * g, bf16) straight from global
-      // memory - every load of a thread is issued before its first use, so the prologue costs one memory
-      // round trip instead of a chain of them
-      const int cpr_t = p.rk / 8;                                // 16-byte chunks per token row
-      constexpr int kMaxItems = 4;                               // 128 * cpr_t / 256 items per thread (rk <= 64)
       int codes[kMaxItems];
 #pragma unroll
       for (int u = 0; u < kMaxItems; ++u) {
@@ -1301,33 +1368,7 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
       }
       ptx::pdl_wait();                                           // g comes from k_attn_fwd
       if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 6);
-      for (int base = 0; base < 128 * cpr_t; base += kMaxItems * 2 * kWorkers) {
-        float4 ga[kMaxItems], gb[kMaxItems];
-#pragma unroll
-        for (int u = 0; u < kMaxItems; ++u) {
-          const int idx = base + wt + u * 2 * kWorkers;
-          const int n = idx / cpr_t, k = (idx - n * cpr_t) * 8;
-          ga[u] = gb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (idx < 128 * cpr_t && n < nt) {
-            if (k < r) ga[u] = *reinterpret_cast<const float4*>(h_in0 + (size_t)(t0 + n) * r + k);
-            if (k + 4 < r) gb[u] = *reinterpret_cast<const float4*>(h_in0 + (size_t)(t0 + n) * r + k + 4);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < kMaxItems; ++u) {
-          const int idx = base + wt + u * 2 * kWorkers;
-          if (idx >= 128 * cpr_t) continue;
-          const int n = idx / cpr_t, chf = idx - n * cpr_t;      // chunk over the full rank
-          const int kb = chf >> 3, ch = chf & 7;
-          int code = codes[u];
-          if (base > 0) code = (n < nt) ? (tokmeta[t0 + n] & MOKA_MOD_MASK) : 0;
-          const float ps = code ? d.post[code] : 0.f;
-          uint4 v;
-          v.x = pack_bf16(ga[u].x * ps, ga[u].y * ps); v.y = pack_bf16(ga[u].z * ps, ga[u].w * ps);
-          v.z = pack_bf16(gb[u].x * ps, gb[u].y * ps); v.w = pack_bf16(gb[u].z * ps, gb[u].w * ps);
-          *reinterpret_cast<uint4*>(gtile + (size_t)kb * 16384 + ptx::sw128_offset((uint32_t)n, (uint32_t)ch)) = v;
-        }
-      }
+      stage_a(t0, nt, codes);
       if (grp_id < nch) store_b(grp_id * 2);
       if (p.bpg == 2 && grp_id + 2 < nch) store_b(grp_id * 2 + 1);
       if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 2);
@@ -1380,7 +1421,25 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
     if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 3);
 
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    for (int j = grp_id; j < nch; j += 2) {
+    // segments: the runs of this CTA's units that share a token tile (exactly one unless stream-K).  BOTH worker
+    // groups walk every segment (one of them may own none of its chunks), so that they meet at the boundaries.
+    for (int j0 = 0, seg = 0; j0 < nch; ++seg) {
+      int j1 = nch;
+      if (p.streamk) {
+        const long long u0 = u_beg + j0;
+        const int tl = (int)(u0 / p.chunks);
+        j1 = (int)min((long long)nch, (long long)(tl + 1) * p.chunks - u_beg);
+        if (seg > 0) {
+          // every epilogue of the previous tile is done once both groups are here, hence all of its MMAs have
+          // retired: the A operand tile may be rewritten for the next token tile
+          named_sync(2, 2 * kWorkers);
+          stage_a(tl * 128, min(128, p.T - tl * 128), nullptr);
+          ptx::fence_proxy_async_smem();
+          named_sync(2, 2 * kWorkers);
+          if (wt == 0) ptx::mbar_arrive(g_full);
+        }
+      }
+    for (int j = j0 + ((grp_id ^ j0) & 1); j < j1; j += 2) {
       const int n = j >> 1;                                      // this group's chunk counter
       const int i = grp_id * 2 + (n & (p.bpg - 1));              // accumulator / B buffer
       const uint32_t ph = (uint32_t)(n / p.bpg) & 1u;
@@ -1406,6 +1465,8 @@ k_up_tc(const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUten
       if (j + ahead < nch) store_b(i);
       if (wl == 0) ptx::prog_mark(5 + grp_id, j + 1);
       if (wl == 0 && j < 6) dbg_stamp(p.dbg, blockIdx.x, 11 + j * 4);
+    }
+      j0 = j1;
     }
     if (wt == 0) dbg_stamp(p.dbg, blockIdx.x, 4);
   }
@@ -1456,6 +1517,15 @@ static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaSt
   p.delta = d.delta;
   p.rot = rot_enabled();
   p.dbg = dbg_enabled();
+  // stream-K (persistent, balanced unit ranges; needs the attention as its own kernel): MOKA_UP_STREAMK=1.  OFF by
+  // default - measured round 2 (T = 32768): 106.4 vs 100.9 us at d_out = 4096, 275 vs 253 us at 11008.  This kernel
+  // reads and re-writes the same rows; with 148 CTAs in flight it already sits at what HBM gives that traffic mix
+  // (~5.3 TB/s), so balancing the tail buys nothing and the per-segment restaging of the A operand costs.
+  static int up_sk_env = -1;
+  if (up_sk_env < 0) { const char* e = getenv("MOKA_UP_STREAMK"); up_sk_env = (e && e[0] == '1') ? 1 : 0; }
+  p.units = (long long)ntiles * p.chunks;
+  p.streamk = (up_sk_env && sep_attn && p.units >= 2) ? 1 : 0;
+  p.grid = p.streamk ? (int)std::min<long long>(num_sms, p.units) : ntiles * p.nsplit;
   CUtensorMap ty0, ty;
   if (!make_tmap(&ty0, d.delta ? a.y : a.y0, (uint64_t)d.T, (uint64_t)d.d_out, 128)) return MOKA_EUNSUPPORTED;
   if (!make_tmap(&ty, a.y, (uint64_t)d.T, (uint64_t)d.d_out, 128)) return MOKA_EUNSUPPORTED;
@@ -1515,12 +1585,12 @@ static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaSt
       if (int rc = check_launch_tc()) return rc;
     }
     if (d.dbg_skip & 2) return MOKA_OK;
-    e = launch_pdl(k_up_tc, dim3(ntiles * p.nsplit), dim3(kUpThreads), smem, st, ty0, ty, d, p,
+    e = launch_pdl(k_up_tc, dim3(p.grid), dim3(kUpThreads), smem, st, ty0, ty, d, p,
                    static_cast<const __nv_bfloat16*>(a.Bw), a.tokmeta, a.kidx, a.klen, (const float*)g_stash,
                    (const float*)nullptr, (float*)nullptr, g_stash);
   } else {
     if (d.dbg_skip & 2) return MOKA_OK;
-    e = launch_pdl(k_up_tc, dim3(ntiles * p.nsplit), dim3(kUpThreads), smem, st, ty0, ty, d, p,
+    e = launch_pdl(k_up_tc, dim3(p.grid), dim3(kUpThreads), smem, st, ty0, ty, d, p,
                    static_cast<const __nv_bfloat16*>(a.Bw), a.tokmeta, a.kidx, a.klen, h0, h1,
                    partials ? a.h_stash : (float*)nullptr, g_stash);
   }
