@@ -90,6 +90,19 @@ class ClockSampler:
                     samples=len(sm))
 
 
+def ncu_traffic(wl, d):
+    """roofline.traffic: measured DRAM bytes of one fwd+bwd call pair at the dominant (hidden -> hidden) shape of this
+    workload, looked up in profiles/r02_ncu_traffic.json by (T, d_in, d_out, r, M, p); None if never captured."""
+    key = f"T={wl['B'] * wl['S']},d_in={d},d_out={d},r={wl['r']},M={wl['M']},p={wl['dropout']}"
+    try:
+        rec = json.load(open(os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')))[key]
+        alg = 2 * wl['B'] * wl['S'] * 7 * d
+        return dict(traffic=rec['traffic_bytes'], traffic_shape=f'one fwd+bwd call pair, {key} (ncu: {rec["source"]})',
+                    traffic_algorithmic=alg)
+    except Exception:
+        return dict(traffic=None, traffic_shape=f'no ncu capture for {key}')
+
+
 def kernel_path_name(wl, d, flags):
     """Which kernels serve the step's square projections, as the library itself reports it."""
     import torch
@@ -497,11 +510,11 @@ def main():
             e2e=dict(value=e2e_value, unit='tokens/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                      ms_per_step=ms_e2e / args.steps, last_loss=last_loss),
             gpu_launches=int(launches),
-            # traffic: dram__bytes_read + dram__bytes_write of one forward + backward chain from the ncu --set
-            # full capture in profiles/r01_ncu_chain_r16_s3.md (T = 8192, 4096 -> 4096, r = 16; algorithmic
-            # 469.8 MB, of which the writes still resident in the 126 MB L2 at kernel end are not counted)
+            # traffic: dram__bytes_read + dram__bytes_write of one forward + backward chain at the step's most
+            # frequent shape, from the ncu --set full capture recorded in profiles/r02_ncu_traffic.json
+            # (tools/ncu_traffic.py); null when no capture matches this workload's shape
             roofline=dict(bound='hbm', achieved=achieved, peak=peak, unit='GB/s', frac=achieved / peak,
-                          traffic=370.0e6, traffic_shape='one fwd+bwd call pair, T=8192 d=4096->4096 r=16 (ncu)',
+                          **ncu_traffic(wl, cfg.hidden_size),
                           peak_source=peak_kind,
                           kernel='fused MokaLinear fwd+bwd (libmoka.so calls, CUDA events per call)',
                           calls=len(events), delta_out_calls=n_delta,
