@@ -3108,6 +3108,8 @@ struct WgradTcParams {
   int has_dx, dbg;
   int delta;                       // MOKA_FLAG_DELTA_OUT: dx tiles are write-only in this pass (no dx read)
   int early_bits;                  // DROP: keep bits generated before the tile's waits (see drop_early_bits)
+  int mod_filter;                  // token tiles this pass visits: -1 all; 0 those holding a token of ANY modality; m > 0
+                                   // those holding a token of modality code m (a per-modality pass of a rank-chunked call)
   int prefetch_dx;                 // dx tiles may be loaded before the dependency wait (false for the later passes of a
                                    // rank-chunked call: the pass in front is still writing dx)
   uint32_t w_box_bytes;            // one 64-column box of the weight slice: (NPW, or 2 NPW with the residual half) x 128 B
@@ -3128,7 +3130,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
            const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
            const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_hc,
            const __grid_constant__ CUtensorMap tm_hct_hi, const __grid_constant__ CUtensorMap tm_hct_lo,
-           WgradTcParams p, DevDesc d, float* __restrict__ dA0, float* __restrict__ dA1, float* __restrict__ dA2) {
+           WgradTcParams p, DevDesc d, float* __restrict__ dA0, float* __restrict__ dA1, float* __restrict__ dA2,
+           const uint8_t* __restrict__ tokmeta) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t hct_blk = p.hct_blk;                         // [NPW rows x 64 tokens] block
@@ -3159,7 +3162,46 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   const int col0 = slice * 128;
   const int tt_beg = (int)((long long)split * p.ntiles / p.tsplit);
   const int tt_end = (int)((long long)(split + 1) * p.ntiles / p.tsplit);
-  const int ntt = tt_end - tt_beg;
+  // The token tiles of the range that this pass has to visit.  A token belongs to one modality, so a per-modality
+  // pass of a rank-chunked call (r = 64 with three modalities, r = 128) only changes dx rows / adds to dA from tiles
+  // that hold a token of ITS modality: visiting just those turns "x and dx streamed once per modality" (3x) into
+  // ~1.25x on the AVT layouts; tiles holding only padding are skipped by every pass.  The token metadata is older
+  // than the call, so the list is built before the dependency wait.
+  constexpr int kWgList = 256;
+  __shared__ unsigned short s_tile[kWgList];
+  __shared__ int s_nl;
+  {
+    const int nall = tt_end - tt_beg;
+    const bool filter = p.mod_filter >= 0 && nall <= kWgList;
+    if (filter) {
+      for (int j = warp; j < nall; j += (int)(blockDim.x >> 5)) {
+        const long long tb = (long long)(tt_beg + j) * 128 + lane * 4;
+        bool hit = false;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int code = (tb + e < p.T) ? (tokmeta[tb + e] & MOKA_MOD_MASK) : 0;
+          hit |= p.mod_filter ? (code == p.mod_filter) : (code != 0);
+        }
+        const unsigned any = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_tile[j] = any ? 1 : 0;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int n = 0;
+      if (nall <= kWgList) {
+        for (int j = 0; j < nall; ++j)
+          if (!filter || s_tile[j]) s_tile[n++] = (unsigned short)j;
+      } else {
+        n = nall;                                           // (identity: the list is not used)
+      }
+      s_nl = n;
+    }
+    __syncthreads();
+  }
+  const int ntt = s_nl;
+  const bool use_list = (tt_end - tt_beg) <= kWgList;
+  auto tile_of = [&](int j) { return tt_beg + (use_list ? (int)s_tile[j] : j); };
   // (walking the token range in a per-slice rotated order was measured 4 % SLOWER: the column slices of a
   // range share their packed dh operand tiles through L2 when they walk it together)
   if (threadIdx.x == 0) { dbg_stamp_g(p.dbg, blockIdx.x, 112); dbg_stamp(p.dbg, blockIdx.x, 1); }
@@ -3217,19 +3259,19 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       for (int j = 0; j < npre_x; ++j) {
         const uint32_t xt = x_a + (uint32_t)j * 32768u;
         ptx::mbar_arrive_expect_tx_w(&x_full[j], 32768u);
-        ptx::tma_load_2d_w(xt, &tm_x, &x_full[j], col0, (tt_beg + j) * 128, ptx::kEvictFirst);
-        ptx::tma_load_2d_w(xt + 16384u, &tm_x, &x_full[j], col0 + 64, (tt_beg + j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d_w(xt, &tm_x, &x_full[j], col0, tile_of(j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d_w(xt + 16384u, &tm_x, &x_full[j], col0 + 64, tile_of(j) * 128, ptx::kEvictFirst);
       }
       for (int j = 0; j < npre_d; ++j) {
         const uint32_t dt = d_a + (uint32_t)j * 32768u;
         if (p.delta) { ptx::mbar_arrive_w(&d_full[j]); continue; }   // write-only dx: a free slot is enough
         ptx::mbar_arrive_expect_tx_w(&d_full[j], 32768u);
-        ptx::tma_load_2d_w(dt, &tm_dx, &d_full[j], col0, (tt_beg + j) * 128, ptx::kEvictFirst);
-        ptx::tma_load_2d_w(dt + 16384u, &tm_dx, &d_full[j], col0 + 64, (tt_beg + j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d_w(dt, &tm_dx, &d_full[j], col0, tile_of(j) * 128, ptx::kEvictFirst);
+        ptx::tma_load_2d_w(dt + 16384u, &tm_dx, &d_full[j], col0 + 64, tile_of(j) * 128, ptx::kEvictFirst);
       }
       ptx::pdl_wait();
       for (int j = 0; j < ntt; ++j) {
-        const int t0 = (tt_beg + j) * 128;
+        const int t0 = tile_of(j) * 128;
         if (j >= npre_x) {   // the big streams first: they have their own ring slots and must never wait on the MMAs
           const int s = j % p.xs;
           const uint32_t ph = (uint32_t)(j / p.xs) & 1u;
@@ -3330,7 +3372,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         const int s = j % p.xs;
         const uint32_t k = (uint32_t)(j / p.xs);
         // keep bits of this thread's two 32-column super-groups: data-independent (early_bits: generated before the waits)
-        const unsigned long long rowbase = dropout_row_base(d, (long long)(tt_beg + j) * 128 + mrow);
+        const unsigned long long rowbase = dropout_row_base(d, (long long)tile_of(j) * 128 + mrow);
         uint32_t k32v[2] = {0xffffffffu, 0xffffffffu};
         if (p.early_bits) {
 #pragma unroll
@@ -3360,7 +3402,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
       for (int j = 0; j < ntt; ++j) {
         const int s = j % p.ds;
         const uint32_t ph = (uint32_t)(j / p.ds) & 1u;
-        const int t0 = (tt_beg + j) * 128;
+        const int t0 = tile_of(j) * 128;
         ptx::mbar_wait_or_trap(&d_done[s], ph, __LINE__);
         uint8_t* dt = dring + (size_t)s * 32768;
         ptx::tma_store_2d(&tm_dx, dt, col0, t0);
@@ -3413,6 +3455,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         if (st) dbg_stamp(p.dbg, blockIdx.x, 11 + j * 4);
       }
     }
+    if (ntt > 0) {                                           // (no tile visited: the accumulator was never written)
     // ---- dA of this column slice: TMEM lane <-> column, TMEM column <-> (modality, rank index)
     if (threadIdx.x == 64) dbg_stamp(p.dbg, blockIdx.x, 4);
     ptx::mbar_wait_or_trap(a_full, 0, __LINE__);
@@ -3444,6 +3487,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         const float4 v = *reinterpret_cast<const float4*>(stage + n * 128 + c4);
         red_add_v4_f32(dAm + (size_t)jj * p.d_in + col0 + c4, v.x, v.y, v.z, v.w);
       }
+    }
     }
     if (threadIdx.x == 64) dbg_stamp(p.dbg, blockIdx.x, 6);
   }
@@ -3574,12 +3618,21 @@ static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParam
 static bool wgrad_plan(const DevDesc& d, bool has_dx, int num_sms, WgradTcParams& p, PackLayout& L, size_t& fixed,
                        int& nchunks) {
   nchunks = 1;
-  if (wgrad_plan1(d, has_dx, num_sms, p, L, fixed)) return true;
-  if (d.r % 64 || d.T % 8 || d.M < 2) return false;
+  const bool single = wgrad_plan1(d, has_dx, num_sms, p, L, fixed);
+  // a single pass whose tiles leave room for only one operand buffer or one x slot (r = 64 with two modalities) runs
+  // its load -> MMA -> reload chain unpipelined; per-modality passes have half the operand width and, since each
+  // pass only visits the token tiles that hold its modality (mod_filter), stream little more than a single pass
+  const bool degraded = single && (p.nop < 2 || p.xs < 2 || (has_dx && p.ds < 2));
+  if (single && !degraded) return true;
+  if (d.r % 64 || d.T % 8 || d.M < 2) return single;
+  WgradTcParams p1 = p;
+  PackLayout L1;
+  size_t fixed1 = 0;
   DevDesc d1 = d;
   d1.M = 1;                                                   // one pass per modality (see launch_wgrad_tc)
-  PackLayout L1;
-  if (!wgrad_plan1(d1, has_dx, num_sms, p, L1, fixed)) return false;
+  if (!wgrad_plan1(d1, has_dx, num_sms, p1, L1, fixed1)) return single;
+  if (single && (p1.nop < 2 || p1.xs < 2)) return true;       // no better: keep the single pass
+  p = p1; fixed = fixed1;
   L = pack_layout(d.T, d.r, d.M);                             // the pack step still produces the full operands
   nchunks = d.M;
   return true;
@@ -3622,13 +3675,13 @@ static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParam
   const size_t km_bytes = d.drop_thresh ? (size_t)(has_dx ? 2 : 4) * 2048 : 0;
   fixed = (size_t)2 * p.w_box_bytes + (size_t)p.nop * p.op_bytes + 1024 + 512 + km_bytes;
   if (fixed + 4 * 32768 > limit) { p.nop = 1; fixed -= p.op_bytes; }
-  if (fixed + 3 * 32768 > limit) return false;
+  if (fixed + 2 * 32768 > limit) return false;
   int slots = (int)((limit - fixed) / 32768);
   if (p.has_dx) {
     p.xs = 2;
     p.ds = min(3, slots - p.xs);
-    if (p.ds < 2) { p.xs = 1; p.ds = slots - 1; }
-    if (p.ds < 2) return false;
+    if (p.ds < 2) { p.xs = 1; p.ds = min(3, slots - 1); }
+    if (p.ds < 1) return false;                               // (one dx slot: unpipelined, still far ahead of the warp-FMA kernel)
   } else {
     p.xs = min(4, slots); p.ds = 0;
   }
@@ -3682,12 +3735,13 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
       if (!make_tmap(&thl_c, hct_lo + (size_t)c * w * d.T, w, (uint64_t)d.T, (uint32_t)w)) return MOKA_EUNSUPPORTED;
       p.prefetch_dx = (c == 0);
       p.delta = (c == 0 && p.has_dx && d.delta) ? 1 : 0;       // later passes add onto what the first one wrote
+      p.mod_filter = p.delta ? -1 : c + 1;                     // (a write-only first pass must store every tile)
       if (d.drop_thresh)
         e = launch_pdl(k_wgrad_tc<true>, dim3(slices * p.tsplit), dim3(kWgradDropThreads), smem, st, tx, tdx, tac, tac, tac,
-                       thc_c, thh_c, thl_c, p, d, dAc, dAc, dAc);
+                       thc_c, thh_c, thl_c, p, d, dAc, dAc, dAc, a.tokmeta);
       else
         e = launch_pdl(k_wgrad_tc<false>, dim3(slices * p.tsplit), dim3(kWgradThreads), smem, st, tx, tdx, tac, tac, tac,
-                       thc_c, thh_c, thl_c, p, d, dAc, dAc, dAc);
+                       thc_c, thh_c, thl_c, p, d, dAc, dAc, dAc, a.tokmeta);
       if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
       if (int rc = check_launch_tc()) return rc;
     }
@@ -3702,12 +3756,13 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
                       ? cudaFuncSetAttribute(k_wgrad_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                       : cudaFuncSetAttribute(k_wgrad_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+  p.mod_filter = p.delta ? -1 : 0;                            // single pass: only tiles made of padding are skipped
   if (d.drop_thresh)
     e = launch_pdl(k_wgrad_tc<true>, dim3(slices * p.tsplit), dim3(kWgradDropThreads), smem, st, tx, tdx, ta[0], ta[1], ta[2],
-                   thc, thh, thl, p, d, a.dA[0], a.dA[d.M > 1 ? 1 : 0], a.dA[d.M > 2 ? 2 : 0]);
+                   thc, thh, thl, p, d, a.dA[0], a.dA[d.M > 1 ? 1 : 0], a.dA[d.M > 2 ? 2 : 0], a.tokmeta);
   else
     e = launch_pdl(k_wgrad_tc<false>, dim3(slices * p.tsplit), dim3(kWgradThreads), smem, st, tx, tdx, ta[0], ta[1], ta[2],
-                   thc, thh, thl, p, d, a.dA[0], a.dA[d.M > 1 ? 1 : 0], a.dA[d.M > 2 ? 2 : 0]);
+                   thc, thh, thl, p, d, a.dA[0], a.dA[d.M > 1 ? 1 : 0], a.dA[d.M > 2 ? 2 : 0], a.tokmeta);
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
   return check_launch_tc();
 }
