@@ -90,6 +90,13 @@ class ClockSampler:
                     samples=len(sm))
 
 
+def _pct(xs):
+    xs = sorted(xs)
+    if not xs:
+        return [0.0, 0.0, 0.0]
+    return [xs[int(0.1 * (len(xs) - 1))], xs[len(xs) // 2], xs[int(0.9 * (len(xs) - 1))]]
+
+
 def ncu_traffic(wl, d):
     """roofline.traffic: measured DRAM bytes of one fwd+bwd call pair at the dominant (hidden -> hidden) shape of this
     workload, looked up in profiles/r02_ncu_traffic.json by (T, d_in, d_out, r, M, p); None if never captured."""
@@ -486,8 +493,10 @@ def main():
         t = ev[0].elapsed_time(ev[1])
         alg_bytes += b; dur_ms += t
         per_kind[kind][0] += b; per_kind[kind][1] += t
-        bs = by_shape.setdefault(f'{d_in}x{d_out}', dict(fwd_ms=0.0, bwd_ms=0.0, fwd_bytes=0.0, bwd_bytes=0.0, calls=0))
+        bs = by_shape.setdefault(f'{d_in}x{d_out}', dict(fwd_ms=0.0, bwd_ms=0.0, fwd_bytes=0.0, bwd_bytes=0.0, calls=0,
+                                                          fwd_list=[], bwd_list=[]))
         bs[kind + '_ms'] += t; bs[kind + '_bytes'] += b; bs['calls'] += 1
+        bs[kind + '_list'].append(t * 1e3)
     peak, peak_kind = peak_hbm()
     achieved = alg_bytes / (dur_ms * 1e-3) / 1e9 if dur_ms > 0 else 0.0
 
@@ -526,6 +535,8 @@ def main():
                           by_shape={k: dict(calls=v['calls'],
                                             fwd_us=round(v['fwd_ms'] * 2e3 / max(v['calls'], 1), 1),
                                             bwd_us=round(v['bwd_ms'] * 2e3 / max(v['calls'], 1), 1),
+                                            fwd_us_p10_p50_p90=[round(float(x), 1) for x in _pct(v['fwd_list'])],
+                                            bwd_us_p10_p50_p90=[round(float(x), 1) for x in _pct(v['bwd_list'])],
                                             frac=round((v['fwd_bytes'] + v['bwd_bytes']) / max(v['fwd_ms'] + v['bwd_ms'], 1e-9)
                                                        / 1e6 / peak, 4))
                                     for k, v in by_shape.items()}),

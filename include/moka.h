@@ -205,6 +205,10 @@ int moka_rope(const void* src, void* dst, int64_t tokens, int32_t S, int32_t H, 
 /* Tuning aid: copies the in-kernel cycle stamps recorded when MOKA_DEBUG_TIMING=1 (host buffer). */
 int moka_debug_read(unsigned long long* host, int32_t n);
 
+/* Tuning aid: enqueues a one-thread kernel on `stream` that writes the GPU's globaltimer into slot `slot` (0..127) of
+ * the last row of the debug stamp buffer - a stream-ordered time marker next to the kernels' own stamps. */
+int moka_debug_mark(int32_t slot, moka_stream_t stream);
+
 /* Tuning / post-mortem aid: registers two words of pinned, device-mapped host memory; a bounded in-kernel wait
  * that times out writes (source line << 32 | block << 12 | thread) there before it traps. */
 int moka_debug_trap_buffer(unsigned long long* host_mapped);

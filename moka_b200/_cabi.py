@@ -24,7 +24,7 @@ EXPORTS = ['moka_workspace_bytes', 'moka_forward', 'moka_backward', 'moka_build_
            'moka_build_token_meta_from_ids', 'moka_build_token_meta_from_segments',
            'moka_dropout_keep_mask', 'moka_effective_dropout_p', 'moka_adamw_step', 'moka_launch_count',
            'moka_uses_tensor_cores', 'moka_supports_delta', 'moka_strerror', 'moka_version', 'moka_rope', 'moka_debug_read',
-           'moka_debug_trap_buffer']
+           'moka_debug_trap_buffer', 'moka_debug_mark']
 
 
 class MokaDesc(Structure):
@@ -81,6 +81,8 @@ def load():
     lib.moka_rope.argtypes = [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p]
     lib.moka_debug_trap_buffer.restype = c_int32
     lib.moka_debug_trap_buffer.argtypes = [c_void_p]
+    lib.moka_debug_mark.restype = c_int32
+    lib.moka_debug_mark.argtypes = [c_int32, c_void_p]
     lib.moka_debug_read.restype = c_int32
     lib.moka_debug_read.argtypes = [c_void_p, c_int32]
     lib.moka_launch_count.restype = c_int64

@@ -303,6 +303,8 @@ int moka_debug_read(unsigned long long* host, int32_t n) {
   return debug_read(host, n);
 }
 
+int moka_debug_mark(int32_t slot, moka_stream_t stream) { return debug_mark(slot, static_cast<cudaStream_t>(stream)); }
+
 int moka_debug_trap_buffer(unsigned long long* host_mapped) { return debug_set_trap_buffer(host_mapped); }
 
 int64_t moka_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -33,6 +33,7 @@ __device__ __forceinline__ void pack_rows2(const DevDesc& d, const AttnPackParam
                                            __nv_bfloat16* __restrict__ hct_lo, int tid, int nthr) {
   const int r = d.r;
   const int cpr = p.KP / 8;
+  if (hc)                                           // (token-major operand: only the round-1 form of k_wgrad_tc reads it)
   for (int i = tid; i < nt * cpr; i += nthr) {
     const int tt = i / cpr, n0 = (i - tt * cpr) * 8;
     const int base = s_base[tt];

@@ -50,6 +50,7 @@ int launch_adamw(int64_t n, float* master, float* m, float* v, const float* grad
 int launch_rope(const void* src, void* dst, long long BS, int S, int H, int D, float theta, float sign, cudaStream_t st);
 
 int debug_read(unsigned long long* host, int n);
+int debug_mark(int slot, cudaStream_t st);
 int tc_dbg_enabled();
 int debug_set_trap_buffer(unsigned long long* mapped);
 

@@ -137,6 +137,16 @@ int tc_dbg_enabled() { return dbg_enabled(); }
 int debug_set_trap_buffer(unsigned long long* mapped) {
   return cudaMemcpyToSymbol(ptx::g_trap_buf, &mapped, sizeof(mapped)) == cudaSuccess ? MOKA_OK : MOKA_ECUDA;
 }
+// tuning aid: a one-thread kernel that stamps globaltimer into slot `slot` of the LAST debug row (stream-ordered marker)
+__global__ void k_dbg_mark(int slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  g_dbg[(kDbgCtas - 1) * kDbgSlots + (slot & (kDbgSlots - 1))] = t;
+}
+int debug_mark(int slot, cudaStream_t st) {
+  k_dbg_mark<<<1, 1, 0, st>>>(slot);
+  return cudaGetLastError() == cudaSuccess ? MOKA_OK : MOKA_ECUDA;
+}
 int debug_read(unsigned long long* host, int n) {
   if (n > kDbgCtas * kDbgSlots) n = kDbgCtas * kDbgSlots;
   return cudaMemcpyFromSymbol(host, g_dbg, (size_t)n * 8) == cudaSuccess ? MOKA_OK : MOKA_ECUDA;
@@ -1679,7 +1689,12 @@ struct DgSegIter {
   }
 };
 
-__global__ void __launch_bounds__(kTcThreads)
+// warps: 0 TMA producer, 1 issues the dG products (and owns TMEM), 2 issues the dB products, 3..6 workers.  Two
+// issuing warps (round 2): the per-stage waits / fence / commits of one overlap the tensor-pipe time of the other's
+// products - with a single issuer the pipe idled ~25 % of every stage, and that share grows as the SM clock drops
+// under the power cap of the surrounding GEMMs.
+constexpr int kDgradThreads = 224;
+__global__ void __launch_bounds__(kDgradThreads)
 k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CUtensorMap tm_bt, DevDesc d,
            DgradTcParams p, const uint8_t* __restrict__ tokmeta,
            const float* __restrict__ g_stash, float* __restrict__ dG0, float* __restrict__ dB,
@@ -1709,7 +1724,7 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
   if (threadIdx.x == 0) { dbg_stamp_g(p.dbg, blockIdx.x, 108); dbg_stamp(p.dbg, blockIdx.x, 0); }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 2); }   // (both issuers commit)
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&d2_full[i], 1); ptx::mbar_init(&d2_empty[i], kWorkerWarps);
       ptx::mbar_init(&dg_full[i], 1); ptx::mbar_init(&dg_empty[i], kWorkerWarps);
@@ -1774,41 +1789,32 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    // ---- MMA issuer: the WHOLE warp runs this loop on warp-uniform values, one elected lane issues (see moka_ptx.cuh)
+    // ---- issuer of MMA1, dG[128 tok, rk] += dY . B.  The WHOLE warp runs this loop on warp-uniform values, one
+    // elected lane issues (see moka_ptx.cuh).  Needs only the TMA data of the stage.
     {
       const uint32_t tb = ptx::uniform_u32(tmem_base);
       const uint32_t idesc1 = ptx::idesc_bf16(128, (uint32_t)p.rk, 0, 0);     // dG: A K-major, B K-major
-      // dB: A MN-major (transposed view of the dY tile); hi and lo halves of g stacked along N, so one
-      // pass over the tile yields both products (the epilogue adds them)
-      const uint32_t idesc2 = ptx::idesc_bf16(128, 2u * (uint32_t)p.rk, 1, 0);
-      const uint32_t gta = ptx::uniform_u32(ptx::smem_u32(gt));
       const uint32_t ring_a = ptx::uniform_u32(ptx::smem_u32(ring));
       // descriptors differ only in their 14-bit start-address field: build once, add offsets (>> 4)
       const uint64_t a1_base = ptx::smem_desc_sw128(0, 1024, 0);
-      const uint64_t a2_base = ptx::smem_desc_sw128(0, 1024, 16384);
-      const uint64_t g_base = a1_base + (uint64_t)(gta >> 4);
-      const uint32_t g2b = g2_block >> 4, gtb = gt_block >> 4;
+      const uint32_t gtb = gt_block >> 4;
       DgSegIter it{u_beg, u_end, p.pairs, 0, 0, 0};
-      // ring slot / accumulator indices and barrier parities are carried along (no division per stage)
-      int j = 0, seg = 0;
+      int j = 0;
       int s = 0; uint32_t s_ph = 0;                   // ring slot of stage j, parity of its `full` phase
-      int i2 = 0; uint32_t i2_ph = 0;                 // dB accumulator set of stage j, parity of its k-th use
       int dgb = 0; uint32_t dg_ph = 0;                // dG accumulator of the segment
       while (it.next()) {
         const uint32_t dg_acc = tb + (uint32_t)dgb * p.dg_cols;
         ptx::mbar_wait_or_trap(&dg_empty[dgb], dg_ph ^ 1u, __LINE__);          // accumulator read out (two segments ago)
         ptx::tc_fence_after_sync();
-        bool gt_ready = false;
         for (int q0 = it.pb; q0 < it.pe; q0 += W, ++j) {
           const int nq = min(W, it.pe - q0);
           ptx::mbar_wait_or_trap(&full[s], s_ph, __LINE__);
           if (lane == 0) { if (j == 0) dbg_stamp(p.dbg, blockIdx.x, 3); if (j < 8) dbg_stamp(p.dbg, blockIdx.x, 8 + j * 3); }
           const uint32_t sa0 = ring_a + (uint32_t)s * p.stage_bytes;
-          // MMA1 (dG += dY B) touches neither the dB accumulators nor the G^T operand: issue it first, so that the
-          // waits below (and their tcgen05 fence, ~190 cycles) run while the tensor pipe works on these
           for (int q = 0; q < nq; ++q) {
             const uint32_t sa = sa0 + (uint32_t)q * 32768u;
             const uint32_t bta = sa0 + dy_bytes + (uint32_t)(2 * q) * gt_block;
+            // K = 128 columns of this pair (two boxes, four 16-wide steps each)
             const uint64_t a1 = a1_base + (uint64_t)(sa >> 4);
             const uint64_t b1 = a1_base + (uint64_t)(bta >> 4);
 #pragma unroll
@@ -1819,16 +1825,41 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
                                b1 + (uint64_t)(box * gtb + ((kk * 32) >> 4)), idesc1, (q0 > it.pb || q > 0 || k > 0) ? 1u : 0u);
             }
           }
+          ptx::umma_commit_w(&empty[s]);
+          if (++s == p.stages) { s = 0; s_ph ^= 1u; }
+        }
+        ptx::umma_commit_w(&dg_full[dgb]);
+        if (++dgb == p.ndg) { dgb = 0; dg_ph ^= 1u; }
+      }
+      if (lane == 0) dbg_stamp(p.dbg, blockIdx.x, 4);
+    }
+  } else if (warp == 2) {
+    // ---- issuer of MMA2, dB[128 cols, 2 rk] = dY^T . [g_hi | g_lo]: A MN-major (transposed view of the dY tile);
+    // hi and lo halves of g stacked along N, so one pass over the tile yields both products (the epilogue adds them).
+    // Needs the G^T operand of the segment and a free set of dB accumulators.
+    {
+      const uint32_t tb = ptx::uniform_u32(tmem_base);
+      const uint32_t idesc2 = ptx::idesc_bf16(128, 2u * (uint32_t)p.rk, 1, 0);
+      const uint32_t gta = ptx::uniform_u32(ptx::smem_u32(gt));
+      const uint32_t ring_a = ptx::uniform_u32(ptx::smem_u32(ring));
+      const uint64_t a2_base = ptx::smem_desc_sw128(0, 1024, 16384);
+      const uint64_t g_base = ptx::smem_desc_sw128(0, 1024, 0) + (uint64_t)(gta >> 4);
+      const uint32_t g2b = g2_block >> 4;
+      DgSegIter it{u_beg, u_end, p.pairs, 0, 0, 0};
+      int j = 0, seg = 0;
+      int s = 0; uint32_t s_ph = 0;
+      int i2 = 0; uint32_t i2_ph = 0;                 // dB accumulator set of stage j, parity of its k-th use
+      while (it.next()) {
+        ptx::mbar_wait_or_trap(gt_full, (uint32_t)seg & 1u, __LINE__);
+        if (lane == 0 && seg == 0) dbg_stamp(p.dbg, blockIdx.x, 2);
+        for (int q0 = it.pb; q0 < it.pe; q0 += W, ++j) {
+          const int nq = min(W, it.pe - q0);
+          ptx::mbar_wait_or_trap(&full[s], s_ph, __LINE__);
           ptx::mbar_wait_or_trap(&d2_empty[i2], i2_ph ^ 1u, __LINE__);
           if (lane == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 9 + j * 3);
-          if (!gt_ready) {
-            ptx::mbar_wait_or_trap(gt_full, (uint32_t)seg & 1u, __LINE__);
-            if (lane == 0 && seg == 0) dbg_stamp(p.dbg, blockIdx.x, 2);
-            gt_ready = true;
-          }
           ptx::tc_fence_after_sync();
-          if (lane == 0 && j == 2) dbg_stamp(p.dbg, blockIdx.x, 48);
-          // MMA2: M = 128 columns (two 64-wide atoms 16 KB apart), K = 128 tokens in 8 steps of 16
+          const uint32_t sa0 = ring_a + (uint32_t)s * p.stage_bytes;
+          // M = 128 columns (two 64-wide atoms 16 KB apart), K = 128 tokens in 8 steps of 16
           for (int q = 0; q < nq; ++q) {
             const uint32_t sa = sa0 + (uint32_t)q * 32768u;
             const uint64_t a2 = a2_base + (uint64_t)(sa >> 4);
@@ -1839,21 +1870,17 @@ k_dgrad_tc(const __grid_constant__ CUtensorMap tm_dy, const __grid_constant__ CU
               ptx::umma_bf16_w(d2, a2 + (uint64_t)((k * 2048) >> 4), g_base + (uint64_t)((k >> 2) * g2b + (((k & 3) * 32) >> 4)),
                                idesc2, k > 0 ? 1u : 0u);
           }
-          if (lane == 0 && j == 2) dbg_stamp(p.dbg, blockIdx.x, 49);
           ptx::umma_commit_w(&empty[s]);
           ptx::umma_commit_w(&d2_full[i2]);
           if (lane == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 10 + j * 3);
           if (++s == p.stages) { s = 0; s_ph ^= 1u; }
           if (++i2 == p.nbuf) { i2 = 0; i2_ph ^= 1u; }
         }
-        ptx::umma_commit_w(&dg_full[dgb]);
         ++seg;
-        if (++dgb == p.ndg) { dgb = 0; dg_ph ^= 1u; }
       }
-      if (lane == 0) dbg_stamp(p.dbg, blockIdx.x, 4);
     }
   } else {
-    const int wt = threadIdx.x - 64;
+    const int wt = threadIdx.x - 96;                           // workers: warps 3..6 (their warp % 4 covers every TMEM lane quadrant)
     const int q4 = warp & 3;
     const int row = q4 * 32 + lane;
     // G^T operand (post_m * g as hi + lo bf16): rows = rank index, K = tokens.  `gq` = 16 rank values of this
@@ -2269,7 +2296,7 @@ static int launch_dgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
     if (int rc = check_launch_tc()) return rc;
   }
   if (!(d.dbg_skip & 8)) {
-    e = launch_pdl(k_dgrad_tc, dim3(p.grid), dim3(kTcThreads), smem, st, tdy, tbt, d, p, a.tokmeta,
+    e = launch_pdl(k_dgrad_tc, dim3(p.grid), dim3(kDgradThreads), smem, st, tdy, tbt, d, p, a.tokmeta,
                    (const float*)(a.h_stash + (size_t)d.T * d.r), a.dh, a.dB, (uint32_t*)nullptr, 0);
     if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
     if (int rc = check_launch_tc()) return rc;
@@ -2417,6 +2444,7 @@ k_pack_dh(DevDesc d, int rp, int NPW, int KP, int lo_off, const uint8_t* __restr
   __syncthreads();
   // dHc rows
   const int cpr = KP / 8;
+  if (hc)
   for (int i = tid; i < nt * cpr; i += 256) {
     const int tt = i / cpr, n0 = (i - tt * cpr) * 8;
     const int base = s_base[tt];
@@ -2474,6 +2502,7 @@ __device__ __forceinline__ void pack_rows(const DevDesc& d, const AttnPackParams
   constexpr int VS = R + 1;
   const int r = d.r;
   const int cpr = p.KP / 8;
+  if (hc)
   for (int i = tid; i < nt * cpr; i += nthr) {
     const int tt = i / cpr, n0 = (i - tt * cpr) * 8;
     const int base = s_base[tt];
@@ -3058,6 +3087,7 @@ k_attn_pack(DevDesc d, AttnPackParams p, const uint8_t* __restrict__ tokmeta, co
     if (tid == 0) dbg_stamp_g(d.dbg, blockIdx.x, 123);
     // pack every parked tile of the round (a candidate without a valid key was packed by its own CTA)
     const int cpr = p.KP / 8;
+    if (hc)
     for (int i = tid; i < nl * TT * cpr; i += NT) {
       const int q = i / (TT * cpr), rem = i - q * TT * cpr;
       const int tt = rem / cpr, n0 = (rem - tt * cpr) * 8;
@@ -3114,6 +3144,12 @@ struct WgradTcParams {
                                    // rank-chunked call: the pass in front is still writing dx)
   uint32_t w_box_bytes;            // one 64-column box of the weight slice: (NPW, or 2 NPW with the residual half) x 128 B
   uint32_t hct_blk;                // one [NPW rows x 64 tokens] block of the transposed operand
+  int use_hc;                      // 0 (default): dx = dHcT^T . A with dHcT (hi + lo) as an MN-major A operand - no dHc tile
+                                   //    in shared memory (16 KB per operand buffer -> one more ring slot), no dHc tensor
+                                   //    to pack, dh at fp32-level accuracy in the dx product.  1: the round-1 form
+  int stack;                       // 1: hi and lo halves of the transposed operand stacked along N ([hi ; lo] per 64-token
+                                   //    block, N = 2 NPW): ONE pass over the x tile per token tile yields both dA products
+                                   //    (8 MMAs instead of 16; the flush adds the two accumulator halves); needs 2 NPW <= 256
   uint32_t op_bytes;               // operand buffer: dHc tile + dHcT hi/lo tiles
   uint32_t tmem_cols;
 };
@@ -3135,7 +3171,9 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t hct_blk = p.hct_blk;                         // [NPW rows x 64 tokens] block
-  const int kbx = p.KP / 64;                                  // K blocks of the dHc tile
+  // (round 2: the token-major dHc tile is gone - the dx product reads the transposed operand dHcT, hi and lo, as an
+  //  MN-major A operand; kbx = 0 K blocks of dHc in the operand buffers)
+  const int kbx = p.use_hc ? p.KP / 64 : 0;
   uint8_t* xring = base;                                      // [xs][2 boxes][128 x 128 B]
   uint8_t* dring = xring + (size_t)p.xs * 32768;              // [ds][2 boxes][128 x 128 B]
   uint8_t* wtile = dring + (size_t)p.ds * 32768;              // [2 boxes][NPW x 128 B]  weights (MN-major B operand)
@@ -3302,8 +3340,11 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
           ptx::mbar_arrive_expect_tx_w(&op_full[ob], op_tx);
           for (int kb = 0; kb < kbx; ++kb) ptx::tma_load_2d_w(hc_t + (uint32_t)kb * 16384u, &tm_hc, &op_full[ob], kb * 64, t0, ptx::kEvictLast);
           for (int kb = 0; kb < 2; ++kb) {
-            ptx::tma_load_2d_w(hct_t + (uint32_t)kb * hct_blk, &tm_hct_hi, &op_full[ob], t0 + kb * 64, 0, ptx::kEvictLast);
-            ptx::tma_load_2d_w(hct_t + (uint32_t)(2 + kb) * hct_blk, &tm_hct_lo, &op_full[ob], t0 + kb * 64, 0, ptx::kEvictLast);
+            // stacked: [hi ; lo] of token block kb are adjacent (one B operand of 2 NPW rows); else hi blocks, then lo blocks
+            const uint32_t hi_off = p.stack ? (uint32_t)(2 * kb) * hct_blk : (uint32_t)kb * hct_blk;
+            const uint32_t lo_off = p.stack ? (uint32_t)(2 * kb + 1) * hct_blk : (uint32_t)(2 + kb) * hct_blk;
+            ptx::tma_load_2d_w(hct_t + hi_off, &tm_hct_hi, &op_full[ob], t0 + kb * 64, 0, ptx::kEvictLast);
+            ptx::tma_load_2d_w(hct_t + lo_off, &tm_hct_lo, &op_full[ob], t0 + kb * 64, 0, ptx::kEvictLast);
           }
         }
       }
@@ -3313,7 +3354,9 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
     {
       const uint32_t tb = ptx::uniform_u32(tmem_base);
       const uint32_t idesc_a = ptx::idesc_bf16(128, (uint32_t)p.NPW, 1, 0);   // X^T (MN-major) . dHcT (K-major)
+      const uint32_t idesc_a2 = ptx::idesc_bf16(128, 2u * (uint32_t)p.NPW, 1, 0);   // ... . [dHcT hi ; dHcT lo]
       const uint32_t idesc_x = ptx::idesc_bf16(128, 128, 0, 1);               // dHc (K-major) . Acat (MN-major)
+      const uint32_t idesc_x2 = ptx::idesc_bf16(128, 128, 1, 1);              // dHcT^T (MN-major) . Acat (MN-major)
       const uint32_t wa = ptx::uniform_u32(ptx::smem_u32(wtile));
       const uint32_t x_a = ptx::uniform_u32(ptx::smem_u32(xring));
       const uint32_t op_a = ptx::uniform_u32(ptx::smem_u32(op));
@@ -3338,8 +3381,23 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         if (lane == 0 && j < 8) dbg_stamp(p.dbg, blockIdx.x, 42 + j * 3);
         ptx::tc_fence_after_sync();
         const uint32_t xa = x_a + (uint32_t)s * 32768u;
-        if (p.has_dx) {
-          // MMA-X first (the epilogue is waiting for it): K = NPW rank rows in steps of 16
+        if (p.has_dx && !p.use_hc) {
+          // MMA-X first (the epilogue is waiting for it): dXadd[128 tok, 128 cols] = dHcT^T . Acat, the transposed
+          // operand read as an MN-major A (two 64-token atoms), hi then lo; K = NPW rank rows in steps of 16
+          const int ksteps = p.NPW / 16;
+          const uint32_t lbo = (p.stack ? 2u : 1u) * hct_blk;                  // distance of the two 64-token atoms
+          const uint64_t d_ha = ptx::smem_desc_sw128(0, 1024, lbo);
+          for (int part = 0; part < 2; ++part) {
+            const uint32_t part_off = p.stack ? (uint32_t)part * hct_blk : (uint32_t)part * 2u * hct_blk;
+            for (int k = 0; k < ksteps; ++k) {
+              const uint64_t adesc = d_ha + (uint64_t)((hcta + part_off + (uint32_t)k * 2048u) >> 4);
+              const uint64_t bdesc = d_w + (uint64_t)((wa + (uint32_t)k * 2048u) >> 4);
+              ptx::umma_bf16_w(tb + (uint32_t)i * 128u, adesc, bdesc, idesc_x2, (part > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          ptx::umma_commit_w(&t_full[i]);
+        } else if (p.has_dx) {
+          // (round-1 form: token-major dHc tile as a K-major A operand)
           const int ksteps = (p.lo_off ? 2 * p.NPW : p.NPW) / 16;   // (+ the residual half of the dHc rows)
           for (int k = 0; k < ksteps; ++k) {
             const uint64_t adesc = d_k + (uint64_t)((hca + (uint32_t)(k >> 2) * 16384u + (k & 3) * 32) >> 4);
@@ -3348,7 +3406,16 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
           }
           ptx::umma_commit_w(&t_full[i]);
         }
-        // MMA-A: K = 128 tokens (8 steps), hi then lo
+        // MMA-A: K = 128 tokens (8 steps)
+        if (p.stack) {
+          // hi and lo stacked along N: one pass over the x tile (the A operand fetch, 4 KB per MMA, is what an MMA costs)
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t adesc = d_x + (uint64_t)((xa + k * 2048) >> 4);
+            const uint64_t bdesc = d_k + (uint64_t)((hcta + (uint32_t)(2 * (k >> 2)) * hct_blk + (k & 3) * 32) >> 4);
+            ptx::umma_bf16_w(tb + d1_col, adesc, bdesc, idesc_a2, (j > 0 || k > 0) ? 1u : 0u);
+          }
+        } else {
 #pragma unroll
         for (int part = 0; part < 2; ++part)
 #pragma unroll
@@ -3357,6 +3424,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
             const uint64_t bdesc = d_k + (uint64_t)((hcta + (uint32_t)(2 * part + (k >> 2)) * hct_blk + (k & 3) * 32) >> 4);
             ptx::umma_bf16_w(tb + d1_col, adesc, bdesc, idesc_a, (j > 0 || part > 0 || k > 0) ? 1u : 0u);
           }
+        }
         ptx::umma_commit_w(&x_empty[s]);
         ptx::umma_commit_w(&op_empty[ob]);
       }
@@ -3473,7 +3541,15 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
     for (int n8 = 0; n8 < p.NPW; n8 += 8) {
       float v[8];
       ptx::tmem_ld8(lane_base + d1_col + (uint32_t)n8, v);
-      ptx::tmem_ld_wait();
+      if (p.stack) {                                             // + the lo half of the stacked accumulator
+        float w[8];
+        ptx::tmem_ld8(lane_base + d1_col + (uint32_t)(p.NPW + n8), w);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] += w[e];
+      } else {
+        ptx::tmem_ld_wait();
+      }
 #pragma unroll
       for (int e = 0; e < 8; ++e) stage[(n8 + e) * 128 + row] = v[e];
     }
@@ -3663,10 +3739,14 @@ static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParam
   p.delta = (has_dx && d.delta) ? 1 : 0;
   p.early_bits = drop_early_bits(0);               // (k_wgrad_tc: 160.3 -> 161.3 us with early bits: off)
   p.dbg = dbg_enabled();
-  p.lo_off = L.lo_off;
+  { static int hc_env = -1; if (hc_env < 0) { const char* e = getenv("MOKA_WGRAD_USE_HC"); hc_env = (e && e[0] == '1') ? 1 : 0; }
+    p.use_hc = hc_env; }
+  p.lo_off = p.use_hc ? L.lo_off : 0;
   p.hct_blk = (uint32_t)p.NPW * 128u;
   p.w_box_bytes = (uint32_t)(p.lo_off ? 2 * p.NPW : p.NPW) * 128u;
-  p.op_bytes = (uint32_t)(p.KP / 64) * 16384u + 4u * p.hct_blk;
+  p.op_bytes = (p.use_hc ? (uint32_t)(p.KP / 64) * 16384u : 0u) + 4u * p.hct_blk;
+  { static int st_env = -1; if (st_env < 0) { const char* e = getenv("MOKA_WGRAD_STACK"); st_env = (e && e[0] == '0') ? 0 : 1; }
+    p.stack = (st_env && 2 * p.NPW <= 256) ? 1 : 0; }
   p.tmem_cols = 512;
   const size_t limit = 226 * 1024;
   // prefer two operand buffers (breaks the MMA -> reload -> MMA chain); the dx ring then gets 2 slots
@@ -3698,7 +3778,7 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   if (!wgrad_plan(d, a.dx != nullptr, num_sms, p, L, fixed, nchunks)) return MOKA_EUNSUPPORTED;
   const int slices = d.d_in / 128;
   char* pk = static_cast<char*>(a.pack);
-  __nv_bfloat16* hc = reinterpret_cast<__nv_bfloat16*>(pk);
+  __nv_bfloat16* hc = p.use_hc ? reinterpret_cast<__nv_bfloat16*>(pk) : nullptr;   // (token-major operand: round-1 form only)
   __nv_bfloat16* hct_hi = reinterpret_cast<__nv_bfloat16*>(pk + L.hc_bytes);
   __nv_bfloat16* hct_lo = reinterpret_cast<__nv_bfloat16*>(pk + L.hc_bytes + L.hct_bytes);
   if (fused) {
@@ -3730,7 +3810,8 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
       const uint64_t w = (uint64_t)L.rp;                       // packed columns of one modality
       CUtensorMap tac, thc_c, thh_c, thl_c;
       if (!make_tmap(&tac, Ac, w, (uint64_t)d.d_in, (uint32_t)w)) return MOKA_EUNSUPPORTED;
-      if (!make_tmap_strided(&thc_c, hc + (size_t)c * w, (uint64_t)d.T, w, (uint64_t)L.KP, 128)) return MOKA_EUNSUPPORTED;
+      // (the token-major operand map is only dereferenced by the round-1 form; any valid map will do otherwise)
+      if (!make_tmap_strided(&thc_c, (hc ? hc : reinterpret_cast<__nv_bfloat16*>(pk)) + (size_t)c * w, (uint64_t)d.T, w, (uint64_t)L.KP, 128)) return MOKA_EUNSUPPORTED;
       if (!make_tmap(&thh_c, hct_hi + (size_t)c * w * d.T, w, (uint64_t)d.T, (uint32_t)w)) return MOKA_EUNSUPPORTED;
       if (!make_tmap(&thl_c, hct_lo + (size_t)c * w * d.T, w, (uint64_t)d.T, (uint32_t)w)) return MOKA_EUNSUPPORTED;
       p.prefetch_dx = (c == 0);
@@ -3749,7 +3830,7 @@ static int launch_wgrad_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cud
   }
   for (int m = 0; m < 3; ++m)
     if (!make_tmap(&ta[m], a.A[m < d.M ? m : 0], (uint64_t)d.r, (uint64_t)d.d_in, (uint32_t)d.r)) return MOKA_EUNSUPPORTED;
-  if (!make_tmap(&thc, hc, (uint64_t)d.T, (uint64_t)L.KP, 128)) return MOKA_EUNSUPPORTED;
+  if (!make_tmap(&thc, hc ? hc : reinterpret_cast<__nv_bfloat16*>(pk), (uint64_t)d.T, (uint64_t)L.KP, 128)) return MOKA_EUNSUPPORTED;
   if (!make_tmap(&thh, hct_hi, (uint64_t)L.NPW, (uint64_t)d.T, (uint32_t)L.NPW)) return MOKA_EUNSUPPORTED;
   if (!make_tmap(&thl, hct_lo, (uint64_t)L.NPW, (uint64_t)d.T, (uint32_t)L.NPW)) return MOKA_EUNSUPPORTED;
   cudaError_t e = d.drop_thresh

@@ -31,7 +31,7 @@ _DTYPES = {torch.bfloat16: _cabi.MOKA_BF16, torch.float32: _cabi.MOKA_F32}
 _WORKSPACE = {}
 
 # optional per-call CUDA-event timing of the C-ABI calls (bench.py turns it on)
-TIMING = {'enabled': False, 'events': []}
+TIMING = {'enabled': False, 'events': [], 'marks': False}      # marks: tools/instep_timeline.py (globaltimer markers)
 
 # Frozen-GEMM epilogue fusion (MOKA_FLAG_DELTA_OUT): the adapter kernels write their term
 # alone (no read of W0 x / W0^T dy) and the cuBLAS GEMM accumulates onto it with beta = 1.  Opt-in
@@ -191,6 +191,8 @@ class _MokaFn(torch.autograd.Function):
         if TIMING['enabled']:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record()
+        if TIMING['marks']:
+            lib.moka_debug_mark(0, stream)
         with torch.cuda.device(dev):
             code = lib.moka_backward(desc, dy2.data_ptr(), x2.data_ptr(), h.data_ptr(),
                                      _cabi.ptr_array([a.data_ptr() for a in Ac]), Bc.data_ptr(),
@@ -199,6 +201,8 @@ class _MokaFn(torch.autograd.Function):
                                      _cabi.ptr_array([g.data_ptr() for g, _ in dAs]), dB.data_ptr(),
                                      ctx.seed, ctx.offset, ws.data_ptr(), ws.numel(), stream)
         _cabi.check(code, 'moka_backward')
+        if TIMING['marks']:
+            lib.moka_debug_mark(1, stream)
         if ev is not None:
             ev[1].record()
             TIMING['events'].append(('bwd', B * S, d_in, d_out, x2.element_size(), ev, delta))
