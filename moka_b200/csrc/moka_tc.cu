@@ -3144,7 +3144,9 @@ struct WgradTcParams {
                                    // rank-chunked call: the pass in front is still writing dx)
   uint32_t w_box_bytes;            // one 64-column box of the weight slice: (NPW, or 2 NPW with the residual half) x 128 B
   uint32_t hct_blk;                // one [NPW rows x 64 tokens] block of the transposed operand
-  int use_hc;                      // 0 (default): dx = dHcT^T . A with dHcT (hi + lo) as an MN-major A operand - no dHc tile
+  int l2pf;                        // token tiles of L2 prefetch distance for the x / dx streams (0: off)
+  int order;                       // CTA order, see the kernel
+  int use_hc;                      // 0: dx = dHcT^T . A with dHcT (hi + lo) as an MN-major A operand - no dHc tile
                                    //    in shared memory (16 KB per operand buffer -> one more ring slot), no dHc tensor
                                    //    to pack, dh at fp32-level accuracy in the dx product.  1: the round-1 form
   int stack;                       // 1: hi and lo halves of the transposed operand stacked along N ([hi ; lo] per 64-token
@@ -3196,7 +3198,11 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
   uint32_t* km_s = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(bars) + 512);   // [xs][128 rows][4 words] (DROP)
 
   const int warp = ptx::uniform_warp_idx(), lane = threadIdx.x & 31;
-  const int slice = blockIdx.x / p.tsplit, split = blockIdx.x % p.tsplit;
+  // CTA order (MOKA_WGRAD_ORDER): 0 = token range fastest (round 1), 1 = column slice fastest: the CTAs in flight then
+  // cover whole token rows (all column slices of a few token ranges) instead of a few 256-byte stripes of every row
+  const int nslices = (int)gridDim.x / p.tsplit;
+  const int slice = p.order ? (int)blockIdx.x % nslices : (int)blockIdx.x / p.tsplit;
+  const int split = p.order ? (int)blockIdx.x / nslices : (int)blockIdx.x % p.tsplit;
   const int col0 = slice * 128;
   const int tt_beg = (int)((long long)split * p.ntiles / p.tsplit);
   const int tt_end = (int)((long long)(split + 1) * p.ntiles / p.tsplit);
@@ -3307,9 +3313,20 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         ptx::tma_load_2d_w(dt, &tm_dx, &d_full[j], col0, tile_of(j) * 128, ptx::kEvictFirst);
         ptx::tma_load_2d_w(dt + 16384u, &tm_dx, &d_full[j], col0 + 64, tile_of(j) * 128, ptx::kEvictFirst);
       }
+      // L2 prefetch of the x / dx tiles the rings have no room for yet (see tma_prefetch_2d_w)
+      auto prefetch_tile = [&](int jj) {
+        if (jj >= ntt) return;
+        const int tp = tile_of(jj) * 128;
+        ptx::tma_prefetch_2d_w(&tm_x, col0, tp);
+        ptx::tma_prefetch_2d_w(&tm_x, col0 + 64, tp);
+        if (p.has_dx && !p.delta) { ptx::tma_prefetch_2d_w(&tm_dx, col0, tp); ptx::tma_prefetch_2d_w(&tm_dx, col0 + 64, tp); }
+      };
+      if (p.l2pf)
+        for (int jj = min(npre_x, npre_d ? npre_d : npre_x); jj < p.xs + p.l2pf; ++jj) prefetch_tile(jj);
       ptx::pdl_wait();
       for (int j = 0; j < ntt; ++j) {
         const int t0 = tile_of(j) * 128;
+        if (p.l2pf) prefetch_tile(j + p.xs + p.l2pf);
         if (j >= npre_x) {   // the big streams first: they have their own ring slots and must never wait on the MMAs
           const int s = j % p.xs;
           const uint32_t ph = (uint32_t)(j / p.xs) & 1u;
@@ -3739,8 +3756,18 @@ static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParam
   p.delta = (has_dx && d.delta) ? 1 : 0;
   p.early_bits = drop_early_bits(0);               // (k_wgrad_tc: 160.3 -> 161.3 us with early bits: off)
   p.dbg = dbg_enabled();
-  { static int hc_env = -1; if (hc_env < 0) { const char* e = getenv("MOKA_WGRAD_USE_HC"); hc_env = (e && e[0] == '1') ? 1 : 0; }
+  // MOKA_WGRAD_USE_HC=0: the dx product reads the transposed operand (MN-major A, hi + lo) and the token-major dHc
+  // tile / tensor disappears.  Measured round 2: equal when timed alone, but 207 vs 177 us inside the 7B step (SM clock
+  // 1.5 GHz): the MN-major A fetch of those 6 MMAs sits on the critical path of every dx epilogue.  Default: 1.
+  { static int hc_env = -1; if (hc_env < 0) { const char* e = getenv("MOKA_WGRAD_USE_HC"); hc_env = (e && e[0] == '0') ? 0 : 1; }
     p.use_hc = hc_env; }
+  // (L2 prefetch ahead of the rings, MOKA_L2_PREFETCH=n tiles: measured slower inside the step - 195 / 204 / 216 us at
+  //  n = 0 / 3 / 6 - so off by default)
+  { static int pf_env = -1; if (pf_env < 0) { const char* e = getenv("MOKA_L2_PREFETCH"); pf_env = e ? atoi(e) : 0; }
+    p.l2pf = pf_env; }
+  // (CTA order: no measurable difference alone or inside the step - 184 vs 187 us; the round-1 order stays)
+  { static int ord_env = -1; if (ord_env < 0) { const char* e = getenv("MOKA_WGRAD_ORDER"); ord_env = e ? atoi(e) : 0; }
+    p.order = ord_env; }
   p.lo_off = p.use_hc ? L.lo_off : 0;
   p.hct_blk = (uint32_t)p.NPW * 128u;
   p.w_box_bytes = (uint32_t)(p.lo_off ? 2 * p.NPW : p.NPW) * 128u;
@@ -3752,7 +3779,10 @@ static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParam
   // prefer two operand buffers (breaks the MMA -> reload -> MMA chain); the dx ring then gets 2 slots
   p.nop = 2;
   // dropout: the masking warps hand the keep bits of each x slot to the epilogue through shared memory
-  const size_t km_bytes = d.drop_thresh ? (size_t)(has_dx ? 2 : 4) * 2048 : 0;
+  static int xs_env = -1;                                       // tuning aid: x slots (the dx ring gets the rest)
+  if (xs_env < 0) { const char* e = getenv("MOKA_WGRAD_XS"); xs_env = e ? atoi(e) : 0; }
+  // (one 2 KB keep-bit block per x slot: two slots next to a dx ring unless more are forced, four without dx)
+  const size_t km_bytes = d.drop_thresh ? (size_t)((has_dx && xs_env <= 2) ? 2 : 4) * 2048 : 0;
   fixed = (size_t)2 * p.w_box_bytes + (size_t)p.nop * p.op_bytes + 1024 + 512 + km_bytes;
   if (fixed + 4 * 32768 > limit) { p.nop = 1; fixed -= p.op_bytes; }
   if (fixed + 2 * 32768 > limit) return false;
@@ -3762,6 +3792,7 @@ static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParam
     p.ds = min(3, slots - p.xs);
     if (p.ds < 2) { p.xs = 1; p.ds = min(3, slots - 1); }
     if (p.ds < 1) return false;                               // (one dx slot: unpipelined, still far ahead of the warp-FMA kernel)
+    if (xs_env > 0 && slots - xs_env >= 1 && xs_env <= 4) { p.xs = xs_env; p.ds = min(3, slots - xs_env); }
   } else {
     p.xs = min(4, slots); p.ds = 0;
   }

@@ -55,6 +55,14 @@ for name, se, sx in slots:
     print('%-10s %5d | %10.2f | %8.2f | %s' % (name, ok.sum(), (x1 - e0) / 1e3, np.median((ext - ent)[ok]) / 1e3, gap))
     prev_end = x1
 
+# wgrad per-tile stamps of the last call (cycles relative to each CTA's first stamp, mean over CTAs)
+w = a[(a[:, 112] > 0) & (a[:, 112] > a[:, 112].max() - 2_000_000)]
+rel = w - w[:, 1:2]
+mm = lambda i: rel[:, i].mean()
+print('wgrad (last call) tiles: workers t_full / d_full / epilogue / done | mma op_full / x_full+ready / t_empty   (cycles)')
+for j in range(8):
+    b = 8 + j * 4
+    print(f'  tile {j}: {mm(b):8.0f} {mm(b+1):8.0f} {mm(b+2):8.0f} {mm(b+3):8.0f} | {mm(40+j*3):8.0f} {mm(41+j*3):8.0f} {mm(42+j*3):8.0f}')
 ev = [e for e in moka_layer.TIMING['events'] if e[0] == 'bwd'][-1]
 print('last bwd call by CUDA events: %.1f us' % (ev[5][0].elapsed_time(ev[5][1]) * 1e3))
 m0, m1 = a[-1, 0], a[-1, 1]
