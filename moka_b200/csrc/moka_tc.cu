@@ -158,7 +158,8 @@ int debug_read(unsigned long long* host, int n) {
 // k_dgrad_tc) are not requested by every SM from the same L2 lines at the same moment.  MOKA_NO_ROT=1: off.
 // Early keep bits: the masking warps generate the keep bits of a stage BEFORE they wait for its data (the bits
 // depend on (row, column group) only), leaving just the sparse zero stores and the fence after the TMA arrival.
-// Same bits, same result.  Timed in round 2: on by default in k_down_tc, off in k_wgrad_tc; MOKA_DROP_EARLY=0/1 forces both.
+// Same bits, same result.  Timed in round 2: on by default in both kernels (inside the step the masking sits on the
+// x-slot turnaround of k_wgrad_tc); MOKA_DROP_EARLY=0/1 forces both.
 static int drop_early_bits(int dflt) {
   static int v = -2;                               // -1: not set in the environment -> per-kernel default
   if (v == -2) { const char* e = getenv("MOKA_DROP_EARLY"); v = e ? ((e[0] == '1') ? 1 : 0) : -1; }
@@ -3754,7 +3755,7 @@ static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParam
   }
   p.has_dx = has_dx;
   p.delta = (has_dx && d.delta) ? 1 : 0;
-  p.early_bits = drop_early_bits(0);               // (k_wgrad_tc: 160.3 -> 161.3 us with early bits: off)
+  p.early_bits = drop_early_bits(1);               // (k_wgrad_tc alone: 160.3 -> 161.3 us; inside the 7B step: 193 -> 188 us)
   p.dbg = dbg_enabled();
   // MOKA_WGRAD_USE_HC=0: the dx product reads the transposed operand (MN-major A, hi + lo) and the token-major dHc
   // tile / tensor disappears.  Measured round 2: equal when timed alone, but 207 vs 177 us inside the 7B step (SM clock

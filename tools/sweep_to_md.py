@@ -12,14 +12,15 @@ def rows(path):
 
 def main():
     p0, p05, out, tag = sys.argv[1], sys.argv[2], sys.argv[3], (sys.argv[4] if len(sys.argv) > 4 else '')
+    rnd = sys.argv[5] if len(sys.argv) > 5 else 'r01'
     L = []
-    L.append(f'# r01 ({tag}): MokaLinear microbench sweep (BASELINE config 5)\n')
+    L.append(f'# {rnd} ({tag}): MokaLinear microbench sweep (BASELINE config 5)\n')
     L.append('B200, `tools/microbench.py`, T = 8192 tokens (4 x 2048), square d -> d, bf16, adapter fwd+bwd through the C ABI, CUDA')
     L.append('events over 10 back-to-back iterations, inputs rotated over three buffer sets (> L2).  `frac` = algorithmic bytes')
     L.append('`2 (4 d_in + 3 d_out) T` / time / 6532.5 GB/s (measured copy bandwidth).  `torch` = the same layer as plain PyTorch on the')
     L.append('same GPU (cuBLAS split GEMMs over all rows, eager softmax attention, autograd backward; W0 GEMM excluded on both sides).')
     L.append('VT = 2 modalities / 64 keys per sample (layout C2), AVT = 3 modalities / 96 keys (layout C3).')
-    L.append('`path`: tc = tcgen05 chain; r = 4 is not a multiple of 8 -> warp-FMA kernels.\n')
+    L.append('`path`: tc = tcgen05 chain (round 2: every r % 4 == 0, r = 4 included); fma = warp-FMA kernels.\n')
     L.append('## lora_dropout = 0\n')
     L.append('| variant | d | r | path | fwd us | bwd us | fwd+bwd us | GB/s | frac | torch us | speed-up |')
     L.append('|---|---|---|---|---|---|---|---|---|---|---|')
