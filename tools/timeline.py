@@ -1,6 +1,6 @@
 """Wall-clock timeline (globaltimer) of one moka_forward + moka_backward chain: per kernel the first CTA
 entry and the last CTA exit, relative to the first kernel's entry.  MOKA_DEBUG_TIMING=1 is set here.
-usage: python tools/timeline.py [avt|vt] [r] [B]"""
+usage: python tools/timeline.py [avt|vt] [r] [B]      (MOKA_TL_D / MOKA_TL_S / MOKA_TL_P: width, sequence length, lora_dropout)"""
 import ctypes, os, sys
 os.environ['MOKA_DEBUG_TIMING'] = '1'
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -17,13 +17,14 @@ r = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 4
 lib = _cabi.load()
 dev = 'cuda:0'
-S, d = 2048, 4096
+S, d = int(os.environ.get('MOKA_TL_S', 2048)), int(os.environ.get('MOKA_TL_D', 4096))
+P_DROP = float(os.environ.get('MOKA_TL_P', 0.0))
 T = B * S
 M = 3 if variant == VARIANT_AVT else 2
 masks = [m.to(dev) for m in layout_masks(variant, B, S, 'c3' if variant == VARIANT_AVT else 'c2')]
 meta = build_token_meta_avt(masks) if variant == VARIANT_AVT else build_token_meta_vt(*masks)
 s = 16.0 / r
-sc = FusedScalars(s, (1, 1, 1), 1.0, 0.0) if variant == VARIANT_AVT else FusedScalars(1.0, (s, s, s), 0.05, 0.0)
+sc = FusedScalars(s, (1, 1, 1), 1.0, P_DROP) if variant == VARIANT_AVT else FusedScalars(1.0, (s, s, s), 0.05, P_DROP)
 bufs = [[torch.randn(T, d, device=dev).bfloat16() for _ in range(4)] for _ in range(3)]
 A = [(torch.randn(r, d, device=dev) * d ** -0.5).bfloat16() for _ in range(M)]
 Bw = (torch.randn(d, r, device=dev) * 0.02).bfloat16()
