@@ -456,7 +456,7 @@ def main():
         for _ in range(n):
             loss = step(dev_batch)
             if not resident:
-                last = float(loss)                 # device -> host read of the step's result
+                last = float(loss.detach())                 # device -> host read of the step's result
         e1.record()
         barrier()
         moka_layer.TIMING['enabled'] = False
