@@ -135,8 +135,8 @@ template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16
 // round(p * 4096).  Twelve pseudo-random words R_i are folded from the least significant bit of T upwards,
 //     x <- bit_i(T) ? (R_i | x) : (R_i & x),
 // which halves-and-shifts the per-bit probability exactly like long division of T by 2^12.  The words are
-// R_i = z_i ^ (z_i >> 15), z_i = (y ^ key_odd) * C_i (odd constants C_i) drawn from one full avalanche
-// y = mix32((idx_lo ^ key_lo) + idx_hi * golden) of the super-group index idx = t * ceil(d_in / 32) + sg
+// R_i = hi16(y C_i) : hi16(y C'_i) (odd constants C_i, C'_i; see the loop) drawn from one full avalanche
+// y = mix32((idx_lo ^ key_lo) + idx_hi * golden) ^ key_odd of the super-group index idx = t * ceil(d_in / 32) + sg
 // (mix32 = the 2-multiply finaliser "lowbias32", C. Wellons); (key_lo, key_odd) come from (seed, offset) by
 // splitmix64 on the host.  ~2 integer ops per element (Philox4x32-10 + compares: ~17), cheap enough to mask
 // the shared-memory tiles of the tensor-core kernels close to HBM rate.  Every kernel and the test hook
@@ -153,12 +153,20 @@ __device__ __forceinline__ uint32_t dropout_keep32(const DevDesc& d, unsigned lo
   constexpr uint32_t C[16] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du,
                               0xFD7046C5u, 0xB55A4F09u, 0x94D049BBu, 0xBF58476Du, 0x2545F491u, 0x6C8E9CF5u,
                               0xE7037ED1u, 0x8EBC6AF1u, 0x589965CDu, 0x1D8E4E27u};
+  constexpr uint32_t C2[12] = {0xA54FF53Bu, 0x72BE5D75u, 0x3C6EF373u, 0xF1BBCDCBu, 0x510E527Fu, 0x9B05688Du,
+                               0x1F83D9ABu, 0x5BE0CD19u, 0xCBBB9D5Du, 0x629A292Bu, 0x9159015Bu, 0x152FECD9u};
   const uint32_t y = mix32(((uint32_t)idx ^ d.key_lo) + (uint32_t)(idx >> 32) * 0x9E3779B1u) ^ d.key_odd;
   uint32_t x = 0u;
 #pragma unroll
   for (int i = 0; i < kDropBits; ++i) {
-    const uint32_t z = y * C[i];
-    const uint32_t R = z ^ (z >> 15);
+    // word i of the group: the HIGH halves of two 32-bit products (the well-mixed bits of a multiplicative hash),
+    // joined by one PRMT: 2 fma-pipe + 2 alu-pipe instructions per word with the fold below.  (Round 1 used one
+    // product, z ^ (z >> 15): 1 + 3, bound by the alu pipe - and its top 17 bits were raw product bits, which left the
+    // joint drop rate of some position pairs inside a group off by ~50 sigma; tests: the pair check of
+    // test_dropout_mask_statistics.  A 64-bit product (IMAD.WIDE, hi ^ lo) is statistically fine but slower.)
+    const uint32_t za = y * C[i], zb = y * C2[i];
+    uint32_t R;
+    asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(R) : "r"(zb), "r"(za));
     const uint32_t m = d.drop_sel[i];                          // all ones where bit i of T is set (constant bank)
     x = (R & x) | (m & (R | x));                               // one LOP3: m ? (R | x) : (R & x)
   }

@@ -373,6 +373,214 @@ k_down_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUte
   if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// ---------------------------------------------------------------------------- k_down_ts
+// Second form of the down-projection (round 2, last session): the x tile never feeds the tensor core from shared
+// memory.  Sixteen worker warps read the TMA-written rows (thread <-> token row x 32-column super-group, 4 x 16 bytes),
+// apply the dropout keep bits IN REGISTERS and store the rows into TMEM (two bf16 per 32-bit cell); the product takes
+// its A operand from there (tcgen05.mma TS form), B = the weight tile in shared memory as before.  What that buys:
+//   * no generic-proxy write of the tile and therefore no fence.proxy.async on the TMA -> MMA path;
+//   * the x slot is handed back to the TMA producer as soon as the workers have READ it - its life no longer
+//     includes the masking hand-off, the products and the commit round trip (~2.5k of ~4.5k cycles per stage inside
+//     the training step, where the SM clock is 1.5 GHz) - so the same shared memory holds ~2x the bytes in flight;
+//   * x and the weight tiles live in two rings of their own depth, and the staged A operands in a third (TMEM).
+// Measured (profiles/r02_dropout_cost.md): alone 52.4 -> 49.8 us at d_in = 4096 and 128.6 -> 123.1 us at 11008
+// (T = 32768); inside the 7B step 1-2 us per forward call - there the dropout path is bound by the instruction issue
+// of the keep-bit generator and the masking arithmetic, not by this hand-off.
+struct DownTsParams {
+  int T, d_in, r, rp, M, NP;
+  int ksplit, kblocks;             // kblocks = d_in / 128 (a stage is always two 64-column boxes)
+  int rot;
+  int xs, ws, ab;                  // ring depths: x stages, weight stages, TMEM A buffers (64 columns each)
+  int drop;                        // 0: keep everything (lora_dropout = 0)
+  int a_col0;                      // first TMEM column of the A buffers
+  uint32_t w_bytes, tmem_cols;     // w_bytes = NP * 128 (one 64-column weight box)
+  float scale;
+  int dbg;
+};
+constexpr int kDownTsThreads = 64 + 512;
+
+__global__ void __launch_bounds__(kDownTsThreads)
+k_down_ts(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_a0,
+          const __grid_constant__ CUtensorMap tm_a1, const __grid_constant__ CUtensorMap tm_a2,
+          DownTsParams p, DevDesc d, const uint8_t* __restrict__ tokmeta, float* __restrict__ h_out0,
+          float* __restrict__ h_out1) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* xring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wring = xring + (size_t)p.xs * 32768;
+  const uint32_t wstage = 2u * p.w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wring + (size_t)p.ws * wstage);
+  uint64_t* full_x = bars;
+  uint64_t* x_empty = full_x + p.xs;
+  uint64_t* full_w = x_empty + p.xs;
+  uint64_t* w_empty = full_w + p.ws;
+  uint64_t* ready = w_empty + p.ws;                             // [ab] A operand staged in TMEM
+  uint64_t* a_empty = ready + p.ab;                             // [ab] ... and consumed
+  uint64_t* tmem_full = a_empty + p.ab;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = ptx::uniform_warp_idx(), lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / p.ksplit, split = blockIdx.x % p.ksplit;
+  const int t0 = tile * 128;
+  if (threadIdx.x == 0) { dbg_stamp_g(p.dbg, blockIdx.x, 100); dbg_stamp(p.dbg, blockIdx.x, 0); }
+  const int kb0 = (int)((long long)split * p.kblocks / p.ksplit);
+  const int kb1 = (int)((long long)(split + 1) * p.kblocks / p.ksplit);
+  const int nkb = kb1 - kb0;
+  const int krot = p.rot ? (int)(((unsigned)tile * 7u + (unsigned)split * 3u) % (unsigned)nkb) : 0;
+
+  // rows of the weight tiles that TMA never writes (padding between modality blocks) must be 0
+  {
+    uint4* w = reinterpret_cast<uint4*>(wring);
+    for (uint32_t i = threadIdx.x; i < (uint32_t)p.ws * wstage / 16; i += blockDim.x) w[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.xs; ++s) { ptx::mbar_init(&full_x[s], 1); ptx::mbar_init(&x_empty[s], 4 * kWorkerWarps); }
+    for (int s = 0; s < p.ws; ++s) { ptx::mbar_init(&full_w[s], 1); ptx::mbar_init(&w_empty[s], 1); }
+    for (int s = 0; s < p.ab; ++s) { ptx::mbar_init(&ready[s], 4 * kWorkerWarps); ptx::mbar_init(&a_empty[s], 1); }
+    ptx::mbar_init(tmem_full, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tm_x); ptx::prefetch_tmap(&tm_a0);
+  }
+  if (warp == 1) ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();
+  ptx::pdl_trigger();
+  if (threadIdx.x == 0) dbg_stamp(p.dbg, blockIdx.x, 2);
+
+  if (warp == 0) {
+    // ---- TMA producer: weights of block `it` as soon as their stage is free, then x
+    const uint32_t wtx = (uint32_t)p.M * (uint32_t)p.r * 128u * 2u;
+    const uint32_t xr_a = ptx::uniform_u32(ptx::smem_u32(xring));
+    const uint32_t wr_a = ptx::uniform_u32(ptx::smem_u32(wring));
+    int sx = 0, sw = 0; uint32_t xph = 0, wph = 0;
+    for (int it = 0; it < nkb; ++it) {
+      const int kb = kb0 + rot_index(it, krot, nkb);
+      ptx::mbar_wait_or_trap(&w_empty[sw], wph ^ 1u, __LINE__);
+      ptx::mbar_arrive_expect_tx_w(&full_w[sw], wtx);
+      for (int bx = 0; bx < 2; ++bx) {
+        const int col = (kb * 2 + bx) * 64;
+        const uint32_t ws_a = wr_a + (uint32_t)sw * wstage + (uint32_t)bx * p.w_bytes;
+        ptx::tma_load_2d_w(ws_a, &tm_a0, &full_w[sw], col, 0, ptx::kEvictLast);
+        if (p.M > 1) ptx::tma_load_2d_w(ws_a + (uint32_t)p.rp * 128u, &tm_a1, &full_w[sw], col, 0, ptx::kEvictLast);
+        if (p.M > 2) ptx::tma_load_2d_w(ws_a + 2u * (uint32_t)p.rp * 128u, &tm_a2, &full_w[sw], col, 0, ptx::kEvictLast);
+      }
+      ptx::mbar_wait_or_trap(&x_empty[sx], xph ^ 1u, __LINE__);
+      ptx::mbar_arrive_expect_tx_w(&full_x[sx], 32768u);
+      const uint32_t xs_a = xr_a + (uint32_t)sx * 32768u;
+      ptx::tma_load_2d_w(xs_a, &tm_x, &full_x[sx], kb * 128, t0, ptx::kEvictFirst);
+      ptx::tma_load_2d_w(xs_a + 16384u, &tm_x, &full_x[sx], kb * 128 + 64, t0, ptx::kEvictFirst);
+      if (++sx == p.xs) { sx = 0; xph ^= 1u; }
+      if (++sw == p.ws) { sw = 0; wph ^= 1u; }
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer: A from TMEM, B = weight tile
+    const uint32_t tb = ptx::uniform_u32(tmem_base);
+    const uint32_t wr_a = ptx::uniform_u32(ptx::smem_u32(wring));
+    const int nparts = p.NP > 256 ? 2 : 1;
+    const int npart = p.NP / nparts;
+    const uint32_t idesc = ptx::idesc_bf16(128, (uint32_t)npart, 0, 0);
+    const uint64_t dbase = ptx::smem_desc_sw128(0, 1024, 0);
+    int sw = 0, ab = 0; uint32_t wph = 0, aph = 0;
+    for (int it = 0; it < nkb; ++it) {
+      ptx::mbar_wait_or_trap(&full_w[sw], wph, __LINE__);
+      ptx::mbar_wait_or_trap(&ready[ab], aph, __LINE__);
+      if (lane == 0 && it == 0) dbg_stamp(p.dbg, blockIdx.x, 3);
+      ptx::tc_fence_after_sync();
+      const uint32_t ta = tb + (uint32_t)p.a_col0 + (uint32_t)ab * 64u;
+      for (int bx = 0; bx < 2; ++bx) {
+        const uint32_t wa = wr_a + (uint32_t)sw * wstage + (uint32_t)bx * p.w_bytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          for (int part = 0; part < nparts; ++part) {
+            const uint64_t bdesc = dbase + (uint64_t)((wa + (uint32_t)part * npart * 128u + k * 32) >> 4);
+            ptx::umma_bf16_ts_w(tb + (uint32_t)part * npart, ta + (uint32_t)(bx * 4 + k) * 8u, bdesc, idesc,
+                                (it > 0 || bx > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+      }
+      ptx::umma_commit_w(&w_empty[sw]);
+      ptx::umma_commit_w(&a_empty[ab]);
+      if (++sw == p.ws) { sw = 0; wph ^= 1u; }
+      if (++ab == p.ab) { ab = 0; aph ^= 1u; }
+    }
+    ptx::umma_commit_w(tmem_full);
+    if (lane == 0) dbg_stamp(p.dbg, blockIdx.x, 4);
+  } else {
+    // ---- workers: warp w <-> TMEM lane quadrant w % 4 (the only lanes it may write), super-group (w - 2) / 4
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int t = t0 + row;
+    const int code = (t < p.T) ? (tokmeta[t] & MOKA_MOD_MASK) : -1;
+    const int part = (warp - 2) >> 2;                            // 0..3
+    const unsigned long long rowbase = dropout_row_base(d, t);
+    const uint32_t row7 = (uint32_t)row & 7u;
+    const uint32_t xrow0 = ptx::smem_u32(xring) + (uint32_t)(part >> 1) * 16384u + (uint32_t)row * 128u;
+    const uint32_t ta_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)p.a_col0 + (uint32_t)part * 16u;
+    int sx = 0, ab = 0; uint32_t xph = 0, aph = 0;
+    for (int it = 0; it < nkb; ++it) {
+      const int kb = kb0 + rot_index(it, krot, nkb);
+      uint32_t k32 = 0xffffffffu;
+      if (p.drop) k32 = dropout_keep32(d, rowbase + (unsigned long long)(kb * 4 + part));
+      ptx::mbar_sleep_or_trap(&full_x[sx], xph, __LINE__);    // (polling instead: no difference, measured)
+      const uint32_t xrow = xrow0 + (uint32_t)sx * 32768u;
+      uint4 v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] = ptx::lds128(xrow + ((((uint32_t)(part & 1) * 4u + (uint32_t)c) ^ row7) << 4));
+      uint32_t w16[16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t W[4];
+        dropout_expand8((k32 >> (8 * c)) & 0xffu, W);
+        w16[c * 4 + 0] = v[c].x & W[0]; w16[c * 4 + 1] = v[c].y & W[1];
+        w16[c * 4 + 2] = v[c].z & W[2]; w16[c * 4 + 3] = v[c].w & W[3];
+      }
+      warp_arrive(&x_empty[sx]);                                 // the rows are in registers: the slot may be reloaded
+      ptx::mbar_wait_or_trap(&a_empty[ab], aph ^ 1u, __LINE__);
+      ptx::tc_fence_after_sync();
+      ptx::tmem_st16(ta_row + (uint32_t)ab * 64u, w16);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before_sync();
+      warp_arrive(&ready[ab]);
+      if (++sx == p.xs) { sx = 0; xph ^= 1u; }
+      if (++ab == p.ab) { ab = 0; aph ^= 1u; }
+    }
+    if (warp < 6) {
+      ptx::mbar_wait_or_trap(tmem_full, 0, __LINE__);
+      if (threadIdx.x == 64) dbg_stamp(p.dbg, blockIdx.x, 5);
+      ptx::tc_fence_after_sync();
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+      float* h_out = split == 0 ? h_out0 : h_out1;
+      for (int m = 0; m < p.M; ++m) {
+        for (int c8 = 0; c8 < p.rp; c8 += 8) {
+          float v8[8];
+          ptx::tmem_ld8(lane_base + (uint32_t)(m * p.rp + c8), v8);
+          ptx::tmem_ld_wait();
+          if (code == m + 1) {
+            float* dst = h_out + (size_t)t * p.r + c8;
+            if (c8 + 8 <= p.r) {
+              *reinterpret_cast<float4*>(dst) = make_float4(v8[0] * p.scale, v8[1] * p.scale, v8[2] * p.scale, v8[3] * p.scale);
+              *reinterpret_cast<float4*>(dst + 4) = make_float4(v8[4] * p.scale, v8[5] * p.scale, v8[6] * p.scale, v8[7] * p.scale);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (c8 + i < p.r) dst[i] = v8[i] * p.scale;
+            }
+          }
+        }
+      }
+      if (code == 0)
+        for (int j = 0; j < p.r; ++j) h_out[(size_t)t * p.r + j] = 0.f;
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (threadIdx.x == 0) { dbg_stamp(p.dbg, blockIdx.x, 6); dbg_stamp_g(p.dbg, blockIdx.x, 101); }
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
 static int check_launch_tc() {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
@@ -430,8 +638,45 @@ static int launch_down_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cuda
   // writes the final h into the stash; unsplit: straight into the stash
   float* h0 = p.ksplit > 1 ? a.hpart : a.h_stash;
   float* h1 = p.ksplit > 1 ? a.hpart + (size_t)d.T * d.r : nullptr;
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 256;
   cudaError_t e;
+  // TS form (k_down_ts): MOKA_DOWN_TS = 0 off, 1 with dropout only, 2 always
+  static int down_ts_env = -1;
+  if (down_ts_env < 0) { const char* ev = getenv("MOKA_DOWN_TS"); down_ts_env = ev ? atoi(ev) : 1; }
+  if (d.d_in % 128 == 0 && (down_ts_env == 2 || (down_ts_env == 1 && d.drop_thresh))) {
+    DownTsParams q;
+    q.T = p.T; q.d_in = p.d_in; q.r = p.r; q.rp = p.rp; q.M = p.M; q.NP = p.NP;
+    q.ksplit = p.ksplit; q.kblocks = d.d_in / 128; q.rot = p.rot; q.drop = d.drop_thresh ? 1 : 0;
+    q.w_bytes = p.w_bytes; q.scale = p.scale; q.dbg = p.dbg;
+    q.a_col0 = round_up(p.NP, 64);
+    const size_t wstage = 2u * (size_t)q.w_bytes;
+    const size_t budget_ts = (one_per_sm ? 216 : 108) * 1024;   // ring bytes per CTA
+    const int tmem_budget = one_per_sm ? 512 : 256;
+    static int ts_xs_env = -1, ts_ws_env = -1;
+    if (ts_xs_env < 0) { const char* ev = getenv("MOKA_DOWN_TS_XS"); ts_xs_env = ev ? atoi(ev) : 0; }
+    if (ts_ws_env < 0) { const char* ev = getenv("MOKA_DOWN_TS_WS"); ts_ws_env = ev ? atoi(ev) : 0; }
+    // x stages first (they hold the HBM stream), at least as many weight stages + 1 (a weight stage lives until the
+    // products that read it have retired), A buffers from what TMEM is left
+    q.xs = one_per_sm ? 4 : 2;
+    if (ts_xs_env > 0) q.xs = ts_xs_env;
+    while (q.xs > 1 && (size_t)q.xs * 32768 + (size_t)(q.xs + 1) * wstage > budget_ts) --q.xs;
+    q.ws = (int)((budget_ts - (size_t)q.xs * 32768) / wstage);
+    if (q.ws > q.xs + 2) q.ws = q.xs + 2;
+    if (ts_ws_env > 0) q.ws = ts_ws_env;
+    q.ab = (tmem_budget - q.a_col0) / 64;
+    if (q.ab > q.ws) q.ab = q.ws;
+    const size_t smem_ts = (size_t)q.xs * 32768 + (size_t)q.ws * wstage + 1024 + 512;
+    if (q.ws >= 2 && q.ab >= 2 && smem_ts <= 227 * 1024 &&
+        (size_t)q.xs * 32768 + (size_t)q.ws * wstage <= budget_ts + 1024) {
+      q.tmem_cols = tmem_cols_for(q.a_col0 + q.ab * 64);
+      e = cudaFuncSetAttribute(k_down_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ts);
+      if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+      e = launch_pdl(k_down_ts, dim3(ntiles * p.ksplit), dim3(kDownTsThreads), smem_ts, st, tx, ta[0], ta[1], ta[2], q, d,
+                     a.tokmeta, h0, h1);
+      if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
+      return check_launch_tc();
+    }
+  }
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + 256;
   if (d.drop_thresh) {
     e = cudaFuncSetAttribute(k_down_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_cuda_error(e); return MOKA_ECUDA; }
@@ -1101,13 +1346,16 @@ __device__ __forceinline__ void add_acc_to_tile(uint32_t tmem_row_addr, uint32_t
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       float* a = &acc[c >> 2][(c & 3) * 8];
+      uint4 v = yv[c];
       if (DROP) {
+        // (a test + select per element - two alu-pipe instructions - costs ~3 us of a 300 us backward call inside the
+        // step; folding the keep bit into the add as an fp32 factor, (km & 2^i) * (0x3F800000 >> i) and an FMA, moves
+        // the work to the fma pipe and was measured 27 us SLOWER: profiles/r02_dropout_cost.md)
         const uint32_t km = (km16[half * 2 + (c >> 2)] >> ((c & 3) * 8)) & 0xffu;   // keep bits of chunk (half, c)
 #pragma unroll
         for (int i = 0; i < 8; ++i)
           if (!((km >> i) & 1u)) a[i] = 0.f;
       }
-      uint4 v = yv[c];
       v.x = pack_bf16(bf16lo(v.x) + a[0], bf16hi(v.x) + a[1]);
       v.y = pack_bf16(bf16lo(v.y) + a[2], bf16hi(v.y) + a[3]);
       v.z = pack_bf16(bf16lo(v.z) + a[4], bf16hi(v.z) + a[5]);
@@ -3139,6 +3387,7 @@ struct WgradTcParams {
   int has_dx, dbg;
   int delta;                       // MOKA_FLAG_DELTA_OUT: dx tiles are write-only in this pass (no dx read)
   int early_bits;                  // DROP: keep bits generated before the tile's waits (see drop_early_bits)
+  int dbg_drop;                    // timing aid (MOKA_DBG_WGRAD_DROP; results NOT valid): 1 no generator, 2 no epilogue masking
   int mod_filter;                  // token tiles this pass visits: -1 all; 0 those holding a token of ANY modality; m > 0
                                    // those holding a token of modality code m (a per-modality pass of a rank-chunked call)
   int prefetch_dx;                 // dx tiles may be loaded before the dependency wait (false for the later passes of a
@@ -3460,14 +3709,14 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
         // keep bits of this thread's two 32-column super-groups: data-independent (early_bits: generated before the waits)
         const unsigned long long rowbase = dropout_row_base(d, (long long)tile_of(j) * 128 + mrow);
         uint32_t k32v[2] = {0xffffffffu, 0xffffffffu};
-        if (p.early_bits) {
+        if (p.early_bits && !(p.dbg_drop & 1)) {
 #pragma unroll
           for (int hs = 0; hs < 2; ++hs)
             k32v[hs] = dropout_keep32(d, rowbase + (unsigned long long)((col0 >> 5) + box * 2 + hs));
         }
         ptx::mbar_sleep_or_trap(&x_full[s], k & 1u, __LINE__);
         if (p.has_dx && k > 0) ptx::mbar_sleep_or_trap(&km_free[s], (k - 1u) & 1u, __LINE__);
-        if (!p.early_bits) {
+        if (!p.early_bits && !(p.dbg_drop & 1)) {
 #pragma unroll
           for (int hs = 0; hs < 2; ++hs)
             k32v[hs] = dropout_keep32(d, rowbase + (unsigned long long)((col0 >> 5) + box * 2 + hs));
@@ -3531,7 +3780,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUt
             add_acc_to_tile<true, true>(lane_base + (uint32_t)(i * 128), ptx::smem_u32(dt), (uint32_t)row, &t_empty[i], km_cur);
           else
             add_acc_to_tile<false, true>(lane_base + (uint32_t)(i * 128), ptx::smem_u32(dt), (uint32_t)row, &t_empty[i]);
-        } else if (DROP)
+        } else if (DROP && !(p.dbg_drop & 2))
           add_acc_to_tile<true>(lane_base + (uint32_t)(i * 128), ptx::smem_u32(dt), (uint32_t)row, &t_empty[i], km_cur);
         else
           add_acc_to_tile(lane_base + (uint32_t)(i * 128), ptx::smem_u32(dt), (uint32_t)row, &t_empty[i]);
@@ -3756,6 +4005,11 @@ static bool wgrad_plan1(const DevDesc& d, bool has_dx, int num_sms, WgradTcParam
   p.has_dx = has_dx;
   p.delta = (has_dx && d.delta) ? 1 : 0;
   p.early_bits = drop_early_bits(1);               // (k_wgrad_tc alone: 160.3 -> 161.3 us; inside the 7B step: 193 -> 188 us)
+  {
+    static int dbg_drop_env = -1;
+    if (dbg_drop_env < 0) { const char* ev = getenv("MOKA_DBG_WGRAD_DROP"); dbg_drop_env = ev ? atoi(ev) : 0; }
+    p.dbg_drop = dbg_drop_env;
+  }
   p.dbg = dbg_enabled();
   // MOKA_WGRAD_USE_HC=0: the dx product reads the transposed operand (MN-major A, hi + lo) and the token-major dHc
   // tile / tensor disappears.  Measured round 2: equal when timed alone, but 207 vs 177 us inside the 7B step (SM clock

@@ -727,5 +727,17 @@ def test_dropout_mask_statistics():
     for a, b_ in ((c[:, :-1], c[:, 1:]), (c[:-1], c[1:]), (c[:, :-32], c[:, 32:]), (c[:-128], c[128:])):
         corr = float((a * b_).mean()) / var
         assert abs(corr) < 5.0 / a.numel() ** 0.5
+    # every PAIR of positions inside a 32-column generator group drops jointly at rate pe^2 (the first generator of
+    # round 2 passed everything above and failed this one by ~50 sigma), and the number of drops per group has the
+    # binomial variance
+    g32 = drop.view(-1, 32).double()
+    joint = (g32.t() @ g32) / g32.shape[0]
+    off = joint - pe * pe
+    off.fill_diagonal_(0.0)
+    assert float(off.abs().max()) < 5.5 * (pe * pe * (1 - pe * pe) / g32.shape[0]) ** 0.5
+    assert abs(float(g32.sum(1).var()) / (32 * pe * (1 - pe)) - 1.0) < 0.02
+    for lag in (2, 3, 4, 8, 16):
+        a, b_ = c[:, :-lag], c[:, lag:]
+        assert abs(float((a * b_).mean()) / var) < 5.0 / a.numel() ** 0.5
     other = 1.0 - gu.keep_mask(B, S, d, d, 16, 3, torch.bfloat16, p, 1234, 78).view(B * S, d).float()
     assert abs(float(((other - pe) * c).mean()) / var) < 5.0 / c.numel() ** 0.5
