@@ -741,3 +741,18 @@ def test_dropout_mask_statistics():
         assert abs(float((a * b_).mean()) / var) < 5.0 / a.numel() ** 0.5
     other = 1.0 - gu.keep_mask(B, S, d, d, 16, 3, torch.bfloat16, p, 1234, 78).view(B * S, d).float()
     assert abs(float(((other - pe) * c).mean()) / var) < 5.0 / c.numel() ** 0.5
+
+
+def test_shared_memory_dropout_path_still_matches():
+    """The dropout form of the down-projection defaults to k_down_ts (masked rows staged in TMEM).  k_down_tc<DROP>
+    (tile masked in place in shared memory) remains the fallback when the TMEM / ring budget does not fit and behind
+    MOKA_DOWN_TS=0; the switch is read once per process, so its parity cases run in a child process."""
+    import subprocess
+    import sys
+    env = dict(os.environ, MOKA_DOWN_TS='0')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(root, 'tests', 'test_gpu_parity.py'), '-q', '-x', '-m', 'gpu',
+                        '-k', 'test_dropout_on_tensor_core_path or test_dropout_matches_oracle_on_same_mask'],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert ' passed' in r.stdout

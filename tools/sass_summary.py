@@ -8,7 +8,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, 'moka_b200', 'libmoka.so')
-MNEMONICS = ['UTCHMMA', 'UTCBAR', 'LDTM', 'UTMALDG', 'UTMASTG', 'SYNCS', 'ELECT', 'R2UR', 'HMMA', 'MUFU.EX2', 'RED.E', 'ACQBULK',
+MNEMONICS = ['UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'SYNCS', 'ELECT', 'R2UR', 'HMMA', 'MUFU.EX2', 'RED.E', 'ACQBULK',
              'UTCATOMSWS', 'UBLKCP', 'FENCE.VIEW.ASYNC']
 
 
@@ -40,16 +40,16 @@ def main():
     tot = collections.Counter()
     lines = ['# r02: SASS summary of moka_b200/libmoka.so (sm_100a)', '',
              f'`cuobjdump -sass moka_b200/libmoka.so`, build stamp `{digest}` (sha256 of csrc/ + include/moka.h + flags).',
-             'UTCHMMA = tcgen05.mma, UTCBAR = tcgen05.commit, LDTM = tcgen05.ld (TMEM -> registers), UTMALDG / UTMASTG = TMA tile',
+             'UTCHMMA = tcgen05.mma, UTCBAR = tcgen05.commit, LDTM / STTM = tcgen05.ld / .st (TMEM <-> registers; k_down_ts stages its A operand with STTM and its UTCHMMA reads `tmem[..], gdesc[..]`: the TS form), UTMALDG / UTMASTG = TMA tile',
              'load / store, SYNCS = mbarrier ops, ELECT = elect.sync (one-lane issue of the whole-warp MMA / TMA loops, round 2),',
              'R2UR = vector -> uniform register moves feeding those instructions, HMMA = warp-level mma.sync (attention kernels).', '',
-             '| kernel | SASS instr | ' + ' | '.join(MNEMONICS[:10]) + ' |', '|---|---|' + '---|' * 10]
+             '| kernel | SASS instr | ' + ' | '.join(MNEMONICS[:11]) + ' |', '|---|---|' + '---|' * 11]
     for k, c in kernels.items():
-        if not any(c[m] for m in MNEMONICS[:5]) and not c['HMMA']:
+        if not any(c[m] for m in MNEMONICS[:6]) and not c['HMMA']:
             continue
-        lines.append(f'| `{k[:70]}` | {c["instructions"]} | ' + ' | '.join(str(c[m]) for m in MNEMONICS[:10]) + ' |')
+        lines.append(f'| `{k[:70]}` | {c["instructions"]} | ' + ' | '.join(str(c[m]) for m in MNEMONICS[:11]) + ' |')
         tot.update(c)
-    lines.append('| **total (kernels listed)** | ' + str(tot['instructions']) + ' | ' + ' | '.join(str(tot[m]) for m in MNEMONICS[:10]) + ' |')
+    lines.append('| **total (kernels listed)** | ' + str(tot['instructions']) + ' | ' + ' | '.join(str(tot[m]) for m in MNEMONICS[:11]) + ' |')
     lines += ['', f'Kernels in the library: {len(kernels)}; the rest (warp-FMA path, metadata builders, AdamW, RoPE, keep-mask hook) use none of the above.']
     open(out, 'w').write('\n'.join(lines) + '\n')
     print('\n'.join(lines[-8:]))
