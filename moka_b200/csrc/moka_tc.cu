@@ -1776,14 +1776,22 @@ static int launch_up_tc(const DevDesc& d, const SimtArgs& a, int num_sms, cudaSt
   p.delta = d.delta;
   p.rot = rot_enabled();
   p.dbg = dbg_enabled();
-  // stream-K (persistent, balanced unit ranges; needs the attention as its own kernel): MOKA_UP_STREAMK=1.  OFF by
-  // default - measured round 2 (T = 32768): 106.4 vs 100.9 us at d_out = 4096, 275 vs 253 us at 11008.  This kernel
-  // reads and re-writes the same rows; with 148 CTAs in flight it already sits at what HBM gives that traffic mix
-  // (~5.3 TB/s), so balancing the tail buys nothing and the per-segment restaging of the A operand costs.
-  static int up_sk_env = -1;
-  if (up_sk_env < 0) { const char* e = getenv("MOKA_UP_STREAMK"); up_sk_env = (e && e[0] == '1') ? 1 : 0; }
+  // stream-K (persistent, balanced unit ranges; needs the attention as its own kernel).  ALONE it is slower (T = 32768:
+  // 106.4 vs 100.9 us at d_out = 4096, 275 vs 253 us at 11008): this kernel reads and re-writes the same rows, and
+  // with 148 CTAs in flight it already sits at what HBM gives that traffic mix (~5.5 TB/s), so balancing the tail buys
+  // nothing and the per-segment restaging of the A operand costs.  INSIDE the training step (SM clock 1.5 GHz, every
+  // CTA's hand-off chain slower) the second, 73 %-full wave of 256 tiles on 148 SMs is what costs: 204.7 -> 200.7 us
+  // per forward call at d_out = 4096, 382.0 -> 374.3 us at 11008 (same box, twice; profiles/r02_dropout_cost.md).
+  // Measured worse at one wave or less (T = 8192: 66.3 -> 68.3 us; T = 16384, r = 64: 167 -> 185 us in the step).
+  // Hence: on when the token tiles make more than one wave with a last wave under 90 % full and the operand is
+  // narrow (r <= 32); MOKA_UP_STREAMK=0 / 1 forces it.
+  static int up_sk_env = -2;
+  if (up_sk_env == -2) { const char* e = getenv("MOKA_UP_STREAMK"); up_sk_env = e ? ((e[0] == '1') ? 1 : 0) : -1; }
   p.units = (long long)ntiles * p.chunks;
-  p.streamk = (up_sk_env && sep_attn && p.units >= 2) ? 1 : 0;
+  const int waves = (ntiles * p.nsplit + num_sms - 1) / num_sms;
+  const bool ragged = waves > 1 && (double)(ntiles * p.nsplit) / ((double)waves * num_sms) < 0.9;
+  const int want_sk = up_sk_env >= 0 ? up_sk_env : ((ragged && p.rk <= 32 && !d.delta) ? 1 : 0);
+  p.streamk = (want_sk && sep_attn && p.units >= 2) ? 1 : 0;
   p.grid = p.streamk ? (int)std::min<long long>(num_sms, p.units) : ntiles * p.nsplit;
   CUtensorMap ty0, ty;
   if (!make_tmap(&ty0, d.delta ? a.y : a.y0, (uint64_t)d.T, (uint64_t)d.d_out, 128)) return MOKA_EUNSUPPORTED;
