@@ -39,6 +39,12 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = 'llama2-7b-avt-m3-r16-s2048'
 
 
+def metric_name(wl) -> str:
+    """BASELINE.json's metric; names the model the workload really runs (13B for configs[3])."""
+    model = {'7b': 'Llama-2-7B', '13b': 'Llama-2-13B'}.get(wl['model'], wl['model'])
+    return f'tokens/sec {model} MokA fine-tune step'
+
+
 def peak_hbm():
     try:
         return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'], 'measured'
@@ -399,7 +405,7 @@ def main():
         if rank != 0:
             return 0
         base, t_layer = cpu_reference_leg(wl, seconds_budget=150.0, steps=max(args.steps, 5), warmup=max(args.warmup, 2))
-        line = dict(metric='tokens/sec Llama-2-7B MokA fine-tune step', value=base['value'], unit='tokens/s',
+        line = dict(metric=metric_name(wl), value=base['value'], unit='tokens/s',
                     impl='reference', n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                     ms_per_step=t_layer * 1e3, higher_is_better=True, scaling='weak', vs_baseline=None,
                     dtype=base['dtype'], data='synthetic',
@@ -505,7 +511,7 @@ def main():
         e2e_value = tokens_per_step * args.steps / (ms_e2e * 1e-3)
         uses_tc = kernel_path_name(wl, cfg.hidden_size, args.flags)
         line = dict(
-            metric='tokens/sec Llama-2-7B MokA fine-tune step', value=value, unit='tokens/s', n_gpus=world,
+            metric=metric_name(wl), value=value, unit='tokens/s', n_gpus=world,
             steps=args.steps, warmup=warmup, ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling='weak',
             vs_baseline=None, dtype='bf16', data='synthetic', impl='moka_b200',
             config=dict(workload=args.workload, micro_batch_per_gpu=wl['B'], seq_len=wl['S'], rank=wl['r'],
