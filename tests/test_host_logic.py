@@ -231,3 +231,16 @@ def test_flag_constants_match_the_header_and_fusion_is_opt_in():
     from moka_b200 import layer
     if os.environ.get('MOKA_DELTA', '0') != '1':
         assert layer.FUSION['enabled'] is False
+
+
+def test_bench_workloads_name_the_baseline_configs():
+    """bench.py: the default workload is BASELINE.json's metric shape (7B, r = 16, three modalities), the other two
+    named workloads are configs[1] and configs[3], and the metric string names the model the workload really runs."""
+    import bench
+    wl = bench.WORKLOADS[bench.DEFAULT_WORKLOAD]
+    assert (wl['model'], wl['r'], wl['M'], wl['S']) == ('7b', 16, 3, 2048)
+    assert bench.metric_name(wl) == 'tokens/sec Llama-2-7B MokA fine-tune step'
+    c2, c4 = bench.WORKLOADS['llama2-7b-vt-m2-r8-s2048'], bench.WORKLOADS['llama2-13b-vt-m2-r64-s4096']
+    assert (c2['variant'], c2['r'], c2['S']) == ('vt', 8, 2048)
+    assert (c4['variant'], c4['r'], c4['S']) == ('vt', 64, 4096)
+    assert bench.metric_name(c4) == 'tokens/sec Llama-2-13B MokA fine-tune step'
